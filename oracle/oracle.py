@@ -1,0 +1,186 @@
+"""ctypes front-end of the CPU ORACLE (test infrastructure, NOT product code).
+
+Wraps ``oracle/libgymoracle.so`` (built from ``oracle/gym_oracle.c``), the plain-C
+restatement of gym 0.26.2's classic-control ``step()/reset()`` path.  Only
+``tests/``, ``__graft_entry__.smoke()`` and ``bench.py``'s ``cpu_baseline`` /
+``--impl reference`` legs may import this module; nothing under ``gym_b200/``
+does.  Parity status: pinned (see ``oracle/gen_golden.py`` and ``tests/golden``).
+"""
+import ctypes
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB_PATH = os.path.join(_HERE, "libgymoracle.so")
+
+KINDS = {
+    "CartPole": 0,
+    "MountainCar": 1,
+    "MountainCarContinuous": 2,
+    "Pendulum": 3,
+    "Acrobot": 4,
+}
+
+# gym/envs/__init__.py:11-60 registry constants restated: id -> (kind, max_episode_steps)
+ENV_IDS = {
+    "CartPole-v0": ("CartPole", 200),
+    "CartPole-v1": ("CartPole", 500),
+    "MountainCar-v0": ("MountainCar", 200),
+    "MountainCarContinuous-v0": ("MountainCarContinuous", 999),
+    "Pendulum-v1": ("Pendulum", 200),
+    "Acrobot-v1": ("Acrobot", 500),
+}
+
+
+def build(force=False):
+    """Compile the oracle with the recipe in oracle/Makefile (gcc, no FMA contraction)."""
+    src = os.path.join(_HERE, "gym_oracle.c")
+    if (force or not os.path.exists(_LIB_PATH)
+            or os.path.getmtime(_LIB_PATH) < os.path.getmtime(src)):
+        subprocess.check_call(["make", "-s", "-C", _HERE, "libgymoracle.so"])
+    return _LIB_PATH
+
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        build()
+        L = ctypes.CDLL(_LIB_PATH)
+        vp, i64, i32, dbl = ctypes.c_void_p, ctypes.c_int64, ctypes.c_int, ctypes.c_double
+        L.orc_vec_create.restype = vp
+        L.orc_vec_create.argtypes = [i32, i64, i32, dbl]
+        L.orc_vec_destroy.argtypes = [vp]
+        L.orc_seed_sequence.argtypes = [vp, vp]
+        L.orc_vec_seed_env.argtypes = [vp, i64, vp]
+        L.orc_vec_seed_range.argtypes = [vp, vp, i64]
+        L.orc_vec_get_rng.argtypes = [vp, vp]
+        L.orc_vec_set_rng.argtypes = [vp, vp]
+        L.orc_vec_next_double.restype = dbl
+        L.orc_vec_next_double.argtypes = [vp, i64]
+        L.orc_vec_reset.argtypes = [vp, vp, vp, vp]
+        L.orc_vec_step.restype = i64
+        L.orc_vec_step.argtypes = [vp, vp, vp, vp, vp, vp, vp, i32]
+        L.orc_vec_get_state.argtypes = [vp, vp, vp]
+        L.orc_vec_set_state.argtypes = [vp, vp, vp]
+        for f in ("orc_obs_dim", "orc_act_dim", "orc_state_dim", "orc_num_actions"):
+            getattr(L, f).argtypes = [i32]
+        _lib = L
+    return _lib
+
+
+def seed_words(seed):
+    """Non-negative int (< 2**128) -> four little-endian uint32 entropy words."""
+    seed = int(seed)
+    if seed < 0 or seed >= 1 << 128:
+        raise ValueError("oracle supports 0 <= seed < 2**128")
+    return np.array([(seed >> (32 * k)) & 0xFFFFFFFF for k in range(4)], dtype=np.uint32)
+
+
+def seed_sequence(seed):
+    """SeedSequence(seed).generate_state(4, np.uint64) through the C restatement."""
+    out = np.zeros(4, dtype=np.uint64)
+    ent = seed_words(seed)
+    lib().orc_seed_sequence(ent.ctypes.data, out.ctypes.data)
+    return out
+
+
+def _ptr(a):
+    return None if a is None else a.ctypes.data
+
+
+class OracleVec:
+    """SyncVectorEnv([make(id)] * n) restated in C: TimeLimit + same-step autoreset fused."""
+
+    def __init__(self, env_id, num_envs, max_episode_steps=None, param0=None):
+        if env_id in ENV_IDS:
+            kind_name, default_max = ENV_IDS[env_id]
+        else:
+            kind_name, default_max = env_id, 0
+        self.kind = KINDS[kind_name]
+        self.kind_name = kind_name
+        self.n = int(num_envs)
+        self.max_episode_steps = default_max if max_episode_steps is None else int(max_episode_steps)
+        if param0 is None:
+            param0 = 10.0 if kind_name == "Pendulum" else 0.0
+        L = lib()
+        self.obs_dim = L.orc_obs_dim(self.kind)
+        self.act_dim = L.orc_act_dim(self.kind)
+        self.state_dim = L.orc_state_dim(self.kind)
+        self.num_actions = L.orc_num_actions(self.kind)
+        self._h = L.orc_vec_create(self.kind, self.n, self.max_episode_steps, float(param0))
+        if not self._h:
+            raise ValueError("orc_vec_create failed")
+
+    def close(self):
+        if getattr(self, "_h", None):
+            lib().orc_vec_destroy(self._h)
+            self._h = None
+
+    __del__ = close
+
+    # -- RNG ------------------------------------------------------------
+    def seed(self, seed, first=0):
+        """int -> env i gets seed+first+i; sequence -> per-env seeds (None keeps the stream)."""
+        L = lib()
+        if isinstance(seed, (int, np.integer)):
+            L.orc_vec_seed_range(self._h, seed_words(seed).ctypes.data, int(first))
+        else:
+            assert len(seed) == self.n
+            for i, s in enumerate(seed):
+                if s is not None:
+                    L.orc_vec_seed_env(self._h, i, seed_words(s).ctypes.data)
+
+    def get_rng(self):
+        out = np.zeros((self.n, 4), dtype=np.uint64)
+        lib().orc_vec_get_rng(self._h, out.ctypes.data)
+        return out
+
+    def set_rng(self, rng):
+        rng = np.ascontiguousarray(rng, dtype=np.uint64).reshape(self.n, 4)
+        lib().orc_vec_set_rng(self._h, rng.ctypes.data)
+
+    def next_double(self, i=0):
+        return lib().orc_vec_next_double(self._h, int(i))
+
+    # -- env API ----------------------------------------------------------
+    def reset(self, seed=None, bounds=None, mask=None):
+        if seed is not None:
+            self.seed(seed)
+        obs = np.zeros((self.n, self.obs_dim), dtype=np.float32)
+        b = None if bounds is None else np.asarray(bounds, dtype=np.float64)
+        m = None if mask is None else np.ascontiguousarray(mask, dtype=np.uint8)
+        lib().orc_vec_reset(self._h, _ptr(m), _ptr(b), obs.ctypes.data)
+        return obs
+
+    def step(self, actions, nthreads=1):
+        if self.act_dim == 0:
+            a = np.ascontiguousarray(actions, dtype=np.int64).reshape(self.n)
+        else:
+            a = np.ascontiguousarray(actions, dtype=np.float32).reshape(self.n, self.act_dim)
+        obs = np.zeros((self.n, self.obs_dim), dtype=np.float32)
+        final_obs = np.zeros((self.n, self.obs_dim), dtype=np.float32)
+        reward = np.zeros(self.n, dtype=np.float64)
+        term = np.zeros(self.n, dtype=np.uint8)
+        trunc = np.zeros(self.n, dtype=np.uint8)
+        bad = lib().orc_vec_step(self._h, a.ctypes.data, obs.ctypes.data, reward.ctypes.data,
+                                 term.ctypes.data, trunc.ctypes.data, final_obs.ctypes.data,
+                                 int(nthreads))
+        if bad:
+            raise AssertionError(f"{bad} invalid discrete action(s)")
+        return obs, reward, term.astype(bool), trunc.astype(bool), final_obs
+
+    def get_state(self):
+        s = np.zeros((self.n, self.state_dim), dtype=np.float64)
+        e = np.zeros(self.n, dtype=np.int32)
+        lib().orc_vec_get_state(self._h, s.ctypes.data, e.ctypes.data)
+        return s, e
+
+    def set_state(self, state=None, elapsed=None):
+        s = None if state is None else np.ascontiguousarray(state, dtype=np.float64)
+        e = None if elapsed is None else np.ascontiguousarray(elapsed, dtype=np.int32)
+        lib().orc_vec_set_state(self._h, _ptr(s), _ptr(e))

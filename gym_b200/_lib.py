@@ -1,0 +1,103 @@
+"""ctypes binding of ``libb200gym.so`` -- the reference-side stub of INTEGRATION.md.
+
+The shared library is built in-tree by ``gym_b200.build.build()`` (nvcc,
+``-gencode arch=compute_100a,code=sm_100a``).  There is no CPU fallback: if the
+library is missing, ``load()`` raises ``DependencyNotInstalled`` and every env
+constructor fails loudly.
+"""
+import ctypes
+import os
+
+from gym_b200 import error
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libb200gym.so")
+
+# enum b200gym_kind (include/b200gym.h)
+KIND_CARTPOLE = 0
+KIND_MOUNTAINCAR = 1
+KIND_MOUNTAINCAR_CONT = 2
+KIND_PENDULUM = 3
+KIND_ACROBOT = 4
+
+# enum b200gym_action_dtype
+ACT_I64, ACT_I32, ACT_U8, ACT_F32 = 0, 1, 2, 3
+
+
+class Config(ctypes.Structure):
+    """struct b200gym_config"""
+    _fields_ = [
+        ("kind", ctypes.c_int32),
+        ("max_episode_steps", ctypes.c_int32),
+        ("autoreset", ctypes.c_int32),
+        ("reserved", ctypes.c_int32),
+        ("param", ctypes.c_double * 4),
+    ]
+
+
+class HostIO(ctypes.Structure):
+    """struct b200gym_host_io"""
+    _fields_ = [
+        ("actions", ctypes.c_void_p),
+        ("obs", ctypes.c_void_p),
+        ("reward", ctypes.c_void_p),
+        ("terminated", ctypes.c_void_p),
+        ("truncated", ctypes.c_void_p),
+        ("final_obs", ctypes.c_void_p),
+    ]
+
+
+# every symbol include/b200gym.h declares: name -> (restype, argtypes)
+_vp, _i64, _i32 = ctypes.c_void_p, ctypes.c_int64, ctypes.c_int
+SIGNATURES = {
+    "b200gym_obs_dim": (_i32, [_i32]),
+    "b200gym_act_dim": (_i32, [_i32]),
+    "b200gym_num_actions": (_i32, [_i32]),
+    "b200gym_state_dim": (_i32, [_i32]),
+    "b200gym_version": (_i32, []),
+    "b200gym_last_error": (ctypes.c_char_p, [_vp]),
+    "b200gym_create": (_i32, [ctypes.POINTER(Config), _i64, _i32, ctypes.POINTER(_vp)]),
+    "b200gym_destroy": (None, [_vp]),
+    "b200gym_num_envs": (_i64, [_vp]),
+    "b200gym_device": (_i32, [_vp]),
+    "b200gym_seed_range": (_i32, [_vp, _vp, _i64, _vp]),
+    "b200gym_seed_each": (_i32, [_vp, _vp, _vp, _vp]),
+    "b200gym_reset": (_i32, [_vp, _vp, _vp, _vp, _vp]),
+    "b200gym_step": (_i32, [_vp, _vp, _i32, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "b200gym_invalid_actions": (_i32, [_vp, _vp, ctypes.POINTER(_i64)]),
+    "b200gym_host_buffers": (_i32, [_vp, ctypes.POINTER(HostIO)]),
+    "b200gym_step_host": (_i32, [_vp, _vp, _i32, _vp, _vp, _vp, _vp, _vp]),
+    "b200gym_reset_host": (_i32, [_vp, _vp, _vp, _vp]),
+    "b200gym_get_state": (_i32, [_vp, _vp, _vp, _vp, _vp]),
+    "b200gym_set_state": (_i32, [_vp, _vp, _vp, _vp, _vp]),
+}
+
+_lib = None
+
+
+def load():
+    """dlopen the in-tree library and type every entry point; raises if it is not built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise error.DependencyNotInstalled(
+            f"{LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+            "(gym_b200 has no CPU fallback)")
+    lib = ctypes.CDLL(LIB_PATH)
+    for name, (restype, argtypes) in SIGNATURES.items():
+        fn = getattr(lib, name)  # AttributeError here = header and library disagree
+        fn.restype = restype
+        fn.argtypes = argtypes
+    _lib = lib
+    return lib
+
+
+def last_error(handle=None):
+    msg = load().b200gym_last_error(handle)
+    return msg.decode() if msg else ""
+
+
+def check(rc, handle=None):
+    if rc != 0:
+        raise RuntimeError("b200gym: " + last_error(handle))

@@ -1,0 +1,625 @@
+// b200gym.cu -- kernels + C ABI of the B200-native vectorised Gym engine.
+//
+// Hot path (reference: SyncVectorEnv.step_wait, gym/vector/sync_vector_env.py:135-169):
+//   ONE kernel launch per vector step; one thread per environment instance;
+//   Env.step + TimeLimit + same-step autoreset (with the env's own PCG64
+//   stream) + observation/reward/flag emission fused.
+//
+// HBM layout (persistent, owned by the handle)
+//   state   float64 [S][n]   SoA: lane i of a warp reads word k of env i -> 256 B
+//                            contiguous per warp per word, fully coalesced
+//   elapsed int32   [n]      TimeLimit._elapsed_steps
+//   flags   uint8   [n]      bit0: "already terminated" (plain-Env mode only)
+//   rng     uint64  [n][4]   numpy PCG64 {state_hi, state_lo, inc_hi, inc_lo}; AoS,
+//                            touched only by lanes that reset
+// I/O buffers are caller-owned (torch.cuda tensors): actions in; obs [n][D]
+// float32, reward float64 [n], terminated/truncated uint8 [n], final_obs [n][D].
+//
+// Built for sm_100a only, with -fmad=false (see envs.cuh).
+#include <cuda_runtime.h>
+
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <string>
+
+#include "../../include/b200gym.h"
+#include "envs.cuh"
+#include "rng.cuh"
+
+using namespace bgym;
+
+// ---------------------------------------------------------------------------
+// handle
+// ---------------------------------------------------------------------------
+struct b200gym {
+    b200gym_config cfg;
+    int64_t n = 0;
+    int device = 0;
+    int S = 0, D = 0, A = 0, NACT = 0;
+    double *state = nullptr;
+    int32_t *elapsed = nullptr;
+    uint8_t *flags = nullptr;
+    uint64_t *rng = nullptr;
+    unsigned long long *invalid = nullptr;  // sticky device counter
+    // host-I/O path (lazily created)
+    b200gym_host_io hio{};
+    b200gym_host_io dio{};  // device mirrors of the staging buffers
+    uint8_t *d_mask = nullptr;
+    cudaStream_t hstream[2] = {nullptr, nullptr};
+    bool host_ready = false;
+    mutable std::string err;
+};
+
+static thread_local std::string g_create_err;
+
+static int fail(const b200gym *h, const char *fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    if (h) h->err = buf;
+    else g_create_err = buf;
+    return 1;
+}
+
+#define CK(h, call)                                                                       \
+    do {                                                                                  \
+        cudaError_t e_ = (call);                                                          \
+        if (e_ != cudaSuccess)                                                            \
+            return fail(h, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
+    } while (0)
+
+static const int k_obs_dim[B200GYM_NUM_KINDS] = {4, 2, 2, 3, 6};
+static const int k_act_dim[B200GYM_NUM_KINDS] = {0, 0, 1, 1, 0};
+static const int k_nact[B200GYM_NUM_KINDS] = {2, 3, 0, 0, 3};
+static const int k_state_dim[B200GYM_NUM_KINDS] = {4, 2, 2, 2, 4};
+
+static bool kind_ok(int k) { return k >= 0 && k < B200GYM_NUM_KINDS; }
+
+extern "C" int b200gym_obs_dim(int kind) { return kind_ok(kind) ? k_obs_dim[kind] : -1; }
+extern "C" int b200gym_act_dim(int kind) { return kind_ok(kind) ? k_act_dim[kind] : -1; }
+extern "C" int b200gym_num_actions(int kind) { return kind_ok(kind) ? k_nact[kind] : -1; }
+extern "C" int b200gym_state_dim(int kind) { return kind_ok(kind) ? k_state_dim[kind] : -1; }
+extern "C" int b200gym_version(void) { return B200GYM_VERSION; }
+extern "C" const char *b200gym_last_error(const b200gym_t *h) {
+    return h ? h->err.c_str() : g_create_err.c_str();
+}
+extern "C" int64_t b200gym_num_envs(const b200gym_t *h) { return h ? h->n : -1; }
+extern "C" int b200gym_device(const b200gym_t *h) { return h ? h->device : -1; }
+
+// ---------------------------------------------------------------------------
+// kernels
+// ---------------------------------------------------------------------------
+constexpr int kThreads = 256;
+
+struct StepArgs {
+    double *state;
+    int32_t *elapsed;
+    uint8_t *flags;
+    uint64_t *rng;
+    unsigned long long *invalid;
+    const void *actions;
+    float *obs;
+    double *reward;
+    uint8_t *terminated;
+    uint8_t *truncated;
+    float *final_obs;
+    int64_t n;        // envs in the handle (SoA stride)
+    int64_t first;    // sub-range processed by this launch
+    int64_t count;
+    int32_t max_steps;
+    int32_t autoreset;
+    double param0;
+};
+
+template <int D>
+__device__ __forceinline__ void store_row(float *base, int64_t i, const float (&v)[D]) {
+    if constexpr (D == 4) {
+        reinterpret_cast<float4 *>(base)[i] = make_float4(v[0], v[1], v[2], v[3]);
+    } else if constexpr (D == 2) {
+        reinterpret_cast<float2 *>(base)[i] = make_float2(v[0], v[1]);
+    } else if constexpr (D == 6) {
+        float2 *p = reinterpret_cast<float2 *>(base) + 3 * i;
+        p[0] = make_float2(v[0], v[1]);
+        p[1] = make_float2(v[2], v[3]);
+        p[2] = make_float2(v[4], v[5]);
+    } else {
+#pragma unroll
+        for (int k = 0; k < D; k++) base[i * D + k] = v[k];
+    }
+}
+
+template <typename ActT>
+__device__ __forceinline__ ActT load_action(const void *actions, int64_t i) {
+    return __ldg(reinterpret_cast<const ActT *>(actions) + i);
+}
+
+// One thread per environment: Env.step + TimeLimit + autoreset, fused.
+template <int KIND, typename ActT>
+__global__ void __launch_bounds__(kThreads) step_kernel(const StepArgs a) {
+    using E = Env<KIND>;
+    const int64_t j = (int64_t)blockIdx.x * kThreads + threadIdx.x;
+    if (j >= a.count) return;
+    const int64_t i = a.first + j;
+
+    double s[E::S];
+#pragma unroll
+    for (int k = 0; k < E::S; k++) s[k] = a.state[k * a.n + i];
+    int32_t elapsed = a.elapsed[i];
+
+    int act = 0;
+    float a0 = 0.0f;
+    if constexpr (E::A == 0) {
+        const long long av = (long long)load_action<ActT>(a.actions, i);
+        if (av < 0 || av >= E::NACT) {
+            // the reference raises (cartpole.py:132 / mountain_car.py:128-130 / acrobot.py:199):
+            // leave the env untouched, flag it, return NaN reward
+            atomicAdd(a.invalid, 1ULL);
+            a.reward[i] = __longlong_as_double(0x7ff8000000000000LL);
+            a.terminated[i] = 0;
+            a.truncated[i] = 0;
+            return;
+        }
+        act = (int)av;
+    } else {
+        a0 = (float)load_action<ActT>(a.actions, i);
+    }
+
+    float obs[E::D];
+    double reward;
+    bool terminated;
+    E::step(s, elapsed == 0, act, a0, a.param0, obs, reward, terminated);
+
+    if (!a.autoreset) {
+        if constexpr (KIND == B200GYM_CARTPOLE) {
+            // cartpole.py:169-184: reward 0.0 once the pole has already fallen
+            const uint8_t f = a.flags[i];
+            if (terminated) {
+                if (f & 1) reward = 0.0;
+                else a.flags[i] = f | 1;
+            }
+        }
+    }
+
+    elapsed += 1;                                                        // time_limit.py:51
+    const bool truncated = (a.max_steps > 0) && (elapsed >= a.max_steps);  // :53-54
+
+    if ((terminated || truncated) && a.autoreset) {                      // sync_vector_env.py:152-156
+        if (a.final_obs) store_row<E::D>(a.final_obs, i, obs);
+        Pcg64 g = pcg64_load(a.rng + 4 * i);
+        double lo, hi;
+        E::default_bounds(lo, hi);
+        E::reset(s, g, lo, hi, obs);
+        pcg64_store(a.rng + 4 * i, g);
+        elapsed = 0;                                                     // time_limit.py:67
+    }
+
+#pragma unroll
+    for (int k = 0; k < E::S; k++) a.state[k * a.n + i] = s[k];
+    a.elapsed[i] = elapsed;
+    store_row<E::D>(a.obs, i, obs);
+    a.reward[i] = reward;
+    a.terminated[i] = terminated ? 1 : 0;
+    a.truncated[i] = truncated ? 1 : 0;
+}
+
+template <int KIND>
+__global__ void __launch_bounds__(kThreads) reset_kernel(double *state, int32_t *elapsed, uint8_t *flags,
+                                                         uint64_t *rng, const uint8_t *mask, float *obs,
+                                                         int64_t n, double lo, double hi) {
+    using E = Env<KIND>;
+    const int64_t i = (int64_t)blockIdx.x * kThreads + threadIdx.x;
+    if (i >= n) return;
+    if (mask && !mask[i]) return;
+    double s[E::S];
+    float o[E::D];
+    Pcg64 g = pcg64_load(rng + 4 * i);
+    E::reset(s, g, lo, hi, o);
+    pcg64_store(rng + 4 * i, g);
+#pragma unroll
+    for (int k = 0; k < E::S; k++) state[k * n + i] = s[k];
+    elapsed[i] = 0;
+    flags[i] = 0;
+    if (obs) store_row<E::D>(obs, i, o);
+}
+
+// SeedSequence(base + first + i) -> PCG64, one thread per env
+__global__ void __launch_bounds__(kThreads) seed_range_kernel(uint64_t *rng, int64_t n, uint32_t b0, uint32_t b1,
+                                                              uint32_t b2, uint32_t b3, uint64_t first) {
+    const int64_t i = (int64_t)blockIdx.x * kThreads + threadIdx.x;
+    if (i >= n) return;
+    const u128 base = ((u128)b3 << 96) | ((u128)b2 << 64) | ((u128)b1 << 32) | (u128)b0;
+    const u128 seed = base + (u128)(first + (uint64_t)i);
+    const uint32_t ent[4] = {(uint32_t)seed, (uint32_t)(seed >> 32), (uint32_t)(seed >> 64), (uint32_t)(seed >> 96)};
+    Pcg64 g;
+    pcg64_from_entropy(g, ent);
+    pcg64_store_full(rng + 4 * i, g);
+}
+
+__global__ void __launch_bounds__(kThreads) seed_each_kernel(uint64_t *rng, int64_t n, const uint32_t *ent,
+                                                             const uint8_t *mask) {
+    const int64_t i = (int64_t)blockIdx.x * kThreads + threadIdx.x;
+    if (i >= n) return;
+    if (mask && !mask[i]) return;
+    const uint32_t e[4] = {ent[4 * i], ent[4 * i + 1], ent[4 * i + 2], ent[4 * i + 3]};
+    Pcg64 g;
+    pcg64_from_entropy(g, e);
+    pcg64_store_full(rng + 4 * i, g);
+}
+
+// [n][S] AoS wire format <-> [S][n] SoA
+__global__ void __launch_bounds__(kThreads) state_get_kernel(const double *soa, double *aos, int64_t n, int S) {
+    const int64_t i = (int64_t)blockIdx.x * kThreads + threadIdx.x;
+    if (i >= n) return;
+    for (int k = 0; k < S; k++) aos[i * S + k] = soa[k * n + i];
+}
+__global__ void __launch_bounds__(kThreads) state_set_kernel(double *soa, const double *aos, int64_t n, int S) {
+    const int64_t i = (int64_t)blockIdx.x * kThreads + threadIdx.x;
+    if (i >= n) return;
+    for (int k = 0; k < S; k++) soa[k * n + i] = aos[i * S + k];
+}
+
+static inline unsigned blocks_for(int64_t n) { return (unsigned)((n + kThreads - 1) / kThreads); }
+
+// ---------------------------------------------------------------------------
+// dispatch
+// ---------------------------------------------------------------------------
+template <int KIND>
+static int launch_step_kind(b200gym *h, const StepArgs &a, int action_dtype, cudaStream_t st) {
+    using E = Env<KIND>;
+    const unsigned grid = blocks_for(a.count);
+    if constexpr (E::A == 0) {
+        switch (action_dtype) {
+        case B200GYM_ACT_I64: step_kernel<KIND, long long><<<grid, kThreads, 0, st>>>(a); break;
+        case B200GYM_ACT_I32: step_kernel<KIND, int><<<grid, kThreads, 0, st>>>(a); break;
+        case B200GYM_ACT_U8: step_kernel<KIND, unsigned char><<<grid, kThreads, 0, st>>>(a); break;
+        default: return fail(h, "Discrete env needs an integer action dtype (got code %d)", action_dtype);
+        }
+    } else {
+        if (action_dtype != B200GYM_ACT_F32)
+            return fail(h, "Box env needs float32 actions (got dtype code %d)", action_dtype);
+        step_kernel<KIND, float><<<grid, kThreads, 0, st>>>(a);
+    }
+    CK(h, cudaGetLastError());
+    return 0;
+}
+
+static int launch_step(b200gym *h, const StepArgs &a, int action_dtype, cudaStream_t st) {
+    switch (h->cfg.kind) {
+    case B200GYM_CARTPOLE: return launch_step_kind<B200GYM_CARTPOLE>(h, a, action_dtype, st);
+    case B200GYM_MOUNTAINCAR: return launch_step_kind<B200GYM_MOUNTAINCAR>(h, a, action_dtype, st);
+    case B200GYM_MOUNTAINCAR_CONT: return launch_step_kind<B200GYM_MOUNTAINCAR_CONT>(h, a, action_dtype, st);
+    case B200GYM_PENDULUM: return launch_step_kind<B200GYM_PENDULUM>(h, a, action_dtype, st);
+    case B200GYM_ACROBOT: return launch_step_kind<B200GYM_ACROBOT>(h, a, action_dtype, st);
+    }
+    return fail(h, "bad kind %d", h->cfg.kind);
+}
+
+template <int KIND>
+static void launch_reset_kind(b200gym *h, const uint8_t *mask, const double *bounds, float *obs, cudaStream_t st) {
+    double lo, hi;
+    Env<KIND>::default_bounds(lo, hi);
+    if (bounds) { lo = bounds[0]; hi = bounds[1]; }
+    reset_kernel<KIND><<<blocks_for(h->n), kThreads, 0, st>>>(h->state, h->elapsed, h->flags, h->rng, mask, obs,
+                                                              h->n, lo, hi);
+}
+
+static int launch_reset(b200gym *h, const uint8_t *mask, const double *bounds, float *obs, cudaStream_t st) {
+    switch (h->cfg.kind) {
+    case B200GYM_CARTPOLE: launch_reset_kind<B200GYM_CARTPOLE>(h, mask, bounds, obs, st); break;
+    case B200GYM_MOUNTAINCAR: launch_reset_kind<B200GYM_MOUNTAINCAR>(h, mask, bounds, obs, st); break;
+    case B200GYM_MOUNTAINCAR_CONT: launch_reset_kind<B200GYM_MOUNTAINCAR_CONT>(h, mask, bounds, obs, st); break;
+    case B200GYM_PENDULUM: launch_reset_kind<B200GYM_PENDULUM>(h, mask, bounds, obs, st); break;
+    case B200GYM_ACROBOT: launch_reset_kind<B200GYM_ACROBOT>(h, mask, bounds, obs, st); break;
+    default: return fail(h, "bad kind %d", h->cfg.kind);
+    }
+    CK(h, cudaGetLastError());
+    return 0;
+}
+
+// ---------------------------------------------------------------------------
+// C ABI
+// ---------------------------------------------------------------------------
+struct DeviceGuard {
+    int prev = -1;
+    explicit DeviceGuard(int dev) {
+        cudaGetDevice(&prev);
+        if (prev != dev) cudaSetDevice(dev);
+        else prev = -1;
+    }
+    ~DeviceGuard() {
+        if (prev >= 0) cudaSetDevice(prev);
+    }
+};
+
+extern "C" int b200gym_create(const b200gym_config *cfg, int64_t num_envs, int device, b200gym_t **out) {
+    if (!cfg || !out) return fail(nullptr, "b200gym_create: null argument");
+    *out = nullptr;
+    if (!kind_ok(cfg->kind)) return fail(nullptr, "b200gym_create: unknown env kind %d", cfg->kind);
+    if (num_envs <= 0) return fail(nullptr, "b200gym_create: num_envs must be positive (got %lld)", (long long)num_envs);
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0)
+        return fail(nullptr, "b200gym_create: no CUDA device available (%s); this engine has no CPU fallback",
+                    cudaGetErrorString(e));
+    if (device < 0 || device >= ndev) return fail(nullptr, "b200gym_create: bad device %d (have %d)", device, ndev);
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, device) == cudaSuccess && prop.major != 10)
+        return fail(nullptr, "b200gym_create: device %d is sm_%d%d; this library contains sm_100a code only",
+                    device, prop.major, prop.minor);
+    b200gym *h = new (std::nothrow) b200gym();
+    if (!h) return fail(nullptr, "b200gym_create: out of host memory");
+    h->cfg = *cfg;
+    h->n = num_envs;
+    h->device = device;
+    h->S = k_state_dim[cfg->kind];
+    h->D = k_obs_dim[cfg->kind];
+    h->A = k_act_dim[cfg->kind];
+    h->NACT = k_nact[cfg->kind];
+    DeviceGuard guard(device);
+    const size_t n = (size_t)num_envs;
+    cudaError_t es[5] = {
+        cudaMalloc(&h->state, sizeof(double) * n * h->S), cudaMalloc(&h->elapsed, sizeof(int32_t) * n),
+        cudaMalloc(&h->flags, n), cudaMalloc(&h->rng, 32 * n), cudaMalloc(&h->invalid, sizeof(unsigned long long))};
+    for (cudaError_t ei : es)
+        if (ei != cudaSuccess) {
+            fail(nullptr, "b200gym_create: cudaMalloc failed: %s", cudaGetErrorString(ei));
+            b200gym_destroy(h);
+            return 1;
+        }
+    cudaMemset(h->state, 0, sizeof(double) * n * h->S);
+    cudaMemset(h->elapsed, 0, sizeof(int32_t) * n);
+    cudaMemset(h->flags, 0, n);
+    cudaMemset(h->rng, 0, 32 * n);
+    cudaMemset(h->invalid, 0, sizeof(unsigned long long));
+    if (cudaDeviceSynchronize() != cudaSuccess) {
+        fail(nullptr, "b200gym_create: device initialisation failed: %s", cudaGetErrorString(cudaGetLastError()));
+        b200gym_destroy(h);
+        return 1;
+    }
+    *out = h;
+    return 0;
+}
+
+static void free_host_io(b200gym *h) {
+    if (!h->host_ready) return;
+    cudaFreeHost(h->hio.actions); cudaFreeHost(h->hio.obs); cudaFreeHost(h->hio.reward);
+    cudaFreeHost(h->hio.terminated); cudaFreeHost(h->hio.truncated); cudaFreeHost(h->hio.final_obs);
+    cudaFree(h->dio.actions); cudaFree(h->dio.obs); cudaFree(h->dio.reward);
+    cudaFree(h->dio.terminated); cudaFree(h->dio.truncated); cudaFree(h->dio.final_obs);
+    cudaFree(h->d_mask);
+    for (cudaStream_t st : h->hstream)
+        if (st) cudaStreamDestroy(st);
+    h->host_ready = false;
+}
+
+extern "C" void b200gym_destroy(b200gym_t *h) {
+    if (!h) return;
+    DeviceGuard guard(h->device);
+    free_host_io(h);
+    cudaFree(h->state);
+    cudaFree(h->elapsed);
+    cudaFree(h->flags);
+    cudaFree(h->rng);
+    cudaFree(h->invalid);
+    delete h;
+}
+
+extern "C" int b200gym_seed_range(b200gym_t *h, const uint32_t base_words[4], int64_t first_index, void *stream) {
+    if (!h || !base_words) return fail(h, "b200gym_seed_range: null argument");
+    if (first_index < 0) return fail(h, "b200gym_seed_range: negative first_index");
+    DeviceGuard guard(h->device);
+    seed_range_kernel<<<blocks_for(h->n), kThreads, 0, (cudaStream_t)stream>>>(
+        h->rng, h->n, base_words[0], base_words[1], base_words[2], base_words[3], (uint64_t)first_index);
+    CK(h, cudaGetLastError());
+    return 0;
+}
+
+extern "C" int b200gym_seed_each(b200gym_t *h, const uint32_t *ent_host, const uint8_t *mask_host, void *stream) {
+    if (!h || !ent_host) return fail(h, "b200gym_seed_each: null argument");
+    DeviceGuard guard(h->device);
+    cudaStream_t st = (cudaStream_t)stream;
+    uint32_t *d_ent = nullptr;
+    uint8_t *d_mask = nullptr;
+    CK(h, cudaMalloc(&d_ent, 16 * (size_t)h->n));
+    cudaError_t e = cudaMemcpyAsync(d_ent, ent_host, 16 * (size_t)h->n, cudaMemcpyHostToDevice, st);
+    if (e == cudaSuccess && mask_host) {
+        e = cudaMalloc(&d_mask, (size_t)h->n);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(d_mask, mask_host, (size_t)h->n, cudaMemcpyHostToDevice, st);
+    }
+    if (e == cudaSuccess) {
+        seed_each_kernel<<<blocks_for(h->n), kThreads, 0, st>>>(h->rng, h->n, d_ent, d_mask);
+        e = cudaGetLastError();
+    }
+    if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+    cudaFree(d_ent);
+    cudaFree(d_mask);
+    if (e != cudaSuccess) return fail(h, "b200gym_seed_each: %s", cudaGetErrorString(e));
+    return 0;
+}
+
+extern "C" int b200gym_reset(b200gym_t *h, const uint8_t *mask_dev, const double *bounds_host, float *obs_dev,
+                             void *stream) {
+    if (!h) return fail(h, "b200gym_reset: null handle");
+    DeviceGuard guard(h->device);
+    return launch_reset(h, mask_dev, bounds_host, obs_dev, (cudaStream_t)stream);
+}
+
+static StepArgs make_args(b200gym *h, const void *actions, float *obs, double *reward, uint8_t *term,
+                          uint8_t *trunc, float *final_obs) {
+    StepArgs a;
+    a.state = h->state; a.elapsed = h->elapsed; a.flags = h->flags; a.rng = h->rng; a.invalid = h->invalid;
+    a.actions = actions; a.obs = obs; a.reward = reward; a.terminated = term; a.truncated = trunc;
+    a.final_obs = final_obs;
+    a.n = h->n; a.first = 0; a.count = h->n;
+    a.max_steps = h->cfg.max_episode_steps; a.autoreset = h->cfg.autoreset; a.param0 = h->cfg.param[0];
+    return a;
+}
+
+extern "C" int b200gym_step(b200gym_t *h, const void *actions_dev, int action_dtype, float *obs_dev,
+                            double *reward_dev, uint8_t *terminated_dev, uint8_t *truncated_dev,
+                            float *final_obs_dev, void *stream) {
+    if (!h) return fail(h, "b200gym_step: null handle");
+    if (!actions_dev || !obs_dev || !reward_dev || !terminated_dev || !truncated_dev)
+        return fail(h, "b200gym_step: null buffer");
+    DeviceGuard guard(h->device);
+    const StepArgs a = make_args(h, actions_dev, obs_dev, reward_dev, terminated_dev, truncated_dev, final_obs_dev);
+    return launch_step(h, a, action_dtype, (cudaStream_t)stream);
+}
+
+extern "C" int b200gym_invalid_actions(b200gym_t *h, void *stream, int64_t *count_out) {
+    if (!h || !count_out) return fail(h, "b200gym_invalid_actions: null argument");
+    DeviceGuard guard(h->device);
+    cudaStream_t st = (cudaStream_t)stream;
+    unsigned long long v = 0;
+    CK(h, cudaMemcpyAsync(&v, h->invalid, sizeof v, cudaMemcpyDeviceToHost, st));
+    CK(h, cudaMemsetAsync(h->invalid, 0, sizeof v, st));
+    CK(h, cudaStreamSynchronize(st));
+    *count_out = (int64_t)v;
+    return 0;
+}
+
+// ---- host-buffer path -------------------------------------------------------
+static int ensure_host_io(b200gym *h) {
+    if (h->host_ready) return 0;
+    const size_t n = (size_t)h->n;
+    const size_t act_bytes = h->A == 0 ? n * sizeof(int64_t) : n * h->A * sizeof(float);
+    const size_t obs_bytes = n * h->D * sizeof(float);
+    for (int k = 0; k < 2; k++) CK(h, cudaStreamCreateWithFlags(&h->hstream[k], cudaStreamNonBlocking));
+    CK(h, cudaHostAlloc(&h->hio.actions, act_bytes, cudaHostAllocDefault));
+    CK(h, cudaHostAlloc((void **)&h->hio.obs, obs_bytes, cudaHostAllocDefault));
+    CK(h, cudaHostAlloc((void **)&h->hio.reward, n * sizeof(double), cudaHostAllocDefault));
+    CK(h, cudaHostAlloc((void **)&h->hio.terminated, n, cudaHostAllocDefault));
+    CK(h, cudaHostAlloc((void **)&h->hio.truncated, n, cudaHostAllocDefault));
+    CK(h, cudaHostAlloc((void **)&h->hio.final_obs, obs_bytes, cudaHostAllocDefault));
+    memset(h->hio.actions, 0, act_bytes);
+    memset(h->hio.final_obs, 0, obs_bytes);
+    CK(h, cudaMalloc(&h->dio.actions, act_bytes));
+    CK(h, cudaMalloc((void **)&h->dio.obs, obs_bytes));
+    CK(h, cudaMalloc((void **)&h->dio.reward, n * sizeof(double)));
+    CK(h, cudaMalloc((void **)&h->dio.terminated, n));
+    CK(h, cudaMalloc((void **)&h->dio.truncated, n));
+    CK(h, cudaMalloc((void **)&h->dio.final_obs, obs_bytes));
+    CK(h, cudaMalloc((void **)&h->d_mask, n));
+    CK(h, cudaMemset(h->dio.final_obs, 0, obs_bytes));
+    h->host_ready = true;
+    return 0;
+}
+
+extern "C" int b200gym_host_buffers(b200gym_t *h, b200gym_host_io *out) {
+    if (!h || !out) return fail(h, "b200gym_host_buffers: null argument");
+    DeviceGuard guard(h->device);
+    if (ensure_host_io(h)) return 1;
+    *out = h->hio;
+    return 0;
+}
+
+static size_t action_size(int action_dtype) {
+    switch (action_dtype) {
+    case B200GYM_ACT_I64: return 8;
+    case B200GYM_ACT_I32: return 4;
+    case B200GYM_ACT_U8: return 1;
+    default: return 4;
+    }
+}
+
+extern "C" int b200gym_step_host(b200gym_t *h, const void *actions_host, int action_dtype, float *obs_host,
+                                 double *reward_host, uint8_t *terminated_host, uint8_t *truncated_host,
+                                 float *final_obs_host) {
+    if (!h) return fail(h, "b200gym_step_host: null handle");
+    DeviceGuard guard(h->device);
+    if (ensure_host_io(h)) return 1;
+    if (h->A == 0 ? (action_dtype == B200GYM_ACT_F32) : (action_dtype != B200GYM_ACT_F32))
+        return fail(h, "b200gym_step_host: action dtype code %d does not fit this env's action space", action_dtype);
+    if (!actions_host) {
+        actions_host = h->hio.actions;
+        action_dtype = h->A == 0 ? B200GYM_ACT_I64 : B200GYM_ACT_F32;
+    }
+    if (!obs_host) obs_host = h->hio.obs;
+    if (!reward_host) reward_host = h->hio.reward;
+    if (!terminated_host) terminated_host = h->hio.terminated;
+    if (!truncated_host) truncated_host = h->hio.truncated;
+    const size_t asz = action_size(action_dtype) * (h->A == 0 ? 1 : h->A);
+    const size_t osz = sizeof(float) * h->D;
+    // chunked 2-stream pipeline: H2D(actions) -> kernel -> D2H(results) per chunk
+    const int64_t n = h->n;
+    int64_t chunks = n >> 17;
+    chunks = chunks < 1 ? 1 : (chunks > 8 ? 8 : chunks);
+    int64_t per = ((n + chunks - 1) / chunks + kThreads - 1) / kThreads * kThreads;
+    StepArgs a = make_args(h, h->dio.actions, h->dio.obs, h->dio.reward, h->dio.terminated, h->dio.truncated,
+                           h->dio.final_obs);
+    int c = 0;
+    for (int64_t lo = 0; lo < n; lo += per, c++) {
+        const int64_t cnt = (lo + per < n) ? per : n - lo;
+        cudaStream_t st = h->hstream[c & 1];
+        CK(h, cudaMemcpyAsync((char *)h->dio.actions + lo * asz, (const char *)actions_host + lo * asz, cnt * asz,
+                              cudaMemcpyHostToDevice, st));
+        a.first = lo;
+        a.count = cnt;
+        if (launch_step(h, a, action_dtype, st)) return 1;
+        CK(h, cudaMemcpyAsync((char *)obs_host + lo * osz, (char *)h->dio.obs + lo * osz, cnt * osz,
+                              cudaMemcpyDeviceToHost, st));
+        CK(h, cudaMemcpyAsync(reward_host + lo, h->dio.reward + lo, cnt * sizeof(double), cudaMemcpyDeviceToHost, st));
+        CK(h, cudaMemcpyAsync(terminated_host + lo, h->dio.terminated + lo, cnt, cudaMemcpyDeviceToHost, st));
+        CK(h, cudaMemcpyAsync(truncated_host + lo, h->dio.truncated + lo, cnt, cudaMemcpyDeviceToHost, st));
+        if (final_obs_host)
+            CK(h, cudaMemcpyAsync((char *)final_obs_host + lo * osz, (char *)h->dio.final_obs + lo * osz, cnt * osz,
+                                  cudaMemcpyDeviceToHost, st));
+    }
+    CK(h, cudaStreamSynchronize(h->hstream[0]));
+    CK(h, cudaStreamSynchronize(h->hstream[1]));
+    return 0;
+}
+
+extern "C" int b200gym_reset_host(b200gym_t *h, const uint8_t *mask_host, const double *bounds_host,
+                                  float *obs_host) {
+    if (!h) return fail(h, "b200gym_reset_host: null handle");
+    DeviceGuard guard(h->device);
+    if (ensure_host_io(h)) return 1;
+    if (!obs_host) obs_host = h->hio.obs;
+    const size_t n = (size_t)h->n;
+    cudaStream_t st = h->hstream[0];
+    if (mask_host) {
+        CK(h, cudaMemcpyAsync(h->d_mask, mask_host, n, cudaMemcpyHostToDevice, st));
+        // keep the rows of the envs that are not reset
+        CK(h, cudaMemcpyAsync(h->dio.obs, obs_host, n * h->D * sizeof(float), cudaMemcpyHostToDevice, st));
+    }
+    if (launch_reset(h, mask_host ? h->d_mask : nullptr, bounds_host, h->dio.obs, st)) return 1;
+    CK(h, cudaMemcpyAsync(obs_host, h->dio.obs, n * h->D * sizeof(float), cudaMemcpyDeviceToHost, st));
+    CK(h, cudaStreamSynchronize(st));
+    return 0;
+}
+
+// ---- state access -----------------------------------------------------------
+extern "C" int b200gym_get_state(b200gym_t *h, double *state_dev, int32_t *elapsed_dev, uint64_t *rng_dev,
+                                 void *stream) {
+    if (!h) return fail(h, "b200gym_get_state: null handle");
+    DeviceGuard guard(h->device);
+    cudaStream_t st = (cudaStream_t)stream;
+    if (state_dev) {
+        state_get_kernel<<<blocks_for(h->n), kThreads, 0, st>>>(h->state, state_dev, h->n, h->S);
+        CK(h, cudaGetLastError());
+    }
+    if (elapsed_dev)
+        CK(h, cudaMemcpyAsync(elapsed_dev, h->elapsed, sizeof(int32_t) * (size_t)h->n, cudaMemcpyDeviceToDevice, st));
+    if (rng_dev) CK(h, cudaMemcpyAsync(rng_dev, h->rng, 32 * (size_t)h->n, cudaMemcpyDeviceToDevice, st));
+    return 0;
+}
+
+extern "C" int b200gym_set_state(b200gym_t *h, const double *state_dev, const int32_t *elapsed_dev,
+                                 const uint64_t *rng_dev, void *stream) {
+    if (!h) return fail(h, "b200gym_set_state: null handle");
+    DeviceGuard guard(h->device);
+    cudaStream_t st = (cudaStream_t)stream;
+    if (state_dev) {
+        state_set_kernel<<<blocks_for(h->n), kThreads, 0, st>>>(h->state, state_dev, h->n, h->S);
+        CK(h, cudaGetLastError());
+    }
+    if (elapsed_dev)
+        CK(h, cudaMemcpyAsync(h->elapsed, elapsed_dev, sizeof(int32_t) * (size_t)h->n, cudaMemcpyDeviceToDevice, st));
+    if (rng_dev) CK(h, cudaMemcpyAsync(h->rng, rng_dev, 32 * (size_t)h->n, cudaMemcpyDeviceToDevice, st));
+    return 0;
+}

@@ -1,0 +1,190 @@
+/*
+ * b200gym.h -- C ABI of the B200-native vectorised Gym environment engine.
+ *
+ * openai/gym 0.26.2 is pure Python: it has no FFI of its own.  The seam this
+ * library sits behind is gym's Python plugin API -- a `gym.vector.VectorEnv`
+ * subclass (reference gym/vector/vector_env.py:12-275) registered through
+ * `gym.envs.registration.register` (gym/envs/registration.py:434-499).  The
+ * entry points below are what such a subclass binds through ctypes (the stub
+ * is shown in INTEGRATION.md and shipped as gym_b200/_lib.py); every one names
+ * the reference behaviour it replaces.
+ *
+ * Conventions
+ *   - plain C types only; no torch / CUDA types in signatures.  `stream` is a
+ *     cudaStream_t passed as void* (NULL = legacy default stream).
+ *   - "dev" pointers are device pointers owned by the caller (e.g. the
+ *     data_ptr() of a torch.cuda tensor); "host" pointers are host memory.
+ *   - every call returns 0 on success, non-zero on failure;
+ *     b200gym_last_error() then describes the failure.
+ *   - calls are asynchronous on `stream` unless stated otherwise; a handle is
+ *     bound to one device and is not thread-safe.
+ *   - there is NO CPU fallback: without a CUDA device create() fails.
+ */
+#ifndef B200GYM_H
+#define B200GYM_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define B200GYM_VERSION 1
+
+/* Environment kinds: the dynamics classes on the hot path. */
+enum b200gym_kind {
+    B200GYM_CARTPOLE = 0,         /* gym/envs/classic_control/cartpole.py:130-207 */
+    B200GYM_MOUNTAINCAR = 1,      /* gym/envs/classic_control/mountain_car.py:127-164 */
+    B200GYM_MOUNTAINCAR_CONT = 2, /* gym/envs/classic_control/continuous_mountain_car.py:142-186 */
+    B200GYM_PENDULUM = 3,         /* gym/envs/classic_control/pendulum.py:119-163 */
+    B200GYM_ACROBOT = 4,          /* gym/envs/classic_control/acrobot.py:181-277,418-465 */
+    B200GYM_NUM_KINDS = 5
+};
+
+/* dtype codes for the `actions` argument of b200gym_step */
+enum b200gym_action_dtype {
+    B200GYM_ACT_I64 = 0, /* Discrete: int64 (numpy default, MultiDiscrete dtype; gym/vector/utils/spaces.py:53-60) */
+    B200GYM_ACT_I32 = 1,
+    B200GYM_ACT_U8 = 2,
+    B200GYM_ACT_F32 = 3  /* Box: float32 [n][act_dim] */
+};
+
+/*
+ * Construction arguments: what `gym.make(id, **kwargs)` resolves from the
+ * registry (gym/envs/__init__.py:11-60, gym/envs/registration.py:502-691).
+ */
+typedef struct b200gym_config {
+    int32_t kind;              /* enum b200gym_kind */
+    int32_t max_episode_steps; /* TimeLimit (gym/wrappers/time_limit.py:39-68); <= 0: no limit */
+    int32_t autoreset;         /* 1: SyncVectorEnv same-step autoreset (gym/vector/sync_vector_env.py:152-156);
+                                  0: plain Env semantics (state keeps evolving after termination) */
+    int32_t reserved;
+    double param[4];           /* param[0]: Pendulum `g` (pendulum.py:95), MountainCar* `goal_velocity`
+                                  (mountain_car.py:103, continuous_mountain_car.py:108) */
+} b200gym_config;
+
+typedef struct b200gym b200gym_t;
+
+/* static shape queries (host only, no device needed) */
+int b200gym_obs_dim(int kind);     /* observation_space.shape[0] */
+int b200gym_act_dim(int kind);     /* 0: Discrete; k: Box(k,) float32 */
+int b200gym_num_actions(int kind); /* Discrete n (0 for Box) */
+int b200gym_state_dim(int kind);   /* float64 words of integrator state per env */
+int b200gym_version(void);
+
+/* Message for the last failing call on `h` (h == NULL: last create failure). */
+const char *b200gym_last_error(const b200gym_t *h);
+
+/*
+ * Replaces: SyncVectorEnv.__init__ building num_envs Python env objects
+ * (gym/vector/sync_vector_env.py:45-76).  Allocates the persistent SoA state
+ * for `num_envs` environments in the HBM of CUDA device `device`:
+ * float64 state[state_dim][n], int32 elapsed[n], PCG64 rng[n] (32 B records).
+ */
+int b200gym_create(const b200gym_config *cfg, int64_t num_envs, int device, b200gym_t **out);
+/* Replaces: VectorEnv.close (gym/vector/vector_env.py:182-206). */
+void b200gym_destroy(b200gym_t *h);
+
+int64_t b200gym_num_envs(const b200gym_t *h);
+int b200gym_device(const b200gym_t *h);
+
+/*
+ * Replaces: the `seed + i` fan-out of SyncVectorEnv.reset_wait
+ * (gym/vector/sync_vector_env.py:106-107) followed, per env, by
+ * Env.reset(seed=) -> seeding.np_random -> Generator(PCG64(SeedSequence(seed)))
+ * (gym/core.py:149-151, gym/utils/seeding.py:9-27), done on the device.
+ * Env i is seeded with the integer  base + first_index + i,  base given as four
+ * little-endian uint32 words (base < 2^128).  `first_index` is the global index
+ * of this handle's env 0 when a batch is sharded over GPUs.
+ */
+int b200gym_seed_range(b200gym_t *h, const uint32_t base_words[4], int64_t first_index, void *stream);
+/*
+ * Per-env seeds (reset(seed=[s0, s1, ...])).  ent_host: [n][4] little-endian
+ * uint32 words; mask_host: [n] bytes, 0 = leave that env's stream untouched
+ * (a None entry), may be NULL.  Synchronous (copies from pageable host memory).
+ */
+int b200gym_seed_each(b200gym_t *h, const uint32_t *ent_host, const uint8_t *mask_host, void *stream);
+
+/*
+ * Replaces: SyncVectorEnv.reset_wait's loop of env.reset() calls
+ * (gym/vector/sync_vector_env.py:90-129; per env e.g. cartpole.py:190-207).
+ * Every env whose mask byte is non-zero (mask_dev == NULL: all) draws a new
+ * initial state from its own PCG64 stream, zeroes its TimeLimit counter and
+ * writes its float32 observation row obs_dev[i][0..obs_dim).
+ * bounds_host: NULL for the defaults, else two doubles: {low, high} of
+ * options={"low","high"} (classic_control/utils.py:17-46) or {x_init, y_init}
+ * for Pendulum (pendulum.py:147-152).  Validation of the bounds (low <= high,
+ * castable) is the caller's job, as in the reference it happens in Python.
+ */
+int b200gym_reset(b200gym_t *h, const uint8_t *mask_dev, const double *bounds_host,
+                  float *obs_dev, void *stream);
+
+/*
+ * Replaces: SyncVectorEnv.step_wait (gym/vector/sync_vector_env.py:135-169) =
+ * for every env: TimeLimit.step (time_limit.py:39-56) around Env.step (e.g.
+ * cartpole.py:130-188) and, when the episode ended and cfg.autoreset, the
+ * unseeded env.reset() of the same call (:152-156).  ONE kernel launch.
+ *   actions_dev   [n] integers of `action_dtype`, or [n][act_dim] float32
+ *   obs_dev       [n][obs_dim] float32   post-autoreset observation
+ *   reward_dev    [n] float64            (SyncVectorEnv._rewards dtype, :69)
+ *   terminated_dev, truncated_dev [n] uint8 (0/1)
+ *   final_obs_dev [n][obs_dim] float32 or NULL: rows written only where
+ *                 terminated|truncated (info["final_observation"], :155)
+ * Out-of-range Discrete actions (the reference raises AssertionError,
+ * cartpole.py:132) leave that env untouched, set reward NaN and bump a sticky
+ * device counter read by b200gym_invalid_actions().
+ */
+int b200gym_step(b200gym_t *h, const void *actions_dev, int action_dtype, float *obs_dev,
+                 double *reward_dev, uint8_t *terminated_dev, uint8_t *truncated_dev,
+                 float *final_obs_dev, void *stream);
+
+/* Number of invalid Discrete actions seen since the last call (synchronises `stream`). */
+int b200gym_invalid_actions(b200gym_t *h, void *stream, int64_t *count_out);
+
+/*
+ * Host-buffer step: the same call for a caller that lives on the CPU (what a
+ * numpy agent does with SyncVectorEnv.step: numpy actions in, numpy results
+ * out).  Copies the actions host->device, runs the step kernel and copies the
+ * results device->host, pipelined over chunks of the env range on two streams
+ * so that the two PCIe directions and the kernel overlap; returns when all
+ * results have landed in host memory.
+ *   actions_host  [n] integers of `action_dtype` / [n][act_dim] float32, or
+ *                 NULL = the library's page-locked staging buffer (see below)
+ *   obs_host, reward_host, terminated_host, truncated_host
+ *                 destination buffers, or NULL = the staging buffers
+ *   final_obs_host destination, or NULL = final observations are not transferred
+ * Page-locked (cudaHostAlloc / cudaHostRegister / torch pin_memory) buffers
+ * copy at full PCIe speed; pageable memory works but is staged by the driver.
+ * b200gym_host_buffers() exposes the library's own page-locked staging buffers
+ * so a caller can fill actions / read results in place.
+ */
+typedef struct b200gym_host_io {
+    void *actions;       /* [n] int64  or [n][act_dim] float32 */
+    float *obs;          /* [n][obs_dim] */
+    double *reward;      /* [n] */
+    uint8_t *terminated; /* [n] */
+    uint8_t *truncated;  /* [n] */
+    float *final_obs;    /* [n][obs_dim] */
+} b200gym_host_io;
+int b200gym_host_buffers(b200gym_t *h, b200gym_host_io *out);
+int b200gym_step_host(b200gym_t *h, const void *actions_host, int action_dtype, float *obs_host,
+                      double *reward_host, uint8_t *terminated_host, uint8_t *truncated_host,
+                      float *final_obs_host);
+/* reset() with the observations delivered to host memory (obs_host NULL = staging). */
+int b200gym_reset_host(b200gym_t *h, const uint8_t *mask_host, const double *bounds_host, float *obs_host);
+
+/*
+ * State access (parity harness, checkpointing; the reference exposes
+ * `env.state` / `env.unwrapped.state` as a Python attribute).
+ * state_dev: float64 [n][state_dim] (AoS on the wire; the library converts
+ * from/to its SoA layout), elapsed_dev: int32 [n], rng_dev: uint64 [n][4] =
+ * {state_hi, state_lo, inc_hi, inc_lo} of numpy's PCG64.  Any pointer may be NULL.
+ */
+int b200gym_get_state(b200gym_t *h, double *state_dev, int32_t *elapsed_dev, uint64_t *rng_dev, void *stream);
+int b200gym_set_state(b200gym_t *h, const double *state_dev, const int32_t *elapsed_dev,
+                      const uint64_t *rng_dev, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B200GYM_H */

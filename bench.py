@@ -236,7 +236,12 @@ def run_b200(args):
         pool = torch.randint(0, inner.single_action_space.n, (16, n), device=dev, dtype=torch.int64, generator=gen)
     else:
         pool = (torch.rand((16, n, 1), device=dev, generator=gen) * 4.0 - 2.0)
-    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev) if world == 1 else None  # > 126 MB L2
+    # L2 flush between timed steps: write 256 MiB (> 126 MB L2), then stream-read another 256 MiB so
+    # that the lines left in L2 are CLEAN (otherwise the timed kernel pays the write-back of the
+    # flush's own dirty lines, which is an artefact of the flush, not of the kernel)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev) if world == 1 else None
+    flush_rd = torch.zeros(32 << 20, dtype=torch.int64, device=dev) if world == 1 else None
+    flush_sink = torch.zeros(1, dtype=torch.int64, device=dev) if world == 1 else None
 
     def barrier():
         if world > 1:
@@ -257,6 +262,7 @@ def run_b200(args):
         # one kernel per step; L2 flushed (256 MB write) before every timed step
         for k in range(K):
             flush.fill_(k & 0xFF)
+            torch.sum(flush_rd, dim=0, keepdim=True, out=flush_sink)
             starts[k].record()
             env.step(pool[k % 16])
             ends[k].record()
@@ -273,7 +279,7 @@ def run_b200(args):
         e0.record()
         barrier()
         warm_ms = s0.elapsed_time(e0) / K
-        l2_note = "flushed before every timed step (256 MiB write); per-step CUDA events summed"
+        l2_note = "flushed before every timed step (256 MiB write, then 256 MiB read so L2 holds clean lines); per-step CUDA events summed"
     else:
         # the gathered outputs (world x 26 MB) exceed L2; K steps back to back incl. the all-gather
         s0, e0 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)

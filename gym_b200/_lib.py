@@ -11,7 +11,8 @@ import os
 from gym_b200 import error
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libb200gym.so")
+# B200GYM_LIB points at an alternative build of the same library (A/B tuning runs only)
+LIB_PATH = os.environ.get("B200GYM_LIB") or os.path.join(_HERE, "libb200gym.so")
 
 # enum b200gym_kind (include/b200gym.h)
 KIND_CARTPOLE = 0
@@ -70,6 +71,7 @@ SIGNATURES = {
     "b200gym_reset_host": (_i32, [_vp, _vp, _vp, _vp]),
     "b200gym_get_state": (_i32, [_vp, _vp, _vp, _vp, _vp]),
     "b200gym_set_state": (_i32, [_vp, _vp, _vp, _vp, _vp]),
+    "b200gym_selftest": (_i32, [_i32, _i64, ctypes.c_uint64, ctypes.POINTER(_i64)]),
 }
 
 _lib = None

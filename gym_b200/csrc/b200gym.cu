@@ -20,6 +20,7 @@
 
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 #include <string>
@@ -43,6 +44,9 @@ struct b200gym {
     uint8_t *flags = nullptr;
     uint64_t *rng = nullptr;
     unsigned long long *invalid = nullptr;  // sticky device counter
+    int sm_count = 148;
+    int occ[B200GYM_NUM_KINDS][3] = {};     // cached CTAs/SM of step_kernel_tma per (kind, action width)
+    bool force_simple = false;              // B200GYM_SIMPLE_KERNEL=1: always use kernel A (A/B measurements)
     // host-I/O path (lazily created)
     b200gym_host_io hio{};
     b200gym_host_io dio{};  // device mirrors of the staging buffers
@@ -132,40 +136,41 @@ __device__ __forceinline__ void store_row(float *base, int64_t i, const float (&
     }
 }
 
-template <typename ActT>
-__device__ __forceinline__ ActT load_action(const void *actions, int64_t i) {
-    return __ldg(reinterpret_cast<const ActT *>(actions) + i);
-}
+// Tuning knobs (overridable at build time for A/B measurements).
+// The per-env work is one long dependent float64 chain, so the SMs are latency-bound and
+// throughput follows the number of resident warps: 8 CTAs x 256 threads = 64 warps/SM (100 %
+// occupancy) needs <= 32 registers per thread.
+#ifndef B200_MIN_CTAS
+#define B200_MIN_CTAS 8
+#endif
+#ifndef B200_STAGES
+#define B200_STAGES 2
+#endif
+template <int KIND>
+struct Tuning {
+    // Acrobot (RK4, ~70 live doubles) would spill heavily below 64 registers
+    static constexpr int kMinCtas = (KIND == B200GYM_ACROBOT) ? 3 : B200_MIN_CTAS;
+};
 
-// One thread per environment: Env.step + TimeLimit + autoreset, fused.
-template <int KIND, typename ActT>
-__global__ void __launch_bounds__(kThreads) step_kernel(const StepArgs a) {
+// Phase 1, by the thread that owns env i (its inputs are in registers): Env.step, TimeLimit,
+// stores of reward / flags / final_obs, and -- unless the episode ended -- of the new state and
+// observation.  Returns true when the env must be reset by phase 2.
+template <int KIND>
+__device__ __forceinline__ bool advance_env(const StepArgs &a, int64_t i, double (&s)[Env<KIND>::S],
+                                            int32_t elapsed, long long action_int, float a0) {
     using E = Env<KIND>;
-    const int64_t j = (int64_t)blockIdx.x * kThreads + threadIdx.x;
-    if (j >= a.count) return;
-    const int64_t i = a.first + j;
-
-    double s[E::S];
-#pragma unroll
-    for (int k = 0; k < E::S; k++) s[k] = a.state[k * a.n + i];
-    int32_t elapsed = a.elapsed[i];
-
     int act = 0;
-    float a0 = 0.0f;
     if constexpr (E::A == 0) {
-        const long long av = (long long)load_action<ActT>(a.actions, i);
-        if (av < 0 || av >= E::NACT) {
+        if (action_int < 0 || action_int >= E::NACT) {
             // the reference raises (cartpole.py:132 / mountain_car.py:128-130 / acrobot.py:199):
             // leave the env untouched, flag it, return NaN reward
             atomicAdd(a.invalid, 1ULL);
             a.reward[i] = __longlong_as_double(0x7ff8000000000000LL);
             a.terminated[i] = 0;
             a.truncated[i] = 0;
-            return;
+            return false;
         }
-        act = (int)av;
-    } else {
-        a0 = (float)load_action<ActT>(a.actions, i);
+        act = (int)action_int;
     }
 
     float obs[E::D];
@@ -186,24 +191,201 @@ __global__ void __launch_bounds__(kThreads) step_kernel(const StepArgs a) {
 
     elapsed += 1;                                                        // time_limit.py:51
     const bool truncated = (a.max_steps > 0) && (elapsed >= a.max_steps);  // :53-54
+    const bool needs_reset = (terminated || truncated) && a.autoreset;   // sync_vector_env.py:152-156
 
-    if ((terminated || truncated) && a.autoreset) {                      // sync_vector_env.py:152-156
-        if (a.final_obs) store_row<E::D>(a.final_obs, i, obs);
-        Pcg64 g = pcg64_load(a.rng + 4 * i);
-        double lo, hi;
-        E::default_bounds(lo, hi);
-        E::reset(s, g, lo, hi, obs);
-        pcg64_store(a.rng + 4 * i, g);
-        elapsed = 0;                                                     // time_limit.py:67
-    }
-
-#pragma unroll
-    for (int k = 0; k < E::S; k++) a.state[k * a.n + i] = s[k];
-    a.elapsed[i] = elapsed;
-    store_row<E::D>(a.obs, i, obs);
     a.reward[i] = reward;
     a.terminated[i] = terminated ? 1 : 0;
     a.truncated[i] = truncated ? 1 : 0;
+    if (needs_reset) {
+        if (a.final_obs) store_row<E::D>(a.final_obs, i, obs);           // info["final_observation"]
+    } else {
+#pragma unroll
+        for (int k = 0; k < E::S; k++) a.state[k * a.n + i] = s[k];
+        a.elapsed[i] = elapsed;
+        store_row<E::D>(a.obs, i, obs);
+    }
+    return needs_reset;
+}
+
+// Phase 2: the unseeded env.reset() of the autoreset (sync_vector_env.py:154) for env i, by
+// whichever thread picked it off the CTA's compacted list.
+template <int KIND>
+__device__ __forceinline__ void reset_env(const StepArgs &a, int64_t i) {
+    using E = Env<KIND>;
+    double s[E::S];
+    float obs[E::D];
+    Pcg64 g = pcg64_load(a.rng + 4 * i);
+    double lo, hi;
+    E::default_bounds(lo, hi);
+    E::reset(s, g, lo, hi, obs);
+    pcg64_store(a.rng + 4 * i, g);
+#pragma unroll
+    for (int k = 0; k < E::S; k++) a.state[k * a.n + i] = s[k];
+    a.elapsed[i] = 0;                                                    // time_limit.py:67
+    store_row<E::D>(a.obs, i, obs);
+}
+
+// Why two phases: only ~1 env in 22 finishes per CartPole step, but then 77 % of the warps
+// contain at least one finishing lane and would all walk the ~170-instruction PCG64 path
+// (4 x 128-bit LCG steps) with 1-2 active lanes.  Instead finishing lanes push their env index
+// onto a shared-memory list and, after one barrier, the first `count` threads of the CTA do
+// the resets with full lanes: ~11 resets per 256-env tile = half a warp instead of 6 warps.
+
+// --- kernel A: one thread per environment, inputs loaded straight from HBM -------------
+// Used for small / ragged / unaligned batches and for the tail of kernel B.
+template <int KIND, typename ActT>
+__global__ void __launch_bounds__(kThreads, Tuning<KIND>::kMinCtas) step_kernel(const StepArgs a) {
+    using E = Env<KIND>;
+    __shared__ int reset_list[kThreads];
+    __shared__ int reset_count;
+    if (threadIdx.x == 0) reset_count = 0;
+    __syncthreads();
+    const int64_t j = (int64_t)blockIdx.x * kThreads + threadIdx.x;
+    if (j < a.count) {
+        const int64_t i = a.first + j;
+        double s[E::S];
+#pragma unroll
+        for (int k = 0; k < E::S; k++) s[k] = a.state[k * a.n + i];
+        const int32_t elapsed = a.elapsed[i];
+        long long action_int = 0;
+        float a0 = 0.0f;
+        const ActT av = __ldg(reinterpret_cast<const ActT *>(a.actions) + i);
+        if constexpr (E::A == 0) action_int = (long long)av;
+        else a0 = (float)av;
+        if (advance_env<KIND>(a, i, s, elapsed, action_int, a0)) reset_list[atomicAdd(&reset_count, 1)] = threadIdx.x;
+    }
+    __syncthreads();
+    const int cnt = reset_count;
+    if ((int)threadIdx.x < cnt)
+        reset_env<KIND>(a, a.first + (int64_t)blockIdx.x * kThreads + reset_list[threadIdx.x]);
+}
+
+// --- kernel B: persistent CTAs, TMA-staged inputs -------------------------------------
+// Persistent grid (SMs x occupancy CTAs), one thread per env of a 256-env tile, tiles strided
+// by gridDim.x.  Each CTA owns a ring of kStages shared-memory stages; one elected thread keeps
+// the inputs of the next tiles (the S float64 state rows, the TimeLimit counters and the
+// actions of 256 envs, ~11 KB per stage) in flight with cp.async.bulk (TMA, 1-D bulk copies
+// completing on an mbarrier; SASS UBLKCP) while all 256 threads advance the current tile out
+// of shared memory, so the loads of a CTA never wait for its float64 arithmetic and the
+// stores are fire-and-forget.
+namespace tma {
+
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void fence_mbar_init() {
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t *bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ void load_1d(void *smem_dst, const void *gmem_src, uint32_t bytes, uint64_t *bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     smem_u32(smem_dst)),
+                 "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred P1;\n"
+        "LAB_WAIT:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
+        "@P1 bra DONE;\n"
+        "bra LAB_WAIT;\n"
+        "DONE:\n"
+        "}" ::"r"(smem_u32(bar)),
+        "r"(parity)
+        : "memory");
+}
+
+}  // namespace tma
+
+constexpr int kStages = B200_STAGES;
+
+template <int KIND, typename ActT>
+struct TileLayout {
+    using E = Env<KIND>;
+    static constexpr int kActPerEnv = E::A == 0 ? 1 : E::A;
+    static constexpr int kStateBytes = kThreads * 8;                          // one float64 row
+    static constexpr int kElapsedOff = E::S * kStateBytes;
+    static constexpr int kActOff = kElapsedOff + kThreads * 4;
+    static constexpr int kActBytes = kThreads * kActPerEnv * (int)sizeof(ActT);
+    static constexpr int kTxBytes = kActOff + kActBytes;                      // bytes TMA delivers per tile
+    static constexpr int kStageBytes = (kTxBytes + 127) / 128 * 128;
+    static_assert(kActBytes % 16 == 0, "cp.async.bulk moves multiples of 16 bytes");
+};
+
+template <int KIND, typename ActT>
+__global__ void __launch_bounds__(kThreads, Tuning<KIND>::kMinCtas) step_kernel_tma(const StepArgs a, const int num_tiles) {
+    using E = Env<KIND>;
+    using L = TileLayout<KIND, ActT>;
+    __shared__ __align__(128) unsigned char stage_mem[kStages * L::kStageBytes];
+    __shared__ __align__(8) uint64_t full_bar[kStages];
+    __shared__ int reset_list[kThreads];
+    __shared__ int reset_count[2];  // ping-pong: iteration `it` uses [it & 1]
+
+    const int tid = threadIdx.x;
+    if (tid == 0) {
+#pragma unroll
+        for (int st = 0; st < kStages; st++) tma::mbar_init(&full_bar[st], 1);
+        tma::fence_mbar_init();
+        reset_count[0] = 0;
+        reset_count[1] = 0;
+    }
+    __syncthreads();
+
+    // producer (thread 0): one expect_tx + (S + 2) bulk copies per tile
+    auto issue = [&](int st, int tile) {
+        const int64_t i0 = a.first + (int64_t)tile * kThreads;
+        unsigned char *dst = stage_mem + st * L::kStageBytes;
+        tma::mbar_arrive_expect_tx(&full_bar[st], (uint32_t)L::kTxBytes);
+#pragma unroll
+        for (int k = 0; k < E::S; k++)
+            tma::load_1d(dst + k * L::kStateBytes, a.state + k * a.n + i0, L::kStateBytes, &full_bar[st]);
+        tma::load_1d(dst + L::kElapsedOff, a.elapsed + i0, kThreads * 4, &full_bar[st]);
+        tma::load_1d(dst + L::kActOff, reinterpret_cast<const ActT *>(a.actions) + i0 * L::kActPerEnv,
+                     L::kActBytes, &full_bar[st]);
+    };
+
+    if (tid == 0) {
+#pragma unroll
+        for (int st = 0; st < kStages; st++) {
+            const int t = blockIdx.x + st * gridDim.x;
+            if (t < num_tiles) issue(st, t);
+        }
+    }
+
+    int it = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+        const int st = it % kStages;
+        tma::mbar_wait(&full_bar[st], (uint32_t)((it / kStages) & 1));
+        const unsigned char *src = stage_mem + st * L::kStageBytes;
+        double s[E::S];
+#pragma unroll
+        for (int k = 0; k < E::S; k++) s[k] = reinterpret_cast<const double *>(src + k * L::kStateBytes)[tid];
+        const int32_t elapsed = reinterpret_cast<const int32_t *>(src + L::kElapsedOff)[tid];
+        const ActT av = reinterpret_cast<const ActT *>(src + L::kActOff)[tid * L::kActPerEnv];
+        __syncthreads();  // every thread has drained this stage: it can be refilled
+        if (tid == 0) {
+            const int next = tile + kStages * gridDim.x;
+            if (next < num_tiles) issue(st, next);
+            reset_count[(it + 1) & 1] = 0;  // last read two barriers ago, next written after the next barrier
+        }
+        long long action_int = 0;
+        float a0 = 0.0f;
+        if constexpr (E::A == 0) action_int = (long long)av;
+        else a0 = (float)av;
+        const int64_t i0 = a.first + (int64_t)tile * kThreads;
+        if (advance_env<KIND>(a, i0 + tid, s, elapsed, action_int, a0))
+            reset_list[atomicAdd(&reset_count[it & 1], 1)] = tid;
+        __syncthreads();
+        const int cnt = reset_count[it & 1];
+        if (tid < cnt) reset_env<KIND>(a, i0 + reset_list[tid]);
+    }
 }
 
 template <int KIND>
@@ -262,29 +444,81 @@ __global__ void __launch_bounds__(kThreads) state_set_kernel(double *soa, const 
     for (int k = 0; k < S; k++) soa[k * n + i] = aos[i * S + k];
 }
 
+// device self-test: div_by_const(x, c, RN(1/c)) must equal x / c bit for bit
+__global__ void __launch_bounds__(kThreads) selftest_div_kernel(int64_t samples, uint64_t seed,
+                                                                unsigned long long *mismatches) {
+    const double cs[4] = {1.1, 0.1 + 1.0, 3.0, 9.8};
+    const int64_t i = (int64_t)blockIdx.x * kThreads + threadIdx.x;
+    if (i >= samples) return;
+    // splitmix64 bits -> doubles spread over many binades, both signs
+    uint64_t z = seed + 0x9E3779B97F4A7C15ULL * (uint64_t)(i + 1);
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ULL;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBULL;
+    z ^= z >> 31;
+    const double mant = 1.0 + (double)(z >> 12) * (1.0 / 4503599627370496.0);
+    const int e = (int)((z >> 3) & 0x3F) - 32;
+    double x = ldexp(mant, e);
+    if (z & 1) x = -x;
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+        const double c = cs[k];
+        const double rc = 1.0 / c;
+        const double fast = div_by_const(x, c, rc);
+        const double ref = x / c;
+        if (__double_as_longlong(fast) != __double_as_longlong(ref)) atomicAdd(mismatches, 1ULL);
+    }
+}
+
 static inline unsigned blocks_for(int64_t n) { return (unsigned)((n + kThreads - 1) / kThreads); }
 
 // ---------------------------------------------------------------------------
 // dispatch
 // ---------------------------------------------------------------------------
+template <int KIND, typename ActT>
+static int launch_step_typed(b200gym *h, const StepArgs &a, cudaStream_t st) {
+    // kernel B needs 16-byte aligned bulk copies: even SoA stride, 16-aligned range start and
+    // action pointer; and enough tiles to be worth a persistent grid
+    const bool aligned = (a.n % 2 == 0) && (a.first % 16 == 0) && ((uintptr_t)a.actions % 16 == 0) &&
+                         ((uintptr_t)a.state % 16 == 0) && ((uintptr_t)a.elapsed % 16 == 0);
+    const int64_t tiles = a.count / kThreads;
+    int64_t done = 0;
+    if (aligned && tiles >= h->sm_count && !h->force_simple) {
+        int &occ = h->occ[KIND][sizeof(ActT) == 8 ? 0 : sizeof(ActT) == 4 ? 1 : 2];
+        if (occ == 0) {
+            CK(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, step_kernel_tma<KIND, ActT>, kThreads, 0));
+            if (occ < 1) occ = 1;
+        }
+        int64_t grid = (int64_t)h->sm_count * occ;
+        if (grid > tiles) grid = tiles;
+        step_kernel_tma<KIND, ActT><<<(unsigned)grid, kThreads, 0, st>>>(a, (int)tiles);
+        CK(h, cudaGetLastError());
+        done = tiles * kThreads;
+    }
+    if (done < a.count) {
+        StepArgs t = a;
+        t.first = a.first + done;
+        t.count = a.count - done;
+        step_kernel<KIND, ActT><<<blocks_for(t.count), kThreads, 0, st>>>(t);
+        CK(h, cudaGetLastError());
+    }
+    return 0;
+}
+
 template <int KIND>
 static int launch_step_kind(b200gym *h, const StepArgs &a, int action_dtype, cudaStream_t st) {
     using E = Env<KIND>;
-    const unsigned grid = blocks_for(a.count);
     if constexpr (E::A == 0) {
         switch (action_dtype) {
-        case B200GYM_ACT_I64: step_kernel<KIND, long long><<<grid, kThreads, 0, st>>>(a); break;
-        case B200GYM_ACT_I32: step_kernel<KIND, int><<<grid, kThreads, 0, st>>>(a); break;
-        case B200GYM_ACT_U8: step_kernel<KIND, unsigned char><<<grid, kThreads, 0, st>>>(a); break;
+        case B200GYM_ACT_I64: return launch_step_typed<KIND, long long>(h, a, st);
+        case B200GYM_ACT_I32: return launch_step_typed<KIND, int>(h, a, st);
+        case B200GYM_ACT_U8: return launch_step_typed<KIND, unsigned char>(h, a, st);
         default: return fail(h, "Discrete env needs an integer action dtype (got code %d)", action_dtype);
         }
     } else {
         if (action_dtype != B200GYM_ACT_F32)
             return fail(h, "Box env needs float32 actions (got dtype code %d)", action_dtype);
-        step_kernel<KIND, float><<<grid, kThreads, 0, st>>>(a);
+        return launch_step_typed<KIND, float>(h, a, st);
     }
-    CK(h, cudaGetLastError());
-    return 0;
 }
 
 static int launch_step(b200gym *h, const StepArgs &a, int action_dtype, cudaStream_t st) {
@@ -359,6 +593,11 @@ extern "C" int b200gym_create(const b200gym_config *cfg, int64_t num_envs, int d
     h->D = k_obs_dim[cfg->kind];
     h->A = k_act_dim[cfg->kind];
     h->NACT = k_nact[cfg->kind];
+    h->sm_count = prop.multiProcessorCount > 0 ? prop.multiProcessorCount : 148;
+    {
+        const char *fs = getenv("B200GYM_SIMPLE_KERNEL");
+        h->force_simple = fs && fs[0] == '1';
+    }
     DeviceGuard guard(device);
     const size_t n = (size_t)num_envs;
     cudaError_t es[5] = {
@@ -479,6 +718,21 @@ extern "C" int b200gym_invalid_actions(b200gym_t *h, void *stream, int64_t *coun
     CK(h, cudaMemsetAsync(h->invalid, 0, sizeof v, st));
     CK(h, cudaStreamSynchronize(st));
     *count_out = (int64_t)v;
+    return 0;
+}
+
+extern "C" int b200gym_selftest(int device, int64_t samples, uint64_t seed, int64_t *mismatches_out) {
+    if (!mismatches_out || samples <= 0) return fail(nullptr, "b200gym_selftest: bad argument");
+    DeviceGuard guard(device);
+    unsigned long long *d = nullptr;
+    if (cudaMalloc(&d, sizeof *d) != cudaSuccess) return fail(nullptr, "b200gym_selftest: cudaMalloc failed");
+    cudaMemset(d, 0, sizeof *d);
+    selftest_div_kernel<<<blocks_for(samples), kThreads>>>(samples, seed, d);
+    unsigned long long v = 0;
+    cudaError_t e = cudaMemcpy(&v, d, sizeof v, cudaMemcpyDeviceToHost);
+    cudaFree(d);
+    if (e != cudaSuccess) return fail(nullptr, "b200gym_selftest: %s", cudaGetErrorString(e));
+    *mismatches_out = (int64_t)v;
     return 0;
 }
 

@@ -35,6 +35,25 @@ __device__ __forceinline__ double clip64(double x, double lo, double hi) {
     return (m > hi) ? hi : m;
 }
 
+// Correctly rounded IEEE-754 x / c for a constant c, without the reciprocal computation of the
+// generic division routine (MUFU.RCP64H + Newton steps + fix-up, ~30 instructions): with
+// rc = RN(1/c) folded at compile time, two residual-correction steps
+//     q <- q + (x - q*c) * rc          (the residual x - q*c is exact in an FMA)
+// land on RN(x/c) (Markstein's theorem; the second step makes the "q within 1 ulp" premise
+// hold with margin).  The explicit fma() calls are not affected by -fmad=false.  Huge, tiny,
+// zero and non-finite x take the generic division so that signed zeros, infinities and the
+// subnormal range behave exactly like `/`.  b200gym_selftest() checks bit-equality with `/`
+// on the device for billions of inputs.
+__device__ __forceinline__ double div_by_const(double x, double c, double rc) {
+    const double ax = fabs(x);
+    if (!(ax < 1e290) || ax < 1e-290) return x / c;
+    double q = x * rc;
+    double r = fma(-q, c, x);
+    q = fma(r, rc, q);
+    r = fma(-q, c, x);
+    return fma(r, rc, q);
+}
+
 // ---------------------------------------------------------------------------
 // CartPole-v0/v1 -- gym/envs/classic_control/cartpole.py
 // ---------------------------------------------------------------------------
@@ -70,12 +89,15 @@ struct Env<B200GYM_CARTPOLE> {
         const double force = (action == 1) ? force_mag : -force_mag;         // :135
         double sintheta, costheta;
         sincos(theta, &sintheta, &costheta);                                 // :136-137
-        const double temp =
-            (force + polemass_length * (theta_dot * theta_dot) * sintheta) / total_mass;  // :141-143
+        const double inv_total_mass = 1.0 / total_mass;  // folded at compile time, correctly rounded
+        const double temp = div_by_const(
+            force + polemass_length * (theta_dot * theta_dot) * sintheta, total_mass, inv_total_mass);  // :141-143
         const double thetaacc =
             (gravity * sintheta - costheta * temp) /
-            (length * (4.0 / 3.0 - masspole * (costheta * costheta) / total_mass));       // :144-146
-        const double xacc = temp - polemass_length * thetaacc * costheta / total_mass;    // :147
+            (length * (4.0 / 3.0 - div_by_const(masspole * (costheta * costheta), total_mass,
+                                                inv_total_mass)));                         // :144-146
+        const double xacc = temp - div_by_const(polemass_length * thetaacc * costheta, total_mass,
+                                                inv_total_mass);                           // :147
         x = x + tau * x_dot;                                                 // :150
         x_dot = x_dot + tau * xacc;                                          // :151
         theta = theta + tau * theta_dot;                                     // :152

@@ -184,6 +184,13 @@ int b200gym_get_state(b200gym_t *h, double *state_dev, int32_t *elapsed_dev, uin
 int b200gym_set_state(b200gym_t *h, const double *state_dev, const int32_t *elapsed_dev,
                       const uint64_t *rng_dev, void *stream);
 
+/*
+ * Device self-test of the kernels' constant-divisor division (csrc/envs.cuh:div_by_const)
+ * against IEEE `/`: `samples` pseudo-random doubles (both signs, 64 binades) x 4 divisors.
+ * Synchronous; *mismatches_out must come back 0.
+ */
+int b200gym_selftest(int device, int64_t samples, uint64_t seed, int64_t *mismatches_out);
+
 #ifdef __cplusplus
 }
 #endif

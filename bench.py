@@ -39,6 +39,8 @@ LOG2_ENVS = 20
 BYTES_PER_ENV_STEP = {"CartPole-v1": 106, "CartPole-v0": 106, "Pendulum-v1": 16 * 2 + 8 + 4 + 12 + 8 + 2,
                       "Acrobot-v1": 32 * 2 + 8 + 8 + 24 + 8 + 2, "MountainCar-v0": 16 * 2 + 8 + 8 + 8 + 8 + 2,
                       "MountainCarContinuous-v0": 16 * 2 + 8 + 4 + 8 + 8 + 2}
+# dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed ncu --set full capture (2^20 envs)
+NCU_DRAM_BYTES_PER_LAUNCH = {"CartPole-v1": 56.23e6 + 23.99e6}
 FALLBACK_HBM_GBS = 6650.0  # /opt/skills/guides/B200_PROFILING.md fallback
 
 
@@ -54,6 +56,8 @@ def parse_args():
     p.add_argument("--cpu-seconds", type=float, default=10.0, help="budget of the cpu_baseline sample")
     p.add_argument("--no-cpu-baseline", action="store_true")
     p.add_argument("--no-e2e", action="store_true")
+    p.add_argument("--gather", default="p2p", choices=["p2p", "nccl"],
+                   help="N>1 exchange: fused NVLink peer stores in the step kernel, or NCCL all-gather")
     return p.parse_args()
 
 
@@ -222,8 +226,15 @@ def run_b200(args):
     n = 1 << args.log2_envs
     K, W = args.steps, max(args.warmup, 3)
 
+    gather = args.gather
     if world > 1:
-        env = ShardedVectorEnv(args.env, n * world)
+        try:
+            env = ShardedVectorEnv(args.env, n * world, gather=gather)
+        except Exception as exc:  # e.g. CUDA IPC unavailable: fall back to the NCCL exchange
+            if rank == 0:
+                print(f"[bench] gather={gather} unavailable ({exc}); using nccl", file=sys.stderr)
+            gather = "nccl"
+            env = ShardedVectorEnv(args.env, n * world, gather=gather)
         inner = env.env
     else:
         env = gym_b200.vector.make(args.env, n)
@@ -298,7 +309,6 @@ def run_b200(args):
             inner_s[k].record()
             inner.step(pool[k % 16])
             inner_e[k].record()
-            env._finish()
         barrier()
         kernel_ms = float(np.mean([s.elapsed_time(e) for s, e in zip(inner_s, inner_e)]))
         warm_ms = None
@@ -357,14 +367,20 @@ def run_b200(args):
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": f"{args.env} num_envs=2^{args.log2_envs} per GPU x {world} GPU(s), random int64 "
                                    "actions resident in HBM, fused step+TimeLimit+autoreset"
-                                   + (", NCCL all-gather of (obs,reward,terminated,truncated) per step"
+                                   + ((", all-gather of (obs,reward,terminated,truncated) per step fused into the "
+                                       "step kernel (NVLink peer stores + flag exchange)" if gather == "p2p" else
+                                       ", NCCL all-gather of (obs,reward,terminated,truncated) per step")
                                       if world > 1 else ""),
                        "state": "float64 (reference-faithful)", "l2": l2_note,
                        "parallelism": f"env-batch data parallel x{world}"},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                         "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                         "frac": achieved / peak, "traffic": NCU_DRAM_BYTES_PER_LAUNCH.get(args.env) if args.log2_envs == 20 else None,
+                         "traffic_source": "profiles/r1_cartpole_step_kernel_tma_ncu_full.txt: dram__bytes_read.sum + "
+                                           "dram__bytes_write.sum of one launch (cold L2; lines still dirty in L2 at "
+                                           "kernel end are not in it)", "peak_source": peak_src,
                          "bytes_per_env_step": BYTES_PER_ENV_STEP.get(args.env), "kernel_ms": kernel_ms,
-                         "kernel": "step_kernel<CARTPOLE, int64>" if args.env.startswith("CartPole") else "step_kernel"},
+                         "kernel": "step_kernel_tma<CARTPOLE, int64>" if args.env.startswith("CartPole")
+                         else "step_kernel_tma"},
             "cpu_baseline": cpu,
             "e2e": e2e,
             "gpu_launches": K,

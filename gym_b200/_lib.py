@@ -48,6 +48,19 @@ class HostIO(ctypes.Structure):
     ]
 
 
+class P2PLayout(ctypes.Structure):
+    """struct b200gym_p2p_layout"""
+    _fields_ = [
+        ("base", ctypes.c_void_p),
+        ("set_bytes", ctypes.c_uint64),
+        ("off_obs", ctypes.c_uint64),
+        ("off_reward", ctypes.c_uint64),
+        ("off_terminated", ctypes.c_uint64),
+        ("off_truncated", ctypes.c_uint64),
+        ("rows", ctypes.c_int64),
+    ]
+
+
 # every symbol include/b200gym.h declares: name -> (restype, argtypes)
 _vp, _i64, _i32 = ctypes.c_void_p, ctypes.c_int64, ctypes.c_int
 SIGNATURES = {
@@ -71,6 +84,9 @@ SIGNATURES = {
     "b200gym_reset_host": (_i32, [_vp, _vp, _vp, _vp]),
     "b200gym_get_state": (_i32, [_vp, _vp, _vp, _vp, _vp]),
     "b200gym_set_state": (_i32, [_vp, _vp, _vp, _vp, _vp]),
+    "b200gym_p2p_create": (_i32, [_vp, _i32, _i32, _vp, _vp]),
+    "b200gym_p2p_connect": (_i32, [_vp, _vp]),
+    "b200gym_step_p2p": (_i32, [_vp, _vp, _i32, _vp, _vp, ctypes.POINTER(_i32)]),
     "b200gym_selftest": (_i32, [_i32, _i64, ctypes.c_uint64, ctypes.POINTER(_i64)]),
 }
 

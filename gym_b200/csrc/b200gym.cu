@@ -47,10 +47,20 @@ struct b200gym {
     int sm_count = 148;
     int occ[B200GYM_NUM_KINDS][3] = {};     // cached CTAs/SM of step_kernel_tma per (kind, action width)
     bool force_simple = false;              // B200GYM_SIMPLE_KERNEL=1: always use kernel A (A/B measurements)
+    // fused all-gather over peer memory (b200gym_p2p_*)
+    struct {
+        int world = 0, rank = 0;
+        unsigned char *base = nullptr;               // this rank's gather allocation (2 sets + flags)
+        unsigned char *peer[B200GYM_MAX_PEERS + 1] = {};  // peer[r]: rank r's allocation mapped here (own = base)
+        size_t set_bytes = 0, off_obs = 0, off_reward = 0, off_term = 0, off_trunc = 0, off_flags = 0, bytes = 0;
+        unsigned long long step = 0;
+        bool connected = false;
+    } p2p;
     // host-I/O path (lazily created)
     b200gym_host_io hio{};
     b200gym_host_io dio{};  // device mirrors of the staging buffers
     uint8_t *d_mask = nullptr;
+    unsigned long long **d_peer_flags = nullptr;
     cudaStream_t hstream[2] = {nullptr, nullptr};
     bool host_ready = false;
     mutable std::string err;
@@ -117,6 +127,13 @@ struct StepArgs {
     int32_t max_steps;
     int32_t autoreset;
     double param0;
+    // fused all-gather (multi-GPU): every result is ALSO stored into the same rows of the peers'
+    // gather buffers over NVLink (peer-mapped pointers, slice offset already applied)
+    int32_t npeer;
+    float *peer_obs[B200GYM_MAX_PEERS];
+    double *peer_reward[B200GYM_MAX_PEERS];
+    uint8_t *peer_term[B200GYM_MAX_PEERS];
+    uint8_t *peer_trunc[B200GYM_MAX_PEERS];
 };
 
 template <int D>
@@ -133,6 +150,24 @@ __device__ __forceinline__ void store_row(float *base, int64_t i, const float (&
     } else {
 #pragma unroll
         for (int k = 0; k < D; k++) base[i * D + k] = v[k];
+    }
+}
+
+template <int D>
+__device__ __forceinline__ void store_obs_all(const StepArgs &a, int64_t i, const float (&v)[D]) {
+    store_row<D>(a.obs, i, v);
+    for (int p = 0; p < a.npeer; p++) store_row<D>(a.peer_obs[p], i, v);
+}
+
+__device__ __forceinline__ void store_scalars_all(const StepArgs &a, int64_t i, double reward, uint8_t term,
+                                                  uint8_t trunc) {
+    a.reward[i] = reward;
+    a.terminated[i] = term;
+    a.truncated[i] = trunc;
+    for (int p = 0; p < a.npeer; p++) {
+        a.peer_reward[p][i] = reward;
+        a.peer_term[p][i] = term;
+        a.peer_trunc[p][i] = trunc;
     }
 }
 
@@ -165,9 +200,7 @@ __device__ __forceinline__ bool advance_env(const StepArgs &a, int64_t i, double
             // the reference raises (cartpole.py:132 / mountain_car.py:128-130 / acrobot.py:199):
             // leave the env untouched, flag it, return NaN reward
             atomicAdd(a.invalid, 1ULL);
-            a.reward[i] = __longlong_as_double(0x7ff8000000000000LL);
-            a.terminated[i] = 0;
-            a.truncated[i] = 0;
+            store_scalars_all(a, i, __longlong_as_double(0x7ff8000000000000LL), 0, 0);
             return false;
         }
         act = (int)action_int;
@@ -193,16 +226,14 @@ __device__ __forceinline__ bool advance_env(const StepArgs &a, int64_t i, double
     const bool truncated = (a.max_steps > 0) && (elapsed >= a.max_steps);  // :53-54
     const bool needs_reset = (terminated || truncated) && a.autoreset;   // sync_vector_env.py:152-156
 
-    a.reward[i] = reward;
-    a.terminated[i] = terminated ? 1 : 0;
-    a.truncated[i] = truncated ? 1 : 0;
+    store_scalars_all(a, i, reward, terminated ? 1 : 0, truncated ? 1 : 0);
     if (needs_reset) {
         if (a.final_obs) store_row<E::D>(a.final_obs, i, obs);           // info["final_observation"]
     } else {
 #pragma unroll
         for (int k = 0; k < E::S; k++) a.state[k * a.n + i] = s[k];
         a.elapsed[i] = elapsed;
-        store_row<E::D>(a.obs, i, obs);
+        store_obs_all<E::D>(a, i, obs);
     }
     return needs_reset;
 }
@@ -222,7 +253,7 @@ __device__ __forceinline__ void reset_env(const StepArgs &a, int64_t i) {
 #pragma unroll
     for (int k = 0; k < E::S; k++) a.state[k * a.n + i] = s[k];
     a.elapsed[i] = 0;                                                    // time_limit.py:67
-    store_row<E::D>(a.obs, i, obs);
+    store_obs_all<E::D>(a, i, obs);
 }
 
 // Why two phases: only ~1 env in 22 finishes per CartPole step, but then 77 % of the warps
@@ -444,6 +475,29 @@ __global__ void __launch_bounds__(kThreads) state_set_kernel(double *soa, const 
     for (int k = 0; k < S; k++) soa[k * n + i] = aos[i * S + k];
 }
 
+// ---- cross-GPU step barrier for the fused all-gather ---------------------------------------
+// flags[r] (uint64, in every rank's gather allocation) = number of steps whose results rank r
+// has fully written into THIS rank's buffers.  signal: after my step kernel (stream order) tell
+// every peer; wait: spin until every peer has told me.  Volatile system-scope accesses.
+__global__ void p2p_signal_kernel(unsigned long long *const *peer_flags, int world, int rank, unsigned long long step) {
+    const int p = threadIdx.x;
+    if (p < world) {
+        __threadfence_system();
+        volatile unsigned long long *f = peer_flags[p] + rank;
+        *f = step;
+    }
+}
+
+__global__ void p2p_wait_kernel(const unsigned long long *flags, int world, unsigned long long step) {
+    const int p = threadIdx.x;
+    if (p < world) {
+        const volatile unsigned long long *f = flags + p;
+        while (*f < step) {
+        }
+        __threadfence_system();
+    }
+}
+
 // device self-test: div_by_const(x, c, RN(1/c)) must equal x / c bit for bit
 __global__ void __launch_bounds__(kThreads) selftest_div_kernel(int64_t samples, uint64_t seed,
                                                                 unsigned long long *mismatches) {
@@ -644,6 +698,12 @@ extern "C" void b200gym_destroy(b200gym_t *h) {
     cudaFree(h->flags);
     cudaFree(h->rng);
     cudaFree(h->invalid);
+    if (h->p2p.base) {
+        for (int r = 0; r < h->p2p.world; r++)
+            if (r != h->p2p.rank && h->p2p.peer[r]) cudaIpcCloseMemHandle(h->p2p.peer[r]);
+        cudaFree(h->p2p.base);
+        cudaFree(h->d_peer_flags);
+    }
     delete h;
 }
 
@@ -695,6 +755,7 @@ static StepArgs make_args(b200gym *h, const void *actions, float *obs, double *r
     a.final_obs = final_obs;
     a.n = h->n; a.first = 0; a.count = h->n;
     a.max_steps = h->cfg.max_episode_steps; a.autoreset = h->cfg.autoreset; a.param0 = h->cfg.param[0];
+    a.npeer = 0;
     return a;
 }
 
@@ -735,6 +796,110 @@ extern "C" int b200gym_selftest(int device, int64_t samples, uint64_t seed, int6
     *mismatches_out = (int64_t)v;
     return 0;
 }
+
+// ---- fused all-gather over NVLink peer memory ----------------------------------------------
+static size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+extern "C" int b200gym_p2p_create(b200gym_t *h, int world, int rank, void *ipc_handle_out /*64 B*/,
+                                  b200gym_p2p_layout *layout_out) {
+    if (!h || !ipc_handle_out || !layout_out) return fail(h, "b200gym_p2p_create: null argument");
+    if (world < 1 || world > B200GYM_MAX_PEERS + 1 || rank < 0 || rank >= world)
+        return fail(h, "b200gym_p2p_create: bad world/rank %d/%d (at most %d ranks)", world, rank, B200GYM_MAX_PEERS + 1);
+    if (h->p2p.base) return fail(h, "b200gym_p2p_create: already created");
+    DeviceGuard guard(h->device);
+    auto &P = h->p2p;
+    const size_t rows = (size_t)world * (size_t)h->n;
+    P.world = world;
+    P.rank = rank;
+    P.off_obs = 0;
+    P.off_reward = align_up(P.off_obs + rows * h->D * sizeof(float), 256);
+    P.off_term = align_up(P.off_reward + rows * sizeof(double), 256);
+    P.off_trunc = align_up(P.off_term + rows, 256);
+    P.set_bytes = align_up(P.off_trunc + rows, 256);
+    P.off_flags = 2 * P.set_bytes;
+    P.bytes = P.off_flags + 256;
+    CK(h, cudaMalloc((void **)&P.base, P.bytes));
+    CK(h, cudaMemset(P.base, 0, P.bytes));
+    CK(h, cudaDeviceSynchronize());
+    cudaIpcMemHandle_t ipc;
+    CK(h, cudaIpcGetMemHandle(&ipc, P.base));
+    static_assert(sizeof(ipc) == 64, "cudaIpcMemHandle_t is 64 bytes");
+    memcpy(ipc_handle_out, &ipc, sizeof ipc);
+    layout_out->base = P.base;
+    layout_out->set_bytes = P.set_bytes;
+    layout_out->off_obs = P.off_obs;
+    layout_out->off_reward = P.off_reward;
+    layout_out->off_terminated = P.off_term;
+    layout_out->off_truncated = P.off_trunc;
+    layout_out->rows = (int64_t)rows;
+    return 0;
+}
+
+extern "C" int b200gym_p2p_connect(b200gym_t *h, const void *all_ipc_handles /*world x 64 B*/) {
+    if (!h || !all_ipc_handles) return fail(h, "b200gym_p2p_connect: null argument");
+    auto &P = h->p2p;
+    if (!P.base) return fail(h, "b200gym_p2p_connect: call b200gym_p2p_create first");
+    if (P.connected) return 0;
+    DeviceGuard guard(h->device);
+    for (int r = 0; r < P.world; r++) {
+        if (r == P.rank) {
+            P.peer[r] = P.base;
+            continue;
+        }
+        cudaIpcMemHandle_t ipc;
+        memcpy(&ipc, (const char *)all_ipc_handles + 64 * r, sizeof ipc);
+        void *ptr = nullptr;
+        CK(h, cudaIpcOpenMemHandle(&ptr, ipc, cudaIpcMemLazyEnablePeerAccess));
+        P.peer[r] = (unsigned char *)ptr;
+    }
+    P.connected = true;
+    return 0;
+}
+
+extern "C" int b200gym_step_p2p(b200gym_t *h, const void *actions_dev, int action_dtype, float *final_obs_dev,
+                                void *stream, int *set_out) {
+    if (!h || !actions_dev) return fail(h, "b200gym_step_p2p: null argument");
+    auto &P = h->p2p;
+    if (!P.connected) return fail(h, "b200gym_step_p2p: peers are not connected");
+    DeviceGuard guard(h->device);
+    cudaStream_t st = (cudaStream_t)stream;
+    P.step += 1;
+    const int set = (int)(P.step & 1);
+    const size_t row0 = (size_t)P.rank * (size_t)h->n;
+    auto obs_of = [&](unsigned char *b) { return (float *)(b + set * P.set_bytes + P.off_obs) + row0 * h->D; };
+    auto rew_of = [&](unsigned char *b) { return (double *)(b + set * P.set_bytes + P.off_reward) + row0; };
+    auto term_of = [&](unsigned char *b) { return (uint8_t *)(b + set * P.set_bytes + P.off_term) + row0; };
+    auto trunc_of = [&](unsigned char *b) { return (uint8_t *)(b + set * P.set_bytes + P.off_trunc) + row0; };
+    StepArgs a = make_args(h, actions_dev, obs_of(P.base), rew_of(P.base), term_of(P.base), trunc_of(P.base),
+                           final_obs_dev);
+    int np = 0;
+    for (int r = 0; r < P.world; r++) {
+        if (r == P.rank) continue;
+        a.peer_obs[np] = obs_of(P.peer[r]);
+        a.peer_reward[np] = rew_of(P.peer[r]);
+        a.peer_term[np] = term_of(P.peer[r]);
+        a.peer_trunc[np] = trunc_of(P.peer[r]);
+        np++;
+    }
+    a.npeer = np;
+    if (launch_step(h, a, action_dtype, st)) return 1;
+    if (P.world > 1) {
+        // tell every peer that my rows of step `P.step` are in its buffers, then wait for theirs
+        unsigned long long *pf[B200GYM_MAX_PEERS + 1];
+        for (int r = 0; r < P.world; r++) pf[r] = (unsigned long long *)(P.peer[r] + P.off_flags);
+        if (!h->d_peer_flags) {
+            CK(h, cudaMalloc((void **)&h->d_peer_flags, sizeof pf));
+            CK(h, cudaMemcpy(h->d_peer_flags, pf, sizeof pf, cudaMemcpyHostToDevice));
+        }
+        p2p_signal_kernel<<<1, 32, 0, st>>>(h->d_peer_flags, P.world, P.rank, P.step);
+        p2p_wait_kernel<<<1, 32, 0, st>>>((const unsigned long long *)(P.base + P.off_flags), P.world, P.step);
+        CK(h, cudaGetLastError());
+    }
+    if (set_out) *set_out = set;
+    return 0;
+}
+
+// reset(): fill this rank's rows of set 0 ... (the reset observations are exchanged by the caller)
 
 // ---- host-buffer path -------------------------------------------------------
 static int ensure_host_io(b200gym *h) {

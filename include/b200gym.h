@@ -185,6 +185,38 @@ int b200gym_set_state(b200gym_t *h, const double *state_dev, const int32_t *elap
                       const uint64_t *rng_dev, void *stream);
 
 /*
+ * Multi-GPU: fused step + all-gather over NVLink peer memory.
+ *
+ * Replaces (no reference counterpart in gym; nearest analogue: AsyncVectorEnv gathering worker
+ * results through shared memory, gym/vector/async_vector_env.py:319-328,
+ * gym/vector/utils/shared_memory.py:164-170).  One process per GPU; rank r of `world` owns the
+ * global envs [r*n, (r+1)*n).  Every rank allocates one "gather allocation" holding two sets
+ * (double buffering by step parity) of the GLOBAL result arrays
+ *     obs float32 [world*n][obs_dim], reward float64 [world*n], terminated/truncated uint8 [world*n]
+ * plus a flag word per rank, exports it as a CUDA IPC handle (b200gym_p2p_create), maps the
+ * peers' allocations (b200gym_p2p_connect, after the caller has all-gathered the 64-byte
+ * handles, e.g. with torch.distributed), and from then on b200gym_step_p2p() runs the SAME fused
+ * step kernel, whose stores go to this rank's rows in the local set AND, through the mapped
+ * peer pointers (NVLink st.global), in every peer's set -- the all-gather is the kernel's own
+ * store stream, tile by tile, with no separate collective.  The step ends with a flag exchange:
+ * each rank publishes "my rows of step k are complete" to all peers and waits on its own flag
+ * words for theirs (two 1-warp kernels on `stream`).
+ */
+#define B200GYM_MAX_PEERS 7
+typedef struct b200gym_p2p_layout {
+    void *base;            /* device pointer of this rank's gather allocation */
+    uint64_t set_bytes;    /* set s (0/1) starts at base + s*set_bytes */
+    uint64_t off_obs, off_reward, off_terminated, off_truncated; /* byte offsets inside a set */
+    int64_t rows;          /* world * n */
+} b200gym_p2p_layout;
+int b200gym_p2p_create(b200gym_t *h, int world, int rank, void *ipc_handle_out /* 64 bytes */,
+                       b200gym_p2p_layout *layout_out);
+int b200gym_p2p_connect(b200gym_t *h, const void *all_ipc_handles /* world x 64 bytes, rank order */);
+/* *set_out = which set (0/1) holds this step's global results once `stream` reaches this point */
+int b200gym_step_p2p(b200gym_t *h, const void *actions_dev, int action_dtype, float *final_obs_dev,
+                     void *stream, int *set_out);
+
+/*
  * Device self-test of the kernels' constant-divisor division (csrc/envs.cuh:div_by_const)
  * against IEEE `/`: `samples` pseudo-random doubles (both signs, 64 binades) x 4 divisors.
  * Synchronous; *mismatches_out must come back 0.

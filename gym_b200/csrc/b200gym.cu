@@ -27,6 +27,7 @@
 
 #include "../../include/b200gym.h"
 #include "envs.cuh"
+#include "lunar.cuh"
 #include "rng.cuh"
 
 using namespace bgym;
@@ -43,6 +44,7 @@ struct b200gym {
     int32_t *elapsed = nullptr;
     uint8_t *flags = nullptr;
     uint64_t *rng = nullptr;
+    uint32_t *lunar_rec = nullptr;          // LunarLander: lunar::kWords 32-bit words per env, SoA
     unsigned long long *invalid = nullptr;  // sticky device counter
     int sm_count = 148;
     int occ[B200GYM_NUM_KINDS][3] = {};     // cached CTAs/SM of step_kernel_tma per (kind, action width)
@@ -86,10 +88,10 @@ static int fail(const b200gym *h, const char *fmt, ...) {
             return fail(h, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
     } while (0)
 
-static const int k_obs_dim[B200GYM_NUM_KINDS] = {4, 2, 2, 3, 6};
-static const int k_act_dim[B200GYM_NUM_KINDS] = {0, 0, 1, 1, 0};
-static const int k_nact[B200GYM_NUM_KINDS] = {2, 3, 0, 0, 3};
-static const int k_state_dim[B200GYM_NUM_KINDS] = {4, 2, 2, 2, 4};
+static const int k_obs_dim[B200GYM_NUM_KINDS] = {4, 2, 2, 3, 6, 8};
+static const int k_act_dim[B200GYM_NUM_KINDS] = {0, 0, 1, 1, 0, 0};
+static const int k_nact[B200GYM_NUM_KINDS] = {2, 3, 0, 0, 3, 4};
+static const int k_state_dim[B200GYM_NUM_KINDS] = {4, 2, 2, 2, 4, 0};
 
 static bool kind_ok(int k) { return k >= 0 && k < B200GYM_NUM_KINDS; }
 
@@ -115,6 +117,7 @@ struct StepArgs {
     uint8_t *flags;
     uint64_t *rng;
     unsigned long long *invalid;
+    uint32_t *lunar_rec;
     const void *actions;
     float *obs;
     double *reward;
@@ -475,6 +478,168 @@ __global__ void __launch_bounds__(kThreads) state_set_kernel(double *soa, const 
     for (int k = 0; k < S; k++) soa[k * n + i] = aos[i * S + k];
 }
 
+// ---- LunarLander-v2 (lunar.cuh): one thread per env, the whole b2World::Step in registers/local ----
+constexpr int kLunarThreads = 128;
+
+template <typename ActT>
+__global__ void __launch_bounds__(kLunarThreads) lunar_step_kernel(const StepArgs a) {
+    const int64_t j = (int64_t)blockIdx.x * kLunarThreads + threadIdx.x;
+    if (j >= a.count) return;
+    const int64_t i = a.first + j;
+    const long long act = (long long)__ldg(reinterpret_cast<const ActT *>(a.actions) + i);
+    if (act < 0 || act > 3) {  // lunar_lander.py:482-484
+        atomicAdd(a.invalid, 1ULL);
+        store_scalars_all(a, i, __longlong_as_double(0x7ff8000000000000LL), 0, 0);
+        return;
+    }
+    lunar::World W;
+    lunar::load_world(W, a.lunar_rec, a.n, i);
+    Pcg64 g = pcg64_load(a.rng + 4 * i);
+    int32_t elapsed = a.elapsed[i];
+    float obs[8];
+    double reward;
+    bool terminated;
+    lunar::env_step(W, g, (int)act, lunar::V(0.0f, 0.0f), obs, reward, terminated);
+    elapsed += 1;                                                        // time_limit.py:51
+    const bool truncated = (a.max_steps > 0) && (elapsed >= a.max_steps);
+    store_scalars_all(a, i, reward, terminated ? 1 : 0, truncated ? 1 : 0);
+    if ((terminated || truncated) && a.autoreset) {                      // sync_vector_env.py:152-156
+        if (a.final_obs) store_row<8>(a.final_obs, i, obs);
+        lunar::env_reset(W, g, obs);
+        elapsed = 0;
+    }
+    lunar::store_world(W, a.lunar_rec, a.n, i);
+    pcg64_store(a.rng + 4 * i, g);
+    a.elapsed[i] = elapsed;
+    store_obs_all<8>(a, i, obs);
+}
+
+__global__ void __launch_bounds__(kLunarThreads) lunar_reset_kernel(uint32_t *rec, int32_t *elapsed, uint64_t *rng,
+                                                                    const uint8_t *mask, float *obs, int64_t n) {
+    const int64_t i = (int64_t)blockIdx.x * kLunarThreads + threadIdx.x;
+    if (i >= n) return;
+    if (mask && !mask[i]) return;
+    lunar::World W;
+    W.flags = rec[(int64_t)lunar::W_FLAGS * n + i] & 16u;  // the b2World object survives reset()
+    Pcg64 g = pcg64_load(rng + 4 * i);
+    float o[8];
+    lunar::env_reset(W, g, o);
+    lunar::store_world(W, rec, n, i);
+    pcg64_store(rng + 4 * i, g);
+    elapsed[i] = 0;
+    if (obs) store_row<8>(obs, i, o);
+}
+
+// bodies of every env as [n][18] floats {c.x, c.y, a, v.x, v.y, w} x 3 + [n][6] int32 flags (parity harness)
+__global__ void lunar_bodies_kernel(const uint32_t *rec, const int32_t *elapsed, float *out, int32_t *flags, int64_t n) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    for (int b = 0; b < 3; b++)
+        for (int k = 0; k < 6; k++) out[i * 18 + 6 * b + k] = __uint_as_float(rec[(int64_t)(lunar::W_BODY + 7 * b + k) * n + i]);
+    const uint32_t f = rec[(int64_t)lunar::W_FLAGS * n + i];
+    const unsigned long long touch = ((unsigned long long)rec[(int64_t)(lunar::W_TOUCH + 1) * n + i] << 32) |
+                                     rec[(int64_t)lunar::W_TOUCH * n + i];
+    flags[i * 6 + 0] = f & 1u; flags[i * 6 + 1] = (f >> 1) & 1u; flags[i * 6 + 2] = (f >> 2) & 1u;
+    flags[i * 6 + 3] = 1; flags[i * 6 + 4] = elapsed[i]; flags[i * 6 + 5] = __popcll(touch);
+}
+
+// Shape / mass constants, evaluated on the host with the float32 operation sequence of
+// b2PolygonShape::Set / ComputeCentroid / ComputeMass and b2Body::ResetMassData.
+static void lunar_shape(lunar::ShapeConst &sh, const lunar::v2 *hull, int n, float density, float friction, bool box) {
+    using lunar::v2;
+    auto V = [](float x, float y) { v2 r; r.x = x; r.y = y; return r; };
+    sh.count = n;
+    sh.friction = friction;
+    for (int i = 0; i < n; i++) sh.verts[i] = hull[i];
+    for (int i = 0; i < n; i++) {
+        const int i2 = i + 1 < n ? i + 1 : 0;
+        const float ex = sh.verts[i2].x - sh.verts[i].x, ey = sh.verts[i2].y - sh.verts[i].y;
+        const float nx = 1.0f * ey, ny = -1.0f * ex;
+        const float len = sqrtf(nx * nx + ny * ny), inv = 1.0f / len;
+        sh.normals[i] = V(inv * nx, inv * ny);
+    }
+    {   // ComputeCentroid
+        float cx = 0.0f, cy = 0.0f, area = 0.0f;
+        const float inv3 = 1.0f / 3.0f;
+        for (int i = 0; i < n; i++) {
+            const v2 p1 = V(0.0f, 0.0f), p2 = sh.verts[i], p3 = i + 1 < n ? sh.verts[i + 1] : sh.verts[0];
+            const float e1x = p2.x - p1.x, e1y = p2.y - p1.y, e2x = p3.x - p1.x, e2y = p3.y - p1.y;
+            const float D = e1x * e2y - e1y * e2x, tri = 0.5f * D;
+            area += tri;
+            const float w = tri * inv3;
+            cx = cx + w * ((p1.x + p2.x) + p3.x);
+            cy = cy + w * ((p1.y + p2.y) + p3.y);
+        }
+        const float ia = 1.0f / area;
+        sh.centroid = V(ia * cx, ia * cy);
+    }
+    if (box) {  // b2PolygonShape::SetAsBox writes exact normals and a zero centroid
+        sh.normals[0] = V(0.0f, -1.0f); sh.normals[1] = V(1.0f, 0.0f); sh.normals[2] = V(0.0f, 1.0f); sh.normals[3] = V(-1.0f, 0.0f);
+        sh.centroid = V(0.0f, 0.0f);
+    }
+    // ComputeMass
+    float sx = 0.0f, sy = 0.0f;
+    for (int i = 0; i < n; i++) { sx = sx + sh.verts[i].x; sy = sy + sh.verts[i].y; }
+    const float invn = 1.0f / (float)n;
+    sx = invn * sx; sy = invn * sy;
+    float cx = 0.0f, cy = 0.0f, area = 0.0f, I = 0.0f;
+    const float inv3 = 1.0f / 3.0f;
+    for (int i = 0; i < n; i++) {
+        const float e1x = sh.verts[i].x - sx, e1y = sh.verts[i].y - sy;
+        const v2 nxt = i + 1 < n ? sh.verts[i + 1] : sh.verts[0];
+        const float e2x = nxt.x - sx, e2y = nxt.y - sy;
+        const float D = e1x * e2y - e1y * e2x, tri = 0.5f * D;
+        area += tri;
+        const float w = tri * inv3;
+        cx = cx + w * (e1x + e2x);
+        cy = cy + w * (e1y + e2y);
+        const float intx2 = e1x * e1x + e2x * e1x + e2x * e2x, inty2 = e1y * e1y + e2y * e1y + e2y * e2y;
+        I += (0.25f * inv3 * D) * (intx2 + inty2);
+    }
+    const float mass = density * area;
+    const float ia = 1.0f / area;
+    cx = ia * cx; cy = ia * cy;
+    const float mcx = cx + sx, mcy = cy + sy;
+    float mI = density * I;
+    mI += mass * ((mcx * mcx + mcy * mcy) - (cx * cx + cy * cy));
+    sh.invMass = 1.0f / mass;
+    const float lcx = sh.invMass * (mass * mcx), lcy = sh.invMass * (mass * mcy);
+    const float bI = mI - mass * (lcx * lcx + lcy * lcy);
+    sh.invI = 1.0f / bI;
+    sh.localCenter = V(lcx, lcy);
+}
+
+static int lunar_upload_consts(b200gym *h) {
+    using lunar::v2;
+    auto V = [](float x, float y) { v2 r; r.x = x; r.y = y; return r; };
+    lunar::Consts c;
+    memset(&c, 0, sizeof c);
+    const double SCALE = 30.0;
+    const double LP[6][2] = {{17, -10}, {17, 0}, {14, 17}, {-14, 17}, {-17, 0}, {-17, -10}};  // hull order of LANDER_POLY
+    v2 hull[6];
+    for (int i = 0; i < 6; i++) hull[i] = V((float)(LP[i][0] / SCALE), (float)(LP[i][1] / SCALE));
+    lunar_shape(c.shape[0], hull, 6, 5.0f, 0.1f, false);                       // lunar_lander.py:354-368
+    const float hx = (float)(2 / SCALE), hy = (float)(8 / SCALE);              // LEG_W, LEG_H
+    const v2 box[4] = {V(-hx, -hy), V(hx, -hy), V(hx, hy), V(-hx, hy)};
+    lunar_shape(c.shape[1], box, 4, 1.0f, 0.2f, true);                         // :379-392
+    for (int li = 0; li < 2; li++) {
+        const int i = li == 0 ? -1 : +1;
+        c.anchorB[li] = V((float)(i * 20 / SCALE), (float)(18 / SCALE));      // :397
+        c.motorSpeed[li] = (float)(+0.3 * i);                                  // :401
+        if (i == -1) { c.lower[li] = (float)(+0.9 - 0.5); c.upper[li] = (float)(+0.9); }   // :403-410
+        else { c.lower[li] = (float)(-0.9); c.upper[li] = (float)(-0.9 + 0.5); }
+        c.leg_x0[li] = (float)(600 / SCALE / 2 - i * 20 / SCALE);             // :381
+        c.leg_a0[li] = (float)(i * 0.05);                                      // :382
+    }
+    const double Wd = 600 / SCALE;
+    for (int e = 0; e < 11; e++) c.chunk_x[e] = (float)(Wd / (11 - 1) * e);    // :327
+    c.world_w = (float)Wd;
+    c.lander_x0 = (float)(600 / SCALE / 2);
+    c.y0 = (float)(400 / SCALE);
+    CK(h, cudaMemcpyToSymbol(lunar::kC, &c, sizeof c));
+    return 0;
+}
+
 // ---- cross-GPU step barrier for the fused all-gather ---------------------------------------
 // flags[r] (uint64, in every rank's gather allocation) = number of steps whose results rank r
 // has fully written into THIS rank's buffers.  signal: after my step kernel (stream order) tell
@@ -582,6 +747,17 @@ static int launch_step(b200gym *h, const StepArgs &a, int action_dtype, cudaStre
     case B200GYM_MOUNTAINCAR_CONT: return launch_step_kind<B200GYM_MOUNTAINCAR_CONT>(h, a, action_dtype, st);
     case B200GYM_PENDULUM: return launch_step_kind<B200GYM_PENDULUM>(h, a, action_dtype, st);
     case B200GYM_ACROBOT: return launch_step_kind<B200GYM_ACROBOT>(h, a, action_dtype, st);
+    case B200GYM_LUNARLANDER: {
+        const unsigned grid = (unsigned)((a.count + kLunarThreads - 1) / kLunarThreads);
+        switch (action_dtype) {
+        case B200GYM_ACT_I64: lunar_step_kernel<long long><<<grid, kLunarThreads, 0, st>>>(a); break;
+        case B200GYM_ACT_I32: lunar_step_kernel<int><<<grid, kLunarThreads, 0, st>>>(a); break;
+        case B200GYM_ACT_U8: lunar_step_kernel<unsigned char><<<grid, kLunarThreads, 0, st>>>(a); break;
+        default: return fail(h, "Discrete env needs an integer action dtype (got code %d)", action_dtype);
+        }
+        CK(h, cudaGetLastError());
+        return 0;
+    }
     }
     return fail(h, "bad kind %d", h->cfg.kind);
 }
@@ -602,6 +778,10 @@ static int launch_reset(b200gym *h, const uint8_t *mask, const double *bounds, f
     case B200GYM_MOUNTAINCAR_CONT: launch_reset_kind<B200GYM_MOUNTAINCAR_CONT>(h, mask, bounds, obs, st); break;
     case B200GYM_PENDULUM: launch_reset_kind<B200GYM_PENDULUM>(h, mask, bounds, obs, st); break;
     case B200GYM_ACROBOT: launch_reset_kind<B200GYM_ACROBOT>(h, mask, bounds, obs, st); break;
+    case B200GYM_LUNARLANDER:
+        lunar_reset_kernel<<<(unsigned)((h->n + kLunarThreads - 1) / kLunarThreads), kLunarThreads, 0, st>>>(
+            h->lunar_rec, h->elapsed, h->rng, mask, obs, h->n);
+        break;
     default: return fail(h, "bad kind %d", h->cfg.kind);
     }
     CK(h, cudaGetLastError());
@@ -655,7 +835,7 @@ extern "C" int b200gym_create(const b200gym_config *cfg, int64_t num_envs, int d
     DeviceGuard guard(device);
     const size_t n = (size_t)num_envs;
     cudaError_t es[5] = {
-        cudaMalloc(&h->state, sizeof(double) * n * h->S), cudaMalloc(&h->elapsed, sizeof(int32_t) * n),
+        cudaMalloc(&h->state, sizeof(double) * n * (h->S > 0 ? h->S : 1)), cudaMalloc(&h->elapsed, sizeof(int32_t) * n),
         cudaMalloc(&h->flags, n), cudaMalloc(&h->rng, 32 * n), cudaMalloc(&h->invalid, sizeof(unsigned long long))};
     for (cudaError_t ei : es)
         if (ei != cudaSuccess) {
@@ -663,6 +843,14 @@ extern "C" int b200gym_create(const b200gym_config *cfg, int64_t num_envs, int d
             b200gym_destroy(h);
             return 1;
         }
+    if (cfg->kind == B200GYM_LUNARLANDER) {
+        if (cudaMalloc(&h->lunar_rec, sizeof(uint32_t) * lunar::kWords * n) != cudaSuccess ||
+            cudaMemset(h->lunar_rec, 0, sizeof(uint32_t) * lunar::kWords * n) != cudaSuccess || lunar_upload_consts(h)) {
+            fail(nullptr, "b200gym_create: LunarLander state allocation failed");
+            b200gym_destroy(h);
+            return 1;
+        }
+    }
     cudaMemset(h->state, 0, sizeof(double) * n * h->S);
     cudaMemset(h->elapsed, 0, sizeof(int32_t) * n);
     cudaMemset(h->flags, 0, n);
@@ -698,6 +886,7 @@ extern "C" void b200gym_destroy(b200gym_t *h) {
     cudaFree(h->flags);
     cudaFree(h->rng);
     cudaFree(h->invalid);
+    cudaFree(h->lunar_rec);
     if (h->p2p.base) {
         for (int r = 0; r < h->p2p.world; r++)
             if (r != h->p2p.rank && h->p2p.peer[r]) cudaIpcCloseMemHandle(h->p2p.peer[r]);
@@ -751,6 +940,7 @@ static StepArgs make_args(b200gym *h, const void *actions, float *obs, double *r
                           uint8_t *trunc, float *final_obs) {
     StepArgs a;
     a.state = h->state; a.elapsed = h->elapsed; a.flags = h->flags; a.rng = h->rng; a.invalid = h->invalid;
+    a.lunar_rec = h->lunar_rec;
     a.actions = actions; a.obs = obs; a.reward = reward; a.terminated = term; a.truncated = trunc;
     a.final_obs = final_obs;
     a.n = h->n; a.first = 0; a.count = h->n;
@@ -1025,6 +1215,16 @@ extern "C" int b200gym_get_state(b200gym_t *h, double *state_dev, int32_t *elaps
     if (elapsed_dev)
         CK(h, cudaMemcpyAsync(elapsed_dev, h->elapsed, sizeof(int32_t) * (size_t)h->n, cudaMemcpyDeviceToDevice, st));
     if (rng_dev) CK(h, cudaMemcpyAsync(rng_dev, h->rng, 32 * (size_t)h->n, cudaMemcpyDeviceToDevice, st));
+    return 0;
+}
+
+extern "C" int b200gym_lunar_get_bodies(b200gym_t *h, float *bodies_dev, int32_t *flags_dev, void *stream) {
+    if (!h || !bodies_dev || !flags_dev) return fail(h, "b200gym_lunar_get_bodies: null argument");
+    if (h->cfg.kind != B200GYM_LUNARLANDER) return fail(h, "b200gym_lunar_get_bodies: not a LunarLander handle");
+    DeviceGuard guard(h->device);
+    lunar_bodies_kernel<<<blocks_for(h->n), kThreads, 0, (cudaStream_t)stream>>>(h->lunar_rec, h->elapsed, bodies_dev,
+                                                                                 flags_dev, h->n);
+    CK(h, cudaGetLastError());
     return 0;
 }
 

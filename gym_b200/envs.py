@@ -47,6 +47,13 @@ def _acrobot_spaces(params):
     return Box(low=-high, high=high, dtype=np.float32), Discrete(3)
 
 
+def _lunar_spaces(params):
+    # lunar_lander.py:248-292
+    low = np.array([-1.5, -1.5, -5.0, -5.0, -math.pi, -5.0, -0.0, -0.0]).astype(np.float32)
+    high = np.array([1.5, 1.5, 5.0, 5.0, math.pi, 5.0, 1.0, 1.0]).astype(np.float32)
+    return Box(low, high), Discrete(4)
+
+
 class KindInfo:
     def __init__(self, name, spaces, kwargs, bounds_keys, default_bounds, attrs, metadata):
         self.name = name
@@ -84,6 +91,10 @@ KINDS = {
              LINK_COM_POS_1=0.5, LINK_COM_POS_2=0.5, LINK_MOI=1.0, MAX_VEL_1=4 * math.pi, MAX_VEL_2=9 * math.pi,
              AVAIL_TORQUE=[-1.0, 0.0, +1], torque_noise_max=0.0, book_or_nips="book"),
         {"render_modes": [], "render_fps": 15}),
+    _lib.KIND_LUNARLANDER: KindInfo(
+        "LunarLander", _lunar_spaces, {}, ("low", "high"), (0.0, 0.0),
+        dict(continuous=False, gravity=-10.0, enable_wind=False, wind_power=15.0, turbulence_power=1.5),
+        {"render_modes": [], "render_fps": 50}),
 }
 
 
@@ -101,7 +112,7 @@ def parse_reset_bounds(kind, options):
     low/high kinds follow maybe_parse_reset_bounds (classic_control/utils.py:17-46);
     Pendulum follows pendulum.py:143-152 (x_init / y_init, symmetric limits).
     """
-    if options is None:
+    if options is None or kind == _lib.KIND_LUNARLANDER:  # LunarLander.reset ignores options
         return None
     info = KINDS[kind]
     k0, k1 = info.bounds_keys
@@ -117,6 +128,16 @@ def resolve_params(kind, kwargs):
     """ctor kwargs (gym.make(id, **kwargs)) -> the four doubles of b200gym_config.param."""
     info = KINDS[kind]
     params = [0.0, 0.0, 0.0, 0.0]
+    if kind == _lib.KIND_LUNARLANDER:
+        # lunar_lander.py:201-234: only the default (discrete, gravity=-10, no wind) variant is built
+        for key, value in kwargs.items():
+            if key == "render_mode" and value is None:
+                continue
+            if key not in info.attrs:
+                raise TypeError(f"LunarLander got an unexpected keyword argument '{key}'")
+            if info.attrs[key] != value and key in ("continuous", "gravity", "enable_wind"):
+                raise NotImplementedError(f"gym_b200 LunarLander supports only {key}={info.attrs[key]!r}")
+        return params
     for key, (slot, default) in info.kwargs.items():
         params[slot] = float(default)
     for key, value in kwargs.items():

@@ -88,3 +88,5 @@ register("Pendulum-v1", _lib.KIND_PENDULUM, "gym.envs.classic_control.pendulum:P
          max_episode_steps=200)
 register("Acrobot-v1", _lib.KIND_ACROBOT, "gym.envs.classic_control.acrobot:AcrobotEnv",
          reward_threshold=-100.0, max_episode_steps=500)
+register("LunarLander-v2", _lib.KIND_LUNARLANDER, "gym.envs.box2d.lunar_lander:LunarLander",
+         reward_threshold=200, max_episode_steps=1000)

@@ -435,6 +435,17 @@ class B200VectorEnv:
                                                self._stream()), self._handle)
         return st, el, rng
 
+    def lunar_bodies(self):
+        """LunarLander only: (bodies float32 (N, 3, 6) = {c.x, c.y, angle, v.x, v.y, omega} of lander, leg(-1),
+        leg(+1); flags int32 (N, 6) = {game_over, leg0, leg1, awake, elapsed, #touching contacts})."""
+        self._assert_open("lunar_bodies")
+        torch = _torch()
+        bodies = torch.empty((self.num_envs, 18), dtype=torch.float32, device=self.device)
+        flags = torch.empty((self.num_envs, 6), dtype=torch.int32, device=self.device)
+        _lib.check(self._lib.b200gym_lunar_get_bodies(self._handle, ctypes.c_void_p(bodies.data_ptr()),
+                                                      ctypes.c_void_p(flags.data_ptr()), self._stream()), self._handle)
+        return bodies.view(self.num_envs, 3, 6), flags
+
     def set_state(self, state=None, elapsed=None, rng=None):
         self._assert_open("set_state")
         torch = _torch()

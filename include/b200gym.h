@@ -38,7 +38,9 @@ enum b200gym_kind {
     B200GYM_MOUNTAINCAR_CONT = 2, /* gym/envs/classic_control/continuous_mountain_car.py:142-186 */
     B200GYM_PENDULUM = 3,         /* gym/envs/classic_control/pendulum.py:119-163 */
     B200GYM_ACROBOT = 4,          /* gym/envs/classic_control/acrobot.py:181-277,418-465 */
-    B200GYM_NUM_KINDS = 5
+    B200GYM_LUNARLANDER = 5,      /* gym/envs/box2d/lunar_lander.py:308-600 (discrete, no wind); the Box2D
+                                     arithmetic it delegates to is re-derived in csrc/lunar.cuh */
+    B200GYM_NUM_KINDS = 6
 };
 
 /* dtype codes for the `actions` argument of b200gym_step */
@@ -183,6 +185,14 @@ int b200gym_reset_host(b200gym_t *h, const uint8_t *mask_host, const double *bou
 int b200gym_get_state(b200gym_t *h, double *state_dev, int32_t *elapsed_dev, uint64_t *rng_dev, void *stream);
 int b200gym_set_state(b200gym_t *h, const double *state_dev, const int32_t *elapsed_dev,
                       const uint64_t *rng_dev, void *stream);
+
+/*
+ * LunarLander only (state_dim is 0 for it; get/set_state handle the TimeLimit counters and RNG):
+ * the three rigid bodies {lander, leg(-1), leg(+1)} of every env as float32 [n][18] =
+ * 3 x {c.x, c.y, angle, v.x, v.y, omega} and int32 [n][6] = {game_over, leg0 contact, leg1 contact,
+ * awake, elapsed, #touching contacts} -- what `env.lander.position` etc. expose in the reference.
+ */
+int b200gym_lunar_get_bodies(b200gym_t *h, float *bodies_dev, int32_t *flags_dev, void *stream);
 
 /*
  * Multi-GPU: fused step + all-gather over NVLink peer memory.

@@ -1,0 +1,20 @@
+/* lunar_oracle.h -- CPU ORACLE for LunarLander-v2 (test infrastructure, NOT product code).
+ * See lunar_oracle.c.  PARITY UNPINNED: Box2D (box2d-py 2.3.5) is not available here. */
+#ifndef LUNAR_ORACLE_H
+#define LUNAR_ORACLE_H
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+typedef struct orc_lunar orc_lunar;
+orc_lunar *orc_lunar_create(int64_t n, int max_episode_steps);
+void orc_lunar_destroy(orc_lunar *v);
+void orc_lunar_seed_range(orc_lunar *v, const uint32_t base[4], int64_t first);
+void orc_lunar_reset(orc_lunar *v, float *obs);
+int64_t orc_lunar_step(orc_lunar *v, const int64_t *actions, float *obs, double *reward, uint8_t *terminated,
+                       uint8_t *truncated, float *final_obs);
+void orc_lunar_get_bodies(const orc_lunar *v, int64_t i, float out[18], int32_t flags[6]);
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -36,9 +36,9 @@ ENV_IDS = {
 
 def build(force=False):
     """Compile the oracle with the recipe in oracle/Makefile (gcc, no FMA contraction)."""
-    src = os.path.join(_HERE, "gym_oracle.c")
+    srcs = [os.path.join(_HERE, f) for f in ("gym_oracle.c", "lunar_oracle.c", "gym_oracle.h", "lunar_oracle.h")]
     if (force or not os.path.exists(_LIB_PATH)
-            or os.path.getmtime(_LIB_PATH) < os.path.getmtime(src)):
+            or os.path.getmtime(_LIB_PATH) < max(os.path.getmtime(s) for s in srcs)):
         subprocess.check_call(["make", "-s", "-C", _HERE, "libgymoracle.so"])
     return _LIB_PATH
 
@@ -67,6 +67,14 @@ def lib():
         L.orc_vec_step.argtypes = [vp, vp, vp, vp, vp, vp, vp, i32]
         L.orc_vec_get_state.argtypes = [vp, vp, vp]
         L.orc_vec_set_state.argtypes = [vp, vp, vp]
+        L.orc_lunar_create.restype = vp
+        L.orc_lunar_create.argtypes = [i64, i32]
+        L.orc_lunar_destroy.argtypes = [vp]
+        L.orc_lunar_seed_range.argtypes = [vp, vp, i64]
+        L.orc_lunar_reset.argtypes = [vp, vp]
+        L.orc_lunar_step.restype = i64
+        L.orc_lunar_step.argtypes = [vp, vp, vp, vp, vp, vp, vp]
+        L.orc_lunar_get_bodies.argtypes = [vp, i64, vp, vp]
         for f in ("orc_obs_dim", "orc_act_dim", "orc_state_dim", "orc_num_actions"):
             getattr(L, f).argtypes = [i32]
         _lib = L
@@ -184,3 +192,69 @@ class OracleVec:
         s = None if state is None else np.ascontiguousarray(state, dtype=np.float64)
         e = None if elapsed is None else np.ascontiguousarray(elapsed, dtype=np.int32)
         lib().orc_vec_set_state(self._h, _ptr(s), _ptr(e))
+
+
+class OracleLunar:
+    """SyncVectorEnv([make("LunarLander-v2")] * n) restated in C (oracle/lunar_oracle.c).
+
+    PARITY UNPINNED: the rigid-body arithmetic restates Box2D 2.3 from its published design;
+    box2d-py is not installable here, so it cannot be checked against the real library."""
+
+    obs_dim, act_dim, num_actions = 8, 0, 4
+
+    def __init__(self, num_envs, max_episode_steps=1000):
+        self.n = int(num_envs)
+        self._h = lib().orc_lunar_create(self.n, int(max_episode_steps or 0))
+
+    def close(self):
+        if getattr(self, "_h", None):
+            lib().orc_lunar_destroy(self._h)
+            self._h = None
+
+    __del__ = close
+
+    def reset(self, seed=None):
+        if seed is not None:
+            lib().orc_lunar_seed_range(self._h, seed_words(seed).ctypes.data, 0)
+        obs = np.zeros((self.n, 8), dtype=np.float32)
+        lib().orc_lunar_reset(self._h, obs.ctypes.data)
+        return obs
+
+    def step(self, actions):
+        a = np.ascontiguousarray(actions, dtype=np.int64).reshape(self.n)
+        obs = np.zeros((self.n, 8), dtype=np.float32)
+        fo = np.zeros((self.n, 8), dtype=np.float32)
+        rew = np.zeros(self.n, dtype=np.float64)
+        te = np.zeros(self.n, dtype=np.uint8)
+        tr = np.zeros(self.n, dtype=np.uint8)
+        bad = lib().orc_lunar_step(self._h, a.ctypes.data, obs.ctypes.data, rew.ctypes.data, te.ctypes.data,
+                                   tr.ctypes.data, fo.ctypes.data)
+        if bad:
+            raise AssertionError(f"{bad} invalid discrete action(s)")
+        return obs, rew, te.astype(bool), tr.astype(bool), fo
+
+    def bodies(self, i=0):
+        out = np.zeros(18, dtype=np.float32)
+        flags = np.zeros(6, dtype=np.int32)
+        lib().orc_lunar_get_bodies(self._h, int(i), out.ctypes.data, flags.ctypes.data)
+        return out.reshape(3, 6), flags
+
+
+def lunar_heuristic(s):
+    """gym/envs/box2d/lunar_lander.py:726-777 (discrete branch), used by the behavioural test."""
+    angle_targ = s[0] * 0.5 + s[2] * 1.0
+    angle_targ = min(max(angle_targ, -0.4), 0.4)
+    hover_targ = 0.55 * np.abs(s[0])
+    angle_todo = (angle_targ - s[4]) * 0.5 - (s[5]) * 1.0
+    hover_todo = (hover_targ - s[1]) * 0.5 - (s[3]) * 0.5
+    if s[6] or s[7]:
+        angle_todo = 0
+        hover_todo = -(s[3]) * 0.5
+    a = 0
+    if hover_todo > np.abs(angle_todo) and hover_todo > 0.05:
+        a = 2
+    elif angle_todo < -0.05:
+        a = 3
+    elif angle_todo > +0.05:
+        a = 1
+    return a

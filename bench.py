@@ -38,7 +38,9 @@ LOG2_ENVS = 20
 # (SURVEY.md 8(d) counts 102 B with a float32 reward; we emit the reference's float64.)
 BYTES_PER_ENV_STEP = {"CartPole-v1": 106, "CartPole-v0": 106, "Pendulum-v1": 16 * 2 + 8 + 4 + 12 + 8 + 2,
                       "Acrobot-v1": 32 * 2 + 8 + 8 + 24 + 8 + 2, "MountainCar-v0": 16 * 2 + 8 + 8 + 8 + 8 + 2,
-                      "MountainCarContinuous-v0": 16 * 2 + 8 + 4 + 8 + 8 + 2}
+                      "MountainCarContinuous-v0": 16 * 2 + 8 + 4 + 8 + 8 + 2,
+                      # LunarLander: 103-word solver record r+w, PCG64 state (2 draws/step), counter, action, outputs
+                      "LunarLander-v2": 103 * 4 * 2 + 32 + 16 + 8 + 8 + 32 + 8 + 2}
 # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed ncu --set full capture (2^20 envs)
 NCU_DRAM_BYTES_PER_LAUNCH = {"CartPole-v1": 56.23e6 + 23.99e6}
 FALLBACK_HBM_GBS = 6650.0  # /opt/skills/guides/B200_PROFILING.md fallback
@@ -132,6 +134,8 @@ def host_threads():
 
 
 def random_actions_np(env_id, n, rng):
+    if env_id.startswith("LunarLander"):
+        return rng.integers(0, 4, size=n).astype(np.int64)
     from oracle.oracle import ENV_IDS, KINDS, lib
     kind = KINDS[ENV_IDS[env_id][0]]
     nact = lib().orc_num_actions(kind)
@@ -142,15 +146,17 @@ def random_actions_np(env_id, n, rng):
 
 def cpu_oracle_throughput(env_id, n, seconds, threads, min_steps=3):
     """Time the C port of the reference path (oracle/) on the host cores: bounded sample."""
-    from oracle.oracle import OracleVec
+    from oracle.oracle import OracleLunar, OracleVec
     rng = np.random.default_rng(0)
-    v = OracleVec(env_id, n)
+    lunar = env_id.startswith("LunarLander")
+    v = OracleLunar(n) if lunar else OracleVec(env_id, n)
     v.reset(seed=0)
     pool = [random_actions_np(env_id, n, rng) for _ in range(4)]
-    v.step(pool[0], nthreads=threads)  # warm-up
+    kw = {} if lunar else {"nthreads": threads}
+    v.step(pool[0], **kw)  # warm-up
     steps, t0 = 0, time.perf_counter()
     while True:
-        v.step(pool[steps % 4], nthreads=threads)
+        v.step(pool[steps % 4], **kw)
         steps += 1
         el = time.perf_counter() - t0
         if steps >= min_steps and el >= seconds:
@@ -352,6 +358,8 @@ def run_b200(args):
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         threads = host_threads()
+        if args.env.startswith("LunarLander"):
+            threads = 1  # oracle/lunar_oracle.c is a scalar single-thread port
         v, cpu_steps, cpu_el = cpu_oracle_throughput(args.env, n, args.cpu_seconds, threads)
         cpu = {"value": v, "unit": "env-steps/s", "cores": threads, "kind": "port",
                "sample": f"{cpu_steps} vector steps of 2^{args.log2_envs} envs ({cpu_el:.1f} s) of the same workload, "

@@ -30,133 +30,16 @@
 #include <stdlib.h>
 #include <string.h>
 
-typedef unsigned __int128 u128;
-
-/* ---------------------------------------------------------------- numpy PCG64 (see gym_oracle.c) */
-typedef struct { u128 state, inc; } pcg64_t;
-#define PCG_MULT ((((u128)0x2360ED051FC65DA4ULL) << 64) | (u128)0x4385DF649FCCF645ULL)
-static inline void pcg_adv(pcg64_t *g) { g->state = g->state * PCG_MULT + g->inc; }
-static inline uint64_t pcg_next64(pcg64_t *g)
-{
-    pcg_adv(g);
-    uint64_t hi = (uint64_t)(g->state >> 64), lo = (uint64_t)g->state, x = hi ^ lo;
-    unsigned rot = (unsigned)(hi >> 58);
-    return (x >> rot) | (x << ((-rot) & 63));
-}
-static inline double pcg_double(pcg64_t *g) { return (double)(pcg_next64(g) >> 11) * (1.0 / 9007199254740992.0); }
-static inline double rng_uniform(pcg64_t *g, double lo, double hi) { double r = hi - lo; return lo + r * pcg_double(g); }
-void orc_seed_sequence(const uint32_t ent[4], uint64_t out[4]); /* gym_oracle.c */
-
-/* ---------------------------------------------------------------- float32 vector helpers */
-typedef struct { float x, y; } v2;
-typedef struct { float s, c; } rot;
-typedef struct { v2 p; rot q; } xform;
-
-static inline v2 V(float x, float y) { v2 r = {x, y}; return r; }
-static inline v2 add(v2 a, v2 b) { return V(a.x + b.x, a.y + b.y); }
-static inline v2 sub(v2 a, v2 b) { return V(a.x - b.x, a.y - b.y); }
-static inline v2 neg(v2 a) { return V(-a.x, -a.y); }
-static inline v2 scl(float s, v2 a) { return V(s * a.x, s * a.y); }
-static inline float dot(v2 a, v2 b) { return a.x * b.x + a.y * b.y; }
-static inline float crs(v2 a, v2 b) { return a.x * b.y - a.y * b.x; }
-static inline v2 crs_vs(v2 a, float s) { return V(s * a.y, -s * a.x); }  /* b2Cross(vec, scalar) */
-static inline v2 crs_sv(float s, v2 a) { return V(-s * a.y, s * a.x); }  /* b2Cross(scalar, vec) */
-static inline v2 rmul(rot q, v2 v) { return V(q.c * v.x - q.s * v.y, q.s * v.x + q.c * v.y); }
-static inline v2 rmulT(rot q, v2 v) { return V(q.c * v.x + q.s * v.y, -q.s * v.x + q.c * v.y); }
-static inline v2 xmul(xform T, v2 v) { return V((T.q.c * v.x - T.q.s * v.y) + T.p.x, (T.q.s * v.x + T.q.c * v.y) + T.p.y); }
-static inline v2 xmulT(xform T, v2 v) { float px = v.x - T.p.x, py = v.y - T.p.y; return V(T.q.c * px + T.q.s * py, -T.q.s * px + T.q.c * py); }
-static inline float fminf_(float a, float b) { return a < b ? a : b; }
-static inline float fmaxf_(float a, float b) { return a > b ? a : b; }
-static inline float clampf(float a, float lo, float hi) { return fmaxf_(lo, fminf_(a, hi)); }
-
-/* sin/cos of a body angle: Cody-Waite reduction by pi/2 (two fmaf) + cephes-style minimax
- * polynomials on [-pi/4, pi/4]; ~1 ulp.  The CUDA kernel evaluates the same sequence. */
-static void lite_sincosf(float x, float *sn, float *cs)
-{
-    float kf = rintf(x * 0.636619772367581343f);
-    int k = (int)kf;
-    float r = fmaf(kf, -1.5707963705062866f, x);
-    r = fmaf(kf, 4.371139000186241e-08f, r);
-    float r2 = r * r;
-    float ps = -1.9515295891e-4f;
-    ps = ps * r2 + 8.3321608736e-3f;
-    ps = ps * r2 + -1.6666654611e-1f;
-    float sr = r + r * r2 * ps;
-    float pc = 2.443315711809948e-5f;
-    pc = pc * r2 + -1.388731625493765e-3f;
-    pc = pc * r2 + 4.166664568298827e-2f;
-    float cr = (1.0f - 0.5f * r2) + r2 * r2 * pc;
-    switch (k & 3) {
-    case 0: *sn = sr; *cs = cr; break;
-    case 1: *sn = cr; *cs = -sr; break;
-    case 2: *sn = -sr; *cs = -cr; break;
-    default: *sn = -cr; *cs = sr; break;
-    }
-}
-static inline rot rot_of(float a) { rot q; lite_sincosf(a, &q.s, &q.c); return q; }
-
-/* ---------------------------------------------------------------- Box2D 2.3 constants (b2Settings.h) */
-#define LINEAR_SLOP 0.005f
-#define ANGULAR_SLOP (2.0f / 180.0f * 3.14159265359f)
-#define POLYGON_RADIUS (2.0f * LINEAR_SLOP)
-#define MAX_LINEAR_CORRECTION 0.2f
-#define MAX_ANGULAR_CORRECTION (8.0f / 180.0f * 3.14159265359f)
-#define MAX_TRANSLATION 2.0f
-#define MAX_ROTATION (0.5f * 3.14159265359f)
-#define BAUMGARTE 0.2f
-#define VELOCITY_THRESHOLD 1.0f
-#define TIME_TO_SLEEP 0.5f
-#define LINEAR_SLEEP_TOL 0.01f
-#define ANGULAR_SLEEP_TOL (2.0f / 180.0f * 3.14159265359f)
-#define AABB_EXTENSION 0.1f
+#include "b2lite.h"
+#include "np_rng.h"
 
 #define NB 3    /* dynamic bodies: 0 lander, 1 leg (i=-1), 2 leg (i=+1) */
 #define NE 11   /* ground edges: 0 base, 1..10 terrain */
-#define MAXV 6
-
-typedef struct {
-    int count;
-    v2 verts[MAXV], normals[MAXV], centroid;
-    float friction;
-    /* body */
-    xform xf;
-    v2 localCenter, c0, c, v, force;
-    float a0, a, w, torque, mass, invMass, I, invI, sleepTime;
-    int awake;
-} body_t;
-
-typedef struct { v2 v1, v2; float friction; } edge_t;
-
-typedef struct {
-    v2 localPoint;
-    float normalImpulse, tangentImpulse;
-    uint32_t id;
-} mpoint_t;
-
-typedef struct {
-    int type; /* 0 = faceA (edge is the reference face), 1 = faceB */
-    v2 localNormal, localPoint;
-    int pointCount;
-    mpoint_t pts[2];
-} manifold_t;
-
-typedef struct { int touching; manifold_t m; } contact_t;
-
-typedef struct {
-    int bodyB;            /* bodyA is always the lander (index 0) */
-    v2 localAnchorA, localAnchorB;
-    float lower, upper, maxMotorTorque, motorSpeed, referenceAngle;
-    float impulse[3], motorImpulse;
-    int limitState;       /* 0 inactive, 1 atLower, 2 atUpper, 3 equal */
-    /* solver temp */
-    v2 rA, rB, lcA, lcB;
-    float mA, mB, iA, iB, K[3][3], motorMass; /* K[col][row] like b2Mat33 ex/ey/ez */
-} joint_t;
 
 typedef struct {
     body_t b[NB];
     edge_t e[NE];
-    contact_t ct[NB][NE];
+    contact_t ct[NB * NE];
     joint_t j[2];
     float inv_dt0;
     int game_over, leg_contact[2];
@@ -172,657 +55,27 @@ struct orc_lunar {
     world_t *w;
 };
 
-/* ---------------------------------------------------------------- shapes & mass (b2PolygonShape) */
-static void poly_set(body_t *b, const v2 *hull, int n)
-{ /* vertices are given already in hull (CCW) order; normals + centroid as b2PolygonShape::Set */
-    b->count = n;
-    for (int i = 0; i < n; i++) b->verts[i] = hull[i];
-    for (int i = 0; i < n; i++) {
-        int i2 = i + 1 < n ? i + 1 : 0;
-        v2 edge = sub(b->verts[i2], b->verts[i]);
-        v2 nr = crs_vs(edge, 1.0f);
-        float len = sqrtf(nr.x * nr.x + nr.y * nr.y);
-        float inv = 1.0f / len;
-        b->normals[i] = V(inv * nr.x, inv * nr.y);
-    }
-    /* ComputeCentroid */
-    v2 c = V(0.0f, 0.0f), pRef = V(0.0f, 0.0f);
-    float area = 0.0f;
-    const float inv3 = 1.0f / 3.0f;
-    for (int i = 0; i < n; i++) {
-        v2 p1 = pRef, p2 = b->verts[i], p3 = i + 1 < n ? b->verts[i + 1] : b->verts[0];
-        v2 e1 = sub(p2, p1), e2 = sub(p3, p1);
-        float D = crs(e1, e2);
-        float tri = 0.5f * D;
-        area += tri;
-        c = add(c, scl(tri * inv3, add(add(p1, p2), p3)));
-    }
-    b->centroid = scl(1.0f / area, c);
-}
-
-static void poly_mass(body_t *b, float density)
-{ /* b2PolygonShape::ComputeMass + b2Body::ResetMassData (single fixture) */
-    int n = b->count;
-    v2 center = V(0.0f, 0.0f), s = V(0.0f, 0.0f);
-    float area = 0.0f, I = 0.0f;
-    for (int i = 0; i < n; i++) s = add(s, b->verts[i]);
-    s = scl(1.0f / (float)n, s);
-    const float inv3 = 1.0f / 3.0f;
-    for (int i = 0; i < n; i++) {
-        v2 e1 = sub(b->verts[i], s), e2 = i + 1 < n ? sub(b->verts[i + 1], s) : sub(b->verts[0], s);
-        float D = crs(e1, e2), tri = 0.5f * D;
-        area += tri;
-        center = add(center, scl(tri * inv3, add(e1, e2)));
-        float ex1 = e1.x, ey1 = e1.y, ex2 = e2.x, ey2 = e2.y;
-        float intx2 = ex1 * ex1 + ex2 * ex1 + ex2 * ex2, inty2 = ey1 * ey1 + ey2 * ey1 + ey2 * ey2;
-        I += (0.25f * inv3 * D) * (intx2 + inty2);
-    }
-    float mass = density * area;
-    center = scl(1.0f / area, center);
-    v2 mcenter = add(center, s);
-    float mI = density * I;
-    mI += mass * (dot(mcenter, mcenter) - dot(center, center));
-    /* ResetMassData */
-    b->mass = mass;
-    b->invMass = 1.0f / mass;
-    v2 lc = scl(b->invMass, scl(mass, mcenter));
-    float bI = mI - mass * dot(lc, lc);
-    b->I = bI;
-    b->invI = 1.0f / bI;
-    b->localCenter = lc;
-}
-
-static void body_place(body_t *b, v2 pos, float angle)
+/* ContactDetector (lunar_lander.py:54-72) */
+static void lunar_event(void *ctx, int body, int begin)
 {
-    b->xf.p = pos;
-    b->xf.q = rot_of(angle);
-    b->c = xmul(b->xf, b->localCenter);
-    b->c0 = b->c;
-    b->a = b->a0 = angle;
-    b->v = V(0.0f, 0.0f);
-    b->w = 0.0f;
-    b->force = V(0.0f, 0.0f);
-    b->torque = 0.0f;
-    b->sleepTime = 0.0f;
-    b->awake = 1;
+    world_t *W = (world_t *)ctx;
+    if (begin) { if (body == 0) W->game_over = 1; else W->leg_contact[body - 1] = 1; }
+    else if (body > 0) W->leg_contact[body - 1] = 0;
 }
 
-static inline void body_sync_xf(body_t *b)
-{ /* b2Body::SynchronizeTransform */
-    b->xf.q = rot_of(b->a);
-    b->xf.p = sub(b->c, rmul(b->xf.q, b->localCenter));
-}
-
-/* ---------------------------------------------------------------- b2CollideEdgeAndPolygon */
-typedef struct { v2 v; uint32_t id; } clipv_t;
-#define ID(ia, ib, ta, tb) ((uint32_t)(ia) | ((uint32_t)(ib) << 8) | ((uint32_t)(ta) << 16) | ((uint32_t)(tb) << 24))
-enum { F_VERTEX = 0, F_FACE = 1 };
-
-static int clip_segment(clipv_t out[2], const clipv_t in[2], v2 normal, float offset, int vertexIndexA)
+/* world.Step(1/50, 180, 60): island order {leg+1, lander, leg-1}, joint of leg+1 first */
+static int world_step(world_t *W, float dt, int velIters, int posIters)
 {
-    int n = 0;
-    float d0 = dot(normal, in[0].v) - offset, d1 = dot(normal, in[1].v) - offset;
-    if (d0 <= 0.0f) out[n++] = in[0];
-    if (d1 <= 0.0f) out[n++] = in[1];
-    if (d0 * d1 < 0.0f) {
-        float interp = d0 / (d0 - d1);
-        out[n].v = add(in[0].v, scl(interp, sub(in[1].v, in[0].v)));
-        out[n].id = ID(vertexIndexA, (in[0].id >> 8) & 0xff, F_VERTEX, F_FACE);
-        n++;
-    }
-    return n;
-}
-
-static void collide_edge_polygon(manifold_t *m, const edge_t *eA, const body_t *pB)
-{ /* the edge's body (the moon) sits at the identity transform, so xf = xfB */
-    const xform xf = pB->xf;
-    const int count = pB->count;
-    v2 centroidB = xmul(xf, pB->centroid);
-    v2 v1 = eA->v1, v2_ = eA->v2;
-    v2 edge1 = sub(v2_, v1);
-    float len = sqrtf(edge1.x * edge1.x + edge1.y * edge1.y);
-    float inv = 1.0f / len;
-    edge1 = V(edge1.x * inv, edge1.y * inv);
-    v2 normal1 = V(edge1.y, -edge1.x);
-    float offset1 = dot(normal1, sub(centroidB, v1));
-    int front = offset1 >= 0.0f;
-    v2 normal, lower, upper;
-    if (front) { normal = normal1; lower = neg(normal1); upper = neg(normal1); }
-    else { normal = neg(normal1); lower = normal1; upper = normal1; }
-    v2 pv[MAXV], pn[MAXV];
-    for (int i = 0; i < count; i++) { pv[i] = xmul(xf, pB->verts[i]); pn[i] = rmul(xf.q, pB->normals[i]); }
-    const float radius = 2.0f * POLYGON_RADIUS;
-    m->pointCount = 0;
-    /* ComputeEdgeSeparation */
-    float edgeSep = 3.402823466e+38f;
-    for (int i = 0; i < count; i++) { float s = dot(normal, sub(pv[i], v1)); if (s < edgeSep) edgeSep = s; }
-    if (edgeSep > radius) return;
-    /* ComputePolygonSeparation */
-    int polyType = 0 /*unknown*/, polyIndex = -1;
-    float polySep = -3.402823466e+38f;
-    v2 perp = V(-normal.y, normal.x);
-    for (int i = 0; i < count; i++) {
-        v2 n = neg(pn[i]);
-        float s1 = dot(n, sub(pv[i], v1)), s2 = dot(n, sub(pv[i], v2_));
-        float s = fminf_(s1, s2);
-        if (s > radius) { polyType = 1; polyIndex = i; polySep = s; break; }
-        if (dot(n, perp) >= 0.0f) { if (dot(sub(n, upper), normal) < -ANGULAR_SLOP) continue; }
-        else { if (dot(sub(n, lower), normal) < -ANGULAR_SLOP) continue; }
-        if (s > polySep) { polyType = 1; polyIndex = i; polySep = s; }
-    }
-    if (polyType != 0 && polySep > radius) return;
-    int primaryEdge; /* 1: edge A is the reference face */
-    if (polyType == 0) primaryEdge = 1;
-    else if (polySep > 0.98f * edgeSep + 0.001f) primaryEdge = 0;
-    else primaryEdge = 1;
-
-    clipv_t ie[2];
-    int rf_i1, rf_i2;
-    v2 rf_v1, rf_v2, rf_normal;
-    if (primaryEdge) {
-        m->type = 0;
-        int best = 0;
-        float bestVal = dot(normal, pn[0]);
-        for (int i = 1; i < count; i++) { float val = dot(normal, pn[i]); if (val < bestVal) { bestVal = val; best = i; } }
-        int i1 = best, i2 = i1 + 1 < count ? i1 + 1 : 0;
-        ie[0].v = pv[i1]; ie[0].id = ID(0, i1, F_FACE, F_VERTEX);
-        ie[1].v = pv[i2]; ie[1].id = ID(0, i2, F_FACE, F_VERTEX);
-        if (front) { rf_i1 = 0; rf_i2 = 1; rf_v1 = v1; rf_v2 = v2_; rf_normal = normal1; }
-        else { rf_i1 = 1; rf_i2 = 0; rf_v1 = v2_; rf_v2 = v1; rf_normal = neg(normal1); }
-    } else {
-        m->type = 1;
-        ie[0].v = v1; ie[0].id = ID(0, polyIndex, F_VERTEX, F_FACE);
-        ie[1].v = v2_; ie[1].id = ID(0, polyIndex, F_VERTEX, F_FACE);
-        rf_i1 = polyIndex; rf_i2 = rf_i1 + 1 < count ? rf_i1 + 1 : 0;
-        rf_v1 = pv[rf_i1]; rf_v2 = pv[rf_i2]; rf_normal = pn[rf_i1];
-    }
-    v2 side1 = V(rf_normal.y, -rf_normal.x), side2 = neg(side1);
-    float off1 = dot(side1, rf_v1), off2 = dot(side2, rf_v2);
-    clipv_t c1[2], c2[2];
-    if (clip_segment(c1, ie, side1, off1, rf_i1) < 2) return;
-    if (clip_segment(c2, c1, side2, off2, rf_i2) < 2) return;
-    if (primaryEdge) { m->localNormal = rf_normal; m->localPoint = rf_v1; }
-    else { m->localNormal = pB->normals[rf_i1]; m->localPoint = pB->verts[rf_i1]; }
-    int pc = 0;
-    for (int i = 0; i < 2; i++) {
-        float sep = dot(rf_normal, sub(c2[i].v, rf_v1));
-        if (sep <= radius) {
-            mpoint_t *cp = &m->pts[pc];
-            if (primaryEdge) { cp->localPoint = xmulT(xf, c2[i].v); cp->id = c2[i].id; }
-            else {
-                uint32_t id = c2[i].id;
-                cp->localPoint = c2[i].v;
-                cp->id = ID((id >> 8) & 0xff, id & 0xff, (id >> 24) & 0xff, (id >> 16) & 0xff);
-            }
-            pc++;
-        }
-    }
-    m->pointCount = pc;
-}
-
-/* b2Contact::Update for one (body, edge) pair; returns +1 on BeginContact, -1 on EndContact */
-static int contact_update(contact_t *c, const edge_t *e, const body_t *b)
-{
-    manifold_t old = c->m;
-    int was = c->touching;
-    /* broad-phase stand-in: fat AABBs (b2_aabbExtension) must overlap, else no manifold */
-    float lox = 3.402823466e+38f, loy = lox, hix = -lox, hiy = -lox;
-    for (int i = 0; i < b->count; i++) {
-        v2 p = xmul(b->xf, b->verts[i]);
-        lox = fminf_(lox, p.x); loy = fminf_(loy, p.y); hix = fmaxf_(hix, p.x); hiy = fmaxf_(hiy, p.y);
-    }
-    const float ext = POLYGON_RADIUS + AABB_EXTENSION;
-    float elox = fminf_(e->v1.x, e->v2.x) - ext, ehix = fmaxf_(e->v1.x, e->v2.x) + ext;
-    float eloy = fminf_(e->v1.y, e->v2.y) - ext, ehiy = fmaxf_(e->v1.y, e->v2.y) + ext;
-    c->m.pointCount = 0;
-    if (!(lox - ext > ehix || elox > hix + ext || loy - ext > ehiy || eloy > hiy + ext))
-        collide_edge_polygon(&c->m, e, b);
-    int touching = c->m.pointCount > 0;
-    for (int i = 0; i < c->m.pointCount; i++) {
-        mpoint_t *mp2 = &c->m.pts[i];
-        mp2->normalImpulse = 0.0f;
-        mp2->tangentImpulse = 0.0f;
-        if (was)
-            for (int j = 0; j < old.pointCount; j++)
-                if (old.pts[j].id == mp2->id) {
-                    mp2->normalImpulse = old.pts[j].normalImpulse;
-                    mp2->tangentImpulse = old.pts[j].tangentImpulse;
-                    break;
-                }
-    }
-    c->touching = touching;
-    return touching - was;
-}
-
-/* ---------------------------------------------------------------- contact solver (b2ContactSolver) */
-typedef struct { v2 rA, rB; float normalImpulse, tangentImpulse, normalMass, tangentMass, velocityBias; } vcp_t;
-typedef struct {
-    int body, edge, pointCount;
-    v2 normal;
-    vcp_t p[2];
-    float K[2][2], nM[2][2]; /* [col][row] */
-    float friction;
-    manifold_t *m;
-} vc_t;
-
-typedef struct { v2 c; float a; v2 v; float w; } bstate_t;
-
-static void world_manifold(const manifold_t *m, xform xfA, xform xfB, float rA, float rB, v2 *normal, v2 pts[2])
-{ /* b2WorldManifold::Initialize for e_faceA / e_faceB */
-    if (m->type == 0) {
-        *normal = rmul(xfA.q, m->localNormal);
-        v2 plane = xmul(xfA, m->localPoint);
-        for (int i = 0; i < m->pointCount; i++) {
-            v2 clip = xmul(xfB, m->pts[i].localPoint);
-            v2 cA = add(clip, scl(rA - dot(sub(clip, plane), *normal), *normal));
-            v2 cB = sub(clip, scl(rB, *normal));
-            pts[i] = scl(0.5f, add(cA, cB));
-        }
-    } else {
-        *normal = rmul(xfB.q, m->localNormal);
-        v2 plane = xmul(xfB, m->localPoint);
-        for (int i = 0; i < m->pointCount; i++) {
-            v2 clip = xmul(xfA, m->pts[i].localPoint);
-            v2 cB = add(clip, scl(rB - dot(sub(clip, plane), *normal), *normal));
-            v2 cA = sub(clip, scl(rA, *normal));
-            pts[i] = scl(0.5f, add(cA, cB));
-        }
-        *normal = neg(*normal);
-    }
-}
-
-static const xform XF_ID = {{0.0f, 0.0f}, {0.0f, 1.0f}};
-
-/* ---------------------------------------------------------------- b2RevoluteJoint */
-static void mat33_solve33(float K[3][3], const float b[3], float x[3])
-{
-    const float *ex = K[0], *ey = K[1], *ez = K[2];
-    float cx = ey[1] * ez[2] - ey[2] * ez[1], cy = ey[2] * ez[0] - ey[0] * ez[2], cz = ey[0] * ez[1] - ey[1] * ez[0];
-    float det = ex[0] * cx + ex[1] * cy + ex[2] * cz;
-    if (det != 0.0f) det = 1.0f / det;
-    x[0] = det * (b[0] * cx + b[1] * cy + b[2] * cz);
-    float bx = b[1] * ez[2] - b[2] * ez[1], by = b[2] * ez[0] - b[0] * ez[2], bz = b[0] * ez[1] - b[1] * ez[0];
-    x[1] = det * (ex[0] * bx + ex[1] * by + ex[2] * bz);
-    float dx = ey[1] * b[2] - ey[2] * b[1], dy = ey[2] * b[0] - ey[0] * b[2], dz = ey[0] * b[1] - ey[1] * b[0];
-    x[2] = det * (ex[0] * dx + ex[1] * dy + ex[2] * dz);
-}
-static v2 mat33_solve22(float K[3][3], v2 b)
-{
-    float a11 = K[0][0], a12 = K[1][0], a21 = K[0][1], a22 = K[1][1];
-    float det = a11 * a22 - a12 * a21;
-    if (det != 0.0f) det = 1.0f / det;
-    return V(det * (a22 * b.x - a12 * b.y), det * (a11 * b.y - a21 * b.x));
-}
-
-static void joint_init(joint_t *j, const body_t *A, const body_t *B, bstate_t *sA, bstate_t *sB, float dtRatio)
-{
-    j->lcA = A->localCenter; j->lcB = B->localCenter;
-    j->mA = A->invMass; j->mB = B->invMass; j->iA = A->invI; j->iB = B->invI;
-    rot qA = rot_of(sA->a), qB = rot_of(sB->a);
-    j->rA = rmul(qA, sub(j->localAnchorA, j->lcA));
-    j->rB = rmul(qB, sub(j->localAnchorB, j->lcB));
-    float mA = j->mA, mB = j->mB, iA = j->iA, iB = j->iB;
-    v2 rA = j->rA, rB = j->rB;
-    j->K[0][0] = mA + mB + rA.y * rA.y * iA + rB.y * rB.y * iB;
-    j->K[1][0] = -rA.y * rA.x * iA - rB.y * rB.x * iB;
-    j->K[2][0] = -rA.y * iA - rB.y * iB;
-    j->K[0][1] = j->K[1][0];
-    j->K[1][1] = mA + mB + rA.x * rA.x * iA + rB.x * rB.x * iB;
-    j->K[2][1] = rA.x * iA + rB.x * iB;
-    j->K[0][2] = j->K[2][0];
-    j->K[1][2] = j->K[2][1];
-    j->K[2][2] = iA + iB;
-    j->motorMass = iA + iB;
-    if (j->motorMass > 0.0f) j->motorMass = 1.0f / j->motorMass;
-    float jointAngle = sB->a - sA->a - j->referenceAngle;
-    if (fabsf(j->upper - j->lower) < 2.0f * ANGULAR_SLOP) j->limitState = 3;
-    else if (jointAngle <= j->lower) { if (j->limitState != 1) j->impulse[2] = 0.0f; j->limitState = 1; }
-    else if (jointAngle >= j->upper) { if (j->limitState != 2) j->impulse[2] = 0.0f; j->limitState = 2; }
-    else { j->limitState = 0; j->impulse[2] = 0.0f; }
-    /* warm start */
-    j->impulse[0] *= dtRatio; j->impulse[1] *= dtRatio; j->impulse[2] *= dtRatio; j->motorImpulse *= dtRatio;
-    v2 P = V(j->impulse[0], j->impulse[1]);
-    sA->v = sub(sA->v, scl(mA, P));
-    sA->w -= iA * (crs(rA, P) + j->motorImpulse + j->impulse[2]);
-    sB->v = add(sB->v, scl(mB, P));
-    sB->w += iB * (crs(rB, P) + j->motorImpulse + j->impulse[2]);
-}
-
-static void joint_solve_velocity(joint_t *j, bstate_t *sA, bstate_t *sB, float dt)
-{
-    float mA = j->mA, mB = j->mB, iA = j->iA, iB = j->iB;
-    v2 vA = sA->v, vB = sB->v;
-    float wA = sA->w, wB = sB->w;
-    if (j->limitState != 3) { /* motor */
-        float Cdot = wB - wA - j->motorSpeed;
-        float impulse = -j->motorMass * Cdot;
-        float oldImpulse = j->motorImpulse, maxImpulse = dt * j->maxMotorTorque;
-        j->motorImpulse = clampf(oldImpulse + impulse, -maxImpulse, maxImpulse);
-        impulse = j->motorImpulse - oldImpulse;
-        wA -= iA * impulse;
-        wB += iB * impulse;
-    }
-    if (j->limitState != 0) {
-        v2 Cdot1 = sub(sub(add(vB, crs_sv(wB, j->rB)), vA), crs_sv(wA, j->rA));
-        float Cdot2 = wB - wA;
-        float Cd[3] = {Cdot1.x, Cdot1.y, Cdot2}, imp[3];
-        mat33_solve33(j->K, Cd, imp);
-        imp[0] = -imp[0]; imp[1] = -imp[1]; imp[2] = -imp[2];
-        if (j->limitState == 3) { j->impulse[0] += imp[0]; j->impulse[1] += imp[1]; j->impulse[2] += imp[2]; }
-        else {
-            float newImpulse = j->impulse[2] + imp[2];
-            int violated = (j->limitState == 1) ? (newImpulse < 0.0f) : (newImpulse > 0.0f);
-            if (violated) {
-                v2 rhs = add(neg(Cdot1), scl(j->impulse[2], V(j->K[2][0], j->K[2][1])));
-                v2 red = mat33_solve22(j->K, rhs);
-                imp[0] = red.x; imp[1] = red.y; imp[2] = -j->impulse[2];
-                j->impulse[0] += red.x; j->impulse[1] += red.y; j->impulse[2] = 0.0f;
-            } else { j->impulse[0] += imp[0]; j->impulse[1] += imp[1]; j->impulse[2] += imp[2]; }
-        }
-        v2 P = V(imp[0], imp[1]);
-        vA = sub(vA, scl(mA, P)); wA -= iA * (crs(j->rA, P) + imp[2]);
-        vB = add(vB, scl(mB, P)); wB += iB * (crs(j->rB, P) + imp[2]);
-    } else {
-        v2 Cdot = sub(sub(add(vB, crs_sv(wB, j->rB)), vA), crs_sv(wA, j->rA));
-        v2 imp = mat33_solve22(j->K, neg(Cdot));
-        j->impulse[0] += imp.x; j->impulse[1] += imp.y;
-        vA = sub(vA, scl(mA, imp)); wA -= iA * crs(j->rA, imp);
-        vB = add(vB, scl(mB, imp)); wB += iB * crs(j->rB, imp);
-    }
-    sA->v = vA; sA->w = wA; sB->v = vB; sB->w = wB;
-}
-
-static int joint_solve_position(joint_t *j, bstate_t *sA, bstate_t *sB)
-{
-    v2 cA = sA->c, cB = sB->c;
-    float aA = sA->a, aB = sB->a, angularError = 0.0f, positionError;
-    if (j->limitState != 0) {
-        float angle = aB - aA - j->referenceAngle, limitImpulse = 0.0f;
-        if (j->limitState == 3) {
-            float C = clampf(angle - j->lower, -MAX_ANGULAR_CORRECTION, MAX_ANGULAR_CORRECTION);
-            limitImpulse = -j->motorMass * C; angularError = fabsf(C);
-        } else if (j->limitState == 1) {
-            float C = angle - j->lower; angularError = -C;
-            C = clampf(C + ANGULAR_SLOP, -MAX_ANGULAR_CORRECTION, 0.0f); limitImpulse = -j->motorMass * C;
-        } else {
-            float C = angle - j->upper; angularError = C;
-            C = clampf(C - ANGULAR_SLOP, 0.0f, MAX_ANGULAR_CORRECTION); limitImpulse = -j->motorMass * C;
-        }
-        aA -= j->iA * limitImpulse;
-        aB += j->iB * limitImpulse;
-    }
-    {
-        rot qA = rot_of(aA), qB = rot_of(aB);
-        v2 rA = rmul(qA, sub(j->localAnchorA, j->lcA)), rB = rmul(qB, sub(j->localAnchorB, j->lcB));
-        v2 C = sub(sub(add(cB, rB), cA), rA);
-        positionError = sqrtf(C.x * C.x + C.y * C.y);
-        float mA = j->mA, mB = j->mB, iA = j->iA, iB = j->iB;
-        float k11 = mA + mB + iA * rA.y * rA.y + iB * rB.y * rB.y;
-        float k12 = -iA * rA.x * rA.y - iB * rB.x * rB.y;
-        float k22 = mA + mB + iA * rA.x * rA.x + iB * rB.x * rB.x;
-        float det = k11 * k22 - k12 * k12;
-        if (det != 0.0f) det = 1.0f / det;
-        v2 imp = V(-(det * (k22 * C.x - k12 * C.y)), -(det * (k11 * C.y - k12 * C.x)));
-        cA = sub(cA, scl(mA, imp)); aA -= iA * crs(rA, imp);
-        cB = add(cB, scl(mB, imp)); aB += iB * crs(rB, imp);
-    }
-    sA->c = cA; sA->a = aA; sB->c = cB; sB->a = aB;
-    return positionError <= LINEAR_SLOP && angularError <= ANGULAR_SLOP;
-}
-
-/* ---------------------------------------------------------------- b2World::Step */
-static void world_step(world_t *W, float dt, int velIters, int posIters)
-{
-    const float inv_dt = 1.0f / dt;
-    const float dtRatio = W->inv_dt0 * dt;
-    const v2 gravity = V(0.0f, -10.0f);
-    /* --- Collide: update manifolds, begin/end events (ContactDetector, lunar_lander.py:54-72);
-     *     pairs are visited in the same (island) order the constraints are built in */
-    static const int order[NB] = {2, 0, 1};
-    for (int oi = 0; oi < NB; oi++) {
-        int b = order[oi];
-        for (int e = NE - 1; e >= 0; e--) {
-            int ev = contact_update(&W->ct[b][e], &W->e[e], &W->b[b]);
-            if (ev > 0) { if (b == 0) W->game_over = 1; else W->leg_contact[b - 1] = 1; }
-            else if (ev < 0 && b > 0) W->leg_contact[b - 1] = 0;
-        }
-    }
-    /* --- Solve: one island {leg+1, lander, leg-1} (+ the static moon) */
-    bstate_t st[NB];
-    for (int i = 0; i < NB; i++) {
-        body_t *b = &W->b[i];
-        b->c0 = b->c; b->a0 = b->a;
-        v2 v = b->v; float w = b->w;
-        v = add(v, scl(dt, add(gravity, scl(b->invMass, b->force))));
-        w = w + dt * b->invI * b->torque;
-        v = scl(1.0f / (1.0f + dt * 0.0f), v);
-        w = w * (1.0f / (1.0f + dt * 0.0f));
-        st[i].c = b->c; st[i].a = b->a; st[i].v = v; st[i].w = w;
-    }
-    /* contact constraints in island order */
-    vc_t vc[NB * NE];
-    int nvc = 0;
-    for (int oi = 0; oi < NB; oi++) {
-        int b = order[oi];
-        for (int e = NE - 1; e >= 0; e--) {
-            contact_t *c = &W->ct[b][e];
-            if (!c->touching) continue;
-            vc_t *k = &vc[nvc++];
-            k->body = b; k->edge = e; k->m = &c->m; k->pointCount = c->m.pointCount;
-            k->friction = sqrtf(W->e[e].friction * W->b[b].friction);
-            for (int p = 0; p < k->pointCount; p++) {
-                k->p[p].normalImpulse = dtRatio * c->m.pts[p].normalImpulse;
-                k->p[p].tangentImpulse = dtRatio * c->m.pts[p].tangentImpulse;
-            }
-        }
-    }
-    /* InitializeVelocityConstraints */
-    for (int ci = 0; ci < nvc; ci++) {
-        vc_t *k = &vc[ci];
-        body_t *B = &W->b[k->body];
-        bstate_t *sB = &st[k->body];
-        float mB = B->invMass, iB = B->invI;
-        xform xfB;
-        xfB.q = rot_of(sB->a);
-        xfB.p = sub(sB->c, rmul(xfB.q, B->localCenter));
-        v2 pts[2];
-        world_manifold(k->m, XF_ID, xfB, POLYGON_RADIUS, POLYGON_RADIUS, &k->normal, pts);
-        for (int p = 0; p < k->pointCount; p++) {
-            vcp_t *cp = &k->p[p];
-            cp->rA = pts[p]; /* cA = 0 */
-            cp->rB = sub(pts[p], sB->c);
-            float rnB = crs(cp->rB, k->normal);
-            float kN = mB + iB * rnB * rnB;
-            cp->normalMass = kN > 0.0f ? 1.0f / kN : 0.0f;
-            v2 tangent = crs_vs(k->normal, 1.0f);
-            float rtB = crs(cp->rB, tangent);
-            float kT = mB + iB * rtB * rtB;
-            cp->tangentMass = kT > 0.0f ? 1.0f / kT : 0.0f;
-            cp->velocityBias = 0.0f;
-            float vRel = dot(k->normal, add(sB->v, crs_sv(sB->w, cp->rB)));
-            if (vRel < -VELOCITY_THRESHOLD) cp->velocityBias = -0.0f * vRel;
-        }
-        if (k->pointCount == 2) {
-            float rn1B = crs(k->p[0].rB, k->normal), rn2B = crs(k->p[1].rB, k->normal);
-            float k11 = mB + iB * rn1B * rn1B, k22 = mB + iB * rn2B * rn2B, k12 = mB + iB * rn1B * rn2B;
-            if (k11 * k11 < 1000.0f * (k11 * k22 - k12 * k12)) {
-                k->K[0][0] = k11; k->K[0][1] = k12; k->K[1][0] = k12; k->K[1][1] = k22;
-                float det = k11 * k22 - k12 * k12;
-                if (det != 0.0f) det = 1.0f / det;
-                k->nM[0][0] = det * k22; k->nM[1][0] = -det * k12; k->nM[0][1] = -det * k12; k->nM[1][1] = det * k11;
-            } else k->pointCount = 1;
-        }
-    }
-    /* WarmStart */
-    for (int ci = 0; ci < nvc; ci++) {
-        vc_t *k = &vc[ci];
-        body_t *B = &W->b[k->body];
-        bstate_t *sB = &st[k->body];
-        v2 tangent = crs_vs(k->normal, 1.0f);
-        for (int p = 0; p < k->pointCount; p++) {
-            v2 P = add(scl(k->p[p].normalImpulse, k->normal), scl(k->p[p].tangentImpulse, tangent));
-            sB->w += B->invI * crs(k->p[p].rB, P);
-            sB->v = add(sB->v, scl(B->invMass, P));
-        }
-    }
-    /* joints: island order = joint of leg+1 first, then leg-1 */
-    static const int jorder[2] = {1, 0};
-    for (int q = 0; q < 2; q++) { joint_t *j = &W->j[jorder[q]]; joint_init(j, &W->b[0], &W->b[j->bodyB], &st[0], &st[j->bodyB], dtRatio); }
-    /* velocity iterations */
-    for (int it = 0; it < velIters; it++) {
-        for (int q = 0; q < 2; q++) { joint_t *j = &W->j[jorder[q]]; joint_solve_velocity(j, &st[0], &st[j->bodyB], dt); }
-        for (int ci = 0; ci < nvc; ci++) {
-            vc_t *k = &vc[ci];
-            body_t *B = &W->b[k->body];
-            float mB = B->invMass, iB = B->invI;
-            v2 vB = st[k->body].v; float wB = st[k->body].w;
-            v2 normal = k->normal, tangent = crs_vs(normal, 1.0f);
-            for (int p = 0; p < k->pointCount; p++) {
-                vcp_t *cp = &k->p[p];
-                v2 dv = add(vB, crs_sv(wB, cp->rB));
-                float vt = dot(dv, tangent) - 0.0f;
-                float lambda = cp->tangentMass * (-vt);
-                float maxF = k->friction * cp->normalImpulse;
-                float newImp = clampf(cp->tangentImpulse + lambda, -maxF, maxF);
-                lambda = newImp - cp->tangentImpulse;
-                cp->tangentImpulse = newImp;
-                v2 P = scl(lambda, tangent);
-                vB = add(vB, scl(mB, P)); wB += iB * crs(cp->rB, P);
-            }
-            if (k->pointCount == 1) {
-                vcp_t *cp = &k->p[0];
-                v2 dv = add(vB, crs_sv(wB, cp->rB));
-                float vn = dot(dv, normal);
-                float lambda = -cp->normalMass * (vn - cp->velocityBias);
-                float newImp = fmaxf_(cp->normalImpulse + lambda, 0.0f);
-                lambda = newImp - cp->normalImpulse;
-                cp->normalImpulse = newImp;
-                v2 P = scl(lambda, normal);
-                vB = add(vB, scl(mB, P)); wB += iB * crs(cp->rB, P);
-            } else {
-                vcp_t *c1 = &k->p[0], *c2 = &k->p[1];
-                v2 a = V(c1->normalImpulse, c2->normalImpulse);
-                v2 dv1 = add(vB, crs_sv(wB, c1->rB)), dv2 = add(vB, crs_sv(wB, c2->rB));
-                float vn1 = dot(dv1, normal), vn2 = dot(dv2, normal);
-                v2 b = V(vn1 - c1->velocityBias, vn2 - c2->velocityBias);
-                b = sub(b, V(k->K[0][0] * a.x + k->K[1][0] * a.y, k->K[0][1] * a.x + k->K[1][1] * a.y));
-                v2 x;
-                int solved = 0;
-                x = V(-(k->nM[0][0] * b.x + k->nM[1][0] * b.y), -(k->nM[0][1] * b.x + k->nM[1][1] * b.y));
-                if (x.x >= 0.0f && x.y >= 0.0f) solved = 1;
-                if (!solved) {
-                    x.x = -c1->normalMass * b.x; x.y = 0.0f;
-                    vn2 = k->K[0][1] * x.x + b.y;
-                    if (x.x >= 0.0f && vn2 >= 0.0f) solved = 1;
-                }
-                if (!solved) {
-                    x.x = 0.0f; x.y = -c2->normalMass * b.y;
-                    vn1 = k->K[1][0] * x.y + b.x;
-                    if (x.y >= 0.0f && vn1 >= 0.0f) solved = 1;
-                }
-                if (!solved) {
-                    x.x = 0.0f; x.y = 0.0f;
-                    if (b.x >= 0.0f && b.y >= 0.0f) solved = 1;
-                }
-                if (solved) {
-                    v2 d = sub(x, a);
-                    v2 P1 = scl(d.x, normal), P2 = scl(d.y, normal);
-                    vB = add(vB, scl(mB, add(P1, P2)));
-                    wB += iB * (crs(c1->rB, P1) + crs(c2->rB, P2));
-                    c1->normalImpulse = x.x; c2->normalImpulse = x.y;
-                }
-            }
-            st[k->body].v = vB; st[k->body].w = wB;
-        }
-    }
-    /* StoreImpulses */
-    for (int ci = 0; ci < nvc; ci++)
-        for (int p = 0; p < vc[ci].pointCount; p++) {
-            vc[ci].m->pts[p].normalImpulse = vc[ci].p[p].normalImpulse;
-            vc[ci].m->pts[p].tangentImpulse = vc[ci].p[p].tangentImpulse;
-        }
-    /* integrate positions */
-    for (int i = 0; i < NB; i++) {
-        v2 v = st[i].v; float w = st[i].w;
-        v2 tr = scl(dt, v);
-        if (dot(tr, tr) > MAX_TRANSLATION * MAX_TRANSLATION) { float ratio = MAX_TRANSLATION / sqrtf(dot(tr, tr)); v = scl(ratio, v); }
-        float rotn = dt * w;
-        if (rotn * rotn > MAX_ROTATION * MAX_ROTATION) { float ratio = MAX_ROTATION / fabsf(rotn); w *= ratio; }
-        st[i].c = add(st[i].c, scl(dt, v));
-        st[i].a = st[i].a + dt * w;
-        st[i].v = v; st[i].w = w;
-    }
-    /* position iterations */
-    int positionSolved = 0;
-    for (int it = 0; it < posIters; it++) {
-        float minSep = 0.0f;
-        for (int ci = 0; ci < nvc; ci++) {
-            vc_t *k = &vc[ci];
-            body_t *B = &W->b[k->body];
-            float mB = B->invMass, iB = B->invI;
-            v2 cB = st[k->body].c; float aB = st[k->body].a;
-            int npts = k->m->pointCount; /* the position solver uses the manifold's own point count */
-            for (int p = 0; p < npts; p++) {
-                xform xfB;
-                xfB.q = rot_of(aB);
-                xfB.p = sub(cB, rmul(xfB.q, B->localCenter));
-                v2 normal, point;
-                float separation;
-                if (k->m->type == 0) {
-                    normal = k->m->localNormal;
-                    v2 plane = k->m->localPoint;
-                    v2 clip = xmul(xfB, k->m->pts[p].localPoint);
-                    separation = dot(sub(clip, plane), normal) - POLYGON_RADIUS - POLYGON_RADIUS;
-                    point = clip;
-                } else {
-                    normal = rmul(xfB.q, k->m->localNormal);
-                    v2 plane = xmul(xfB, k->m->localPoint);
-                    v2 clip = k->m->pts[p].localPoint;
-                    separation = dot(sub(clip, plane), normal) - POLYGON_RADIUS - POLYGON_RADIUS;
-                    point = clip;
-                    normal = neg(normal);
-                }
-                v2 rB = sub(point, cB);
-                minSep = fminf_(minSep, separation);
-                float C = clampf(BAUMGARTE * (separation + LINEAR_SLOP), -MAX_LINEAR_CORRECTION, 0.0f);
-                float rnB = crs(rB, normal);
-                float K = mB + iB * rnB * rnB;
-                float impulse = K > 0.0f ? -C / K : 0.0f;
-                v2 P = scl(impulse, normal);
-                cB = add(cB, scl(mB, P));
-                aB += iB * crs(rB, P);
-            }
-            st[k->body].c = cB; st[k->body].a = aB;
-        }
-        int contactsOkay = minSep >= -3.0f * LINEAR_SLOP;
-        int jointsOkay = 1;
-        for (int q = 0; q < 2; q++) {
-            joint_t *j = &W->j[jorder[q]];
-            int ok = joint_solve_position(j, &st[0], &st[j->bodyB]);
-            jointsOkay = jointsOkay && ok;
-        }
-        if (contactsOkay && jointsOkay) { positionSolved = 1; break; }
-    }
-    /* copy back, sleep */
-    for (int i = 0; i < NB; i++) {
-        body_t *b = &W->b[i];
-        b->c = st[i].c; b->a = st[i].a; b->v = st[i].v; b->w = st[i].w;
-        body_sync_xf(b);
-    }
-    float minSleep = 3.402823466e+38f;
-    const float linTol = LINEAR_SLEEP_TOL * LINEAR_SLEEP_TOL, angTol = ANGULAR_SLEEP_TOL * ANGULAR_SLEEP_TOL;
-    for (int i = 0; i < NB; i++) {
-        body_t *b = &W->b[i];
-        if (b->w * b->w > angTol || dot(b->v, b->v) > linTol) { b->sleepTime = 0.0f; minSleep = 0.0f; }
-        else { b->sleepTime += dt; minSleep = fminf_(minSleep, b->sleepTime); }
-    }
-    if (minSleep >= TIME_TO_SLEEP && positionSolved)
-        for (int i = 0; i < NB; i++) {
-            body_t *b = &W->b[i];
-            b->awake = 0; b->sleepTime = 0.0f; b->v = V(0.0f, 0.0f); b->w = 0.0f;
-        }
-    for (int i = 0; i < NB; i++) { W->b[i].force = V(0.0f, 0.0f); W->b[i].torque = 0.0f; }
-    W->inv_dt0 = inv_dt;
+    static const int order[NB] = {2, 0, 1}, jorder[2] = {1, 0};
+    b2l_world S;
+    S.nb = NB; S.nj = 2; S.ne = NE;
+    S.b = W->b; S.j = W->j; S.e = W->e; S.ct = W->ct;
+    S.body_order = order; S.joint_order = jorder;
+    S.inv_dt0 = W->inv_dt0;
+    S.event = lunar_event; S.ctx = W;
+    b2l_step(&S, dt, velIters, posIters);
+    W->inv_dt0 = S.inv_dt0;
+    return S.awake;
 }
 
 /* ---------------------------------------------------------------- the environment */
@@ -893,6 +146,7 @@ static void lunar_reset_one(world_t *W, float *obs)
         leg->friction = 0.2f;
         body_place(leg, V((float)(VIEWPORT_W / SCALE / 2 - i * LEG_AWAY / SCALE), (float)initial_y), (float)(i * 0.05));
         joint_t *j = &W->j[li];
+        j->bodyA = 0;
         j->bodyB = 1 + li;
         j->localAnchorA = V(0.0f, 0.0f);
         j->localAnchorB = V((float)(i * LEG_AWAY / SCALE), (float)(LEG_DOWN / SCALE));
@@ -946,7 +200,7 @@ static void lunar_step_one(world_t *W, int action, float *obs, double *reward, i
             L->w += L->invI * crs(sub(pt, L->c), imp);
         }
     }
-    world_step(W, (float)(1.0 / FPS), 6 * 30, 2 * 30);                                     /* :556 */
+    int awake = world_step(W, (float)(1.0 / FPS), 6 * 30, 2 * 30);                         /* :556 */
     double st[8];
     st[0] = ((double)L->xf.p.x - VIEWPORT_W / SCALE / 2) / (VIEWPORT_W / SCALE / 2);       /* :560-569 */
     st[1] = ((double)L->xf.p.y - (W->helipad_y + LEG_DOWN / SCALE)) / (VIEWPORT_H / SCALE / 2);
@@ -966,7 +220,7 @@ static void lunar_step_one(world_t *W, int action, float *obs, double *reward, i
     r -= s_power * 0.03;
     int term = 0;
     if (W->game_over || fabs(st[0]) >= 1.0) { term = 1; r = -100; }                        /* :590-593 */
-    if (!L->awake) { term = 1; r = +100; }                                                 /* :594-596 */
+    if (!awake) { term = 1; r = +100; }                                                 /* :594-596 */
     for (int k = 0; k < 8; k++) obs[k] = (float)st[k];                                     /* :600 */
     *reward = r;
     *terminated = term;
@@ -991,14 +245,7 @@ void orc_lunar_seed_range(orc_lunar *v, const uint32_t base[4], int64_t first)
     for (int64_t i = 0; i < v->n; i++) {
         u128 s = b + (u128)(uint64_t)(first + i);
         uint32_t ent[4] = {(uint32_t)s, (uint32_t)(s >> 32), (uint32_t)(s >> 64), (uint32_t)(s >> 96)};
-        uint64_t w[4];
-        orc_seed_sequence(ent, w);
-        pcg64_t *g = &v->w[i].rng;
-        g->state = 0;
-        g->inc = (((((u128)w[2]) << 64) | w[3]) << 1) | 1;
-        pcg_adv(g);
-        g->state += (((u128)w[0]) << 64) | w[1];
-        pcg_adv(g);
+        pcg_seed_from_words(&v->w[i].rng, ent);
     }
 }
 
@@ -1042,5 +289,5 @@ void orc_lunar_get_bodies(const orc_lunar *v, int64_t i, float out[18], int32_t 
     }
     flags[0] = W->game_over; flags[1] = W->leg_contact[0]; flags[2] = W->leg_contact[1];
     flags[3] = W->b[0].awake; flags[4] = W->elapsed; flags[5] = 0;
-    for (int b = 0; b < NB; b++) for (int e = 0; e < NE; e++) flags[5] += W->ct[b][e].touching;
+    for (int k = 0; k < NB * NE; k++) flags[5] += W->ct[k].touching;
 }

@@ -36,7 +36,8 @@ ENV_IDS = {
 
 def build(force=False):
     """Compile the oracle with the recipe in oracle/Makefile (gcc, no FMA contraction)."""
-    srcs = [os.path.join(_HERE, f) for f in ("gym_oracle.c", "lunar_oracle.c", "gym_oracle.h", "lunar_oracle.h")]
+    srcs = [os.path.join(_HERE, f) for f in ("gym_oracle.c", "lunar_oracle.c", "walker_oracle.c", "gym_oracle.h", "lunar_oracle.h",
+                                           "walker_oracle.h", "b2lite.h", "np_rng.h")]
     if (force or not os.path.exists(_LIB_PATH)
             or os.path.getmtime(_LIB_PATH) < max(os.path.getmtime(s) for s in srcs)):
         subprocess.check_call(["make", "-s", "-C", _HERE, "libgymoracle.so"])
@@ -75,6 +76,16 @@ def lib():
         L.orc_lunar_step.restype = i64
         L.orc_lunar_step.argtypes = [vp, vp, vp, vp, vp, vp, vp]
         L.orc_lunar_get_bodies.argtypes = [vp, i64, vp, vp]
+        L.orc_walker_create.restype = vp
+        L.orc_walker_create.argtypes = [i64, i32]
+        L.orc_walker_destroy.argtypes = [vp]
+        L.orc_walker_seed_range.argtypes = [vp, vp, i64]
+        L.orc_walker_reset.argtypes = [vp, vp]
+        L.orc_walker_step.restype = None
+        L.orc_walker_step.argtypes = [vp, vp, vp, vp, vp, vp, vp]
+        L.orc_walker_get_terrain.argtypes = [vp, i64, vp]
+        L.orc_walker_get_bodies.argtypes = [vp, i64, vp, vp]
+        L.orc_rng_sequence.argtypes = [vp, vp, i64, vp]
         for f in ("orc_obs_dim", "orc_act_dim", "orc_state_dim", "orc_num_actions"):
             getattr(L, f).argtypes = [i32]
         _lib = L
@@ -238,6 +249,62 @@ class OracleLunar:
         flags = np.zeros(6, dtype=np.int32)
         lib().orc_lunar_get_bodies(self._h, int(i), out.ctypes.data, flags.ctypes.data)
         return out.reshape(3, 6), flags
+
+
+class OracleWalker:
+    """SyncVectorEnv([make("BipedalWalker-v3")] * n) restated in C (oracle/walker_oracle.c).
+    PARITY UNPINNED for the Box2D arithmetic (see oracle/b2lite.h)."""
+
+    obs_dim, act_dim, num_actions = 24, 4, 0
+
+    def __init__(self, num_envs, max_episode_steps=1600):
+        self.n = int(num_envs)
+        self._h = lib().orc_walker_create(self.n, int(max_episode_steps or 0))
+
+    def close(self):
+        if getattr(self, "_h", None):
+            lib().orc_walker_destroy(self._h)
+            self._h = None
+
+    __del__ = close
+
+    def reset(self, seed=None):
+        if seed is not None:
+            lib().orc_walker_seed_range(self._h, seed_words(seed).ctypes.data, 0)
+        obs = np.zeros((self.n, 24), dtype=np.float32)
+        lib().orc_walker_reset(self._h, obs.ctypes.data)
+        return obs
+
+    def step(self, actions):
+        a = np.ascontiguousarray(actions, dtype=np.float32).reshape(self.n, 4)
+        obs = np.zeros((self.n, 24), dtype=np.float32)
+        fo = np.zeros((self.n, 24), dtype=np.float32)
+        rew = np.zeros(self.n, dtype=np.float64)
+        te = np.zeros(self.n, dtype=np.uint8)
+        tr = np.zeros(self.n, dtype=np.uint8)
+        lib().orc_walker_step(self._h, a.ctypes.data, obs.ctypes.data, rew.ctypes.data, te.ctypes.data,
+                              tr.ctypes.data, fo.ctypes.data)
+        return obs, rew, te.astype(bool), tr.astype(bool), fo
+
+    def terrain(self, i=0):
+        y = np.zeros(200, dtype=np.float32)
+        lib().orc_walker_get_terrain(self._h, int(i), y.ctypes.data)
+        return y
+
+    def bodies(self, i=0):
+        out = np.zeros(30, dtype=np.float32)
+        flags = np.zeros(4, dtype=np.int32)
+        lib().orc_walker_get_bodies(self._h, int(i), out.ctypes.data, flags.ctypes.data)
+        return out.reshape(5, 6), flags
+
+
+def rng_sequence(seed, ops):
+    """Draws of Generator(PCG64(SeedSequence(seed))): op 0 uniform(-1,1), 1 integers(5,10), 2 random(),
+    3 integers(1,5) -- through the C restatement (oracle/np_rng.h)."""
+    ops = np.ascontiguousarray(ops, dtype=np.int32)
+    out = np.zeros(len(ops), dtype=np.float64)
+    lib().orc_rng_sequence(seed_words(seed).ctypes.data, ops.ctypes.data, len(ops), out.ctypes.data)
+    return out
 
 
 def lunar_heuristic(s):

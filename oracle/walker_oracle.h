@@ -1,0 +1,22 @@
+/* walker_oracle.h -- CPU ORACLE for BipedalWalker-v3 (test infrastructure, NOT product code).
+ * See walker_oracle.c.  PARITY UNPINNED for the Box2D arithmetic; the numpy RNG side is pinned. */
+#ifndef WALKER_ORACLE_H
+#define WALKER_ORACLE_H
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+typedef struct orc_walker orc_walker;
+orc_walker *orc_walker_create(int64_t n, int max_episode_steps);
+void orc_walker_destroy(orc_walker *v);
+void orc_walker_seed_range(orc_walker *v, const uint32_t base[4], int64_t first);
+void orc_walker_reset(orc_walker *v, float *obs);
+void orc_walker_step(orc_walker *v, const float *actions, float *obs, double *reward, uint8_t *terminated,
+                     uint8_t *truncated, float *final_obs);
+void orc_walker_get_terrain(const orc_walker *v, int64_t i, float *y200);
+void orc_walker_get_bodies(const orc_walker *v, int64_t i, float out[30], int32_t flags[4]);
+void orc_rng_sequence(const uint32_t ent[4], const int32_t *ops, int64_t n, double *out);
+#ifdef __cplusplus
+}
+#endif
+#endif

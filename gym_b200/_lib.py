@@ -21,6 +21,7 @@ KIND_MOUNTAINCAR_CONT = 2
 KIND_PENDULUM = 3
 KIND_ACROBOT = 4
 KIND_LUNARLANDER = 5
+KIND_BIPEDALWALKER = 6
 
 # enum b200gym_action_dtype
 ACT_I64, ACT_I32, ACT_U8, ACT_F32 = 0, 1, 2, 3
@@ -86,6 +87,7 @@ SIGNATURES = {
     "b200gym_get_state": (_i32, [_vp, _vp, _vp, _vp, _vp]),
     "b200gym_set_state": (_i32, [_vp, _vp, _vp, _vp, _vp]),
     "b200gym_lunar_get_bodies": (_i32, [_vp, _vp, _vp, _vp]),
+    "b200gym_walker_get_bodies": (_i32, [_vp, _vp, _vp, _vp]),
     "b200gym_p2p_create": (_i32, [_vp, _i32, _i32, _vp, _vp]),
     "b200gym_p2p_connect": (_i32, [_vp, _vp]),
     "b200gym_step_p2p": (_i32, [_vp, _vp, _i32, _vp, _vp, ctypes.POINTER(_i32)]),

@@ -28,6 +28,7 @@
 #include "../../include/b200gym.h"
 #include "envs.cuh"
 #include "lunar.cuh"
+#include "walker.cuh"
 #include "rng.cuh"
 
 using namespace bgym;
@@ -44,7 +45,7 @@ struct b200gym {
     int32_t *elapsed = nullptr;
     uint8_t *flags = nullptr;
     uint64_t *rng = nullptr;
-    uint32_t *lunar_rec = nullptr;          // LunarLander: lunar::kWords 32-bit words per env, SoA
+    uint32_t *lunar_rec = nullptr;          // LunarLander / BipedalWalker: solver record, kWords 32-bit words per env, SoA
     unsigned long long *invalid = nullptr;  // sticky device counter
     int sm_count = 148;
     int occ[B200GYM_NUM_KINDS][3] = {};     // cached CTAs/SM of step_kernel_tma per (kind, action width)
@@ -88,10 +89,10 @@ static int fail(const b200gym *h, const char *fmt, ...) {
             return fail(h, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
     } while (0)
 
-static const int k_obs_dim[B200GYM_NUM_KINDS] = {4, 2, 2, 3, 6, 8};
-static const int k_act_dim[B200GYM_NUM_KINDS] = {0, 0, 1, 1, 0, 0};
-static const int k_nact[B200GYM_NUM_KINDS] = {2, 3, 0, 0, 3, 4};
-static const int k_state_dim[B200GYM_NUM_KINDS] = {4, 2, 2, 2, 4, 0};
+static const int k_obs_dim[B200GYM_NUM_KINDS] = {4, 2, 2, 3, 6, 8, 24};
+static const int k_act_dim[B200GYM_NUM_KINDS] = {0, 0, 1, 1, 0, 0, 4};
+static const int k_nact[B200GYM_NUM_KINDS] = {2, 3, 0, 0, 3, 4, 0};
+static const int k_state_dim[B200GYM_NUM_KINDS] = {4, 2, 2, 2, 4, 0, 0};
 
 static bool kind_ok(int k) { return k >= 0 && k < B200GYM_NUM_KINDS; }
 
@@ -145,6 +146,10 @@ __device__ __forceinline__ void store_row(float *base, int64_t i, const float (&
         reinterpret_cast<float4 *>(base)[i] = make_float4(v[0], v[1], v[2], v[3]);
     } else if constexpr (D == 2) {
         reinterpret_cast<float2 *>(base)[i] = make_float2(v[0], v[1]);
+    } else if constexpr (D == 8 || D == 24) {
+        float4 *p = reinterpret_cast<float4 *>(base) + (D / 4) * i;
+#pragma unroll
+        for (int k = 0; k < D / 4; k++) p[k] = make_float4(v[4 * k], v[4 * k + 1], v[4 * k + 2], v[4 * k + 3]);
     } else if constexpr (D == 6) {
         float2 *p = reinterpret_cast<float2 *>(base) + 3 * i;
         p[0] = make_float2(v[0], v[1]);
@@ -537,16 +542,16 @@ __global__ void lunar_bodies_kernel(const uint32_t *rec, const int32_t *elapsed,
     for (int b = 0; b < 3; b++)
         for (int k = 0; k < 6; k++) out[i * 18 + 6 * b + k] = __uint_as_float(rec[(int64_t)(lunar::W_BODY + 7 * b + k) * n + i]);
     const uint32_t f = rec[(int64_t)lunar::W_FLAGS * n + i];
-    const unsigned long long touch = ((unsigned long long)rec[(int64_t)(lunar::W_TOUCH + 1) * n + i] << 32) |
-                                     rec[(int64_t)lunar::W_TOUCH * n + i];
+    int touching = 0;
+    for (int sl = 0; sl < lunar::kSlots; sl++) touching += (rec[(int64_t)(lunar::W_SLOT + 7 * sl) * n + i] >> 16) != 0;
     flags[i * 6 + 0] = f & 1u; flags[i * 6 + 1] = (f >> 1) & 1u; flags[i * 6 + 2] = (f >> 2) & 1u;
-    flags[i * 6 + 3] = 1; flags[i * 6 + 4] = elapsed[i]; flags[i * 6 + 5] = __popcll(touch);
+    flags[i * 6 + 3] = 1; flags[i * 6 + 4] = elapsed[i]; flags[i * 6 + 5] = touching;
 }
 
 // Shape / mass constants, evaluated on the host with the float32 operation sequence of
 // b2PolygonShape::Set / ComputeCentroid / ComputeMass and b2Body::ResetMassData.
-static void lunar_shape(lunar::ShapeConst &sh, const lunar::v2 *hull, int n, float density, float friction, bool box) {
-    using lunar::v2;
+static void b2l_shape(b2l::ShapeConst &sh, const b2l::v2 *hull, int n, float density, float friction, bool box) {
+    using b2l::v2;
     auto V = [](float x, float y) { v2 r; r.x = x; r.y = y; return r; };
     sh.count = n;
     sh.friction = friction;
@@ -610,7 +615,7 @@ static void lunar_shape(lunar::ShapeConst &sh, const lunar::v2 *hull, int n, flo
 }
 
 static int lunar_upload_consts(b200gym *h) {
-    using lunar::v2;
+    using b2l::v2;
     auto V = [](float x, float y) { v2 r; r.x = x; r.y = y; return r; };
     lunar::Consts c;
     memset(&c, 0, sizeof c);
@@ -618,16 +623,19 @@ static int lunar_upload_consts(b200gym *h) {
     const double LP[6][2] = {{17, -10}, {17, 0}, {14, 17}, {-14, 17}, {-17, 0}, {-17, -10}};  // hull order of LANDER_POLY
     v2 hull[6];
     for (int i = 0; i < 6; i++) hull[i] = V((float)(LP[i][0] / SCALE), (float)(LP[i][1] / SCALE));
-    lunar_shape(c.shape[0], hull, 6, 5.0f, 0.1f, false);                       // lunar_lander.py:354-368
+    b2l_shape(c.shape[0], hull, 6, 5.0f, 0.1f, false);                       // lunar_lander.py:354-368
     const float hx = (float)(2 / SCALE), hy = (float)(8 / SCALE);              // LEG_W, LEG_H
     const v2 box[4] = {V(-hx, -hy), V(hx, -hy), V(hx, hy), V(-hx, hy)};
-    lunar_shape(c.shape[1], box, 4, 1.0f, 0.2f, true);                         // :379-392
+    b2l_shape(c.shape[1], box, 4, 1.0f, 0.2f, true);                         // :379-392
     for (int li = 0; li < 2; li++) {
         const int i = li == 0 ? -1 : +1;
-        c.anchorB[li] = V((float)(i * 20 / SCALE), (float)(18 / SCALE));      // :397
+        c.jd[li].bodyA = 0;
+        c.jd[li].bodyB = 1 + li;
+        c.jd[li].anchorA = V(0.0f, 0.0f);                                      // :396
+        c.jd[li].anchorB = V((float)(i * 20 / SCALE), (float)(18 / SCALE));   // :397
         c.motorSpeed[li] = (float)(+0.3 * i);                                  // :401
-        if (i == -1) { c.lower[li] = (float)(+0.9 - 0.5); c.upper[li] = (float)(+0.9); }   // :403-410
-        else { c.lower[li] = (float)(-0.9); c.upper[li] = (float)(-0.9 + 0.5); }
+        if (i == -1) { c.jd[li].lower = (float)(+0.9 - 0.5); c.jd[li].upper = (float)(+0.9); }   // :403-410
+        else { c.jd[li].lower = (float)(-0.9); c.jd[li].upper = (float)(-0.9 + 0.5); }
         c.leg_x0[li] = (float)(600 / SCALE / 2 - i * 20 / SCALE);             // :381
         c.leg_a0[li] = (float)(i * 0.05);                                      // :382
     }
@@ -637,6 +645,116 @@ static int lunar_upload_consts(b200gym *h) {
     c.lander_x0 = (float)(600 / SCALE / 2);
     c.y0 = (float)(400 / SCALE);
     CK(h, cudaMemcpyToSymbol(lunar::kC, &c, sizeof c));
+    return 0;
+}
+
+// ---- BipedalWalker-v3 (walker.cuh): one thread per env --------------------------------------------
+__global__ void __launch_bounds__(kLunarThreads) walker_step_kernel(const StepArgs a) {
+    const int64_t j = (int64_t)blockIdx.x * kLunarThreads + threadIdx.x;
+    if (j >= a.count) return;
+    const int64_t i = a.first + j;
+    const float4 av = __ldg(reinterpret_cast<const float4 *>(a.actions) + i);
+    const float action[4] = {av.x, av.y, av.z, av.w};
+    walker::World W;
+    walker::Rng rng;
+    walker::load_world(W, a.lunar_rec, a.n, i, rng);
+    int32_t elapsed = a.elapsed[i];
+    float obs[24];
+    double reward;
+    bool terminated;
+    walker::env_step(W, action, false, walker::V(0.0f, 0.0f), obs, reward, terminated);
+    elapsed += 1;                                                        // time_limit.py:51
+    const bool truncated = (a.max_steps > 0) && (elapsed >= a.max_steps);
+    store_scalars_all(a, i, reward, terminated ? 1 : 0, truncated ? 1 : 0);
+    if ((terminated || truncated) && a.autoreset) {                      // sync_vector_env.py:152-156
+        if (a.final_obs) store_row<24>(a.final_obs, i, obs);
+        rng.g = pcg64_load(a.rng + 4 * i);
+        walker::env_reset(W, rng, obs);
+        pcg64_store(a.rng + 4 * i, rng.g);
+        elapsed = 0;
+    }
+    walker::store_world(W, a.lunar_rec, a.n, i, rng);
+    a.elapsed[i] = elapsed;
+    store_obs_all<24>(a, i, obs);
+}
+
+__global__ void __launch_bounds__(kLunarThreads) walker_reset_kernel(uint32_t *rec, int32_t *elapsed, uint64_t *rng,
+                                                                     const uint8_t *mask, float *obs, int64_t n) {
+    const int64_t i = (int64_t)blockIdx.x * kLunarThreads + threadIdx.x;
+    if (i >= n) return;
+    if (mask && !mask[i]) return;
+    walker::World W;
+    walker::Rng r;
+    walker::bind_world(W, rec, n, i);
+    W.flags = rec[(int64_t)walker::W_FLAGS * n + i] & b2l::kFlagStepped;  // the b2World object survives reset()
+    r.has32 = rec[(int64_t)walker::W_RNG32 * n + i];
+    r.val32 = rec[(int64_t)(walker::W_RNG32 + 1) * n + i];
+    r.g = pcg64_load(rng + 4 * i);
+    float o[24];
+    walker::env_reset(W, r, o);
+    walker::store_world(W, rec, n, i, r);
+    pcg64_store(rng + 4 * i, r.g);
+    elapsed[i] = 0;
+    if (obs) store_row<24>(obs, i, o);
+}
+
+// a fresh Generator has an empty 32-bit cache: clear {has_uint32, uinteger} of the (re)seeded envs
+__global__ void walker_clear_rng32_kernel(uint32_t *rec, const uint8_t *mask, int64_t n) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n || (mask && !mask[i])) return;
+    rec[(int64_t)walker::W_RNG32 * n + i] = 0u;
+    rec[(int64_t)(walker::W_RNG32 + 1) * n + i] = 0u;
+}
+
+__global__ void walker_bodies_kernel(const uint32_t *rec, float *out, int32_t *flags, int64_t n) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    for (int b = 0; b < walker::NB; b++)
+        for (int k = 0; k < 6; k++) out[i * 30 + 6 * b + k] = __uint_as_float(rec[(int64_t)(walker::W_BODY + 7 * b + k) * n + i]);
+    const uint32_t f = rec[(int64_t)walker::W_FLAGS * n + i];
+    int touching = 0;
+    for (int sl = 0; sl < walker::kSlots; sl++) touching += (rec[(int64_t)(walker::W_SLOT + 7 * sl) * n + i] >> 16) != 0;
+    flags[i * 4 + 0] = f & 1u; flags[i * 4 + 1] = (f >> 1) & 1u; flags[i * 4 + 2] = (f >> 2) & 1u; flags[i * 4 + 3] = touching;
+}
+
+static int walker_upload_consts(b200gym *h) {
+    using b2l::v2;
+    auto V = [](float x, float y) { v2 r; r.x = x; r.y = y; return r; };
+    walker::Consts c;
+    memset(&c, 0, sizeof c);
+    const double SCALE = 30.0, LEG_DOWN = -8 / SCALE, LEG_W = 8 / SCALE, LEG_H = 34 / SCALE;
+    const double TERRAIN_STEP = 14 / SCALE, TERRAIN_HEIGHT = 400 / SCALE / 4;
+    const double HP[5][2] = {{34, -8}, {34, 1}, {6, 9}, {-30, 9}, {-30, -8}};  // hull order of HULL_POLY
+    v2 hull[5];
+    for (int i = 0; i < 5; i++) hull[i] = V((float)(HP[i][0] / SCALE), (float)(HP[i][1] / SCALE));
+    b2l_shape(c.shape[0], hull, 5, 5.0f, 0.1f, false);                         // HULL_FD, bipedal_walker.py:55-62
+    {
+        const float hx = (float)(LEG_W / 2), hy = (float)(LEG_H / 2);
+        const v2 box[4] = {V(-hx, -hy), V(hx, -hy), V(hx, hy), V(-hx, hy)};
+        b2l_shape(c.shape[1], box, 4, 1.0f, 0.2f, true);                       // LEG_FD :64-70
+    }
+    {
+        const float hx = (float)(0.8 * LEG_W / 2), hy = (float)(LEG_H / 2);
+        const v2 box[4] = {V(-hx, -hy), V(hx, -hy), V(hx, hy), V(-hx, hy)};
+        b2l_shape(c.shape[2], box, 4, 1.0f, 0.2f, true);                       // LOWER_FD :72-78
+    }
+    for (int li = 0; li < 2; li++) {
+        const int i = li == 0 ? -1 : +1;
+        b2l::JointDef &hip = c.jd[2 * li], &knee = c.jd[2 * li + 1];
+        hip.bodyA = 0; hip.bodyB = 1 + 2 * li;                                 // :465-476
+        hip.anchorA = V(0.0f, (float)LEG_DOWN); hip.anchorB = V(0.0f, (float)(LEG_H / 2));
+        hip.lower = -0.8f; hip.upper = 1.1f;
+        knee.bodyA = 1 + 2 * li; knee.bodyB = 2 + 2 * li;                      // :487-498
+        knee.anchorA = V(0.0f, (float)(-LEG_H / 2)); knee.anchorB = V(0.0f, (float)(LEG_H / 2));
+        knee.lower = -1.6f; knee.upper = -0.1f;
+        c.leg_a0[li] = (float)(i * 0.05);
+    }
+    const double init_x = TERRAIN_STEP * 20 / 2, init_y = TERRAIN_HEIGHT + 2 * LEG_H;   // :442-443
+    c.init_x = (float)init_x;
+    c.init_y = (float)init_y;
+    c.leg_y = (float)(init_y - LEG_H / 2 - LEG_DOWN);
+    c.lower_y = (float)(init_y - LEG_H * 3 / 2 - LEG_DOWN);
+    CK(h, cudaMemcpyToSymbol(walker::kC, &c, sizeof c));
     return 0;
 }
 
@@ -758,6 +876,13 @@ static int launch_step(b200gym *h, const StepArgs &a, int action_dtype, cudaStre
         CK(h, cudaGetLastError());
         return 0;
     }
+    case B200GYM_BIPEDALWALKER: {
+        if (action_dtype != B200GYM_ACT_F32) return fail(h, "Box env needs float32 actions (got dtype code %d)", action_dtype);
+        if ((uintptr_t)a.actions % 16 != 0) return fail(h, "BipedalWalker actions must be 16-byte aligned");
+        walker_step_kernel<<<(unsigned)((a.count + kLunarThreads - 1) / kLunarThreads), kLunarThreads, 0, st>>>(a);
+        CK(h, cudaGetLastError());
+        return 0;
+    }
     }
     return fail(h, "bad kind %d", h->cfg.kind);
 }
@@ -780,6 +905,10 @@ static int launch_reset(b200gym *h, const uint8_t *mask, const double *bounds, f
     case B200GYM_ACROBOT: launch_reset_kind<B200GYM_ACROBOT>(h, mask, bounds, obs, st); break;
     case B200GYM_LUNARLANDER:
         lunar_reset_kernel<<<(unsigned)((h->n + kLunarThreads - 1) / kLunarThreads), kLunarThreads, 0, st>>>(
+            h->lunar_rec, h->elapsed, h->rng, mask, obs, h->n);
+        break;
+    case B200GYM_BIPEDALWALKER:
+        walker_reset_kernel<<<(unsigned)((h->n + kLunarThreads - 1) / kLunarThreads), kLunarThreads, 0, st>>>(
             h->lunar_rec, h->elapsed, h->rng, mask, obs, h->n);
         break;
     default: return fail(h, "bad kind %d", h->cfg.kind);
@@ -843,10 +972,13 @@ extern "C" int b200gym_create(const b200gym_config *cfg, int64_t num_envs, int d
             b200gym_destroy(h);
             return 1;
         }
-    if (cfg->kind == B200GYM_LUNARLANDER) {
-        if (cudaMalloc(&h->lunar_rec, sizeof(uint32_t) * lunar::kWords * n) != cudaSuccess ||
-            cudaMemset(h->lunar_rec, 0, sizeof(uint32_t) * lunar::kWords * n) != cudaSuccess || lunar_upload_consts(h)) {
-            fail(nullptr, "b200gym_create: LunarLander state allocation failed");
+    if (cfg->kind == B200GYM_LUNARLANDER || cfg->kind == B200GYM_BIPEDALWALKER) {
+        const bool lun = cfg->kind == B200GYM_LUNARLANDER;
+        const size_t words = lun ? lunar::kWords : walker::kWords;
+        if (cudaMalloc(&h->lunar_rec, sizeof(uint32_t) * words * n) != cudaSuccess ||
+            cudaMemset(h->lunar_rec, 0, sizeof(uint32_t) * words * n) != cudaSuccess ||
+            (lun ? lunar_upload_consts(h) : walker_upload_consts(h))) {
+            fail(nullptr, "b200gym_create: Box2D-task state allocation failed");
             b200gym_destroy(h);
             return 1;
         }
@@ -903,6 +1035,10 @@ extern "C" int b200gym_seed_range(b200gym_t *h, const uint32_t base_words[4], in
     seed_range_kernel<<<blocks_for(h->n), kThreads, 0, (cudaStream_t)stream>>>(
         h->rng, h->n, base_words[0], base_words[1], base_words[2], base_words[3], (uint64_t)first_index);
     CK(h, cudaGetLastError());
+    if (h->cfg.kind == B200GYM_BIPEDALWALKER) {
+        walker_clear_rng32_kernel<<<blocks_for(h->n), kThreads, 0, (cudaStream_t)stream>>>(h->lunar_rec, nullptr, h->n);
+        CK(h, cudaGetLastError());
+    }
     return 0;
 }
 
@@ -920,6 +1056,8 @@ extern "C" int b200gym_seed_each(b200gym_t *h, const uint32_t *ent_host, const u
     }
     if (e == cudaSuccess) {
         seed_each_kernel<<<blocks_for(h->n), kThreads, 0, st>>>(h->rng, h->n, d_ent, d_mask);
+        if (h->cfg.kind == B200GYM_BIPEDALWALKER)
+            walker_clear_rng32_kernel<<<blocks_for(h->n), kThreads, 0, st>>>(h->lunar_rec, d_mask, h->n);
         e = cudaGetLastError();
     }
     if (e == cudaSuccess) e = cudaStreamSynchronize(st);
@@ -1224,6 +1362,15 @@ extern "C" int b200gym_lunar_get_bodies(b200gym_t *h, float *bodies_dev, int32_t
     DeviceGuard guard(h->device);
     lunar_bodies_kernel<<<blocks_for(h->n), kThreads, 0, (cudaStream_t)stream>>>(h->lunar_rec, h->elapsed, bodies_dev,
                                                                                  flags_dev, h->n);
+    CK(h, cudaGetLastError());
+    return 0;
+}
+
+extern "C" int b200gym_walker_get_bodies(b200gym_t *h, float *bodies_dev, int32_t *flags_dev, void *stream) {
+    if (!h || !bodies_dev || !flags_dev) return fail(h, "b200gym_walker_get_bodies: null argument");
+    if (h->cfg.kind != B200GYM_BIPEDALWALKER) return fail(h, "b200gym_walker_get_bodies: not a BipedalWalker handle");
+    DeviceGuard guard(h->device);
+    walker_bodies_kernel<<<blocks_for(h->n), kThreads, 0, (cudaStream_t)stream>>>(h->lunar_rec, bodies_dev, flags_dev, h->n);
     CK(h, cudaGetLastError());
     return 0;
 }

@@ -54,6 +54,16 @@ def _lunar_spaces(params):
     return Box(low, high), Discrete(4)
 
 
+def _walker_spaces(params):
+    # bipedal_walker.py:192-237
+    low = np.array([-math.pi, -5.0, -5.0, -5.0, -math.pi, -5.0, -math.pi, -5.0, -0.0, -math.pi, -5.0, -math.pi, -5.0,
+                    -0.0] + [-1.0] * 10).astype(np.float32)
+    high = np.array([math.pi, 5.0, 5.0, 5.0, math.pi, 5.0, math.pi, 5.0, 5.0, math.pi, 5.0, math.pi, 5.0, 5.0]
+                    + [1.0] * 10).astype(np.float32)
+    act = Box(np.array([-1, -1, -1, -1]).astype(np.float32), np.array([1, 1, 1, 1]).astype(np.float32))
+    return Box(low, high), act
+
+
 class KindInfo:
     def __init__(self, name, spaces, kwargs, bounds_keys, default_bounds, attrs, metadata):
         self.name = name
@@ -95,6 +105,9 @@ KINDS = {
         "LunarLander", _lunar_spaces, {}, ("low", "high"), (0.0, 0.0),
         dict(continuous=False, gravity=-10.0, enable_wind=False, wind_power=15.0, turbulence_power=1.5),
         {"render_modes": [], "render_fps": 50}),
+    _lib.KIND_BIPEDALWALKER: KindInfo(
+        "BipedalWalker", _walker_spaces, {}, ("low", "high"), (0.0, 0.0), dict(hardcore=False),
+        {"render_modes": [], "render_fps": 50}),
 }
 
 
@@ -112,7 +125,7 @@ def parse_reset_bounds(kind, options):
     low/high kinds follow maybe_parse_reset_bounds (classic_control/utils.py:17-46);
     Pendulum follows pendulum.py:143-152 (x_init / y_init, symmetric limits).
     """
-    if options is None or kind == _lib.KIND_LUNARLANDER:  # LunarLander.reset ignores options
+    if options is None or kind in (_lib.KIND_LUNARLANDER, _lib.KIND_BIPEDALWALKER):  # their reset() ignores options
         return None
     info = KINDS[kind]
     k0, k1 = info.bounds_keys
@@ -137,6 +150,15 @@ def resolve_params(kind, kwargs):
                 raise TypeError(f"LunarLander got an unexpected keyword argument '{key}'")
             if info.attrs[key] != value and key in ("continuous", "gravity", "enable_wind"):
                 raise NotImplementedError(f"gym_b200 LunarLander supports only {key}={info.attrs[key]!r}")
+        return params
+    if kind == _lib.KIND_BIPEDALWALKER:
+        for key, value in kwargs.items():
+            if key == "render_mode" and value is None:
+                continue
+            if key != "hardcore":
+                raise TypeError(f"BipedalWalker got an unexpected keyword argument '{key}'")
+            if value:
+                raise NotImplementedError("gym_b200 BipedalWalker supports only hardcore=False")
         return params
     for key, (slot, default) in info.kwargs.items():
         params[slot] = float(default)

@@ -446,6 +446,17 @@ class B200VectorEnv:
                                                       ctypes.c_void_p(flags.data_ptr()), self._stream()), self._handle)
         return bodies.view(self.num_envs, 3, 6), flags
 
+    def walker_bodies(self):
+        """BipedalWalker only: (bodies float32 (N, 5, 6) of hull, leg(-1), lower(-1), leg(+1), lower(+1);
+        flags int32 (N, 4) = {game_over, legs[1] contact, legs[3] contact, #touching contacts})."""
+        self._assert_open("walker_bodies")
+        torch = _torch()
+        bodies = torch.empty((self.num_envs, 30), dtype=torch.float32, device=self.device)
+        flags = torch.empty((self.num_envs, 4), dtype=torch.int32, device=self.device)
+        _lib.check(self._lib.b200gym_walker_get_bodies(self._handle, ctypes.c_void_p(bodies.data_ptr()),
+                                                       ctypes.c_void_p(flags.data_ptr()), self._stream()), self._handle)
+        return bodies.view(self.num_envs, 5, 6), flags
+
     def set_state(self, state=None, elapsed=None, rng=None):
         self._assert_open("set_state")
         torch = _torch()

@@ -40,7 +40,9 @@ enum b200gym_kind {
     B200GYM_ACROBOT = 4,          /* gym/envs/classic_control/acrobot.py:181-277,418-465 */
     B200GYM_LUNARLANDER = 5,      /* gym/envs/box2d/lunar_lander.py:308-600 (discrete, no wind); the Box2D
                                      arithmetic it delegates to is re-derived in csrc/lunar.cuh */
-    B200GYM_NUM_KINDS = 6
+    B200GYM_BIPEDALWALKER = 6,    /* gym/envs/box2d/bipedal_walker.py:277-606 (non-hardcore); Box2D arithmetic
+                                     re-derived in csrc/b2lite.cuh */
+    B200GYM_NUM_KINDS = 7
 };
 
 /* dtype codes for the `actions` argument of b200gym_step */
@@ -193,6 +195,9 @@ int b200gym_set_state(b200gym_t *h, const double *state_dev, const int32_t *elap
  * awake, elapsed, #touching contacts} -- what `env.lander.position` etc. expose in the reference.
  */
 int b200gym_lunar_get_bodies(b200gym_t *h, float *bodies_dev, int32_t *flags_dev, void *stream);
+/* BipedalWalker: float32 [n][30] = 5 x {c.x, c.y, angle, v.x, v.y, omega} (hull, leg(-1), lower(-1), leg(+1),
+ * lower(+1)) and int32 [n][4] = {game_over, legs[1] contact, legs[3] contact, #touching contacts}. */
+int b200gym_walker_get_bodies(b200gym_t *h, float *bodies_dev, int32_t *flags_dev, void *stream);
 
 /*
  * Multi-GPU: fused step + all-gather over NVLink peer memory.

@@ -34,10 +34,10 @@ def test_library_builds_and_exports_every_declared_symbol():
 def test_shape_queries_need_no_device():
     lib = _lib.load()
     assert lib.b200gym_version() == 1
-    assert [lib.b200gym_obs_dim(k) for k in range(6)] == [4, 2, 2, 3, 6, 8]
-    assert [lib.b200gym_act_dim(k) for k in range(6)] == [0, 0, 1, 1, 0, 0]
-    assert [lib.b200gym_num_actions(k) for k in range(6)] == [2, 3, 0, 0, 3, 4]
-    assert [lib.b200gym_state_dim(k) for k in range(6)] == [4, 2, 2, 2, 4, 0]
+    assert [lib.b200gym_obs_dim(k) for k in range(7)] == [4, 2, 2, 3, 6, 8, 24]
+    assert [lib.b200gym_act_dim(k) for k in range(7)] == [0, 0, 1, 1, 0, 0, 4]
+    assert [lib.b200gym_num_actions(k) for k in range(7)] == [2, 3, 0, 0, 3, 4, 0]
+    assert [lib.b200gym_state_dim(k) for k in range(7)] == [4, 2, 2, 2, 4, 0, 0]
     assert lib.b200gym_obs_dim(99) == -1
 
 
@@ -80,7 +80,7 @@ def test_registry_matches_reference_table():
     # gym/envs/__init__.py:11-60
     want = {"CartPole-v0": (200, 195.0), "CartPole-v1": (500, 475.0), "MountainCar-v0": (200, -110.0),
             "MountainCarContinuous-v0": (999, 90.0), "Pendulum-v1": (200, None), "Acrobot-v1": (500, -100.0),
-            "LunarLander-v2": (1000, 200)}
+            "LunarLander-v2": (1000, 200), "BipedalWalker-v3": (1600, 300)}
     for env_id, (steps, thr) in want.items():
         s = gym_b200.spec(env_id)
         assert s.max_episode_steps == steps and s.reward_threshold == thr

@@ -40,7 +40,9 @@ BYTES_PER_ENV_STEP = {"CartPole-v1": 106, "CartPole-v0": 106, "Pendulum-v1": 16 
                       "Acrobot-v1": 32 * 2 + 8 + 8 + 24 + 8 + 2, "MountainCar-v0": 16 * 2 + 8 + 8 + 8 + 8 + 2,
                       "MountainCarContinuous-v0": 16 * 2 + 8 + 4 + 8 + 8 + 2,
                       # LunarLander: 103-word solver record r+w, PCG64 state (2 draws/step), counter, action, outputs
-                      "LunarLander-v2": 103 * 4 * 2 + 32 + 16 + 8 + 8 + 32 + 8 + 2}
+                      "LunarLander-v2": 101 * 4 * 2 + 32 + 16 + 8 + 8 + 32 + 8 + 2,
+                      # BipedalWalker: 130-word record r+w (the 200 terrain words are read on demand), action, outputs
+                      "BipedalWalker-v3": 130 * 4 * 2 + 8 + 16 + 96 + 8 + 2}
 # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed ncu --set full capture (2^20 envs)
 NCU_DRAM_BYTES_PER_LAUNCH = {"CartPole-v1": 56.23e6 + 23.99e6}
 FALLBACK_HBM_GBS = 6650.0  # /opt/skills/guides/B200_PROFILING.md fallback
@@ -136,6 +138,8 @@ def host_threads():
 def random_actions_np(env_id, n, rng):
     if env_id.startswith("LunarLander"):
         return rng.integers(0, 4, size=n).astype(np.int64)
+    if env_id.startswith("BipedalWalker"):
+        return rng.uniform(-1.0, 1.0, size=(n, 4)).astype(np.float32)
     from oracle.oracle import ENV_IDS, KINDS, lib
     kind = KINDS[ENV_IDS[env_id][0]]
     nact = lib().orc_num_actions(kind)
@@ -146,10 +150,11 @@ def random_actions_np(env_id, n, rng):
 
 def cpu_oracle_throughput(env_id, n, seconds, threads, min_steps=3):
     """Time the C port of the reference path (oracle/) on the host cores: bounded sample."""
-    from oracle.oracle import OracleLunar, OracleVec
+    from oracle.oracle import OracleLunar, OracleVec, OracleWalker
     rng = np.random.default_rng(0)
-    lunar = env_id.startswith("LunarLander")
-    v = OracleLunar(n) if lunar else OracleVec(env_id, n)
+    lunar = env_id.startswith(("LunarLander", "BipedalWalker"))
+    v = OracleLunar(n) if env_id.startswith("LunarLander") else (
+        OracleWalker(n) if env_id.startswith("BipedalWalker") else OracleVec(env_id, n))
     v.reset(seed=0)
     pool = [random_actions_np(env_id, n, rng) for _ in range(4)]
     kw = {} if lunar else {"nthreads": threads}
@@ -252,7 +257,8 @@ def run_b200(args):
     if inner.discrete:
         pool = torch.randint(0, inner.single_action_space.n, (16, n), device=dev, dtype=torch.int64, generator=gen)
     else:
-        pool = (torch.rand((16, n, 1), device=dev, generator=gen) * 4.0 - 2.0)
+        scale = 2.0 if inner.act_dim == 1 else 1.0
+        pool = (torch.rand((16, n, inner.act_dim), device=dev, generator=gen) * 2.0 - 1.0) * scale
     # L2 flush between timed steps: write 256 MiB (> 126 MB L2), then stream-read another 256 MiB so
     # that the lines left in L2 are CLEAN (otherwise the timed kernel pays the write-back of the
     # flush's own dirty lines, which is an artefact of the flush, not of the kernel)
@@ -358,8 +364,8 @@ def run_b200(args):
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         threads = host_threads()
-        if args.env.startswith("LunarLander"):
-            threads = 1  # oracle/lunar_oracle.c is a scalar single-thread port
+        if args.env.startswith(("LunarLander", "BipedalWalker")):
+            threads = 1  # the Box2D-task oracles are scalar single-thread ports
         v, cpu_steps, cpu_el = cpu_oracle_throughput(args.env, n, args.cpu_seconds, threads)
         cpu = {"value": v, "unit": "env-steps/s", "cores": threads, "kind": "port",
                "sample": f"{cpu_steps} vector steps of 2^{args.log2_envs} envs ({cpu_el:.1f} s) of the same workload, "

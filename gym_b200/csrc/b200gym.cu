@@ -758,6 +758,114 @@ static int walker_upload_consts(b200gym *h) {
     return 0;
 }
 
+// ---- vector-aware wrappers fused on the device ---------------------------------------
+// RecordEpisodeStatistics (gym/wrappers/record_episode_statistics.py:103-151): the reference walks the
+// batch in a Python loop; here one launch updates the float32 return / int32 length accumulators,
+// emits infos["episode"]["r"/"l"] + the `_episode` mask, and appends finished episodes to a small ring
+// (the return_queue / length_queue deques).
+__global__ void __launch_bounds__(kThreads) episode_stats_kernel(const double *reward, const uint8_t *term,
+                                                                const uint8_t *trunc, float *ret_acc, int32_t *len_acc,
+                                                                float *ep_r, int32_t *ep_l, uint8_t *ep_mask,
+                                                                float *ring_r, int32_t *ring_l,
+                                                                unsigned long long *counter, int ring_size, int64_t n) {
+    const int64_t i = (int64_t)blockIdx.x * kThreads + threadIdx.x;
+    if (i >= n) return;
+    // `self.episode_returns += rewards` on a float32 array with float64 rewards: add in float64, round to float32
+    const float ret = (float)((double)ret_acc[i] + reward[i]);
+    const int32_t len = len_acc[i] + 1;
+    const bool done = term[i] | trunc[i];
+    ep_mask[i] = done ? 1 : 0;
+    if (done) {
+        ep_r[i] = ret;
+        ep_l[i] = len;
+        if (ring_size > 0) {
+            const unsigned long long slot = atomicAdd(counter, 1ULL);
+            ring_r[slot % (unsigned long long)ring_size] = ret;
+            ring_l[slot % (unsigned long long)ring_size] = len;
+        } else atomicAdd(counter, 1ULL);
+        ret_acc[i] = 0.0f;
+        len_acc[i] = 0;
+    } else {
+        ret_acc[i] = ret;
+        len_acc[i] = len;
+    }
+}
+
+// NormalizeObservation / NormalizeReward (gym/wrappers/normalize.py:8-144): RunningMeanStd over the
+// batch axis.  Pass 1 accumulates per-column sum and sum of squared deviations from a pivot (the
+// current running mean: numerically tame) in float64 with one atomic per CTA and column; pass 2
+// (one thread per column) folds the batch moments into the running ones (Chan et al., normalize.py:32-46);
+// pass 3 normalises.  `x` is float32 [n][D] (observations) or float64 [n] (discounted returns, D = 1).
+template <typename T>
+__global__ void __launch_bounds__(kThreads) moments_kernel(const T *x, int64_t n, int D, const double *pivot,
+                                                           double *sum, double *sumsq) {
+    __shared__ double sh[2][kThreads / 32];
+    for (int d = 0; d < D; d++) {
+        double s = 0.0, q = 0.0;
+        const double pv = pivot[d];
+        for (int64_t i = (int64_t)blockIdx.x * kThreads + threadIdx.x; i < n; i += (int64_t)gridDim.x * kThreads) {
+            const double v = (double)x[i * D + d] - pv;
+            s += v;
+            q += v * v;
+        }
+        for (int o = 16; o > 0; o >>= 1) { s += __shfl_xor_sync(0xffffffffu, s, o); q += __shfl_xor_sync(0xffffffffu, q, o); }
+        if ((threadIdx.x & 31) == 0) { sh[0][threadIdx.x >> 5] = s; sh[1][threadIdx.x >> 5] = q; }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            double ts = 0.0, tq = 0.0;
+            for (int w = 0; w < kThreads / 32; w++) { ts += sh[0][w]; tq += sh[1][w]; }
+            atomicAdd(&sum[d], ts);
+            atomicAdd(&sumsq[d], tq);
+        }
+        __syncthreads();
+    }
+}
+
+__global__ void rms_update_kernel(double *mean, double *var, double *count, double *sum, double *sumsq, int64_t n, int D) {
+    const int d = blockIdx.x * blockDim.x + threadIdx.x;
+    if (d >= D) return;
+    // batch mean / (population) variance from the pivoted sums
+    const double bn = (double)n;
+    const double dm = sum[d] / bn;                 // batch_mean - pivot (pivot = old mean)
+    const double batch_var = sumsq[d] / bn - dm * dm;
+    const double cnt = count[0];
+    // update_mean_var_count_from_moments (normalize.py:32-46)
+    const double delta = dm;                       // batch_mean - mean
+    const double tot = cnt + bn;
+    const double new_mean = mean[d] + delta * bn / tot;
+    const double m2 = var[d] * cnt + batch_var * bn + delta * delta * cnt * bn / tot;
+    mean[d] = new_mean;
+    var[d] = m2 / tot;
+    sum[d] = 0.0;
+    sumsq[d] = 0.0;
+    __syncthreads();
+    if (d == 0) count[0] = tot;
+}
+
+__global__ void __launch_bounds__(kThreads) normalize_obs_kernel(const float *x, float *out, int64_t total, int D,
+                                                                 const double *mean, const double *var, double eps) {
+    const int64_t k = (int64_t)blockIdx.x * kThreads + threadIdx.x;
+    if (k >= total) return;
+    const int d = (int)(k % D);
+    out[k] = (float)(((double)x[k] - mean[d]) / sqrt(var[d] + eps));   // normalize.py:95
+}
+
+// NormalizeReward.step (normalize.py:130-138): returns = returns * gamma + reward ... returns[dones] = 0
+__global__ void __launch_bounds__(kThreads) discounted_return_kernel(double *returns, const double *reward, double gamma,
+                                                                     int64_t n) {
+    const int64_t i = (int64_t)blockIdx.x * kThreads + threadIdx.x;
+    if (i >= n) return;
+    returns[i] = returns[i] * gamma + reward[i];
+}
+__global__ void __launch_bounds__(kThreads) normalize_reward_kernel(const double *reward, double *out, double *returns,
+                                                                    const uint8_t *term, const uint8_t *trunc, int64_t n,
+                                                                    const double *var, double eps) {
+    const int64_t i = (int64_t)blockIdx.x * kThreads + threadIdx.x;
+    if (i >= n) return;
+    out[i] = reward[i] / sqrt(var[0] + eps);                           // normalize.py:143
+    if (term[i] | trunc[i]) returns[i] = 0.0;                          // :135-136
+}
+
 // ---- cross-GPU step barrier for the fused all-gather ---------------------------------------
 // flags[r] (uint64, in every rank's gather allocation) = number of steps whose results rank r
 // has fully written into THIS rank's buffers.  signal: after my step kernel (stream order) tell
@@ -1228,6 +1336,57 @@ extern "C" int b200gym_step_p2p(b200gym_t *h, const void *actions_dev, int actio
 }
 
 // reset(): fill this rank's rows of set 0 ... (the reset observations are exchanged by the caller)
+
+// ---- stateless device utilities for the vector-aware wrappers -----------------------
+extern "C" int b200gym_episode_stats(const double *reward_dev, const uint8_t *terminated_dev, const uint8_t *truncated_dev,
+                                     float *return_acc_dev, int32_t *length_acc_dev, float *episode_r_dev,
+                                     int32_t *episode_l_dev, uint8_t *episode_mask_dev, float *ring_r_dev,
+                                     int32_t *ring_l_dev, uint64_t *counter_dev, int ring_size, int64_t n, void *stream) {
+    if (!reward_dev || !terminated_dev || !truncated_dev || !return_acc_dev || !length_acc_dev || !episode_r_dev ||
+        !episode_l_dev || !episode_mask_dev || !counter_dev || n <= 0 || (ring_size > 0 && (!ring_r_dev || !ring_l_dev)))
+        return fail(nullptr, "b200gym_episode_stats: bad argument");
+    episode_stats_kernel<<<blocks_for(n), kThreads, 0, (cudaStream_t)stream>>>(
+        reward_dev, terminated_dev, truncated_dev, return_acc_dev, length_acc_dev, episode_r_dev, episode_l_dev,
+        episode_mask_dev, ring_r_dev, ring_l_dev, (unsigned long long *)counter_dev, ring_size, n);
+    CK(nullptr, cudaGetLastError());
+    return 0;
+}
+
+extern "C" int b200gym_running_norm_obs(const float *obs_dev, float *out_dev, int64_t n, int dim, double *mean_dev,
+                                        double *var_dev, double *count_dev, double *scratch_dev /* 2*dim doubles, zeroed */,
+                                        double epsilon, int update, void *stream) {
+    if (!obs_dev || !out_dev || !mean_dev || !var_dev || !count_dev || !scratch_dev || n <= 0 || dim <= 0)
+        return fail(nullptr, "b200gym_running_norm_obs: bad argument");
+    cudaStream_t st = (cudaStream_t)stream;
+    if (update) {
+        int64_t g = (n + kThreads - 1) / kThreads;
+        if (g > 592) g = 592;
+        moments_kernel<float><<<(unsigned)g, kThreads, 0, st>>>(obs_dev, n, dim, mean_dev, scratch_dev, scratch_dev + dim);
+        rms_update_kernel<<<1, 32 * ((dim + 31) / 32), 0, st>>>(mean_dev, var_dev, count_dev, scratch_dev, scratch_dev + dim, n, dim);
+    }
+    normalize_obs_kernel<<<blocks_for(n * dim), kThreads, 0, st>>>(obs_dev, out_dev, n * dim, dim, mean_dev, var_dev, epsilon);
+    CK(nullptr, cudaGetLastError());
+    return 0;
+}
+
+extern "C" int b200gym_running_norm_reward(const double *reward_dev, const uint8_t *terminated_dev,
+                                           const uint8_t *truncated_dev, double *returns_dev, double *out_dev, int64_t n,
+                                           double *mean_dev, double *var_dev, double *count_dev,
+                                           double *scratch_dev /* 2 doubles, zeroed */, double gamma, double epsilon,
+                                           void *stream) {
+    if (!reward_dev || !terminated_dev || !truncated_dev || !returns_dev || !out_dev || !mean_dev || !var_dev || !count_dev || !scratch_dev || n <= 0)
+        return fail(nullptr, "b200gym_running_norm_reward: bad argument");
+    cudaStream_t st = (cudaStream_t)stream;
+    discounted_return_kernel<<<blocks_for(n), kThreads, 0, st>>>(returns_dev, reward_dev, gamma, n);
+    int64_t g = (n + kThreads - 1) / kThreads;
+    if (g > 592) g = 592;
+    moments_kernel<double><<<(unsigned)g, kThreads, 0, st>>>(returns_dev, n, 1, mean_dev, scratch_dev, scratch_dev + 1);
+    rms_update_kernel<<<1, 32, 0, st>>>(mean_dev, var_dev, count_dev, scratch_dev, scratch_dev + 1, n, 1);
+    normalize_reward_kernel<<<blocks_for(n), kThreads, 0, st>>>(reward_dev, out_dev, returns_dev, terminated_dev, truncated_dev, n,
+                                                                var_dev, epsilon);
+    CK(nullptr, cudaGetLastError());
+    return 0;
+}
 
 // ---- host-buffer path -------------------------------------------------------
 static int ensure_host_io(b200gym *h) {

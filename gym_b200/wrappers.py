@@ -1,0 +1,234 @@
+"""Vector-aware wrappers of the reference, re-built for device-resident batches.
+
+* ``RecordEpisodeStatistics``  gym/wrappers/record_episode_statistics.py:79-151
+* ``NormalizeObservation`` / ``NormalizeReward``  gym/wrappers/normalize.py:50-144
+* ``VectorListInfo``  gym/wrappers/vector_list_info.py:56-111
+* ``step_api_compatibility``  gym/utils/step_api_compatibility.py:24-161
+
+The first three run as fused CUDA kernels through the C ABI (one or a few launches per step,
+no Python loop over the batch, no host synchronisation); the last two are host-side adapters.
+They wrap a ``B200VectorEnv`` with ``backend="torch"``.
+"""
+import ctypes
+import time
+from collections import deque
+
+import numpy as np
+
+from gym_b200 import _lib
+
+
+def _p(t):
+    return ctypes.c_void_p(t.data_ptr())
+
+
+class VectorWrapper:
+    """Minimal ``gym.vector.VectorEnvWrapper`` (gym/vector/vector_env.py:277-332): forwards everything."""
+
+    def __init__(self, env):
+        self.env = env
+
+    def __getattr__(self, name):
+        if name.startswith("_"):
+            raise AttributeError(name)
+        return getattr(self.env, name)
+
+    def reset(self, **kwargs):
+        return self.env.reset(**kwargs)
+
+    def step(self, actions):
+        return self.env.step(actions)
+
+    def close(self, **kwargs):
+        return self.env.close(**kwargs)
+
+    @property
+    def unwrapped(self):
+        return self.env.unwrapped
+
+
+class RecordEpisodeStatistics(VectorWrapper):
+    """Cumulative reward and length of every episode, kept on the device.
+
+    ``infos["episode"] = {"r": float32 (N,), "l": int32 (N,), "t": float}`` with the ``_episode`` mask
+    (rows valid where the mask is set), every step and without a host sync.  ``return_queue`` /
+    ``length_queue`` (the last ``deque_size`` finished episodes) and ``episode_count`` synchronise on access.
+    """
+
+    def __init__(self, env, deque_size=100):
+        super().__init__(env)
+        import torch
+        self._torch = torch
+        n, dev = env.num_envs, env.device
+        self.num_envs = n
+        self.is_vector_env = True
+        self.t0 = time.perf_counter()
+        self.deque_size = int(deque_size)
+        self.episode_returns = torch.zeros(n, dtype=torch.float32, device=dev)
+        self.episode_lengths = torch.zeros(n, dtype=torch.int32, device=dev)
+        self._ep_r = [torch.zeros(n, dtype=torch.float32, device=dev) for _ in range(2)]
+        self._ep_l = [torch.zeros(n, dtype=torch.int32, device=dev) for _ in range(2)]
+        self._ep_m = [torch.zeros(n, dtype=torch.bool, device=dev) for _ in range(2)]
+        self._ring_r = torch.zeros(max(self.deque_size, 1), dtype=torch.float32, device=dev)
+        self._ring_l = torch.zeros(max(self.deque_size, 1), dtype=torch.int32, device=dev)
+        self._counter = torch.zeros(1, dtype=torch.int64, device=dev)
+        self._flip = 0
+
+    def reset(self, **kwargs):
+        out = self.env.reset(**kwargs)
+        self.episode_returns.zero_()
+        self.episode_lengths.zero_()
+        return out
+
+    def step(self, actions):
+        obs, rew, term, trunc, infos = self.env.step(actions)
+        self._flip ^= 1
+        k = self._flip
+        env = self.env.unwrapped
+        _lib.check(env._lib.b200gym_episode_stats(
+            _p(rew), _p(term), _p(trunc), _p(self.episode_returns), _p(self.episode_lengths), _p(self._ep_r[k]),
+            _p(self._ep_l[k]), _p(self._ep_m[k]), _p(self._ring_r), _p(self._ring_l), _p(self._counter),
+            self.deque_size, self.num_envs, env._stream()))
+        infos["episode"] = {"r": self._ep_r[k], "l": self._ep_l[k], "t": round(time.perf_counter() - self.t0, 6)}
+        infos["_episode"] = self._ep_m[k]
+        return obs, rew, term, trunc, infos
+
+    @property
+    def episode_count(self):
+        return int(self._counter.item())
+
+    def _queue(self, ring):
+        count = self.episode_count
+        k = min(count, self.deque_size)
+        vals = ring.cpu().numpy()
+        order = [(count - k + j) % max(self.deque_size, 1) for j in range(k)]
+        return deque((vals[i].item() for i in order), maxlen=self.deque_size)
+
+    @property
+    def return_queue(self):
+        return self._queue(self._ring_r)
+
+    @property
+    def length_queue(self):
+        return self._queue(self._ring_l)
+
+
+class _RunningMeanStd:
+    """Device copy of RunningMeanStd's state (normalize.py:8-29): mean 0, var 1, count epsilon."""
+
+    def __init__(self, torch, shape, device, epsilon=1e-4):
+        self.mean = torch.zeros(shape, dtype=torch.float64, device=device)
+        self.var = torch.ones(shape, dtype=torch.float64, device=device)
+        self.count = torch.full((1,), epsilon, dtype=torch.float64, device=device)
+        self.scratch = torch.zeros(2 * max(int(np.prod(shape)), 1), dtype=torch.float64, device=device)
+
+
+class NormalizeObservation(VectorWrapper):
+    """obs -> (obs - running_mean) / sqrt(running_var + epsilon), statistics over the whole batch."""
+
+    def __init__(self, env, epsilon=1e-8):
+        super().__init__(env)
+        import torch
+        self._torch = torch
+        self.num_envs, self.is_vector_env = env.num_envs, True
+        self.epsilon = float(epsilon)
+        d = env.single_observation_space.shape[0]
+        self.obs_rms = _RunningMeanStd(torch, (d,), env.device)
+        self._out = [torch.zeros((env.num_envs, d), dtype=torch.float32, device=env.device) for _ in range(2)]
+        self._flip = 0
+
+    def _normalize(self, obs):
+        self._flip ^= 1
+        out = self._out[self._flip]
+        env = self.env.unwrapped
+        r = self.obs_rms
+        _lib.check(env._lib.b200gym_running_norm_obs(_p(obs), _p(out), obs.shape[0], obs.shape[1], _p(r.mean), _p(r.var),
+                                                     _p(r.count), _p(r.scratch), self.epsilon, 1, env._stream()))
+        return out
+
+    def reset(self, **kwargs):
+        obs, info = self.env.reset(**kwargs)
+        return self._normalize(obs), info
+
+    def step(self, actions):
+        obs, rew, term, trunc, infos = self.env.step(actions)
+        return self._normalize(obs), rew, term, trunc, infos
+
+
+class NormalizeReward(VectorWrapper):
+    """Scale rewards so that the discounted return has unit running variance (normalize.py:98-144)."""
+
+    def __init__(self, env, gamma=0.99, epsilon=1e-8):
+        super().__init__(env)
+        import torch
+        self.num_envs, self.is_vector_env = env.num_envs, True
+        self.gamma, self.epsilon = float(gamma), float(epsilon)
+        self.return_rms = _RunningMeanStd(torch, (1,), env.device)
+        self.returns = torch.zeros(env.num_envs, dtype=torch.float64, device=env.device)
+        self._out = [torch.zeros(env.num_envs, dtype=torch.float64, device=env.device) for _ in range(2)]
+        self._flip = 0
+
+    def step(self, actions):
+        obs, rew, term, trunc, infos = self.env.step(actions)
+        self._flip ^= 1
+        out = self._out[self._flip]
+        env = self.env.unwrapped
+        r = self.return_rms
+        _lib.check(env._lib.b200gym_running_norm_reward(_p(rew), _p(term), _p(trunc), _p(self.returns), _p(out),
+                                                        self.num_envs, _p(r.mean), _p(r.var), _p(r.count), _p(r.scratch),
+                                                        self.gamma, self.epsilon, env._stream()))
+        return obs, out, term, trunc, infos
+
+
+class VectorListInfo(VectorWrapper):
+    """Dict-of-arrays ``infos`` -> list of per-env dicts (vector_list_info.py:56-111).
+
+    Host-side adapter for agents that expect the pre-0.25 info format; it synchronises and walks the
+    batch in Python, so it is meant for small batches."""
+
+    def _to_host(self, v):
+        return v.detach().cpu().numpy() if hasattr(v, "detach") else v
+
+    def _convert(self, infos):
+        n = self.env.num_envs
+        out = [{} for _ in range(n)]
+        for k in list(infos.keys()):
+            if k.startswith("_"):
+                continue
+            mask = np.asarray(self._to_host(infos[f"_{k}"])).astype(bool)
+            if k == "episode":  # vector_list_info.py:86-111
+                ep = {kk: self._to_host(vv) for kk, vv in infos[k].items()}
+                for i in np.flatnonzero(mask):
+                    out[i]["episode"] = {kk: (vv[i] if np.ndim(vv) else vv) for kk, vv in ep.items()}
+                continue
+            vals = self._to_host(infos[k])
+            for i in np.flatnonzero(mask):
+                out[i][k] = vals[i]
+        return out
+
+    def reset(self, **kwargs):
+        obs, infos = self.env.reset(**kwargs)
+        return obs, self._convert(infos)
+
+    def step(self, actions):
+        obs, rew, term, trunc, infos = self.env.step(actions)
+        return obs, rew, term, trunc, self._convert(infos)
+
+
+def step_api_compatibility(step_returns, output_truncation_bool=True, is_vector_env=True):
+    """5-tuple <-> 4-tuple step API for vector envs (gym/utils/step_api_compatibility.py:24-161).
+
+    Works on numpy arrays and torch tensors alike (``|``, ``&``, ``~`` only)."""
+    if output_truncation_bool:
+        if len(step_returns) == 5:
+            return step_returns
+        obs, rew, dones, infos = step_returns
+        trunc_key = infos.get("TimeLimit.truncated") if isinstance(infos, dict) else None
+        truncated = trunc_key if trunc_key is not None else dones & ~dones
+        return obs, rew, dones & ~truncated, truncated, infos
+    if len(step_returns) == 4:
+        return step_returns
+    obs, rew, terminated, truncated, infos = step_returns
+    if isinstance(infos, dict):
+        infos["TimeLimit.truncated"] = truncated & ~terminated
+    return obs, rew, terminated | truncated, infos

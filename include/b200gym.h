@@ -232,6 +232,34 @@ int b200gym_step_p2p(b200gym_t *h, const void *actions_dev, int action_dtype, fl
                      void *stream, int *set_out);
 
 /*
+ * Vector-aware wrappers of the reference, fused on the device.  Stateless utilities:
+ * all state lives in caller-owned device buffers; errors are reported through b200gym_last_error(NULL).
+ *
+ * b200gym_episode_stats replaces RecordEpisodeStatistics.step's Python loop over the batch
+ * (gym/wrappers/record_episode_statistics.py:103-151): float32 return / int32 length accumulators,
+ * infos["episode"]["r"/"l"] rows + `_episode` mask for finishing envs, and a ring of the last
+ * `ring_size` finished episodes (return_queue / length_queue); *counter_dev counts finished episodes.
+ */
+int b200gym_episode_stats(const double *reward_dev, const uint8_t *terminated_dev, const uint8_t *truncated_dev,
+                          float *return_acc_dev, int32_t *length_acc_dev, float *episode_r_dev, int32_t *episode_l_dev,
+                          uint8_t *episode_mask_dev, float *ring_r_dev, int32_t *ring_l_dev, uint64_t *counter_dev,
+                          int ring_size, int64_t n, void *stream);
+/*
+ * NormalizeObservation (gym/wrappers/normalize.py:50-95): fold this batch into the running mean /
+ * variance / count (RunningMeanStd, :8-46; float64 [dim], [dim], [1]) when `update`, then write
+ * (obs - mean) / sqrt(var + epsilon) as float32.  scratch_dev: 2*dim float64, zero on first use.
+ */
+int b200gym_running_norm_obs(const float *obs_dev, float *out_dev, int64_t n, int dim, double *mean_dev, double *var_dev,
+                             double *count_dev, double *scratch_dev, double epsilon, int update, void *stream);
+/*
+ * NormalizeReward (gym/wrappers/normalize.py:98-144): returns = returns * gamma + reward, fold `returns`
+ * into the scalar running statistics, out = reward / sqrt(var + epsilon), returns[terminated|truncated] = 0.
+ */
+int b200gym_running_norm_reward(const double *reward_dev, const uint8_t *terminated_dev, const uint8_t *truncated_dev,
+                                double *returns_dev, double *out_dev, int64_t n, double *mean_dev, double *var_dev,
+                                double *count_dev, double *scratch_dev, double gamma, double epsilon, void *stream);
+
+/*
  * Device self-test of the kernels' constant-divisor division (csrc/envs.cuh:div_by_const)
  * against IEEE `/`: `samples` pseudo-random doubles (both signs, 64 binades) x 4 divisors.
  * Synchronous; *mismatches_out must come back 0.

@@ -72,7 +72,7 @@ def test_invariants_and_api():
         assert bool(((o[:, [8, 13]] == 0) | (o[:, [8, 13]] == 1)).all())
         assert bool((o[:, 14:] >= 0).all()) and bool((o[:, 14:] <= 1).all())
         assert bool((r[te] == -100).all())          # nobody reaches the far end with random torques
-        assert bool((r[~te] > -5).all())
+        assert bool((r[~te] > -30).all())       # shaping deltas: a few points per step at most
         total_term += int(te.sum())
     assert total_term > N
     with pytest.raises(NotImplementedError):

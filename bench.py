@@ -44,7 +44,7 @@ BYTES_PER_ENV_STEP = {"CartPole-v1": 106, "CartPole-v0": 106, "Pendulum-v1": 16 
                       # BipedalWalker: 130-word record r+w (the 200 terrain words are read on demand), action, outputs
                       "BipedalWalker-v3": 130 * 4 * 2 + 8 + 16 + 96 + 8 + 2}
 # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed ncu --set full capture (2^20 envs)
-NCU_DRAM_BYTES_PER_LAUNCH = {"CartPole-v1": 56.23e6 + 23.99e6}
+NCU_DRAM_BYTES_PER_LAUNCH = {"CartPole-v1": 56.20e6 + 25.84e6}
 FALLBACK_HBM_GBS = 6650.0  # /opt/skills/guides/B200_PROFILING.md fallback
 
 
@@ -389,12 +389,12 @@ def run_b200(args):
                        "parallelism": f"env-batch data parallel x{world}"},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "traffic": NCU_DRAM_BYTES_PER_LAUNCH.get(args.env) if args.log2_envs == 20 else None,
-                         "traffic_source": "profiles/r1_cartpole_step_kernel_tma_ncu_full.txt: dram__bytes_read.sum + "
+                         "traffic_source": "profiles/r1_cartpole_step_kernel_A_ncu_full.txt: dram__bytes_read.sum + "
                                            "dram__bytes_write.sum of one launch (cold L2; lines still dirty in L2 at "
                                            "kernel end are not in it)", "peak_source": peak_src,
                          "bytes_per_env_step": BYTES_PER_ENV_STEP.get(args.env), "kernel_ms": kernel_ms,
-                         "kernel": "step_kernel_tma<CARTPOLE, int64>" if args.env.startswith("CartPole")
-                         else "step_kernel_tma"},
+                         "kernel": ("step_kernel_tma" if os.environ.get("B200GYM_KERNEL", "a") == "b" else "step_kernel")
+                         + ("<CARTPOLE, int64>" if args.env.startswith("CartPole") else "")},
             "cpu_baseline": cpu,
             "e2e": e2e,
             "gpu_launches": K,

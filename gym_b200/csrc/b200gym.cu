@@ -49,7 +49,9 @@ struct b200gym {
     unsigned long long *invalid = nullptr;  // sticky device counter
     int sm_count = 148;
     int occ[B200GYM_NUM_KINDS][3] = {};     // cached CTAs/SM of step_kernel_tma per (kind, action width)
-    bool force_simple = false;              // B200GYM_SIMPLE_KERNEL=1: always use kernel A (A/B measurements)
+    int kernel_choice = 0;                  // 0: kernel A (default: fastest measured), 1: kernel B (TMA-staged tiles);
+                                            // B200GYM_KERNEL=a|b overrides
+    int block_a = 256;                      // CTA size of kernel A (B200GYM_BLOCK_A=64|128|256, tuning runs)
     // fused all-gather over peer memory (b200gym_p2p_*)
     struct {
         int world = 0, rank = 0;
@@ -279,7 +281,7 @@ __global__ void __launch_bounds__(kThreads, Tuning<KIND>::kMinCtas) step_kernel(
     __shared__ int reset_count;
     if (threadIdx.x == 0) reset_count = 0;
     __syncthreads();
-    const int64_t j = (int64_t)blockIdx.x * kThreads + threadIdx.x;
+    const int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (j < a.count) {
         const int64_t i = a.first + j;
         double s[E::S];
@@ -296,7 +298,7 @@ __global__ void __launch_bounds__(kThreads, Tuning<KIND>::kMinCtas) step_kernel(
     __syncthreads();
     const int cnt = reset_count;
     if ((int)threadIdx.x < cnt)
-        reset_env<KIND>(a, a.first + (int64_t)blockIdx.x * kThreads + reset_list[threadIdx.x]);
+        reset_env<KIND>(a, a.first + (int64_t)blockIdx.x * blockDim.x + reset_list[threadIdx.x]);
 }
 
 // --- kernel B: persistent CTAs, TMA-staged inputs -------------------------------------
@@ -925,9 +927,9 @@ static int launch_step_typed(b200gym *h, const StepArgs &a, cudaStream_t st) {
     // action pointer; and enough tiles to be worth a persistent grid
     const bool aligned = (a.n % 2 == 0) && (a.first % 16 == 0) && ((uintptr_t)a.actions % 16 == 0) &&
                          ((uintptr_t)a.state % 16 == 0) && ((uintptr_t)a.elapsed % 16 == 0);
-    const int64_t tiles = a.count / kThreads;
     int64_t done = 0;
-    if (aligned && tiles >= h->sm_count && !h->force_simple) {
+    const int64_t tiles = a.count / kThreads;
+    if (aligned && tiles >= h->sm_count && h->kernel_choice == 1) {
         int &occ = h->occ[KIND][sizeof(ActT) == 8 ? 0 : sizeof(ActT) == 4 ? 1 : 2];
         if (occ == 0) {
             CK(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, step_kernel_tma<KIND, ActT>, kThreads, 0));
@@ -943,7 +945,8 @@ static int launch_step_typed(b200gym *h, const StepArgs &a, cudaStream_t st) {
         StepArgs t = a;
         t.first = a.first + done;
         t.count = a.count - done;
-        step_kernel<KIND, ActT><<<blocks_for(t.count), kThreads, 0, st>>>(t);
+        const int bs = h->block_a;
+        step_kernel<KIND, ActT><<<(unsigned)((t.count + bs - 1) / bs), bs, 0, st>>>(t);
         CK(h, cudaGetLastError());
     }
     return 0;
@@ -1067,7 +1070,11 @@ extern "C" int b200gym_create(const b200gym_config *cfg, int64_t num_envs, int d
     h->sm_count = prop.multiProcessorCount > 0 ? prop.multiProcessorCount : 148;
     {
         const char *fs = getenv("B200GYM_SIMPLE_KERNEL");
-        h->force_simple = fs && fs[0] == '1';
+        const char *kc = getenv("B200GYM_KERNEL");
+        if (kc && (kc[0] == 'a' || kc[0] == 'b')) h->kernel_choice = kc[0] - 'a';
+        if (fs && fs[0] == '1') h->kernel_choice = 0;
+        const char *ba = getenv("B200GYM_BLOCK_A");
+        if (ba && (atoi(ba) == 64 || atoi(ba) == 128 || atoi(ba) == 256)) h->block_a = atoi(ba);
     }
     DeviceGuard guard(device);
     const size_t n = (size_t)num_envs;

@@ -54,6 +54,51 @@ __device__ __forceinline__ double div_by_const(double x, double c, double rc) {
     return fma(r, rc, q);
 }
 
+// sin and cos of a small angle without range reduction.  CartPole's pole angle stays inside
+// +-0.42 rad for every state that is still stepped under autoreset, so the generic sincos()
+// (Cody-Waite reduction, quadrant logic, ~75 instructions of which many only materialise
+// 64-bit immediates) is replaced by the two minimax kernels of the classic fdlibm
+// __kernel_sin / __kernel_cos (|x| <= pi/4, < 1 ulp), evaluated with explicit FMAs and with the
+// coefficients read from the constant bank.  Larger angles (plain-Env mode after termination)
+// take the library path.
+__constant__ double kSinCoef[6] = {-1.66666666666666324348e-01, 8.33333333332248946124e-03,
+                                   -1.98412698298579493134e-04, 2.75573137070700676789e-06,
+                                   -2.50507602534068634195e-08, 1.58969099521155010221e-10};
+__constant__ double kCosCoef[6] = {4.16666666666666019037e-02, -1.38888888888741095749e-03,
+                                   2.48015872894767294178e-05, -2.75573143513906633035e-07,
+                                   2.08757232129817482790e-09, -1.13596475577881948265e-11};
+
+__device__ __forceinline__ void sincos_small(double x, double &sn, double &cs) {
+    if (fabs(x) < 0.7) {
+        const double z = x * x;
+        double r = kSinCoef[5];
+        r = fma(r, z, kSinCoef[4]);
+        r = fma(r, z, kSinCoef[3]);
+        r = fma(r, z, kSinCoef[2]);
+        r = fma(r, z, kSinCoef[1]);
+        const double v = z * x;
+        sn = fma(v, fma(z, r, kSinCoef[0]), x);
+        double c = kCosCoef[5];
+        c = fma(c, z, kCosCoef[4]);
+        c = fma(c, z, kCosCoef[3]);
+        c = fma(c, z, kCosCoef[2]);
+        c = fma(c, z, kCosCoef[1]);
+        c = fma(c, z, kCosCoef[0]);
+        const double zr = z * c;
+        // 1 - (z/2 - z*r), with the fdlibm split that keeps the subtraction exact near |x| ~ 0.3 .. 0.7
+        const double qx = fabs(x) < 0.3 ? 0.0 : 0.25 * fabs(x);
+        const double hz = fma(0.5, z, -qx);
+        cs = (1.0 - qx) - (hz - z * zr);
+    } else {
+        sincos(x, &sn, &cs);
+    }
+}
+
+__constant__ double kInvTotalMass = 1.0 / (0.1 + 1.0);
+
+// CartPole's physical constants, also kept in the constant bank (float64 immediates cost two UMOVs each)
+__constant__ double kCartPole[10] = {9.8, 0.1, 0.1 + 1.0, 0.5, 0.1 * 0.5, 10.0, 0.02, 12 * 2 * B200_PI / 360, 2.4, 4.0 / 3.0};
+
 // ---------------------------------------------------------------------------
 // CartPole-v0/v1 -- gym/envs/classic_control/cartpole.py
 // ---------------------------------------------------------------------------
@@ -77,24 +122,24 @@ struct Env<B200GYM_CARTPOLE> {
     // cartpole.py:130-188, "euler" integrator (:149-153)
     __device__ static void step(double (&s)[S], bool /*fresh*/, int action, float /*a0*/,
                                 double /*param0*/, float (&obs)[D], double &reward, bool &terminated) {
-        const double gravity = 9.8, masscart = 1.0, masspole = 0.1;          // :90-92
-        const double total_mass = masspole + masscart;                       // :93
-        const double length = 0.5;                                           // :94
-        const double polemass_length = masspole * length;                    // :95
-        const double force_mag = 10.0, tau = 0.02;                           // :96-97
-        const double theta_threshold = 12 * 2 * B200_PI / 360;               // :101
-        const double x_threshold = 2.4;                                      // :102
+        const double gravity = kCartPole[0], masspole = kCartPole[1];        // :90-92 (masscart = 1.0)
+        const double total_mass = kCartPole[2];                              // :93  masspole + masscart
+        const double length = kCartPole[3];                                  // :94
+        const double polemass_length = kCartPole[4];                         // :95  masspole * length
+        const double force_mag = kCartPole[5], tau = kCartPole[6];           // :96-97
+        const double theta_threshold = kCartPole[7];                         // :101 12 * 2 * pi / 360
+        const double x_threshold = kCartPole[8];                             // :102
 
         double x = s[0], x_dot = s[1], theta = s[2], theta_dot = s[3];
         const double force = (action == 1) ? force_mag : -force_mag;         // :135
         double sintheta, costheta;
-        sincos(theta, &sintheta, &costheta);                                 // :136-137
-        const double inv_total_mass = 1.0 / total_mass;  // folded at compile time, correctly rounded
+        sincos_small(theta, sintheta, costheta);                             // :136-137
+        const double inv_total_mass = kInvTotalMass;     // RN(1 / total_mass), folded by the compiler
         const double temp = div_by_const(
             force + polemass_length * (theta_dot * theta_dot) * sintheta, total_mass, inv_total_mass);  // :141-143
         const double thetaacc =
             (gravity * sintheta - costheta * temp) /
-            (length * (4.0 / 3.0 - div_by_const(masspole * (costheta * costheta), total_mass,
+            (length * (kCartPole[9] - div_by_const(masspole * (costheta * costheta), total_mass,
                                                 inv_total_mass)));                         // :144-146
         const double xacc = temp - div_by_const(polemass_length * thetaacc * costheta, total_mass,
                                                 inv_total_mass);                           // :147

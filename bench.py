@@ -353,7 +353,10 @@ def run_b200(args):
         el = float(tt.item())
         D = inner.obs_dim
         h2d = n * (8 if inner.discrete else 4 * inner.act_dim)
-        d2h = n * (4 * D + 8 + 1 + 1 + 4 * D)  # obs + reward + 2 flags + final_observation
+        # obs + reward + 2 flags, plus the compacted final observations (index + row) of the envs that
+        # finished in the last step
+        n_done = int((term | trunc).sum())
+        d2h = n * (4 * D + 8 + 1 + 1) + n_done * (4 + 4 * D) + 8
         e2e = {"value": world * n * E / el, "unit": "env-steps/s", "h2d_bytes_per_step": h2d * world,
                "d2h_bytes_per_step": d2h * world, "steps": E, "ms_per_step": 1e3 * el / E,
                "api": "B200VectorEnv(backend='numpy').step(pinned numpy actions) -> numpy results "

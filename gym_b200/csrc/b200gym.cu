@@ -65,6 +65,11 @@ struct b200gym {
     b200gym_host_io hio{};
     b200gym_host_io dio{};  // device mirrors of the staging buffers
     uint8_t *d_mask = nullptr;
+    // compacted final observations of the host path: only the rows of finishing envs cross PCIe
+    int32_t *d_fin_idx = nullptr, *h_fin_idx = nullptr;
+    float *d_fin_rows = nullptr, *h_fin_rows = nullptr;
+    unsigned long long *d_fin_count = nullptr, *h_fin_count = nullptr;
+    cudaEvent_t hevent = nullptr;
     unsigned long long **d_peer_flags = nullptr;
     cudaStream_t hstream[2] = {nullptr, nullptr};
     bool host_ready = false;
@@ -891,6 +896,22 @@ __global__ void p2p_wait_kernel(const unsigned long long *flags, int world, unsi
     }
 }
 
+// host path: gather the final observations of the envs that finished in [first, first+count) into a
+// dense list (order irrelevant: every entry carries its env index)
+__global__ void __launch_bounds__(kThreads) compact_final_kernel(const uint8_t *term, const uint8_t *trunc,
+                                                                const float *final_obs, int D, int64_t first,
+                                                                int64_t count, int32_t *idx_out, float *rows_out,
+                                                                unsigned long long *counter) {
+    const int64_t j = (int64_t)blockIdx.x * kThreads + threadIdx.x;
+    if (j >= count) return;
+    const int64_t i = first + j;
+    if (term[i] | trunc[i]) {
+        const unsigned long long slot = atomicAdd(counter, 1ULL);
+        idx_out[slot] = (int32_t)i;
+        for (int k = 0; k < D; k++) rows_out[slot * D + k] = final_obs[i * D + k];
+    }
+}
+
 // device self-test: div_by_const(x, c, RN(1/c)) must equal x / c bit for bit
 __global__ void __launch_bounds__(kThreads) selftest_div_kernel(int64_t samples, uint64_t seed,
                                                                 unsigned long long *mismatches) {
@@ -1119,6 +1140,9 @@ static void free_host_io(b200gym *h) {
     cudaFree(h->dio.actions); cudaFree(h->dio.obs); cudaFree(h->dio.reward);
     cudaFree(h->dio.terminated); cudaFree(h->dio.truncated); cudaFree(h->dio.final_obs);
     cudaFree(h->d_mask);
+    cudaFree(h->d_fin_idx); cudaFree(h->d_fin_rows); cudaFree(h->d_fin_count);
+    cudaFreeHost(h->h_fin_idx); cudaFreeHost(h->h_fin_rows); cudaFreeHost(h->h_fin_count);
+    if (h->hevent) cudaEventDestroy(h->hevent);
     for (cudaStream_t st : h->hstream)
         if (st) cudaStreamDestroy(st);
     h->host_ready = false;
@@ -1417,6 +1441,13 @@ static int ensure_host_io(b200gym *h) {
     CK(h, cudaMalloc((void **)&h->dio.truncated, n));
     CK(h, cudaMalloc((void **)&h->dio.final_obs, obs_bytes));
     CK(h, cudaMalloc((void **)&h->d_mask, n));
+    CK(h, cudaMalloc((void **)&h->d_fin_idx, n * sizeof(int32_t)));
+    CK(h, cudaMalloc((void **)&h->d_fin_rows, obs_bytes));
+    CK(h, cudaMalloc((void **)&h->d_fin_count, sizeof(unsigned long long)));
+    CK(h, cudaHostAlloc((void **)&h->h_fin_idx, n * sizeof(int32_t), cudaHostAllocDefault));
+    CK(h, cudaHostAlloc((void **)&h->h_fin_rows, obs_bytes, cudaHostAllocDefault));
+    CK(h, cudaHostAlloc((void **)&h->h_fin_count, sizeof(unsigned long long), cudaHostAllocDefault));
+    CK(h, cudaEventCreateWithFlags(&h->hevent, cudaEventDisableTiming));
     CK(h, cudaMemset(h->dio.final_obs, 0, obs_bytes));
     h->host_ready = true;
     return 0;
@@ -1461,9 +1492,19 @@ extern "C" int b200gym_step_host(b200gym_t *h, const void *actions_host, int act
     const int64_t n = h->n;
     int64_t chunks = n >> 17;
     chunks = chunks < 1 ? 1 : (chunks > 8 ? 8 : chunks);
+    if (const char *hc = getenv("B200GYM_HOST_CHUNKS")) {  // tuning runs
+        const int v = atoi(hc);
+        if (v >= 1 && v <= 64) chunks = v;
+    }
     int64_t per = ((n + chunks - 1) / chunks + kThreads - 1) / kThreads * kThreads;
     StepArgs a = make_args(h, h->dio.actions, h->dio.obs, h->dio.reward, h->dio.terminated, h->dio.truncated,
                            h->dio.final_obs);
+    const bool want_final = final_obs_host != nullptr && h->cfg.autoreset;
+    if (want_final) CK(h, cudaMemsetAsync(h->d_fin_count, 0, sizeof(unsigned long long), h->hstream[0]));
+    if (want_final && chunks > 1) {  // stream 1 must see the cleared counter
+        CK(h, cudaEventRecord(h->hevent, h->hstream[0]));
+        CK(h, cudaStreamWaitEvent(h->hstream[1], h->hevent, 0));
+    }
     int c = 0;
     for (int64_t lo = 0; lo < n; lo += per, c++) {
         const int64_t cnt = (lo + per < n) ? per : n - lo;
@@ -1478,12 +1519,30 @@ extern "C" int b200gym_step_host(b200gym_t *h, const void *actions_host, int act
         CK(h, cudaMemcpyAsync(reward_host + lo, h->dio.reward + lo, cnt * sizeof(double), cudaMemcpyDeviceToHost, st));
         CK(h, cudaMemcpyAsync(terminated_host + lo, h->dio.terminated + lo, cnt, cudaMemcpyDeviceToHost, st));
         CK(h, cudaMemcpyAsync(truncated_host + lo, h->dio.truncated + lo, cnt, cudaMemcpyDeviceToHost, st));
-        if (final_obs_host)
-            CK(h, cudaMemcpyAsync((char *)final_obs_host + lo * osz, (char *)h->dio.final_obs + lo * osz, cnt * osz,
-                                  cudaMemcpyDeviceToHost, st));
+        if (want_final) {
+            compact_final_kernel<<<blocks_for(cnt), kThreads, 0, st>>>(h->dio.terminated, h->dio.truncated,
+                                                                      h->dio.final_obs, h->D, lo, cnt, h->d_fin_idx,
+                                                                      h->d_fin_rows, h->d_fin_count);
+            CK(h, cudaGetLastError());
+        }
     }
-    CK(h, cudaStreamSynchronize(h->hstream[0]));
     CK(h, cudaStreamSynchronize(h->hstream[1]));
+    if (want_final)
+        CK(h, cudaMemcpyAsync(h->h_fin_count, h->d_fin_count, sizeof(unsigned long long), cudaMemcpyDeviceToHost,
+                              h->hstream[0]));
+    CK(h, cudaStreamSynchronize(h->hstream[0]));
+    if (want_final) {
+        // only the rows of the envs that finished cross PCIe; they are scattered into the dense
+        // [n][obs_dim] host array (rows of the other envs keep their previous content)
+        const size_t m = (size_t)*h->h_fin_count;
+        if (m > 0) {
+            CK(h, cudaMemcpyAsync(h->h_fin_idx, h->d_fin_idx, m * sizeof(int32_t), cudaMemcpyDeviceToHost, h->hstream[0]));
+            CK(h, cudaMemcpyAsync(h->h_fin_rows, h->d_fin_rows, m * osz, cudaMemcpyDeviceToHost, h->hstream[0]));
+            CK(h, cudaStreamSynchronize(h->hstream[0]));
+            for (size_t k = 0; k < m; k++)
+                memcpy((char *)final_obs_host + (size_t)h->h_fin_idx[k] * osz, (const char *)h->h_fin_rows + k * osz, osz);
+        }
+    }
     return 0;
 }
 

@@ -354,9 +354,12 @@ class B200VectorEnv:
                 if not np.issubdtype(a.dtype, np.integer):
                     raise error.InvalidAction(f"Discrete actions must be integers, got {a.dtype}")
                 a = np.ascontiguousarray(a.reshape(self.num_envs))
-                if a.size and (a.min() < 0 or a.max() >= self.single_action_space.n):
+                # small batches are validated before anything is stepped, like the reference's assert
+                # (cartpole.py:131-132); large ones rely on the kernel's own check (two passes over 2^20
+                # actions on the host would cost more than the whole step) and raise right after the call
+                if a.size <= 4096 and a.size and (a.min() < 0 or a.max() >= self.single_action_space.n):
                     bad = a[(a < 0) | (a >= self.single_action_space.n)][0]
-                    raise error.InvalidAction(f"{bad!r} ({type(bad)}) invalid")  # cartpole.py:131-132
+                    raise error.InvalidAction(f"{bad!r} ({type(bad)}) invalid")
                 code = {np.dtype(np.int64): _lib.ACT_I64, np.dtype(np.int32): _lib.ACT_I32,
                         np.dtype(np.uint8): _lib.ACT_U8}.get(a.dtype)
                 if code is None:
@@ -369,6 +372,12 @@ class B200VectorEnv:
             _lib.check(self._lib.b200gym_step_host(
                 self._handle, a.ctypes.data, code, None, None, None, None,
                 h["final_obs"].ctypes.data if self.autoreset else None), self._handle)
+            if self.discrete and a.size > 4096:
+                count = ctypes.c_int64(0)
+                _lib.check(self._lib.b200gym_invalid_actions(self._handle, None, ctypes.byref(count)), self._handle)
+                if count.value:
+                    raise error.InvalidAction(f"{count.value} out-of-range Discrete action(s) were passed to step(); "
+                                              "the other environments have been stepped")
         self._state = _STATE_WAITING_STEP
 
     def step_wait(self, timeout=None):

@@ -22,6 +22,10 @@ KIND_PENDULUM = 3
 KIND_ACROBOT = 4
 KIND_LUNARLANDER = 5
 KIND_BIPEDALWALKER = 6
+KIND_LUNARLANDER_CONT = 7
+
+# b200gym_config.flags
+LUNAR_ENABLE_WIND = 1
 
 # enum b200gym_action_dtype
 ACT_I64, ACT_I32, ACT_U8, ACT_F32 = 0, 1, 2, 3
@@ -33,7 +37,7 @@ class Config(ctypes.Structure):
         ("kind", ctypes.c_int32),
         ("max_episode_steps", ctypes.c_int32),
         ("autoreset", ctypes.c_int32),
-        ("reserved", ctypes.c_int32),
+        ("flags", ctypes.c_int32),
         ("param", ctypes.c_double * 4),
     ]
 
@@ -87,6 +91,7 @@ SIGNATURES = {
     "b200gym_get_state": (_i32, [_vp, _vp, _vp, _vp, _vp]),
     "b200gym_set_state": (_i32, [_vp, _vp, _vp, _vp, _vp]),
     "b200gym_lunar_get_bodies": (_i32, [_vp, _vp, _vp, _vp]),
+    "b200gym_lunar_wind_idx": (_i32, [_vp, _vp, _vp, _i32]),
     "b200gym_walker_get_bodies": (_i32, [_vp, _vp, _vp, _vp]),
     "b200gym_p2p_create": (_i32, [_vp, _i32, _i32, _vp, _vp]),
     "b200gym_p2p_connect": (_i32, [_vp, _vp]),

@@ -46,6 +46,8 @@ struct b200gym {
     uint8_t *flags = nullptr;
     uint64_t *rng = nullptr;
     uint32_t *lunar_rec = nullptr;          // LunarLander / BipedalWalker: solver record, kWords 32-bit words per env, SoA
+    bool is_lunar = false, is_walker = false;
+    lunar::Opts lunar_opts{};
     unsigned long long *invalid = nullptr;  // sticky device counter
     int sm_count = 148;
     int occ[B200GYM_NUM_KINDS][3] = {};     // cached CTAs/SM of step_kernel_tma per (kind, action width)
@@ -96,10 +98,10 @@ static int fail(const b200gym *h, const char *fmt, ...) {
             return fail(h, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
     } while (0)
 
-static const int k_obs_dim[B200GYM_NUM_KINDS] = {4, 2, 2, 3, 6, 8, 24};
-static const int k_act_dim[B200GYM_NUM_KINDS] = {0, 0, 1, 1, 0, 0, 4};
-static const int k_nact[B200GYM_NUM_KINDS] = {2, 3, 0, 0, 3, 4, 0};
-static const int k_state_dim[B200GYM_NUM_KINDS] = {4, 2, 2, 2, 4, 0, 0};
+static const int k_obs_dim[B200GYM_NUM_KINDS] = {4, 2, 2, 3, 6, 8, 24, 8};
+static const int k_act_dim[B200GYM_NUM_KINDS] = {0, 0, 1, 1, 0, 0, 4, 2};
+static const int k_nact[B200GYM_NUM_KINDS] = {2, 3, 0, 0, 3, 4, 0, 0};
+static const int k_state_dim[B200GYM_NUM_KINDS] = {4, 2, 2, 2, 4, 0, 0, 0};
 
 static bool kind_ok(int k) { return k >= 0 && k < B200GYM_NUM_KINDS; }
 
@@ -138,6 +140,7 @@ struct StepArgs {
     int32_t max_steps;
     int32_t autoreset;
     double param0;
+    lunar::Opts lunar_opts;   // LunarLander constructor variants (uniform over the batch)
     // fused all-gather (multi-GPU): every result is ALSO stored into the same rows of the peers'
     // gather buffers over NVLink (peer-mapped pointers, slice offset already applied)
     int32_t npeer;
@@ -493,53 +496,72 @@ __global__ void __launch_bounds__(kThreads) state_set_kernel(double *soa, const 
 // ---- LunarLander-v2 (lunar.cuh): one thread per env, the whole b2World::Step in registers/local ----
 constexpr int kLunarThreads = 128;
 
-template <typename ActT>
+template <typename ActT, bool CONT>
 __global__ void __launch_bounds__(kLunarThreads) lunar_step_kernel(const StepArgs a) {
     const int64_t j = (int64_t)blockIdx.x * kLunarThreads + threadIdx.x;
     if (j >= a.count) return;
     const int64_t i = a.first + j;
-    const long long act = (long long)__ldg(reinterpret_cast<const ActT *>(a.actions) + i);
-    if (act < 0 || act > 3) {  // lunar_lander.py:482-484
-        atomicAdd(a.invalid, 1ULL);
-        store_scalars_all(a, i, __longlong_as_double(0x7ff8000000000000LL), 0, 0);
-        return;
+    long long act = 0;
+    float ca0 = 0.0f, ca1 = 0.0f;
+    if constexpr (CONT) {
+        const float2 c = __ldg(reinterpret_cast<const float2 *>(a.actions) + i);   // Box(2) float32, lunar_lander.py:285-287
+        ca0 = c.x; ca1 = c.y;
+    } else {
+        act = (long long)__ldg(reinterpret_cast<const ActT *>(a.actions) + i);
+        if (act < 0 || act > 3) {  // lunar_lander.py:482-484
+            atomicAdd(a.invalid, 1ULL);
+            store_scalars_all(a, i, __longlong_as_double(0x7ff8000000000000LL), 0, 0);
+            return;
+        }
     }
+    const lunar::Opts &O = a.lunar_opts;
     lunar::World W;
-    lunar::load_world(W, a.lunar_rec, a.n, i);
+    lunar::load_world(W, a.lunar_rec, a.n, i, O.wind != 0);
     Pcg64 g = pcg64_load(a.rng + 4 * i);
     int32_t elapsed = a.elapsed[i];
     float obs[8];
     double reward;
     bool terminated;
-    lunar::env_step(W, g, (int)act, lunar::V(0.0f, 0.0f), obs, reward, terminated);
+    lunar::env_step(W, g, O, (int)act, ca0, ca1, lunar::V(0.0f, 0.0f), obs, reward, terminated);
     elapsed += 1;                                                        // time_limit.py:51
     const bool truncated = (a.max_steps > 0) && (elapsed >= a.max_steps);
     store_scalars_all(a, i, reward, terminated ? 1 : 0, truncated ? 1 : 0);
     if ((terminated || truncated) && a.autoreset) {                      // sync_vector_env.py:152-156
         if (a.final_obs) store_row<8>(a.final_obs, i, obs);
-        lunar::env_reset(W, g, obs);
+        lunar::env_reset(W, g, O, obs);
         elapsed = 0;
     }
-    lunar::store_world(W, a.lunar_rec, a.n, i);
+    lunar::store_world(W, a.lunar_rec, a.n, i, O.wind != 0);
     pcg64_store(a.rng + 4 * i, g);
     a.elapsed[i] = elapsed;
     store_obs_all<8>(a, i, obs);
 }
 
 __global__ void __launch_bounds__(kLunarThreads) lunar_reset_kernel(uint32_t *rec, int32_t *elapsed, uint64_t *rng,
-                                                                    const uint8_t *mask, float *obs, int64_t n) {
+                                                                    const uint8_t *mask, float *obs, int64_t n,
+                                                                    const lunar::Opts O) {
     const int64_t i = (int64_t)blockIdx.x * kLunarThreads + threadIdx.x;
     if (i >= n) return;
     if (mask && !mask[i]) return;
     lunar::World W;
     W.flags = rec[(int64_t)lunar::W_FLAGS * n + i] & 16u;  // the b2World object survives reset()
+    W.wind_idx = O.wind ? (int32_t)rec[(int64_t)lunar::W_WIND * n + i] : 0;          // so do wind_idx / torque_idx
+    W.torque_idx = O.wind ? (int32_t)rec[(int64_t)(lunar::W_WIND + 1) * n + i] : 0;
     Pcg64 g = pcg64_load(rng + 4 * i);
     float o[8];
-    lunar::env_reset(W, g, o);
-    lunar::store_world(W, rec, n, i);
+    lunar::env_reset(W, g, O, o);
+    lunar::store_world(W, rec, n, i, O.wind != 0);
     pcg64_store(rng + 4 * i, g);
     elapsed[i] = 0;
     if (obs) store_row<8>(obs, i, o);
+}
+
+// wind_idx / torque_idx of every env (lunar_lander.py:234-235): two int32 SoA rows of the record
+__global__ void lunar_wind_idx_kernel(uint32_t *rec, int32_t *wind, int32_t *torque, int64_t n, int set) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    if (set) { rec[(int64_t)lunar::W_WIND * n + i] = (uint32_t)wind[i]; rec[(int64_t)(lunar::W_WIND + 1) * n + i] = (uint32_t)torque[i]; }
+    else { wind[i] = (int32_t)rec[(int64_t)lunar::W_WIND * n + i]; torque[i] = (int32_t)rec[(int64_t)(lunar::W_WIND + 1) * n + i]; }
 }
 
 // bodies of every env as [n][18] floats {c.x, c.y, a, v.x, v.y, w} x 3 + [n][6] int32 flags (parity harness)
@@ -1000,11 +1022,18 @@ static int launch_step(b200gym *h, const StepArgs &a, int action_dtype, cudaStre
     case B200GYM_LUNARLANDER: {
         const unsigned grid = (unsigned)((a.count + kLunarThreads - 1) / kLunarThreads);
         switch (action_dtype) {
-        case B200GYM_ACT_I64: lunar_step_kernel<long long><<<grid, kLunarThreads, 0, st>>>(a); break;
-        case B200GYM_ACT_I32: lunar_step_kernel<int><<<grid, kLunarThreads, 0, st>>>(a); break;
-        case B200GYM_ACT_U8: lunar_step_kernel<unsigned char><<<grid, kLunarThreads, 0, st>>>(a); break;
+        case B200GYM_ACT_I64: lunar_step_kernel<long long, false><<<grid, kLunarThreads, 0, st>>>(a); break;
+        case B200GYM_ACT_I32: lunar_step_kernel<int, false><<<grid, kLunarThreads, 0, st>>>(a); break;
+        case B200GYM_ACT_U8: lunar_step_kernel<unsigned char, false><<<grid, kLunarThreads, 0, st>>>(a); break;
         default: return fail(h, "Discrete env needs an integer action dtype (got code %d)", action_dtype);
         }
+        CK(h, cudaGetLastError());
+        return 0;
+    }
+    case B200GYM_LUNARLANDER_CONT: {
+        if (action_dtype != B200GYM_ACT_F32) return fail(h, "Box env needs float32 actions (got dtype code %d)", action_dtype);
+        if ((uintptr_t)a.actions % 8 != 0) return fail(h, "LunarLanderContinuous actions must be 8-byte aligned");
+        lunar_step_kernel<float, true><<<(unsigned)((a.count + kLunarThreads - 1) / kLunarThreads), kLunarThreads, 0, st>>>(a);
         CK(h, cudaGetLastError());
         return 0;
     }
@@ -1036,8 +1065,9 @@ static int launch_reset(b200gym *h, const uint8_t *mask, const double *bounds, f
     case B200GYM_PENDULUM: launch_reset_kind<B200GYM_PENDULUM>(h, mask, bounds, obs, st); break;
     case B200GYM_ACROBOT: launch_reset_kind<B200GYM_ACROBOT>(h, mask, bounds, obs, st); break;
     case B200GYM_LUNARLANDER:
+    case B200GYM_LUNARLANDER_CONT:
         lunar_reset_kernel<<<(unsigned)((h->n + kLunarThreads - 1) / kLunarThreads), kLunarThreads, 0, st>>>(
-            h->lunar_rec, h->elapsed, h->rng, mask, obs, h->n);
+            h->lunar_rec, h->elapsed, h->rng, mask, obs, h->n, h->lunar_opts);
         break;
     case B200GYM_BIPEDALWALKER:
         walker_reset_kernel<<<(unsigned)((h->n + kLunarThreads - 1) / kLunarThreads), kLunarThreads, 0, st>>>(
@@ -1068,6 +1098,9 @@ extern "C" int b200gym_create(const b200gym_config *cfg, int64_t num_envs, int d
     if (!cfg || !out) return fail(nullptr, "b200gym_create: null argument");
     *out = nullptr;
     if (!kind_ok(cfg->kind)) return fail(nullptr, "b200gym_create: unknown env kind %d", cfg->kind);
+    if ((cfg->kind == B200GYM_LUNARLANDER || cfg->kind == B200GYM_LUNARLANDER_CONT) && cfg->param[0] != 0.0 &&
+        !(-12.0 < cfg->param[0] && cfg->param[0] < 0.0))  // the assert of lunar_lander.py:210-212
+        return fail(nullptr, "b200gym_create: gravity (current value: %g) must be between -12 and 0", cfg->param[0]);
     if (num_envs <= 0) return fail(nullptr, "b200gym_create: num_envs must be positive (got %lld)", (long long)num_envs);
     int ndev = 0;
     cudaError_t e = cudaGetDeviceCount(&ndev);
@@ -1108,8 +1141,17 @@ extern "C" int b200gym_create(const b200gym_config *cfg, int64_t num_envs, int d
             b200gym_destroy(h);
             return 1;
         }
-    if (cfg->kind == B200GYM_LUNARLANDER || cfg->kind == B200GYM_BIPEDALWALKER) {
-        const bool lun = cfg->kind == B200GYM_LUNARLANDER;
+    h->is_lunar = cfg->kind == B200GYM_LUNARLANDER || cfg->kind == B200GYM_LUNARLANDER_CONT;
+    h->is_walker = cfg->kind == B200GYM_BIPEDALWALKER;
+    if (h->is_lunar) {  // LunarLander.__init__ arguments (lunar_lander.py:194-233)
+        h->lunar_opts.continuous = cfg->kind == B200GYM_LUNARLANDER_CONT;
+        h->lunar_opts.wind = (cfg->flags & B200GYM_LUNAR_ENABLE_WIND) != 0;
+        h->lunar_opts.gravity = (float)(cfg->param[0] == 0.0 ? -10.0 : cfg->param[0]);
+        h->lunar_opts.wind_power = cfg->param[1];
+        h->lunar_opts.turbulence_power = cfg->param[2];
+    }
+    if (h->is_lunar || h->is_walker) {
+        const bool lun = h->is_lunar;
         const size_t words = lun ? lunar::kWords : walker::kWords;
         if (cudaMalloc(&h->lunar_rec, sizeof(uint32_t) * words * n) != cudaSuccess ||
             cudaMemset(h->lunar_rec, 0, sizeof(uint32_t) * words * n) != cudaSuccess ||
@@ -1222,6 +1264,7 @@ static StepArgs make_args(b200gym *h, const void *actions, float *obs, double *r
     a.final_obs = final_obs;
     a.n = h->n; a.first = 0; a.count = h->n;
     a.max_steps = h->cfg.max_episode_steps; a.autoreset = h->cfg.autoreset; a.param0 = h->cfg.param[0];
+    a.lunar_opts = h->lunar_opts;
     a.npeer = 0;
     return a;
 }
@@ -1583,11 +1626,36 @@ extern "C" int b200gym_get_state(b200gym_t *h, double *state_dev, int32_t *elaps
 
 extern "C" int b200gym_lunar_get_bodies(b200gym_t *h, float *bodies_dev, int32_t *flags_dev, void *stream) {
     if (!h || !bodies_dev || !flags_dev) return fail(h, "b200gym_lunar_get_bodies: null argument");
-    if (h->cfg.kind != B200GYM_LUNARLANDER) return fail(h, "b200gym_lunar_get_bodies: not a LunarLander handle");
+    if (!h->is_lunar) return fail(h, "b200gym_lunar_get_bodies: not a LunarLander handle");
     DeviceGuard guard(h->device);
     lunar_bodies_kernel<<<blocks_for(h->n), kThreads, 0, (cudaStream_t)stream>>>(h->lunar_rec, h->elapsed, bodies_dev,
                                                                                  flags_dev, h->n);
     CK(h, cudaGetLastError());
+    return 0;
+}
+
+extern "C" int b200gym_lunar_wind_idx(b200gym_t *h, int32_t *wind_idx_host, int32_t *torque_idx_host, int set) {
+    if (!h || !wind_idx_host || !torque_idx_host) return fail(h, "b200gym_lunar_wind_idx: null argument");
+    if (!h->is_lunar) return fail(h, "b200gym_lunar_wind_idx: not a LunarLander handle");
+    DeviceGuard guard(h->device);
+    int32_t *d = nullptr;
+    const size_t bytes = sizeof(int32_t) * (size_t)h->n;
+    CK(h, cudaMalloc((void **)&d, 2 * bytes));
+    cudaError_t e = cudaSuccess;
+    if (set) {
+        e = cudaMemcpy(d, wind_idx_host, bytes, cudaMemcpyHostToDevice);
+        if (e == cudaSuccess) e = cudaMemcpy(d + h->n, torque_idx_host, bytes, cudaMemcpyHostToDevice);
+    }
+    if (e == cudaSuccess) {
+        lunar_wind_idx_kernel<<<blocks_for(h->n), kThreads>>>(h->lunar_rec, d, d + h->n, h->n, set);
+        e = cudaDeviceSynchronize();
+    }
+    if (e == cudaSuccess && !set) {
+        e = cudaMemcpy(wind_idx_host, d, bytes, cudaMemcpyDeviceToHost);
+        if (e == cudaSuccess) e = cudaMemcpy(torque_idx_host, d + h->n, bytes, cudaMemcpyDeviceToHost);
+    }
+    cudaFree(d);
+    if (e != cudaSuccess) return fail(h, "b200gym_lunar_wind_idx: %s", cudaGetErrorString(e));
     return 0;
 }
 

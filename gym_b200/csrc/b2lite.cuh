@@ -385,14 +385,16 @@ __device__ __noinline__ bool joint_solve_position(const Joint &j, const JointDef
 // ---- b2World::Step(1/50, 180, 60) for one env ------------------------------------------------------
 // Scene supplies: NB, NJ, kSlots, kMaxVC, World (with b[], j[], flags, slot_*), shape(b), jdef(k),
 // body_order(k), joint_order(k), edge(W, e, v1, v2, friction), edge_range(W, lox, hix, lo, hi),
-// on_event(W, body, begin).  `force0` is the force accumulated on body 0 before the step.
+// on_event(W, body, begin).  `force0` / `torque0` are the force and torque accumulated on body 0 before the
+// step (b2Body::ApplyForceToCenter / ApplyTorque), `gravity_y` the world's gravity (0, gravity_y).
 template <typename Scene>
-__device__ __noinline__ void world_step(typename Scene::World &W, v2 force0, bool &island_awake) {
+__device__ __noinline__ void world_step(typename Scene::World &W, v2 force0, float torque0, float gravity_y,
+                                        bool &island_awake) {
     constexpr int NB = Scene::NB, NJ = Scene::NJ, kSlots = Scene::kSlots, kMaxVC = Scene::kMaxVC;
     const float dt = (float)(1.0 / 50);
     const float inv_dt0 = (W.flags & kFlagStepped) ? 1.0f / dt : 0.0f;
     const float dtRatio = inv_dt0 * dt;
-    const v2 gravity = V(0.0f, -10.0f);
+    const v2 gravity = V(0.0f, gravity_y);
 
     // --- Collide + begin/end events; touching pairs become velocity constraints in island order
     VC vc[kMaxVC];
@@ -466,7 +468,7 @@ __device__ __noinline__ void world_step(typename Scene::World &W, v2 force0, boo
         float w = W.b[i].w;
         const v2 force = i == 0 ? force0 : V(0.0f, 0.0f);
         v = add(v, scl(dt, add(gravity, scl(sh.invMass, force))));
-        w = w + dt * sh.invI * 0.0f;
+        w = w + dt * sh.invI * (i == 0 ? torque0 : 0.0f);
         v = scl(1.0f / (1.0f + dt * 0.0f), v);
         w = w * (1.0f / (1.0f + dt * 0.0f));
         st[i].c = W.b[i].c; st[i].a = W.b[i].a; st[i].v = v; st[i].w = w;

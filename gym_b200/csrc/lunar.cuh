@@ -1,4 +1,5 @@
-// lunar.cuh -- LunarLander-v2 on the device (scene + environment logic on top of b2lite.cuh).
+// lunar.cuh -- LunarLander-v2 / LunarLanderContinuous-v2 on the device (scene + environment logic on top of
+// b2lite.cuh), with the constructor variants of the reference: continuous actions, gravity, wind.
 //
 // Reference: gym/envs/box2d/lunar_lander.py (reset :308-420, step :444-600, ContactDetector
 // :54-72).  Scene: lander (6-gon, density 5) + two legs (boxes, density 1) tied by two revolute
@@ -40,11 +41,21 @@ constexpr int W_TERRAIN = 31; // smooth_y[11]
 constexpr int W_FLAGS = 42;   // bit0 game_over, bit1/2 leg contact, bit3 has_prev_shaping, bit4 world has stepped
 constexpr int W_SHAPING = 43; // prev_shaping (double, 2 words)
 constexpr int W_SLOT = 45;    // kSlots x {key, id0, nI0, tI0, id1, nI1, tI1}
-constexpr int kWords = W_SLOT + 7 * kSlots;  // 101
+constexpr int W_WIND = W_SLOT + 7 * kSlots;  // wind_idx, torque_idx (int32; touched only when wind is enabled)
+constexpr int kWords = W_WIND + 2;           // 103
+
+// constructor arguments of LunarLander (lunar_lander.py:194-199), uniform over the batch
+struct Opts {
+    float gravity;           // b2World(gravity=(0, gravity)), :240
+    uint32_t continuous;     // :247
+    uint32_t wind;           // enable_wind, :233
+    double wind_power, turbulence_power;
+};
 
 struct World : WorldBase<NB, NJ, kSlots> {
     float terrain[NE];
     double prev_shaping;
+    int32_t wind_idx, torque_idx;   // :234-235, drawn once per env object, never reset
 };
 
 struct Scene {
@@ -68,44 +79,80 @@ struct Scene {
 };
 
 // ---- the environment ---------------------------------------------------------------------------
-// lunar_lander.py:444-600, discrete actions, no wind
-LD void env_step(World &W, Pcg64 &rng, int action, v2 lander_force, float (&obs)[8], double &reward, bool &terminated) {
+// lunar_lander.py:444-600.  `action` is the Discrete(4) action, `ca` the Box(2) float32 action of the
+// continuous variant.  In the continuous branch m_power / s_power / direction are numpy float32 scalars:
+// under NEP 50 every Python float they meet is rounded to float32 first, which is what the casts restate.
+LD void env_step(World &W, Pcg64 &rng, const Opts &O, int action, float ca0, float ca1, v2 lander_force,
+                 float (&obs)[8], double &reward, bool &terminated) {
     const double SCALE = 30.0, FPS = 50;
     const double VW = 600 / SCALE, VH = 400 / SCALE;
     Body &L = W.b[0];
     const ShapeConst &sh = kC.shape[0];
+    float torque = 0.0f;
+    if (O.wind && !(W.flags & 6u)) {                                             // :449-477
+        const double kPi = 3.141592653589793;
+        const double wind_mag = tanh(sin(0.02 * W.wind_idx) + sin(kPi * 0.01 * W.wind_idx)) * O.wind_power;
+        W.wind_idx += 1;
+        lander_force = add(lander_force, V((float)wind_mag, 0.0f));              // ApplyForceToCenter
+        const double torque_mag = tanh(sin(0.02 * W.torque_idx) + sin(kPi * 0.01 * W.torque_idx)) * O.turbulence_power;
+        W.torque_idx += 1;
+        torque += (float)torque_mag;                                             // ApplyTorque
+    }
     const double ang = (double)L.a;
     double tip0, tip1;
     sincos(ang, &tip0, &tip1);                                                   // :487
     const double side0 = -tip1, side1 = tip0;
     const double disp0 = bgym::pcg64_uniform(rng, -1.0, +1.0) / SCALE;          // :489
     const double disp1 = bgym::pcg64_uniform(rng, -1.0, +1.0) / SCALE;
-    double m_power = 0.0;
-    if (action == 2) {                                                           // :491-520
-        m_power = 1.0;
+    float a0 = 0.0f, a1 = 0.0f;
+    if (O.continuous) {                                                          // :480
+        a0 = ca0 < -1.0f ? -1.0f : (ca0 > 1.0f ? 1.0f : ca0);
+        a1 = ca1 < -1.0f ? -1.0f : (ca1 > 1.0f ? 1.0f : ca1);
+    }
+    double main_cost = 0.0, side_cost = 0.0;
+    if (O.continuous ? (a0 > 0.0f) : (action == 2)) {                           // :491-520
         const double ox = tip0 * (4 / SCALE + 2 * disp0) + side0 * disp1;
         const double oy = -tip1 * (4 / SCALE + 2 * disp0) - side1 * disp1;
-        const double px = (double)L.xf.p.x + ox, py = (double)L.xf.p.y + oy;
-        const v2 imp = V((float)(-ox * 13.0 * m_power), (float)(-oy * 13.0 * m_power));
-        const v2 pt = V((float)px, (float)py);
+        const v2 pt = V((float)((double)L.xf.p.x + ox), (float)((double)L.xf.p.y + oy));
+        v2 imp;
+        if (O.continuous) {
+            const float c = a0 < 0.0f ? 0.0f : (a0 > 1.0f ? 1.0f : a0);
+            const float m_power = (c + 1.0f) * 0.5f;                             // :497
+            imp = V((float)(-ox * 13.0) * m_power, (float)(-oy * 13.0) * m_power);
+            main_cost = (double)(m_power * 0.30f);
+        } else {
+            imp = V((float)(-ox * 13.0 * 1.0), (float)(-oy * 13.0 * 1.0));
+            main_cost = 1.0 * 0.30;
+        }
         L.v = add(L.v, scl(sh.invMass, imp));                                   // b2Body::ApplyLinearImpulse
         L.w += sh.invI * crs(sub(pt, L.c), imp);
     }
-    double s_power = 0.0;
-    if (action == 1 || action == 3) {                                            // :522-554
-        const double direction = action - 2;
-        s_power = 1.0;
-        const double ox = tip0 * disp0 + side0 * (3 * disp1 + direction * 12.0 / SCALE);
-        const double oy = -tip1 * disp0 - side1 * (3 * disp1 + direction * 12.0 / SCALE);
-        const double px = (double)L.xf.p.x + ox - tip0 * 17 / SCALE;
-        const double py = (double)L.xf.p.y + oy + tip1 * 14.0 / SCALE;
-        const v2 imp = V((float)(-ox * 0.6 * s_power), (float)(-oy * 0.6 * s_power));
-        const v2 pt = V((float)px, (float)py);
+    if (O.continuous ? (fabsf(a1) > 0.5f) : (action == 1 || action == 3)) {      // :522-554
+        v2 imp, pt;
+        if (O.continuous) {
+            const float direction = a1 > 0.0f ? 1.0f : -1.0f;                    // np.sign with |a1| > 0.5
+            const float ab = fabsf(a1);
+            const float s_power = ab < 0.5f ? 0.5f : (ab > 1.0f ? 1.0f : ab);
+            const float t = direction * 12.0f / 30.0f;
+            const float u = (float)(3 * disp1) + t;
+            const float ox = (float)(tip0 * disp0) + (float)side0 * u;
+            const float oy = (float)(-tip1 * disp0) - (float)side1 * u;
+            pt = V((L.xf.p.x + ox) - (float)(tip0 * 17 / SCALE), (L.xf.p.y + oy) + (float)(tip1 * 14.0 / SCALE));
+            imp = V((-ox * 0.6f) * s_power, (-oy * 0.6f) * s_power);
+            side_cost = (double)(s_power * 0.03f);
+        } else {
+            const double direction = action - 2;
+            const double ox = tip0 * disp0 + side0 * (3 * disp1 + direction * 12.0 / SCALE);
+            const double oy = -tip1 * disp0 - side1 * (3 * disp1 + direction * 12.0 / SCALE);
+            pt = V((float)((double)L.xf.p.x + ox - tip0 * 17 / SCALE), (float)((double)L.xf.p.y + oy + tip1 * 14.0 / SCALE));
+            imp = V((float)(-ox * 0.6 * 1.0), (float)(-oy * 0.6 * 1.0));
+            side_cost = 1.0 * 0.03;
+        }
         L.v = add(L.v, scl(sh.invMass, imp));
         L.w += sh.invI * crs(sub(pt, L.c), imp);
     }
     bool awake;
-    world_step<Scene>(W, lander_force, awake);                                          // :556
+    world_step<Scene>(W, lander_force, torque, O.gravity, awake);                                          // :556
     double st[8];
     const double helipad_y = VH / 4;
     st[0] = ((double)L.xf.p.x - VW / 2) / (VW / 2);                              // :560-569
@@ -122,8 +169,8 @@ LD void env_step(World &W, Pcg64 &rng, int action, v2 lander_force, float (&obs)
     if (W.flags & 8u) r = shaping - W.prev_shaping;                              // :581-583
     W.prev_shaping = shaping;
     W.flags |= 8u;
-    r -= m_power * 0.30;                                                         // :585-588
-    r -= s_power * 0.03;
+    r -= main_cost;                                                              // :585-588
+    r -= side_cost;
     bool term = false;
     if ((W.flags & 1u) || fabs(st[0]) >= 1.0) { term = true; r = -100; }         // :590-593
     if (!awake) { term = true; r = +100; }                                       // :594-596
@@ -134,7 +181,7 @@ LD void env_step(World &W, Pcg64 &rng, int action, v2 lander_force, float (&obs)
 }
 
 // lunar_lander.py:308-420 (the b2World object survives reset(): bit4 of flags is kept)
-LD void env_reset(World &W, Pcg64 &rng, float (&obs)[8]) {
+LD void env_reset(World &W, Pcg64 &rng, const Opts &O, float (&obs)[8]) {
     const double SCALE = 30.0;
     const double Wd = 600 / SCALE, Hd = 400 / SCALE;
     const uint32_t stepped = W.flags & 16u;
@@ -169,11 +216,11 @@ LD void env_reset(World &W, Pcg64 &rng, float (&obs)[8]) {
     const double fy = bgym::pcg64_uniform(rng, -1000.0, 1000.0);
     double r;
     bool t;
-    env_step(W, rng, 0, V((float)fx, (float)fy), obs, r, t);                     // :420
+    env_step(W, rng, O, 0, 0.0f, 0.0f, V((float)fx, (float)fy), obs, r, t);      // :420
 }
 
 // ---- HBM <-> registers/local ---------------------------------------------------------------------
-LD void load_world(World &W, const uint32_t *rec, int64_t n, int64_t i) {
+LD void load_world(World &W, const uint32_t *rec, int64_t n, int64_t i, bool wind) {
     auto ld = [&](int k) { return rec[(int64_t)k * n + i]; };
     for (int b = 0; b < NB; b++) {
         Body &B = W.b[b];
@@ -192,6 +239,8 @@ LD void load_world(World &W, const uint32_t *rec, int64_t n, int64_t i) {
     }
     for (int e = 0; e < NE; e++) W.terrain[e] = __uint_as_float(ld(W_TERRAIN + e));
     W.flags = ld(W_FLAGS);
+    W.wind_idx = wind ? (int32_t)ld(W_WIND) : 0;
+    W.torque_idx = wind ? (int32_t)ld(W_WIND + 1) : 0;
     W.prev_shaping = __longlong_as_double((long long)(((unsigned long long)ld(W_SHAPING + 1) << 32) | ld(W_SHAPING)));
     for (int s = 0; s < kSlots; s++) {
         W.slot_key[s] = ld(W_SLOT + 7 * s);
@@ -203,7 +252,7 @@ LD void load_world(World &W, const uint32_t *rec, int64_t n, int64_t i) {
     }
 }
 
-LD void store_world(const World &W, uint32_t *rec, int64_t n, int64_t i) {
+LD void store_world(const World &W, uint32_t *rec, int64_t n, int64_t i, bool wind) {
     auto st = [&](int k, uint32_t v) { rec[(int64_t)k * n + i] = v; };
     for (int b = 0; b < NB; b++) {
         const Body &B = W.b[b];
@@ -219,6 +268,7 @@ LD void store_world(const World &W, uint32_t *rec, int64_t n, int64_t i) {
     }
     for (int e = 0; e < NE; e++) st(W_TERRAIN + e, __float_as_uint(W.terrain[e]));
     st(W_FLAGS, W.flags);
+    if (wind) { st(W_WIND, (uint32_t)W.wind_idx); st(W_WIND + 1, (uint32_t)W.torque_idx); }
     const unsigned long long ps = (unsigned long long)__double_as_longlong(W.prev_shaping);
     st(W_SHAPING, (uint32_t)ps); st(W_SHAPING + 1, (uint32_t)(ps >> 32));
     for (int s = 0; s < kSlots; s++) {

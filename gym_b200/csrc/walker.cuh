@@ -143,7 +143,7 @@ __device__ __noinline__ void env_step(World &W, const float (&action)[4], bool f
         W.j[k].maxMotorTorque = 80.0f * clip01_abs(action[k]);
     }
     bool awake;
-    world_step<Scene>(W, hull_force, awake);                                     // :545
+    world_step<Scene>(W, hull_force, 0.0f, -10.0f, awake);                                     // :545
     const Body &H = W.b[0];
     const double posx = (double)H.xf.p.x, posy = (double)H.xf.p.y;
     double st[24];

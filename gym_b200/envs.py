@@ -5,6 +5,7 @@ an agent reads) and parse in ``reset(options=...)``; the dynamics themselves
 live in ``csrc/envs.cuh``.
 """
 import math
+import warnings
 
 import numpy as np
 
@@ -52,6 +53,11 @@ def _lunar_spaces(params):
     low = np.array([-1.5, -1.5, -5.0, -5.0, -math.pi, -5.0, -0.0, -0.0]).astype(np.float32)
     high = np.array([1.5, 1.5, 5.0, 5.0, math.pi, 5.0, 1.0, 1.0]).astype(np.float32)
     return Box(low, high), Discrete(4)
+
+
+def _lunar_cont_spaces(params):
+    # lunar_lander.py:285-287: Box(-1, +1, (2,), dtype=np.float32)
+    return _lunar_spaces(params)[0], Box(-1, +1, (2,), dtype=np.float32)
 
 
 def _walker_spaces(params):
@@ -105,6 +111,10 @@ KINDS = {
         "LunarLander", _lunar_spaces, {}, ("low", "high"), (0.0, 0.0),
         dict(continuous=False, gravity=-10.0, enable_wind=False, wind_power=15.0, turbulence_power=1.5),
         {"render_modes": [], "render_fps": 50}),
+    _lib.KIND_LUNARLANDER_CONT: KindInfo(
+        "LunarLander", _lunar_cont_spaces, {}, ("low", "high"), (0.0, 0.0),
+        dict(continuous=True, gravity=-10.0, enable_wind=False, wind_power=15.0, turbulence_power=1.5),
+        {"render_modes": [], "render_fps": 50}),
     _lib.KIND_BIPEDALWALKER: KindInfo(
         "BipedalWalker", _walker_spaces, {}, ("low", "high"), (0.0, 0.0), dict(hardcore=False),
         {"render_modes": [], "render_fps": 50}),
@@ -125,7 +135,8 @@ def parse_reset_bounds(kind, options):
     low/high kinds follow maybe_parse_reset_bounds (classic_control/utils.py:17-46);
     Pendulum follows pendulum.py:143-152 (x_init / y_init, symmetric limits).
     """
-    if options is None or kind in (_lib.KIND_LUNARLANDER, _lib.KIND_BIPEDALWALKER):  # their reset() ignores options
+    if options is None or kind in (_lib.KIND_LUNARLANDER, _lib.KIND_LUNARLANDER_CONT, _lib.KIND_BIPEDALWALKER):
+        # their reset() ignores options
         return None
     info = KINDS[kind]
     k0, k1 = info.bounds_keys
@@ -137,20 +148,43 @@ def parse_reset_bounds(kind, options):
     return (b0, b1)
 
 
+def resolve_variant(kind, kwargs):
+    """ctor kwargs (gym.make(id, **kwargs)) -> (kind, flags) of b200gym_config: `continuous=True` selects the
+    continuous-action kind (the reference registers it as LunarLanderContinuous-v2, gym/envs/__init__.py:62-68),
+    `enable_wind=True` sets the wind flag."""
+    flags = 0
+    if kind in (_lib.KIND_LUNARLANDER, _lib.KIND_LUNARLANDER_CONT):
+        if "continuous" in kwargs:
+            kind = _lib.KIND_LUNARLANDER_CONT if kwargs["continuous"] else _lib.KIND_LUNARLANDER
+        if kwargs.get("enable_wind", False):
+            flags |= _lib.LUNAR_ENABLE_WIND
+    return kind, flags
+
+
 def resolve_params(kind, kwargs):
     """ctor kwargs (gym.make(id, **kwargs)) -> the four doubles of b200gym_config.param."""
     info = KINDS[kind]
     params = [0.0, 0.0, 0.0, 0.0]
-    if kind == _lib.KIND_LUNARLANDER:
-        # lunar_lander.py:201-234: only the default (discrete, gravity=-10, no wind) variant is built
+    if kind in (_lib.KIND_LUNARLANDER, _lib.KIND_LUNARLANDER_CONT):
+        # LunarLander.__init__, lunar_lander.py:191-233
+        values = dict(info.attrs)
         for key, value in kwargs.items():
             if key == "render_mode" and value is None:
                 continue
+            if key in ("wind_idx", "torque_idx"):   # engine extension: see B200VectorEnv
+                continue
             if key not in info.attrs:
                 raise TypeError(f"LunarLander got an unexpected keyword argument '{key}'")
-            if info.attrs[key] != value and key in ("continuous", "gravity", "enable_wind"):
-                raise NotImplementedError(f"gym_b200 LunarLander supports only {key}={info.attrs[key]!r}")
-        return params
+            values[key] = value
+        gravity = float(values["gravity"])
+        assert -12.0 < gravity and gravity < 0.0, f"gravity (current value: {gravity}) must be between -12 and 0"
+        wind_power, turbulence_power = float(values["wind_power"]), float(values["turbulence_power"])
+        if 0.0 > wind_power or wind_power > 20.0:
+            warnings.warn(f"WARN: wind_power value is recommended to be between 0.0 and 20.0, (current value: {wind_power})")
+        if 0.0 > turbulence_power or turbulence_power > 2.0:
+            warnings.warn("WARN: turbulence_power value is recommended to be between 0.0 and 2.0, "
+                          f"(current value: {turbulence_power})")
+        return [gravity, wind_power, turbulence_power, 0.0]
     if kind == _lib.KIND_BIPEDALWALKER:
         for key, value in kwargs.items():
             if key == "render_mode" and value is None:

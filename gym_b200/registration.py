@@ -90,5 +90,7 @@ register("Acrobot-v1", _lib.KIND_ACROBOT, "gym.envs.classic_control.acrobot:Acro
          reward_threshold=-100.0, max_episode_steps=500)
 register("LunarLander-v2", _lib.KIND_LUNARLANDER, "gym.envs.box2d.lunar_lander:LunarLander",
          reward_threshold=200, max_episode_steps=1000)
+register("LunarLanderContinuous-v2", _lib.KIND_LUNARLANDER_CONT, "gym.envs.box2d.lunar_lander:LunarLander",
+         reward_threshold=200, max_episode_steps=1000, continuous=True)
 register("BipedalWalker-v3", _lib.KIND_BIPEDALWALKER, "gym.envs.box2d.bipedal_walker:BipedalWalker",
          reward_threshold=300, max_episode_steps=1600)

@@ -116,16 +116,16 @@ class B200VectorEnv:
         self.dense_infos = bool(dense_infos)
         self.closed = True  # until construction succeeds
         self._handle = None
-        self.kind = self.spec.kind
+        ctor_kwargs = dict(self.spec.kwargs)
+        ctor_kwargs.update(kwargs)
+        self.kind, cfg_flags = _envs.resolve_variant(self.spec.kind, ctor_kwargs)
         self._info = _envs.KINDS[self.kind]
         self.metadata = dict(self._info.metadata)
         self.render_mode = None
         self.reward_range = (-float("inf"), float("inf"))
 
-        ctor_kwargs = dict(self.spec.kwargs)
-        ctor_kwargs.update(kwargs)
         params = _envs.resolve_params(self.kind, ctor_kwargs)
-        self.env_kwargs = {k: v for k, v in ctor_kwargs.items() if k != "render_mode"}
+        self.env_kwargs = {k: v for k, v in ctor_kwargs.items() if k not in ("render_mode", "wind_idx", "torque_idx")}
         mes = self.spec.max_episode_steps if max_episode_steps is None else max_episode_steps
         self.max_episode_steps = None if (mes is None or int(mes) <= 0) else int(mes)
 
@@ -153,7 +153,7 @@ class B200VectorEnv:
         with torch.cuda.device(self.device):
             torch.empty(1, device=self.device)  # make sure the primary context exists
             cfg = _lib.Config(kind=self.kind, max_episode_steps=self.max_episode_steps or 0,
-                              autoreset=1 if autoreset else 0, reserved=0)
+                              autoreset=1 if autoreset else 0, flags=cfg_flags)
             for k in range(4):
                 cfg.param[k] = params[k]
             handle = ctypes.c_void_p()
@@ -161,6 +161,16 @@ class B200VectorEnv:
         self._lib = lib
         self._handle = handle
         self.autoreset = bool(autoreset)
+        if cfg_flags & _lib.LUNAR_ENABLE_WIND:
+            # LunarLander.__init__ draws wind_idx, then torque_idx, from numpy's GLOBAL generator, once per env
+            # object (lunar_lander.py:234-235); SyncVectorEnv builds the objects in index order.  `wind_idx=` /
+            # `torque_idx=` (ints or arrays) pin them instead -- an engine extension for reproducible runs.
+            draws = np.random.randint(-9999, 9999, size=2 * self.num_envs).reshape(self.num_envs, 2)
+            wind = np.ascontiguousarray(np.broadcast_to(ctor_kwargs.get("wind_idx", draws[:, 0]), (self.num_envs,)),
+                                        dtype=np.int32)
+            torque = np.ascontiguousarray(np.broadcast_to(ctor_kwargs.get("torque_idx", draws[:, 1]), (self.num_envs,)),
+                                          dtype=np.int32)
+            _lib.check(lib.b200gym_lunar_wind_idx(handle, wind.ctypes.data, torque.ctypes.data, 1), handle)
         self.closed = False
         self._seeded = False
         self._has_reset = False
@@ -455,6 +465,15 @@ class B200VectorEnv:
                                                       ctypes.c_void_p(flags.data_ptr()), self._stream()), self._handle)
         return bodies.view(self.num_envs, 3, 6), flags
 
+    def lunar_wind_idx(self):
+        """LunarLander(enable_wind=True) only: the per-env (wind_idx, torque_idx) int32 arrays
+        (lunar_lander.py:234-235,461,472), read back from the device."""
+        self._assert_open("lunar_wind_idx")
+        wind = np.zeros(self.num_envs, dtype=np.int32)
+        torque = np.zeros(self.num_envs, dtype=np.int32)
+        _lib.check(self._lib.b200gym_lunar_wind_idx(self._handle, wind.ctypes.data, torque.ctypes.data, 0), self._handle)
+        return wind, torque
+
     def walker_bodies(self):
         """BipedalWalker only: (bodies float32 (N, 5, 6) of hull, leg(-1), lower(-1), leg(+1), lower(+1);
         flags int32 (N, 4) = {game_over, legs[1] contact, legs[3] contact, #touching contacts})."""
@@ -495,6 +514,8 @@ class B200VectorEnv:
 
     def call_wait(self, timeout=None):
         name, args, kwargs = self._call
+        if name in ("wind_idx", "torque_idx") and self.env_kwargs.get("enable_wind", False):
+            return tuple(int(v) for v in self.lunar_wind_idx()[name == "torque_idx"])
         value = self._attr(name)
         return tuple([value] * self.num_envs)
 

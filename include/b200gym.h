@@ -42,8 +42,13 @@ enum b200gym_kind {
                                      arithmetic it delegates to is re-derived in csrc/lunar.cuh */
     B200GYM_BIPEDALWALKER = 6,    /* gym/envs/box2d/bipedal_walker.py:277-606 (non-hardcore); Box2D arithmetic
                                      re-derived in csrc/b2lite.cuh */
-    B200GYM_NUM_KINDS = 7
+    B200GYM_LUNARLANDER_CONT = 7, /* LunarLanderContinuous-v2 = LunarLander(continuous=True), gym/envs/__init__.py:71-77,
+                                     lunar_lander.py:152-160,479-481,496-533: Box(2) float32 actions */
+    B200GYM_NUM_KINDS = 8
 };
+
+/* b200gym_config.flags */
+#define B200GYM_LUNAR_ENABLE_WIND 1 /* LunarLander(enable_wind=True), lunar_lander.py:449-477 */
 
 /* dtype codes for the `actions` argument of b200gym_step */
 enum b200gym_action_dtype {
@@ -62,9 +67,12 @@ typedef struct b200gym_config {
     int32_t max_episode_steps; /* TimeLimit (gym/wrappers/time_limit.py:39-68); <= 0: no limit */
     int32_t autoreset;         /* 1: SyncVectorEnv same-step autoreset (gym/vector/sync_vector_env.py:152-156);
                                   0: plain Env semantics (state keeps evolving after termination) */
-    int32_t reserved;
+    int32_t flags;             /* B200GYM_LUNAR_ENABLE_WIND, else 0 */
     double param[4];           /* param[0]: Pendulum `g` (pendulum.py:95), MountainCar* `goal_velocity`
-                                  (mountain_car.py:103, continuous_mountain_car.py:108) */
+                                  (mountain_car.py:103, continuous_mountain_car.py:108), LunarLander* `gravity`
+                                  (lunar_lander.py:195,210-213; 0 = the default -10.0; must lie in (-12, 0));
+                                  param[1], param[2]: LunarLander* `wind_power`, `turbulence_power`
+                                  (lunar_lander.py:197-198), read only with B200GYM_LUNAR_ENABLE_WIND */
 } b200gym_config;
 
 typedef struct b200gym b200gym_t;
@@ -195,6 +203,14 @@ int b200gym_set_state(b200gym_t *h, const double *state_dev, const int32_t *elap
  * awake, elapsed, #touching contacts} -- what `env.lander.position` etc. expose in the reference.
  */
 int b200gym_lunar_get_bodies(b200gym_t *h, float *bodies_dev, int32_t *flags_dev, void *stream);
+/*
+ * LunarLander with B200GYM_LUNAR_ENABLE_WIND: the per-env wind phase counters.  Replaces
+ * `self.wind_idx = np.random.randint(-9999, 9999)` / `self.torque_idx = ...` of LunarLander.__init__
+ * (lunar_lander.py:234-235; drawn from numpy's GLOBAL generator, once per env object, advanced by one per windy
+ * step and never reset): the caller draws them and hands them over.  set != 0: copy the two host arrays [n] into
+ * the env state; set == 0: read them back.  Synchronous.
+ */
+int b200gym_lunar_wind_idx(b200gym_t *h, int32_t *wind_idx_host, int32_t *torque_idx_host, int set);
 /* BipedalWalker: float32 [n][30] = 5 x {c.x, c.y, angle, v.x, v.y, omega} (hull, leg(-1), lower(-1), leg(+1),
  * lower(+1)) and int32 [n][4] = {game_over, legs[1] contact, legs[3] contact, #touching contacts}. */
 int b200gym_walker_get_bodies(b200gym_t *h, float *bodies_dev, int32_t *flags_dev, void *stream);

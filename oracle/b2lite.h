@@ -101,6 +101,11 @@ typedef struct {
 
 typedef struct { v2 v1, v2; float friction; } edge_t;
 
+/* a static 4-gon (fixture of a static body at the identity transform): BipedalWalkerHardcore's stumps, stair steps
+ * and pit walls.  verts / normals as b2PolygonShape::Set leaves them for an axis-aligned box. */
+#define B2L_MAX_SPOLY 40
+typedef struct { int count; v2 verts[4], normals[4]; float friction; } spoly_t;
+
 typedef struct {
     v2 localPoint;
     float normalImpulse, tangentImpulse;
@@ -135,9 +140,13 @@ typedef struct {
     joint_t *j;
     const edge_t *e;
     contact_t *ct;
+    int np, np_cap;          /* static polygons in use / row stride of ctp */
+    const spoly_t *sp;
+    contact_t *ctp;          /* [nb][np_cap] contact table of the (body, static polygon) pairs */
     const int *body_order;   /* island order of the bodies (contacts are built in this order) */
     const int *joint_order;  /* island order of the joints */
     float inv_dt0;
+    float gravity_y;         /* b2World gravity = (0, gravity_y) */
     int awake;               /* out: 0 when the island went to sleep in this step */
     void (*event)(void *ctx, int body, int begin); /* Begin/EndContact listener */
     void *ctx;
@@ -365,6 +374,168 @@ static int contact_update(contact_t *c, const edge_t *e, const body_t *b)
     return touching - was;
 }
 
+/* ---------------------------------------------------------------- static polygons (b2CollidePolygons, v2.3.1+) */
+/* b2PolygonShape::Set on the four corners of an axis-aligned box: the gift wrapping starts at the right-most
+ * (lowest) corner and runs counter-clockwise; normals = normalised b2Cross(edge, 1). */
+static void spoly_set_box(spoly_t *s, float x0, float ylo, float x1, float yhi, float friction)
+{
+    s->count = 4;
+    s->verts[0] = V(x1, ylo); s->verts[1] = V(x1, yhi); s->verts[2] = V(x0, yhi); s->verts[3] = V(x0, ylo);
+    for (int i = 0; i < 4; i++) {
+        int i2 = i + 1 < 4 ? i + 1 : 0;
+        v2 edge = sub(s->verts[i2], s->verts[i]);
+        v2 nr = crs_vs(edge, 1.0f);
+        float len = sqrtf(nr.x * nr.x + nr.y * nr.y);
+        float inv = 1.0f / len;
+        s->normals[i] = V(inv * nr.x, inv * nr.y);
+    }
+    s->friction = friction;
+}
+
+static inline rot rot_mulT(rot q, rot r) { rot o; o.s = q.c * r.s - q.s * r.c; o.c = q.c * r.c + q.s * r.s; return o; }
+static inline xform xf_mulT(xform A, xform B) { xform C; C.q = rot_mulT(A.q, B.q); C.p = rmulT(A.q, sub(B.p, A.p)); return C; }
+
+/* b2FindMaxSeparation(poly1, xf1, poly2, xf2) */
+static float find_max_separation(int *edgeIndex, int count1, const v2 *n1s, const v2 *v1s, xform xf1, int count2,
+                                 const v2 *v2s, xform xf2)
+{
+    xform xf = xf_mulT(xf2, xf1);
+    int bestIndex = 0;
+    float maxSeparation = -3.402823466e+38f;
+    for (int i = 0; i < count1; i++) {
+        v2 n = rmul(xf.q, n1s[i]);
+        v2 v1 = xmul(xf, v1s[i]);
+        float si = 3.402823466e+38f;
+        for (int j = 0; j < count2; j++) { float sij = dot(n, sub(v2s[j], v1)); if (sij < si) si = sij; }
+        if (si > maxSeparation) { maxSeparation = si; bestIndex = i; }
+    }
+    *edgeIndex = bestIndex;
+    return maxSeparation;
+}
+
+/* b2CollidePolygons(manifold, polyA = static polygon at the identity, polyB = body polygon) */
+static void collide_polygons(manifold_t *m, const spoly_t *A, const body_t *B)
+{
+    static const xform XFI = {{0.0f, 0.0f}, {0.0f, 1.0f}};
+    const xform xfA = XFI, xfB = B->xf;
+    m->pointCount = 0;
+    const float totalRadius = POLYGON_RADIUS + POLYGON_RADIUS;
+    int edgeA = 0, edgeB = 0;
+    float separationA = find_max_separation(&edgeA, A->count, A->normals, A->verts, xfA, B->count, B->verts, xfB);
+    if (separationA > totalRadius) return;
+    float separationB = find_max_separation(&edgeB, B->count, B->normals, B->verts, xfB, A->count, A->verts, xfA);
+    if (separationB > totalRadius) return;
+    const v2 *verts1, *normals1, *verts2, *normals2;
+    int count1, count2, edge1, flip;
+    xform xf1, xf2;
+    const float k_tol = 0.1f * LINEAR_SLOP;
+    if (separationB > separationA + k_tol) {
+        verts1 = B->verts; normals1 = B->normals; count1 = B->count; verts2 = A->verts; normals2 = A->normals; count2 = A->count;
+        xf1 = xfB; xf2 = xfA; edge1 = edgeB; m->type = 1; flip = 1;
+    } else {
+        verts1 = A->verts; normals1 = A->normals; count1 = A->count; verts2 = B->verts; normals2 = B->normals; count2 = B->count;
+        xf1 = xfA; xf2 = xfB; edge1 = edgeA; m->type = 0; flip = 0;
+    }
+    /* b2FindIncidentEdge */
+    clipv_t ie[2];
+    {
+        v2 normal1 = rmulT(xf2.q, rmul(xf1.q, normals1[edge1]));
+        int index = 0;
+        float minDot = 3.402823466e+38f;
+        for (int i = 0; i < count2; i++) { float d = dot(normal1, normals2[i]); if (d < minDot) { minDot = d; index = i; } }
+        int i1 = index, i2 = i1 + 1 < count2 ? i1 + 1 : 0;
+        ie[0].v = xmul(xf2, verts2[i1]); ie[0].id = ID(edge1, i1, F_FACE, F_VERTEX);
+        ie[1].v = xmul(xf2, verts2[i2]); ie[1].id = ID(edge1, i2, F_FACE, F_VERTEX);
+    }
+    int iv1 = edge1, iv2 = edge1 + 1 < count1 ? edge1 + 1 : 0;
+    v2 v11 = verts1[iv1], v12 = verts1[iv2];
+    v2 localTangent = sub(v12, v11);
+    {
+        float len = sqrtf(localTangent.x * localTangent.x + localTangent.y * localTangent.y);
+        if (len >= 1.1920929e-07f) { float inv = 1.0f / len; localTangent.x *= inv; localTangent.y *= inv; }
+    }
+    v2 localNormal = crs_vs(localTangent, 1.0f);
+    v2 planePoint = scl(0.5f, add(v11, v12));
+    v2 tangent = rmul(xf1.q, localTangent);
+    v2 normal = crs_vs(tangent, 1.0f);
+    v11 = xmul(xf1, v11); v12 = xmul(xf1, v12);
+    float frontOffset = dot(normal, v11);
+    float sideOffset1 = -dot(tangent, v11) + totalRadius;
+    float sideOffset2 = dot(tangent, v12) + totalRadius;
+    clipv_t c1[2], c2[2];
+    if (clip_segment(c1, ie, neg(tangent), sideOffset1, iv1) < 2) return;
+    if (clip_segment(c2, c1, tangent, sideOffset2, iv2) < 2) return;
+    m->localNormal = localNormal;
+    m->localPoint = planePoint;
+    int pc = 0;
+    for (int i = 0; i < 2; i++) {
+        float separation = dot(normal, c2[i].v) - frontOffset;
+        if (separation <= totalRadius) {
+            mpoint_t *cp = &m->pts[pc];
+            cp->localPoint = xmulT(xf2, c2[i].v);
+            uint32_t id = c2[i].id;
+            cp->id = flip ? ID((id >> 8) & 0xff, id & 0xff, (id >> 24) & 0xff, (id >> 16) & 0xff) : id;
+            pc++;
+        }
+    }
+    m->pointCount = pc;
+}
+
+/* b2Contact::Update for one (body, static polygon) pair; returns +1 on BeginContact, -1 on EndContact */
+static int contact_update_poly(contact_t *c, const spoly_t *sp, const body_t *b)
+{
+    manifold_t old = c->m;
+    int was = c->touching;
+    float lox = 3.402823466e+38f, loy = lox, hix = -lox, hiy = -lox;
+    for (int i = 0; i < b->count; i++) {
+        v2 p = xmul(b->xf, b->verts[i]);
+        lox = fminf_(lox, p.x); loy = fminf_(loy, p.y); hix = fmaxf_(hix, p.x); hiy = fmaxf_(hiy, p.y);
+    }
+    const float ext = POLYGON_RADIUS + AABB_EXTENSION;
+    /* verts: 0 (x1, ylo), 2 (x0, yhi) */
+    float elox = sp->verts[2].x - ext, ehix = sp->verts[0].x + ext, eloy = sp->verts[0].y - ext, ehiy = sp->verts[2].y + ext;
+    c->m.pointCount = 0;
+    if (!(lox - ext > ehix || elox > hix + ext || loy - ext > ehiy || eloy > hiy + ext))
+        collide_polygons(&c->m, sp, b);
+    int touching = c->m.pointCount > 0;
+    for (int i = 0; i < c->m.pointCount; i++) {
+        mpoint_t *mp2 = &c->m.pts[i];
+        mp2->normalImpulse = 0.0f;
+        mp2->tangentImpulse = 0.0f;
+        if (was)
+            for (int j = 0; j < old.pointCount; j++)
+                if (old.pts[j].id == mp2->id) {
+                    mp2->normalImpulse = old.pts[j].normalImpulse;
+                    mp2->tangentImpulse = old.pts[j].tangentImpulse;
+                    break;
+                }
+    }
+    c->touching = touching;
+    return touching - was;
+}
+
+/* b2PolygonShape::RayCast against a static polygon at the identity transform; returns 1 and *t on a hit */
+static int spoly_raycast(const spoly_t *s, v2 p1_, v2 p2_, float maxFraction, float *t_out)
+{
+    static const xform XFI = {{0.0f, 0.0f}, {0.0f, 1.0f}};
+    v2 p1 = rmulT(XFI.q, sub(p1_, XFI.p)), p2 = rmulT(XFI.q, sub(p2_, XFI.p));
+    v2 d = sub(p2, p1);
+    float lower = 0.0f, upper = maxFraction;
+    int index = -1;
+    for (int i = 0; i < s->count; i++) {
+        float numerator = dot(s->normals[i], sub(s->verts[i], p1));
+        float denominator = dot(s->normals[i], d);
+        if (denominator == 0.0f) { if (numerator < 0.0f) return 0; }
+        else {
+            if (denominator < 0.0f && numerator < lower * denominator) { lower = numerator / denominator; index = i; }
+            else if (denominator > 0.0f && numerator < upper * denominator) upper = numerator / denominator;
+        }
+        if (upper < lower) return 0;
+    }
+    if (index >= 0) { *t_out = lower; return 1; }
+    return 0;
+}
+
 /* ---------------------------------------------------------------- contact solver (b2ContactSolver) */
 typedef struct { v2 rA, rB; float normalImpulse, tangentImpulse, normalMass, tangentMass, velocityBias; } vcp_t;
 typedef struct {
@@ -546,13 +717,17 @@ static void b2l_step(b2l_world *W, float dt, int velIters, int posIters)
 {
     const float inv_dt = 1.0f / dt;
     const float dtRatio = W->inv_dt0 * dt;
-    const v2 gravity = V(0.0f, -10.0f);
+    const v2 gravity = V(0.0f, W->gravity_y);
     /* --- Collide: update manifolds, begin/end events (the env's ContactDetector);
      *     pairs are visited in the same (island) order the constraints are built in */
     const int NB = W->nb, NE = W->ne;
     const int *order = W->body_order, *jorder = W->joint_order;
     for (int oi = 0; oi < NB; oi++) {
         int b = order[oi];
+        for (int p = W->np - 1; p >= 0; p--) {  /* static polygons first (descending), then the edges */
+            int ev = contact_update_poly(&W->ctp[b * W->np_cap + p], &W->sp[p], &W->b[b]);
+            if (ev != 0 && W->event) W->event(W->ctx, b, ev > 0);
+        }
         for (int e = NE - 1; e >= 0; e--) {
             int ev = contact_update(&W->ct[b * NE + e], &W->e[e], &W->b[b]);
             if (ev != 0 && W->event) W->event(W->ctx, b, ev > 0);
@@ -575,12 +750,15 @@ static void b2l_step(b2l_world *W, float dt, int velIters, int posIters)
     int nvc = 0;
     for (int oi = 0; oi < NB; oi++) {
         int b = order[oi];
-        for (int e = NE - 1; e >= 0; e--) {
-            contact_t *c = &W->ct[b * NE + e];
+        for (int f = 0; f < W->np + NE; f++) {
+            /* f < np: polygon np-1-f; else edge NE-1-(f-np) */
+            const int isp = f < W->np;
+            const int e = isp ? W->np - 1 - f : NE - 1 - (f - W->np);
+            contact_t *c = isp ? &W->ctp[b * W->np_cap + e] : &W->ct[b * NE + e];
             if (!c->touching || nvc >= B2L_MAX_CONTACTS) continue;
             vc_t *k = &vc[nvc++];
-            k->body = b; k->edge = e; k->m = &c->m; k->pointCount = c->m.pointCount;
-            k->friction = sqrtf(W->e[e].friction * W->b[b].friction);
+            k->body = b; k->edge = isp ? NE + e : e; k->m = &c->m; k->pointCount = c->m.pointCount;
+            k->friction = sqrtf((isp ? W->sp[e].friction : W->e[e].friction) * W->b[b].friction);
             for (int p = 0; p < k->pointCount; p++) {
                 k->p[p].normalImpulse = dtRatio * c->m.pts[p].normalImpulse;
                 k->p[p].tangentImpulse = dtRatio * c->m.pts[p].tangentImpulse;

@@ -47,11 +47,18 @@ typedef struct {
     double prev_shaping, helipad_y;
     pcg64_t rng;
     int32_t elapsed;
+    int32_t wind_idx, torque_idx; /* lunar_lander.py:234-235: drawn once per env object, never reset */
 } world_t;
+
+typedef struct {
+    int continuous, enable_wind;              /* lunar_lander.py:194-199 */
+    double gravity, wind_power, turbulence_power;
+} opts_t;
 
 struct orc_lunar {
     int64_t n;
     int max_steps;
+    opts_t o;
     world_t *w;
 };
 
@@ -64,14 +71,16 @@ static void lunar_event(void *ctx, int body, int begin)
 }
 
 /* world.Step(1/50, 180, 60): island order {leg+1, lander, leg-1}, joint of leg+1 first */
-static int world_step(world_t *W, float dt, int velIters, int posIters)
+static int world_step(world_t *W, float gravity_y, float dt, int velIters, int posIters)
 {
     static const int order[NB] = {2, 0, 1}, jorder[2] = {1, 0};
     b2l_world S;
     S.nb = NB; S.nj = 2; S.ne = NE;
     S.b = W->b; S.j = W->j; S.e = W->e; S.ct = W->ct;
     S.body_order = order; S.joint_order = jorder;
+    S.np = 0; S.np_cap = 0; S.sp = NULL; S.ctp = NULL;
     S.inv_dt0 = W->inv_dt0;
+    S.gravity_y = gravity_y;
     S.event = lunar_event; S.ctx = W;
     b2l_step(&S, dt, velIters, posIters);
     W->inv_dt0 = S.inv_dt0;
@@ -94,17 +103,18 @@ static int world_step(world_t *W, float dt, int velIters, int posIters)
 #define SIDE_ENGINE_HEIGHT 14.0
 #define SIDE_ENGINE_AWAY 12.0
 
-static void lunar_step_one(world_t *W, int action, float *obs, double *reward, int *terminated);
+static void lunar_step_one(world_t *W, const opts_t *O, int action, const float *caction, float *obs, double *reward,
+                           int *terminated);
 
 /* lunar_lander.py:308-420 */
-static void lunar_reset_one(world_t *W, float *obs)
+static void lunar_reset_one(world_t *W, const opts_t *O, float *obs)
 {
     pcg64_t rng = W->rng;
-    int32_t elapsed_dummy = 0;
     float inv_dt0 = W->inv_dt0; /* the b2World object survives reset() */
+    int32_t wind_idx = W->wind_idx, torque_idx = W->torque_idx;
     memset(W, 0, sizeof *W);
     W->inv_dt0 = inv_dt0;
-    (void)elapsed_dummy;
+    W->wind_idx = wind_idx; W->torque_idx = torque_idx;
     const double Wd = VIEWPORT_W / SCALE, Hd = VIEWPORT_H / SCALE;
     enum { CHUNKS = 11 };
     double height[CHUNKS + 1], chunk_x[CHUNKS], smooth_y[CHUNKS];
@@ -160,47 +170,109 @@ static void lunar_reset_one(world_t *W, float *obs)
     W->elapsed = 0;
     double r;
     int t;
-    lunar_step_one(W, 0, obs, &r, &t);                                                     /* :420 */
+    const float zero[2] = {0.0f, 0.0f};
+    lunar_step_one(W, O, 0, zero, obs, &r, &t);                                            /* :420 */
 }
 
-/* lunar_lander.py:444-600 (discrete actions, no wind) */
-static void lunar_step_one(world_t *W, int action, float *obs, double *reward, int *terminated)
+/* The two engines of lunar_lander.py:486-554: impulse on the lander and its application point, both as the
+ * float32 pairs Box2D receives.  The discrete branch is Python-float (f64) arithmetic rounded once on entry
+ * to Box2D; in the continuous branch m_power / s_power / direction are numpy float32 scalars and, under
+ * NEP 50 (numpy >= 2), every Python float they meet is first rounded to float32 -- the roundings below
+ * are pinned against numpy itself by tests/test_oracle_box2d.py. */
+typedef struct {
+    int main_on, side_on;
+    v2 main_imp, main_pt, side_imp, side_pt;
+    double main_cost, side_cost;   /* m_power * 0.30, s_power * 0.03 as added to the reward (:585-588) */
+} engines_t;
+
+static void lunar_engines(engines_t *E, int continuous, int action, const float *ca, double ang, double posx, double posy,
+                          double disp0, double disp1)
 {
-    body_t *L = &W->b[0];
-    double ang = (double)L->a;
     double tip0 = sin(ang), tip1 = cos(ang);                                               /* :487 */
     double side0 = -tip1, side1 = tip0;
-    double disp0 = rng_uniform(&W->rng, -1.0, +1.0) / SCALE;                               /* :489 */
-    double disp1 = rng_uniform(&W->rng, -1.0, +1.0) / SCALE;
-    double m_power = 0.0;
-    if (action == 2) {                                                                     /* :491-520 */
-        m_power = 1.0;
+    memset(E, 0, sizeof *E);
+    float a0 = 0.0f, a1 = 0.0f;
+    if (continuous) {                                                                      /* :480 */
+        a0 = ca[0] < -1.0f ? -1.0f : (ca[0] > 1.0f ? 1.0f : ca[0]);
+        a1 = ca[1] < -1.0f ? -1.0f : (ca[1] > 1.0f ? 1.0f : ca[1]);
+    }
+    if (continuous ? (a0 > 0.0f) : (action == 2)) {                                        /* :491-520 */
         double ox = tip0 * (4 / SCALE + 2 * disp0) + side0 * disp1;
         double oy = -tip1 * (4 / SCALE + 2 * disp0) - side1 * disp1;
-        double px = (double)L->xf.p.x + ox, py = (double)L->xf.p.y + oy;
-        v2 imp = V((float)(-ox * MAIN_ENGINE_POWER * m_power), (float)(-oy * MAIN_ENGINE_POWER * m_power));
-        v2 pt = V((float)px, (float)py);
-        if (L->awake) { /* b2Body::ApplyLinearImpulse */
-            L->v = add(L->v, scl(L->invMass, imp));
-            L->w += L->invI * crs(sub(pt, L->c), imp);
+        E->main_on = 1;
+        E->main_pt = V((float)(posx + ox), (float)(posy + oy));
+        if (continuous) {
+            float c = a0 < 0.0f ? 0.0f : (a0 > 1.0f ? 1.0f : a0);
+            float m_power = (c + 1.0f) * 0.5f;                                             /* :497, float32 */
+            E->main_imp = V((float)(-ox * MAIN_ENGINE_POWER) * m_power, (float)(-oy * MAIN_ENGINE_POWER) * m_power);
+            E->main_cost = (double)(m_power * 0.30f);
+        } else {
+            E->main_imp = V((float)(-ox * MAIN_ENGINE_POWER * 1.0), (float)(-oy * MAIN_ENGINE_POWER * 1.0));
+            E->main_cost = 1.0 * 0.30;
         }
     }
-    double s_power = 0.0;
-    if (action == 1 || action == 3) {                                                      /* :522-554 */
-        double direction = action - 2;
-        s_power = 1.0;
-        double ox = tip0 * disp0 + side0 * (3 * disp1 + direction * SIDE_ENGINE_AWAY / SCALE);
-        double oy = -tip1 * disp0 - side1 * (3 * disp1 + direction * SIDE_ENGINE_AWAY / SCALE);
-        double px = (double)L->xf.p.x + ox - tip0 * 17 / SCALE;
-        double py = (double)L->xf.p.y + oy + tip1 * SIDE_ENGINE_HEIGHT / SCALE;
-        v2 imp = V((float)(-ox * SIDE_ENGINE_POWER * s_power), (float)(-oy * SIDE_ENGINE_POWER * s_power));
-        v2 pt = V((float)px, (float)py);
-        if (L->awake) {
-            L->v = add(L->v, scl(L->invMass, imp));
-            L->w += L->invI * crs(sub(pt, L->c), imp);
+    if (continuous ? (fabsf(a1) > 0.5f) : (action == 1 || action == 3)) {                  /* :522-554 */
+        E->side_on = 1;
+        if (continuous) {
+            float direction = a1 > 0.0f ? 1.0f : -1.0f;                                    /* np.sign, |a1| > 0.5 */
+            float ab = fabsf(a1);
+            float s_power = ab < 0.5f ? 0.5f : (ab > 1.0f ? 1.0f : ab);
+            float t = direction * 12.0f / 30.0f;
+            float u = (float)(3 * disp1) + t;
+            float ox = (float)(tip0 * disp0) + (float)side0 * u;
+            float oy = (float)(-tip1 * disp0) - (float)side1 * u;
+            E->side_pt = V(((float)posx + ox) - (float)(tip0 * 17 / SCALE), ((float)posy + oy) + (float)(tip1 * SIDE_ENGINE_HEIGHT / SCALE));
+            E->side_imp = V((-ox * 0.6f) * s_power, (-oy * 0.6f) * s_power);
+            E->side_cost = (double)(s_power * 0.03f);
+        } else {
+            double direction = action - 2;
+            double ox = tip0 * disp0 + side0 * (3 * disp1 + direction * SIDE_ENGINE_AWAY / SCALE);
+            double oy = -tip1 * disp0 - side1 * (3 * disp1 + direction * SIDE_ENGINE_AWAY / SCALE);
+            E->side_pt = V((float)(posx + ox - tip0 * 17 / SCALE), (float)(posy + oy + tip1 * SIDE_ENGINE_HEIGHT / SCALE));
+            E->side_imp = V((float)(-ox * SIDE_ENGINE_POWER * 1.0), (float)(-oy * SIDE_ENGINE_POWER * 1.0));
+            E->side_cost = 1.0 * 0.03;
         }
     }
-    int awake = world_step(W, (float)(1.0 / FPS), 6 * 30, 2 * 30);                         /* :556 */
+}
+
+/* test hook: the engine arithmetic alone (out = main imp.x, imp.y, pt.x, pt.y, side imp.x, imp.y, pt.x, pt.y) */
+void orc_lunar_engines(int continuous, int action, const float *caction, double ang, double posx, double posy,
+                       double disp0, double disp1, float out[8], double cost[2], int32_t on[2])
+{
+    engines_t E;
+    lunar_engines(&E, continuous, action, caction, ang, posx, posy, disp0, disp1);
+    out[0] = E.main_imp.x; out[1] = E.main_imp.y; out[2] = E.main_pt.x; out[3] = E.main_pt.y;
+    out[4] = E.side_imp.x; out[5] = E.side_imp.y; out[6] = E.side_pt.x; out[7] = E.side_pt.y;
+    cost[0] = E.main_cost; cost[1] = E.side_cost;
+    on[0] = E.main_on; on[1] = E.side_on;
+}
+
+/* lunar_lander.py:444-600 */
+static void lunar_step_one(world_t *W, const opts_t *O, int action, const float *caction, float *obs, double *reward,
+                           int *terminated)
+{
+    body_t *L = &W->b[0];
+    if (O->enable_wind && !(W->leg_contact[0] || W->leg_contact[1])) {                     /* :449-477 */
+        double wind_mag = tanh(sin(0.02 * W->wind_idx) + sin(M_PI * 0.01 * W->wind_idx)) * O->wind_power;
+        W->wind_idx += 1;
+        L->force = add(L->force, V((float)wind_mag, 0.0f));                                /* ApplyForceToCenter */
+        double torque_mag = tanh(sin(0.02 * W->torque_idx) + sin(M_PI * 0.01 * W->torque_idx)) * O->turbulence_power;
+        W->torque_idx += 1;
+        L->torque += (float)torque_mag;                                                    /* ApplyTorque */
+    }
+    double disp0 = rng_uniform(&W->rng, -1.0, +1.0) / SCALE;                               /* :489 */
+    double disp1 = rng_uniform(&W->rng, -1.0, +1.0) / SCALE;
+    engines_t E;
+    lunar_engines(&E, O->continuous, action, caction, (double)L->a, (double)L->xf.p.x, (double)L->xf.p.y, disp0, disp1);
+    if (E.main_on) { /* b2Body::ApplyLinearImpulse(impulse, point, wake=True) */
+        L->v = add(L->v, scl(L->invMass, E.main_imp));
+        L->w += L->invI * crs(sub(E.main_pt, L->c), E.main_imp);
+    }
+    if (E.side_on) {
+        L->v = add(L->v, scl(L->invMass, E.side_imp));
+        L->w += L->invI * crs(sub(E.side_pt, L->c), E.side_imp);
+    }
+    int awake = world_step(W, (float)O->gravity, (float)(1.0 / FPS), 6 * 30, 2 * 30);                         /* :556 */
     double st[8];
     st[0] = ((double)L->xf.p.x - VIEWPORT_W / SCALE / 2) / (VIEWPORT_W / SCALE / 2);       /* :560-569 */
     st[1] = ((double)L->xf.p.y - (W->helipad_y + LEG_DOWN / SCALE)) / (VIEWPORT_H / SCALE / 2);
@@ -216,8 +288,8 @@ static void lunar_step_one(world_t *W, int action, float *obs, double *reward, i
     if (W->has_prev_shaping) r = shaping - W->prev_shaping;                                /* :581-583 */
     W->prev_shaping = shaping;
     W->has_prev_shaping = 1;
-    r -= m_power * 0.30;                                                                   /* :585-588 */
-    r -= s_power * 0.03;
+    r -= E.main_cost;                                                                      /* :585-588 */
+    r -= E.side_cost;
     int term = 0;
     if (W->game_over || fabs(st[0]) >= 1.0) { term = 1; r = -100; }                        /* :590-593 */
     if (!awake) { term = 1; r = +100; }                                                 /* :594-596 */
@@ -227,14 +299,30 @@ static void lunar_step_one(world_t *W, int action, float *obs, double *reward, i
 }
 
 /* ---------------------------------------------------------------- vector API */
-orc_lunar *orc_lunar_create(int64_t n, int max_episode_steps)
+orc_lunar *orc_lunar_create_ex(int64_t n, int max_episode_steps, int continuous, int enable_wind, double gravity,
+                               double wind_power, double turbulence_power)
 {
     if (n <= 0) return NULL;
     orc_lunar *v = (orc_lunar *)calloc(1, sizeof *v);
     v->n = n;
     v->max_steps = max_episode_steps;
+    v->o.continuous = continuous; v->o.enable_wind = enable_wind;
+    v->o.gravity = gravity; v->o.wind_power = wind_power; v->o.turbulence_power = turbulence_power;
     v->w = (world_t *)calloc((size_t)n, sizeof(world_t));
     return v;
+}
+orc_lunar *orc_lunar_create(int64_t n, int max_episode_steps)
+{
+    return orc_lunar_create_ex(n, max_episode_steps, 0, 0, -10.0, 15.0, 1.5);
+}
+/* the two np.random.randint(-9999, 9999) draws of LunarLander.__init__ (:234-235), one pair per env */
+void orc_lunar_set_wind_idx(orc_lunar *v, const int32_t *wind_idx, const int32_t *torque_idx)
+{
+    for (int64_t i = 0; i < v->n; i++) { v->w[i].wind_idx = wind_idx[i]; v->w[i].torque_idx = torque_idx[i]; }
+}
+void orc_lunar_get_wind_idx(const orc_lunar *v, int32_t *wind_idx, int32_t *torque_idx)
+{
+    for (int64_t i = 0; i < v->n; i++) { wind_idx[i] = v->w[i].wind_idx; torque_idx[i] = v->w[i].torque_idx; }
 }
 void orc_lunar_destroy(orc_lunar *v) { if (v) { free(v->w); free(v); } }
 
@@ -251,32 +339,47 @@ void orc_lunar_seed_range(orc_lunar *v, const uint32_t base[4], int64_t first)
 
 void orc_lunar_reset(orc_lunar *v, float *obs)
 {
-    for (int64_t i = 0; i < v->n; i++) lunar_reset_one(&v->w[i], obs + 8 * i);
+    for (int64_t i = 0; i < v->n; i++) lunar_reset_one(&v->w[i], &v->o, obs + 8 * i);
+}
+
+static void lunar_vec_one(orc_lunar *v, int64_t i, int action, const float *ca, float *obs, double *reward,
+                          uint8_t *terminated, uint8_t *truncated, float *final_obs)
+{
+    world_t *W = &v->w[i];
+    float o[8];
+    double r;
+    int term;
+    lunar_step_one(W, &v->o, action, ca, o, &r, &term);
+    W->elapsed += 1;
+    int trunc = v->max_steps > 0 && W->elapsed >= v->max_steps;
+    reward[i] = r;
+    terminated[i] = (uint8_t)term;
+    truncated[i] = (uint8_t)trunc;
+    if (term || trunc) {
+        if (final_obs) memcpy(final_obs + 8 * i, o, sizeof o);
+        lunar_reset_one(W, &v->o, o);
+    }
+    memcpy(obs + 8 * i, o, sizeof o);
 }
 
 int64_t orc_lunar_step(orc_lunar *v, const int64_t *actions, float *obs, double *reward, uint8_t *terminated,
                        uint8_t *truncated, float *final_obs)
 {
     int64_t invalid = 0;
+    const float zero[2] = {0.0f, 0.0f};
     for (int64_t i = 0; i < v->n; i++) {
-        world_t *W = &v->w[i];
         if (actions[i] < 0 || actions[i] > 3) { invalid++; continue; }                     /* :482-484 */
-        float o[8];
-        double r;
-        int term;
-        lunar_step_one(W, (int)actions[i], o, &r, &term);
-        W->elapsed += 1;
-        int trunc = v->max_steps > 0 && W->elapsed >= v->max_steps;
-        reward[i] = r;
-        terminated[i] = (uint8_t)term;
-        truncated[i] = (uint8_t)trunc;
-        if (term || trunc) {
-            if (final_obs) memcpy(final_obs + 8 * i, o, sizeof o);
-            lunar_reset_one(W, o);
-        }
-        memcpy(obs + 8 * i, o, sizeof o);
+        lunar_vec_one(v, i, (int)actions[i], zero, obs, reward, terminated, truncated, final_obs);
     }
     return invalid;
+}
+
+/* continuous=True: actions [n][2] float32, clipped to [-1, 1] inside the step (:480) */
+void orc_lunar_step_cont(orc_lunar *v, const float *actions, float *obs, double *reward, uint8_t *terminated,
+                         uint8_t *truncated, float *final_obs)
+{
+    for (int64_t i = 0; i < v->n; i++)
+        lunar_vec_one(v, i, 0, actions + 2 * i, obs, reward, terminated, truncated, final_obs);
 }
 
 /* debugging / parity: dump the 3 bodies (c.x, c.y, a, v.x, v.y, w) + flags of env i */

@@ -8,6 +8,14 @@ extern "C" {
 #endif
 typedef struct orc_lunar orc_lunar;
 orc_lunar *orc_lunar_create(int64_t n, int max_episode_steps);
+orc_lunar *orc_lunar_create_ex(int64_t n, int max_episode_steps, int continuous, int enable_wind, double gravity,
+                               double wind_power, double turbulence_power);
+void orc_lunar_set_wind_idx(orc_lunar *v, const int32_t *wind_idx, const int32_t *torque_idx);
+void orc_lunar_get_wind_idx(const orc_lunar *v, int32_t *wind_idx, int32_t *torque_idx);
+void orc_lunar_step_cont(orc_lunar *v, const float *actions, float *obs, double *reward, uint8_t *terminated,
+                         uint8_t *truncated, float *final_obs);
+void orc_lunar_engines(int continuous, int action, const float *caction, double ang, double posx, double posy,
+                       double disp0, double disp1, float out[8], double cost[2], int32_t on[2]);
 void orc_lunar_destroy(orc_lunar *v);
 void orc_lunar_seed_range(orc_lunar *v, const uint32_t base[4], int64_t first);
 void orc_lunar_reset(orc_lunar *v, float *obs);

@@ -70,6 +70,12 @@ def lib():
         L.orc_vec_set_state.argtypes = [vp, vp, vp]
         L.orc_lunar_create.restype = vp
         L.orc_lunar_create.argtypes = [i64, i32]
+        L.orc_lunar_create_ex.restype = vp
+        L.orc_lunar_create_ex.argtypes = [i64, i32, i32, i32, dbl, dbl, dbl]
+        L.orc_lunar_set_wind_idx.argtypes = [vp, vp, vp]
+        L.orc_lunar_get_wind_idx.argtypes = [vp, vp, vp]
+        L.orc_lunar_step_cont.argtypes = [vp, vp, vp, vp, vp, vp, vp]
+        L.orc_lunar_engines.argtypes = [i32, i32, vp, dbl, dbl, dbl, dbl, dbl, vp, vp, vp]
         L.orc_lunar_destroy.argtypes = [vp]
         L.orc_lunar_seed_range.argtypes = [vp, vp, i64]
         L.orc_lunar_reset.argtypes = [vp, vp]
@@ -78,6 +84,10 @@ def lib():
         L.orc_lunar_get_bodies.argtypes = [vp, i64, vp, vp]
         L.orc_walker_create.restype = vp
         L.orc_walker_create.argtypes = [i64, i32]
+        L.orc_walker_create_ex.restype = vp
+        L.orc_walker_create_ex.argtypes = [i64, i32, i32]
+        L.orc_walker_get_polys.restype = i32
+        L.orc_walker_get_polys.argtypes = [vp, i64, vp]
         L.orc_walker_destroy.argtypes = [vp]
         L.orc_walker_seed_range.argtypes = [vp, vp, i64]
         L.orc_walker_reset.argtypes = [vp, vp]
@@ -213,9 +223,23 @@ class OracleLunar:
 
     obs_dim, act_dim, num_actions = 8, 0, 4
 
-    def __init__(self, num_envs, max_episode_steps=1000):
+    def __init__(self, num_envs, max_episode_steps=1000, continuous=False, gravity=-10.0, enable_wind=False,
+                 wind_power=15.0, turbulence_power=1.5, wind_idx=None, torque_idx=None):
         self.n = int(num_envs)
-        self._h = lib().orc_lunar_create(self.n, int(max_episode_steps or 0))
+        self.continuous = bool(continuous)
+        self._h = lib().orc_lunar_create_ex(self.n, int(max_episode_steps or 0), int(self.continuous), int(bool(enable_wind)),
+                                            float(gravity), float(wind_power), float(turbulence_power))
+        if wind_idx is not None:
+            # the per-object np.random.randint(-9999, 9999) draws of LunarLander.__init__ (lunar_lander.py:234-235)
+            wi = np.ascontiguousarray(np.broadcast_to(wind_idx, (self.n,)), dtype=np.int32)
+            ti = np.ascontiguousarray(np.broadcast_to(torque_idx, (self.n,)), dtype=np.int32)
+            lib().orc_lunar_set_wind_idx(self._h, wi.ctypes.data, ti.ctypes.data)
+
+    def wind_idx(self):
+        wi = np.zeros(self.n, dtype=np.int32)
+        ti = np.zeros(self.n, dtype=np.int32)
+        lib().orc_lunar_get_wind_idx(self._h, wi.ctypes.data, ti.ctypes.data)
+        return wi, ti
 
     def close(self):
         if getattr(self, "_h", None):
@@ -232,12 +256,17 @@ class OracleLunar:
         return obs
 
     def step(self, actions):
-        a = np.ascontiguousarray(actions, dtype=np.int64).reshape(self.n)
         obs = np.zeros((self.n, 8), dtype=np.float32)
         fo = np.zeros((self.n, 8), dtype=np.float32)
         rew = np.zeros(self.n, dtype=np.float64)
         te = np.zeros(self.n, dtype=np.uint8)
         tr = np.zeros(self.n, dtype=np.uint8)
+        if self.continuous:
+            a = np.ascontiguousarray(actions, dtype=np.float32).reshape(self.n, 2)
+            lib().orc_lunar_step_cont(self._h, a.ctypes.data, obs.ctypes.data, rew.ctypes.data, te.ctypes.data,
+                                      tr.ctypes.data, fo.ctypes.data)
+            return obs, rew, te.astype(bool), tr.astype(bool), fo
+        a = np.ascontiguousarray(actions, dtype=np.int64).reshape(self.n)
         bad = lib().orc_lunar_step(self._h, a.ctypes.data, obs.ctypes.data, rew.ctypes.data, te.ctypes.data,
                                    tr.ctypes.data, fo.ctypes.data)
         if bad:
@@ -257,9 +286,9 @@ class OracleWalker:
 
     obs_dim, act_dim, num_actions = 24, 4, 0
 
-    def __init__(self, num_envs, max_episode_steps=1600):
+    def __init__(self, num_envs, max_episode_steps=1600, hardcore=False):
         self.n = int(num_envs)
-        self._h = lib().orc_walker_create(self.n, int(max_episode_steps or 0))
+        self._h = lib().orc_walker_create_ex(self.n, int(max_episode_steps or 0), int(bool(hardcore)))
 
     def close(self):
         if getattr(self, "_h", None):
@@ -291,11 +320,71 @@ class OracleWalker:
         lib().orc_walker_get_terrain(self._h, int(i), y.ctypes.data)
         return y
 
+    def polys(self, i=0):
+        """hardcore obstacles of env i as rows {x0, ylo, x1, yhi} (float32), in creation order"""
+        out = np.zeros((40, 4), dtype=np.float32)
+        k = lib().orc_walker_get_polys(self._h, int(i), out.ctypes.data)
+        return out[:k].copy()
+
     def bodies(self, i=0):
         out = np.zeros(30, dtype=np.float32)
         flags = np.zeros(4, dtype=np.int32)
         lib().orc_walker_get_bodies(self._h, int(i), out.ctypes.data, flags.ctypes.data)
         return out.reshape(5, 6), flags
+
+
+class WalkerHeuristic:
+    """The demo gait controller of gym/envs/box2d/bipedal_walker.py:775-854 ("suboptimal, have no notion of
+    balance"): a three-state machine (stay on one leg / put the other down / push off) with PD targets on the hip
+    and knee angles.  One instance drives one env; call it with the observation, get the next action."""
+
+    STAY_ON_ONE_LEG, PUT_OTHER_DOWN, PUSH_OFF = 1, 2, 3
+    SPEED = 0.29
+    SUPPORT_KNEE_ANGLE = +0.1
+
+    def __init__(self):
+        self.state = self.STAY_ON_ONE_LEG
+        self.moving_leg = 0
+        self.supporting_knee_angle = self.SUPPORT_KNEE_ANGLE
+        self.a = np.array([0.0, 0.0, 0.0, 0.0])
+
+    def __call__(self, s):
+        moving, supporting = self.moving_leg, 1 - self.moving_leg
+        mb, sb = 4 + 5 * moving, 4 + 5 * supporting
+        hip_targ, knee_targ = [None, None], [None, None]
+        hip_todo, knee_todo = [0.0, 0.0], [0.0, 0.0]
+        if self.state == self.STAY_ON_ONE_LEG:
+            hip_targ[moving] = 1.1
+            knee_targ[moving] = -0.6
+            self.supporting_knee_angle += 0.03
+            if s[2] > self.SPEED:
+                self.supporting_knee_angle += 0.03
+            self.supporting_knee_angle = min(self.supporting_knee_angle, self.SUPPORT_KNEE_ANGLE)
+            knee_targ[supporting] = self.supporting_knee_angle
+            if s[sb + 0] < 0.10:
+                self.state = self.PUT_OTHER_DOWN
+        if self.state == self.PUT_OTHER_DOWN:
+            hip_targ[moving] = +0.1
+            knee_targ[moving] = self.SUPPORT_KNEE_ANGLE
+            knee_targ[supporting] = self.supporting_knee_angle
+            if s[mb + 4]:
+                self.state = self.PUSH_OFF
+                self.supporting_knee_angle = min(s[mb + 2], self.SUPPORT_KNEE_ANGLE)
+        if self.state == self.PUSH_OFF:
+            knee_targ[moving] = self.supporting_knee_angle
+            knee_targ[supporting] = +1.0
+            if s[sb + 2] > 0.88 or s[2] > 1.2 * self.SPEED:
+                self.state = self.STAY_ON_ONE_LEG
+                self.moving_leg = 1 - moving
+        for leg in (0, 1):
+            if hip_targ[leg]:
+                hip_todo[leg] = 0.9 * (hip_targ[leg] - s[4 + 5 * leg]) - 0.25 * s[5 + 5 * leg]
+            if knee_targ[leg]:
+                knee_todo[leg] = 4.0 * (knee_targ[leg] - s[6 + 5 * leg]) - 0.25 * s[7 + 5 * leg]
+            hip_todo[leg] -= 0.9 * (0 - s[0]) - 1.5 * s[1]
+            knee_todo[leg] -= 15.0 * s[3]
+        a = np.array([hip_todo[0], knee_todo[0], hip_todo[1], knee_todo[1]])
+        return np.clip(0.5 * a, -1.0, 1.0)
 
 
 def rng_sequence(seed, ops):
@@ -307,8 +396,24 @@ def rng_sequence(seed, ops):
     return out
 
 
-def lunar_heuristic(s):
-    """gym/envs/box2d/lunar_lander.py:726-777 (discrete branch), used by the behavioural test."""
+def lunar_engines(continuous, action, ang, posx, posy, disp0, disp1):
+    """The engine arithmetic of lunar_oracle.c alone (test hook): impulses / points as Box2D receives them."""
+    ca = np.zeros(2, dtype=np.float32)
+    act = 0
+    if continuous:
+        ca[:] = action
+    else:
+        act = int(action)
+    out = np.zeros(8, dtype=np.float32)
+    cost = np.zeros(2, dtype=np.float64)
+    on = np.zeros(2, dtype=np.int32)
+    lib().orc_lunar_engines(int(continuous), act, ca.ctypes.data, float(ang), float(posx), float(posy), float(disp0),
+                            float(disp1), out.ctypes.data, cost.ctypes.data, on.ctypes.data)
+    return out, cost, on
+
+
+def lunar_heuristic(s, continuous=False):
+    """gym/envs/box2d/lunar_lander.py:726-777, used by the behavioural test."""
     angle_targ = s[0] * 0.5 + s[2] * 1.0
     angle_targ = min(max(angle_targ, -0.4), 0.4)
     hover_targ = 0.55 * np.abs(s[0])
@@ -317,6 +422,8 @@ def lunar_heuristic(s):
     if s[6] or s[7]:
         angle_todo = 0
         hover_todo = -(s[3]) * 0.5
+    if continuous:
+        return np.clip(np.array([hover_todo * 20 - 1, -angle_todo * 20]), -1, +1)
     a = 0
     if hover_todo > np.abs(angle_todo) and hover_todo > 0.05:
         a = 2

@@ -4,7 +4,8 @@
  * Restates gym/envs/box2d/bipedal_walker.py (reset :425-515, _generate_terrain :277-402,
  * _generate_clouds :404-423, step :517-606, ContactDetector :80-98, LidarCallback :504-510) on top
  * of oracle/b2lite.h, the from-scratch restatement of the Box2D 2.3 subset the env exercises.
- * Non-hardcore terrain only (BipedalWalker-v3; the hardcore obstacles are a listed "next" row).
+ * Both terrains: BipedalWalker-v3 and BipedalWalkerHardcore-v3 (hardcore=True: stumps, stairs, pits as static
+ * box polygons on top of the edge chain, :300-373).
  *
  * PARITY UNPINNED for the rigid-body arithmetic (no Box2D here, see b2lite.h).  The numpy side --
  * Generator.uniform / integers / random streams that shape the terrain -- IS pinned against numpy
@@ -47,6 +48,9 @@ typedef struct {
     joint_t j[NJ];
     edge_t e[NE];
     contact_t ct[NB * NE];
+    spoly_t sp[B2L_MAX_SPOLY];          /* hardcore obstacles, in creation (ascending x) order */
+    int np;
+    contact_t ctp[NB * B2L_MAX_SPOLY];
     float inv_dt0;
     int game_over, leg_contact[2]; /* legs[1] = body 2, legs[3] = body 4 */
     int has_prev_shaping;
@@ -58,6 +62,7 @@ typedef struct {
 struct orc_walker {
     int64_t n;
     int max_steps;
+    int hardcore;
     wworld_t *w;
 };
 
@@ -84,7 +89,9 @@ static void wworld_step(wworld_t *W)
     S.nb = NB; S.nj = NJ; S.ne = NE;
     S.b = W->b; S.j = W->j; S.e = W->e; S.ct = W->ct;
     S.body_order = order; S.joint_order = jorder;
+    S.np = W->np; S.np_cap = B2L_MAX_SPOLY; S.sp = W->sp; S.ctp = W->ctp;
     S.inv_dt0 = W->inv_dt0;
+    S.gravity_y = -10.0f;
     S.event = walker_event; S.ctx = W;
     b2l_step(&S, (float)(1.0 / FPS), 6 * 30, 2 * 30);
     W->inv_dt0 = S.inv_dt0;
@@ -120,35 +127,70 @@ static int edge_raycast(const edge_t *e, v2 p1, v2 p2, float maxFraction, float 
 static void walker_step_one(wworld_t *W, const float *action, int from_reset, float *obs, double *reward, int *terminated);
 
 /* bipedal_walker.py:425-515 */
-static void walker_reset_one(wworld_t *W, float *obs)
+static void walker_reset_one(wworld_t *W, int hardcore, float *obs)
 {
     pcg64_t rng = W->rng;
     float inv_dt0 = W->inv_dt0; /* self.world survives reset() */
     memset(W, 0, sizeof *W);
     W->inv_dt0 = inv_dt0;
-    /* _generate_terrain(hardcore=False) :277-402 */
+    /* _generate_terrain(hardcore) :277-402 */
     double terrain_x[TERRAIN_LENGTH], terrain_y[TERRAIN_LENGTH];
     {
-        double velocity = 0.0, y = TERRAIN_HEIGHT;
-        int counter = TERRAIN_STARTPAD, oneshot = 0;
+        enum { GRASS = 0, STUMP, STAIRS, PIT, STATES };
+        int state = GRASS;
+        double velocity = 0.0, y = TERRAIN_HEIGHT, original_y = 0;
+        int64_t counter = TERRAIN_STARTPAD, stair_steps = 0, stair_width = 0, stair_height = 0;
+        int oneshot = 0;
         for (int i = 0; i < TERRAIN_LENGTH; i++) {
             double x = i * TERRAIN_STEP;
             terrain_x[i] = x;
-            if (!oneshot) { /* state == GRASS and not oneshot */
+            if (state == GRASS && !oneshot) {
                 double d = TERRAIN_HEIGHT - y;
                 double sgn = d > 0 ? 1.0 : (d < 0 ? -1.0 : 0.0);
                 velocity = 0.8 * velocity + 0.01 * sgn;                              /* :296 */
                 if (i > TERRAIN_STARTPAD) velocity += rng_uniform(&rng, -1, 1) / SCALE; /* :297-298 */
                 y += velocity;
+            } else if (state == PIT && oneshot) {                                     /* :301-323 */
+                counter = rng_integers(&rng, 3, 5);
+                /* poly = (x, y), (x+STEP, y), (x+STEP, y-4 STEP), (x, y-4 STEP), and the same shifted by STEP*counter */
+                spoly_set_box(&W->sp[W->np++], (float)x, (float)(y - 4 * TERRAIN_STEP), (float)(x + TERRAIN_STEP), (float)y, FRICTION);
+                spoly_set_box(&W->sp[W->np++], (float)(x + TERRAIN_STEP * counter), (float)(y - 4 * TERRAIN_STEP),
+                              (float)(x + TERRAIN_STEP + TERRAIN_STEP * counter), (float)y, FRICTION);
+                counter += 2;
+                original_y = y;
+            } else if (state == PIT && !oneshot) {                                    /* :325-328 */
+                y = original_y;
+                if (counter > 1) y -= 4 * TERRAIN_STEP;
+            } else if (state == STUMP && oneshot) {                                   /* :330-341 */
+                counter = rng_integers(&rng, 1, 3);
+                spoly_set_box(&W->sp[W->np++], (float)x, (float)y, (float)(x + counter * TERRAIN_STEP),
+                              (float)(y + counter * TERRAIN_STEP), FRICTION);
+            } else if (state == STAIRS && oneshot) {                                  /* :343-371 */
+                stair_height = pcg_double(&rng) > 0.5 ? +1 : -1;
+                stair_width = rng_integers(&rng, 4, 5);
+                stair_steps = rng_integers(&rng, 3, 5);
+                original_y = y;
+                for (int64_t st = 0; st < stair_steps; st++)
+                    spoly_set_box(&W->sp[W->np++], (float)(x + (st * stair_width) * TERRAIN_STEP),
+                                  (float)(y + (-1 + st * stair_height) * TERRAIN_STEP),
+                                  (float)(x + ((1 + st) * stair_width) * TERRAIN_STEP),
+                                  (float)(y + (st * stair_height) * TERRAIN_STEP), FRICTION);
+                counter = stair_steps * stair_width;
+            } else if (state == STAIRS && !oneshot) {                                 /* :373-376 */
+                int64_t sq = stair_steps * stair_width - counter - stair_height;
+                double nn = (double)sq / (double)stair_width;
+                y = original_y + (nn * stair_height) * TERRAIN_STEP;
             }
             oneshot = 0;
             terrain_y[i] = y;
             counter -= 1;
             if (counter == 0) {
-                counter = (int)rng_integers(&rng, TERRAIN_GRASS / 2, TERRAIN_GRASS);   /* :379 */
-                oneshot = 1;                                                           /* :384-385 */
+                counter = rng_integers(&rng, TERRAIN_GRASS / 2, TERRAIN_GRASS);       /* :379 */
+                if (state == GRASS && hardcore) { state = (int)rng_integers(&rng, 1, STATES); oneshot = 1; }  /* :380-382 */
+                else { state = GRASS; oneshot = 1; }                                   /* :383-385 */
             }
         }
+        if (W->np > B2L_MAX_SPOLY) abort();  /* cannot happen: at most 39 */
     }
     for (int i = 0; i < NE; i++) {                                                     /* :387-396 */
         W->e[i].v1 = V((float)terrain_x[i], (float)terrain_y[i]);
@@ -236,6 +278,10 @@ static void walker_step_one(wworld_t *W, const float *action, int from_reset, fl
             float t;
             if (edge_raycast(&W->e[e], p1, p2, maxFraction, &t)) { frac = t; maxFraction = t; }
         }
+        for (int q = 0; q < W->np; q++) {  /* LidarCallback accepts every fixture with categoryBits & 1 (:504-510) */
+            float t;
+            if (spoly_raycast(&W->sp[q], p1, p2, maxFraction, &t)) { frac = t; maxFraction = t; }
+        }
         lidar[i] = frac;
     }
     double st[24];
@@ -279,12 +325,15 @@ static void walker_step_one(wworld_t *W, const float *action, int from_reset, fl
 }
 
 /* ---------------------------------------------------------------- vector API */
-orc_walker *orc_walker_create(int64_t n, int max_episode_steps)
+orc_walker *orc_walker_create(int64_t n, int max_episode_steps) { return orc_walker_create_ex(n, max_episode_steps, 0); }
+
+orc_walker *orc_walker_create_ex(int64_t n, int max_episode_steps, int hardcore)
 {
     if (n <= 0) return NULL;
     orc_walker *v = (orc_walker *)calloc(1, sizeof *v);
     v->n = n;
     v->max_steps = max_episode_steps;
+    v->hardcore = hardcore;
     v->w = (wworld_t *)calloc((size_t)n, sizeof(wworld_t));
     return v;
 }
@@ -303,7 +352,7 @@ void orc_walker_seed_range(orc_walker *v, const uint32_t base[4], int64_t first)
 
 void orc_walker_reset(orc_walker *v, float *obs)
 {
-    for (int64_t i = 0; i < v->n; i++) walker_reset_one(&v->w[i], obs + 24 * i);
+    for (int64_t i = 0; i < v->n; i++) walker_reset_one(&v->w[i], v->hardcore, obs + 24 * i);
 }
 
 void orc_walker_step(orc_walker *v, const float *actions, float *obs, double *reward, uint8_t *terminated,
@@ -322,7 +371,7 @@ void orc_walker_step(orc_walker *v, const float *actions, float *obs, double *re
         truncated[i] = (uint8_t)trunc;
         if (term || trunc) {
             if (final_obs) memcpy(final_obs + 24 * i, o, sizeof o);
-            walker_reset_one(W, o);
+            walker_reset_one(W, v->hardcore, o);
         }
         memcpy(obs + 24 * i, o, sizeof o);
     }
@@ -335,6 +384,17 @@ void orc_walker_get_terrain(const orc_walker *v, int64_t i, float *y200)
     y200[NE] = W->e[NE - 1].v2.y;
 }
 
+/* hardcore obstacles of env i: out[k] = {x0, ylo, x1, yhi}; returns their number */
+int orc_walker_get_polys(const orc_walker *v, int64_t i, float *out)
+{
+    const wworld_t *W = &v->w[i];
+    for (int k = 0; k < W->np; k++) {
+        out[4 * k + 0] = W->sp[k].verts[2].x; out[4 * k + 1] = W->sp[k].verts[0].y;
+        out[4 * k + 2] = W->sp[k].verts[0].x; out[4 * k + 3] = W->sp[k].verts[2].y;
+    }
+    return W->np;
+}
+
 void orc_walker_get_bodies(const orc_walker *v, int64_t i, float out[30], int32_t flags[4])
 {
     const wworld_t *W = &v->w[i];
@@ -344,6 +404,7 @@ void orc_walker_get_bodies(const orc_walker *v, int64_t i, float out[30], int32_
     }
     flags[0] = W->game_over; flags[1] = W->leg_contact[0]; flags[2] = W->leg_contact[1]; flags[3] = 0;
     for (int k = 0; k < NB * NE; k++) flags[3] += W->ct[k].touching;
+    for (int k = 0; k < NB * B2L_MAX_SPOLY; k++) flags[3] += W->ctp[k].touching;
 }
 
 /* Generator KATs for tests: draws[k] = op(k): 0 uniform(-1,1), 1 integers(5,10), 2 random() */

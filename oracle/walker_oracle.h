@@ -1,4 +1,4 @@
-/* walker_oracle.h -- CPU ORACLE for BipedalWalker-v3 (test infrastructure, NOT product code).
+/* walker_oracle.h -- CPU ORACLE for BipedalWalker-v3 / BipedalWalkerHardcore-v3 (test infrastructure, NOT product code).
  * See walker_oracle.c.  PARITY UNPINNED for the Box2D arithmetic; the numpy RNG side is pinned. */
 #ifndef WALKER_ORACLE_H
 #define WALKER_ORACLE_H
@@ -8,6 +8,8 @@ extern "C" {
 #endif
 typedef struct orc_walker orc_walker;
 orc_walker *orc_walker_create(int64_t n, int max_episode_steps);
+orc_walker *orc_walker_create_ex(int64_t n, int max_episode_steps, int hardcore);
+int orc_walker_get_polys(const orc_walker *v, int64_t i, float *out);
 void orc_walker_destroy(orc_walker *v);
 void orc_walker_seed_range(orc_walker *v, const uint32_t base[4], int64_t first);
 void orc_walker_reset(orc_walker *v, float *obs);

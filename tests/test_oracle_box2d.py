@@ -1,0 +1,368 @@
+"""CPU tests of the Box2D-task oracles (oracle/lunar_oracle.c, oracle/walker_oracle.c).
+
+PARITY UNPINNED for the rigid-body arithmetic (box2d-py is not installable here).  What can be pinned
+on the CPU and is pinned here:
+  * the reference's own behavioural test at this boundary (tests/envs/test_env_implementation.py:13-17:
+    the heuristic controller scores > 100 on LunarLander-v2 at seed 1), discrete and continuous;
+  * the numpy dtype flow (NEP 50) of the engine arithmetic in LunarLander.step (lunar_lander.py:479-554),
+    checked against numpy scalars evaluating the same expressions;
+  * the wind / gravity / continuous-action variants' documented semantics (lunar_lander.py:449-477,
+    211-213, 480).
+"""
+import math
+
+import numpy as np
+import pytest
+
+from oracle import oracle as orc
+
+
+def _run_heuristic(env, continuous, seed, max_steps=1000):
+    s = env.reset(seed=seed)[0]
+    total, steps = 0.0, 0
+    while True:
+        a = orc.lunar_heuristic(s, continuous=continuous)
+        obs, r, te, tr, fo = env.step(np.asarray([a]))
+        total += float(r[0])
+        steps += 1
+        if te[0] or tr[0] or steps >= max_steps:
+            return total, steps, bool(te[0])
+        s = obs[0]
+
+
+def test_reference_behavioural_test_heuristic_lands_discrete():
+    total, steps, term = _run_heuristic(orc.OracleLunar(1), False, seed=1)
+    assert term and total > 100, (total, steps)
+
+
+def test_heuristic_lands_continuous():
+    """demo_heuristic_lander with continuous=True (lunar_lander.py:766-768): same criterion."""
+    total, steps, term = _run_heuristic(orc.OracleLunar(1, continuous=True), True, seed=1)
+    assert term and total > 100, (total, steps)
+
+
+def _numpy_engines(continuous, action, ang, posx, posy, disp0, disp1):
+    """LunarLander.step's engine arithmetic (lunar_lander.py:479-554) evaluated by numpy/Python scalars with
+    the types the reference has at each point: tip/side/dispersion/position are Python floats, the clipped
+    continuous action is a float32 array.  Returns what Box2D receives (float32 pairs) + the fuel costs."""
+    SCALE, MAIN, SIDE = 30.0, 13.0, 0.6
+    if continuous:
+        action = np.clip(action, -1, +1).astype(np.float32)
+    tip = (math.sin(ang), math.cos(ang))
+    side = (-tip[1], tip[0])
+    dispersion = [disp0, disp1]
+    out = np.zeros(8, dtype=np.float32)
+    cost = [0.0, 0.0]
+    on = [0, 0]
+    m_power = 0.0
+    if (continuous and action[0] > 0.0) or (not continuous and action == 2):
+        m_power = (np.clip(action[0], 0.0, 1.0) + 1.0) * 0.5 if continuous else 1.0
+        ox = tip[0] * (4 / SCALE + 2 * dispersion[0]) + side[0] * dispersion[1]
+        oy = -tip[1] * (4 / SCALE + 2 * dispersion[0]) - side[1] * dispersion[1]
+        impulse_pos = (posx + ox, posy + oy)
+        out[0:4] = [-ox * MAIN * m_power, -oy * MAIN * m_power, impulse_pos[0], impulse_pos[1]]
+        on[0] = 1
+    s_power = 0.0
+    if (continuous and np.abs(action[1]) > 0.5) or (not continuous and action in [1, 3]):
+        if continuous:
+            direction = np.sign(action[1])
+            s_power = np.clip(np.abs(action[1]), 0.5, 1.0)
+        else:
+            direction = action - 2
+            s_power = 1.0
+        ox = tip[0] * dispersion[0] + side[0] * (3 * dispersion[1] + direction * 12.0 / SCALE)
+        oy = -tip[1] * dispersion[0] - side[1] * (3 * dispersion[1] + direction * 12.0 / SCALE)
+        impulse_pos = (posx + ox - tip[0] * 17 / SCALE, posy + oy + tip[1] * 14.0 / SCALE)
+        out[4:8] = [-ox * SIDE * s_power, -oy * SIDE * s_power, impulse_pos[0], impulse_pos[1]]
+        on[1] = 1
+    reward = np.float64(0.0)
+    r1 = reward - m_power * 0.30
+    r2 = reward - s_power * 0.03
+    cost = [float(-r1), float(-r2)]
+    return out, np.asarray(cost), np.asarray(on)
+
+
+@pytest.mark.parametrize("continuous", [False, True])
+def test_engine_arithmetic_follows_numpy_dtype_flow(continuous):
+    rng = np.random.default_rng(5)
+    for k in range(4000):
+        ang = float(np.float32(rng.uniform(-1.5, 1.5)))
+        posx = float(np.float32(rng.uniform(0, 20)))
+        posy = float(np.float32(rng.uniform(0, 14)))
+        d0, d1 = rng.uniform(-1.0, 1.0) / 30.0, rng.uniform(-1.0, 1.0) / 30.0
+        if continuous:
+            action = rng.uniform(-1.5, 1.5, size=2).astype(np.float32)
+            if k % 17 == 0:
+                action[1] = np.float32(0.5)      # boundary of the side-engine dead zone
+            if k % 19 == 0:
+                action[0] = np.float32(0.0)
+        else:
+            action = int(rng.integers(0, 4))
+        want, wcost, won = _numpy_engines(continuous, action, ang, posx, posy, d0, d1)
+        got, gcost, gon = orc.lunar_engines(continuous, action, ang, posx, posy, d0, d1)
+        assert np.array_equal(won, gon), (k, action)
+        assert np.array_equal(want.view(np.uint32), got.view(np.uint32)), (k, action, want, got)
+        assert np.array_equal(wcost, gcost), (k, action, wcost, gcost)
+
+
+def test_continuous_actions_are_clipped_and_dead_zones_hold():
+    """lunar_lander.py:152-160,480: main engine off for a0 <= 0, side engines off for |a1| <= 0.5; values
+    beyond +-1 behave as +-1."""
+    def roll(a, steps=30):
+        e = orc.OracleLunar(1, continuous=True)
+        e.reset(seed=3)
+        out = []
+        for _ in range(steps):
+            out.append(e.step(np.asarray([a], dtype=np.float32))[0][0].copy())
+        return np.stack(out)
+    assert np.array_equal(roll([0.0, 0.0]), roll([-0.7, 0.5]))      # both dead zones
+    assert np.array_equal(roll([1.0, 1.0]), roll([3.0, 7.0]))       # clipped
+    assert not np.array_equal(roll([0.0, 0.0]), roll([0.01, 0.0]))  # main engine fires at 50 % from a0 > 0
+    assert not np.array_equal(roll([0.0, 0.0]), roll([0.0, -0.51]))
+    # discrete action 0 == continuous [0, 0]; discrete 2 == continuous [1, 0] (m_power 1.0)
+    d = orc.OracleLunar(1)
+    d.reset(seed=3)
+    dn = np.stack([d.step(np.asarray([0]))[0][0].copy() for _ in range(30)])
+    assert np.array_equal(dn, roll([0.0, 0.0]))
+
+
+def test_gravity_parameter_sets_free_fall():
+    """lunar_lander.py:211-213,240: world gravity (0, gravity).  One free-fall step changes v_y by g*dt."""
+    dv = {}
+    for g in (-10.0, -3.5, -11.9):
+        e = orc.OracleLunar(1, gravity=g)
+        e.reset(seed=0)
+        v0 = e.bodies(0)[0][0, 4]
+        e.step(np.asarray([0]))
+        dv[g] = float(e.bodies(0)[0][0, 4] - v0)
+        # the legs hang on motorised joints, so the lander's own dv is g*dt only up to their (g-independent) pull
+        assert abs(dv[g] - g / 50.0) < 0.02, (g, dv[g])
+    assert abs((dv[-10.0] - dv[-3.5]) - (-6.5 / 50.0)) < 1e-3, dv
+    assert abs((dv[-11.9] - dv[-10.0]) - (-1.9 / 50.0)) < 1e-3, dv
+    a = orc.OracleLunar(1, gravity=-10.0)
+    b = orc.OracleLunar(1)
+    assert np.array_equal(a.reset(seed=4), b.reset(seed=4))
+
+
+def test_wind_semantics():
+    """lunar_lander.py:449-477: wind only while neither leg touches; wind_idx/torque_idx advance by one per windy
+    step, are per-object (drawn in __init__, :234-235) and survive reset()."""
+    wi0, ti0 = 1234, -4321
+    e = orc.OracleLunar(2, enable_wind=True, wind_idx=[wi0, wi0 + 7], torque_idx=[ti0, ti0])
+    calm = orc.OracleLunar(2)
+    o1 = e.reset(seed=9)
+    o0 = calm.reset(seed=9)
+    assert not np.array_equal(o1, o0)                     # the embedded step(0) of reset() already feels the wind
+    wi, ti = e.wind_idx()
+    assert wi.tolist() == [wi0 + 1, wi0 + 8] and ti.tolist() == [ti0 + 1, ti0 + 1]
+    resets = 0
+    for t in range(400):
+        obs, r, te, trn, fo = e.step(np.asarray([0, 0]))
+        wi2, ti2 = e.wind_idx()
+        d = (wi2 - wi)
+        assert set(d.tolist()) <= {0, 1, 2}                # 2: a windy step + the embedded step of an autoreset
+        assert np.array_equal(wi2 - wi, ti2 - ti)
+        resets += int((te | trn).sum())
+        wi, ti = wi2, ti2
+    assert resets >= 1                                     # crashed at least once: indices kept counting across reset
+    assert (wi > np.asarray([wi0, wi0 + 7]) + 50).all()
+    # zero wind power / zero turbulence == no wind at all (forces of exactly 0.0 are added)
+    z = orc.OracleLunar(1, enable_wind=True, wind_power=0.0, turbulence_power=0.0, wind_idx=[5], torque_idx=[6])
+    c = orc.OracleLunar(1)
+    assert np.array_equal(z.reset(seed=2), c.reset(seed=2))
+    for _ in range(50):
+        assert np.array_equal(z.step(np.asarray([2]))[0], c.step(np.asarray([2]))[0])
+
+
+def test_wind_stops_while_a_leg_touches_the_ground():
+    e = orc.OracleLunar(1, enable_wind=True, wind_idx=[100], torque_idx=[200], wind_power=2.0, turbulence_power=0.1)
+    s = e.reset(seed=1)[0]
+    stalled = 0
+    for _ in range(600):
+        wi = e.wind_idx()[0][0]
+        legs = bool(s[6] or s[7])
+        obs, r, te, trn, fo = e.step(np.asarray([orc.lunar_heuristic(s)]))
+        if te[0] or trn[0]:
+            break
+        d = e.wind_idx()[0][0] - wi
+        assert d == (0 if legs else 1)
+        stalled += legs
+        s = obs[0]
+    assert stalled > 0
+
+
+def test_lunar_oracle_is_deterministic_and_seed_fanout_is_seed_plus_index():
+    a = orc.OracleLunar(4)
+    b = orc.OracleLunar(1)
+    oa = a.reset(seed=10)
+    ob = b.reset(seed=12)
+    assert np.array_equal(oa[2], ob[0])
+    rng = np.random.default_rng(0)
+    for _ in range(150):
+        act = rng.integers(0, 4, size=4)
+        oa = a.step(act)[0]
+        ob = b.step(act[2:3])[0]
+        assert np.array_equal(oa[2], ob[0])
+
+
+def test_walker_oracle_invariants():
+    """bipedal_walker.py:517-606: obs shape/dtype, lidar fractions in [0, 1], leg contact flags binary, reward
+    -100 exactly on termination, truncation only from the TimeLimit."""
+    e = orc.OracleWalker(8, max_episode_steps=300)
+    o = e.reset(seed=0)
+    assert o.shape == (8, 24) and o.dtype == np.float32
+    rng = np.random.default_rng(1)
+    saw_term = False
+    for t in range(320):
+        o, r, te, tr, fo = e.step(rng.uniform(-1, 1, size=(8, 4)).astype(np.float32))
+        assert np.isfinite(o).all() and np.isfinite(r).all()
+        assert ((o[:, 14:] >= 0) & (o[:, 14:] <= 1)).all()
+        assert np.isin(o[:, 8], (0.0, 1.0)).all() and np.isin(o[:, 13], (0.0, 1.0)).all()
+        assert (r[te] == -100).all()
+        saw_term |= bool(te.any())
+    assert saw_term
+
+
+# ---------------------------------------------------------------------------------------------------------
+# BipedalWalker / BipedalWalkerHardcore
+# ---------------------------------------------------------------------------------------------------------
+def _numpy_terrain(seed, hardcore):
+    """BipedalWalker._generate_terrain (bipedal_walker.py:277-402) driven by a real numpy Generator: returns the
+    200 terrain heights and the obstacle boxes (x0, ylo, x1, yhi) as float32, in creation order."""
+    g = np.random.Generator(np.random.PCG64(np.random.SeedSequence(seed)))
+    SCALE = 30.0
+    STEP, LENGTH, HEIGHT, GRASS_LEN, STARTPAD = 14 / SCALE, 200, 400 / SCALE / 4, 10, 20
+    GRASS, STUMP, STAIRS, PIT, STATES = range(5)
+    state, velocity, y, counter, oneshot = GRASS, 0.0, HEIGHT, STARTPAD, False
+    ys, boxes = [], []
+    steps = width = height = 0
+    original_y = 0
+    for i in range(LENGTH):
+        x = i * STEP
+        if state == GRASS and not oneshot:
+            velocity = 0.8 * velocity + 0.01 * np.sign(HEIGHT - y)
+            if i > STARTPAD:
+                velocity += g.uniform(-1, 1) / SCALE
+            y += velocity
+        elif state == PIT and oneshot:
+            counter = g.integers(3, 5)
+            boxes.append((x, y - 4 * STEP, x + STEP, y))
+            boxes.append((x + STEP * counter, y - 4 * STEP, x + STEP + STEP * counter, y))
+            counter += 2
+            original_y = y
+        elif state == PIT and not oneshot:
+            y = original_y
+            if counter > 1:
+                y -= 4 * STEP
+        elif state == STUMP and oneshot:
+            counter = g.integers(1, 3)
+            boxes.append((x, y, x + counter * STEP, y + counter * STEP))
+        elif state == STAIRS and oneshot:
+            height = +1 if g.random() > 0.5 else -1
+            width = g.integers(4, 5)
+            steps = g.integers(3, 5)
+            original_y = y
+            for s in range(steps):
+                boxes.append((x + (s * width) * STEP, y + (-1 + s * height) * STEP,
+                              x + ((1 + s) * width) * STEP, y + (s * height) * STEP))
+            counter = steps * width
+        elif state == STAIRS and not oneshot:
+            s = steps * width - counter - height
+            n = s / width
+            y = original_y + (n * height) * STEP
+        oneshot = False
+        ys.append(y)
+        counter -= 1
+        if counter == 0:
+            counter = g.integers(GRASS_LEN / 2, GRASS_LEN)
+            if state == GRASS and hardcore:
+                state = g.integers(1, STATES)
+            else:
+                state = GRASS
+            oneshot = True
+    return np.asarray(ys, dtype=np.float32), np.asarray(boxes, dtype=np.float32).reshape(-1, 4)
+
+
+@pytest.mark.parametrize("hardcore", [False, True])
+def test_walker_terrain_is_pinned_to_numpy(hardcore):
+    n = 24
+    e = orc.OracleWalker(n, hardcore=hardcore)
+    e.reset(seed=100)
+    kinds = set()
+    for i in range(n):
+        ys, boxes = _numpy_terrain(100 + i, hardcore)
+        assert np.array_equal(e.terrain(i).view(np.uint32), ys.view(np.uint32)), i
+        got = e.polys(i)
+        assert got.shape == boxes.shape and np.array_equal(got.view(np.uint32), boxes.view(np.uint32)), i
+        assert len(boxes) <= 39
+        if hardcore:
+            assert len(boxes) >= 10
+            w = np.round((boxes[:, 2] - boxes[:, 0]) / (14 / 30.0)).astype(int)
+            kinds |= set(w.tolist())
+        else:
+            assert len(boxes) == 0
+    if hardcore:
+        assert {1, 2, 4} <= kinds          # pit walls / small stumps (1), big stumps (2), stair steps (4)
+
+
+def _walk(hardcore, seed, max_steps):
+    e = orc.OracleWalker(1, hardcore=hardcore, max_episode_steps=max_steps)
+    s = e.reset(seed=seed)[0]
+    gait = orc.WalkerHeuristic()
+    a = np.zeros(4)
+    total, track = 0.0, []
+    for t in range(max_steps):
+        obs, r, te, tr, fo = e.step(a.astype(np.float32)[None])
+        total += float(r[0])
+        if te[0] or tr[0]:
+            return total, t + 1, bool(te[0]), float(r[0]), track, e
+        track.append((e.bodies(0)[0].copy(), obs[0].copy()))
+        a = gait(obs[0])
+    return total, max_steps, False, 0.0, track, e
+
+
+def test_walker_demo_gait_walks_the_course():
+    """The reference's own demo controller (bipedal_walker.py:775-854) on the re-derived physics: it has to carry
+    the walker over most of the 200-segment course (reward_threshold of the task is 300, gym/envs/__init__.py:74)."""
+    totals = [_walk(False, seed, 1600)[0] for seed in (2, 3, 4)]
+    assert min(totals) > 300, totals
+
+
+def test_hardcore_obstacles_are_solid_and_seen_by_the_lidar():
+    stopped = 0
+    for seed in range(4):
+        total, steps, term, last_r, track, e = _walk(True, seed, 2000)
+        assert term and last_r == -100.0           # the demo gait cannot pass the obstacles: it falls at one
+        stopped += 1
+    assert stopped == 4
+    # geometry: replay seed 0 and look at the lower legs' corners against the obstacle boxes
+    e = orc.OracleWalker(1, hardcore=True, max_episode_steps=2000)
+    s = e.reset(seed=0)[0]
+    boxes = e.polys(0)
+    gait = orc.WalkerHeuristic()
+    a = np.zeros(4)
+    hx, hy = 0.8 * (8 / 30.0) / 2, (34 / 30.0) / 2
+    corners = np.array([[-hx, -hy], [hx, -hy], [hx, hy], [-hx, hy]])
+    deepest, min_lidar, reached = 0.0, 1.0, False
+    for t in range(2000):
+        obs, r, te, tr, fo = e.step(a.astype(np.float32)[None])
+        if te[0] or tr[0]:
+            break
+        bodies = e.bodies(0)[0]
+        for b in (2, 4):
+            cx, cy, ang = bodies[b, 0], bodies[b, 1], bodies[b, 2]
+            R = np.array([[np.cos(ang), -np.sin(ang)], [np.sin(ang), np.cos(ang)]])
+            pts = corners @ R.T + np.array([cx, cy])
+            for (x0, ylo, x1, yhi) in boxes:
+                inside = (pts[:, 0] > x0) & (pts[:, 0] < x1) & (pts[:, 1] > ylo) & (pts[:, 1] < yhi)
+                if inside.any():
+                    d = np.minimum.reduce([pts[inside, 0] - x0, x1 - pts[inside, 0], pts[inside, 1] - ylo, yhi - pts[inside, 1]])
+                    deepest = max(deepest, float(d.max()))
+        reached |= bool(bodies[0, 0] + 1.5 > boxes[0, 0])
+        min_lidar = min(min_lidar, float(obs[0, 14:].min()))
+        a = gait(obs[0])
+    assert reached                                   # the walker got to the first obstacle
+    # ... and never sank into a box by more than one step of a ~6 m/s impact (no continuous collision in this
+    # restatement; resting contacts stay within the solver's 0.005 slop + 0.01 skin)
+    assert deepest < 0.15, deepest
+    assert min_lidar < 0.35

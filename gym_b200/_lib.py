@@ -23,6 +23,7 @@ KIND_ACROBOT = 4
 KIND_LUNARLANDER = 5
 KIND_BIPEDALWALKER = 6
 KIND_LUNARLANDER_CONT = 7
+KIND_BIPEDALWALKER_HARDCORE = 8
 
 # b200gym_config.flags
 LUNAR_ENABLE_WIND = 1
@@ -93,6 +94,7 @@ SIGNATURES = {
     "b200gym_lunar_get_bodies": (_i32, [_vp, _vp, _vp, _vp]),
     "b200gym_lunar_wind_idx": (_i32, [_vp, _vp, _vp, _i32]),
     "b200gym_walker_get_bodies": (_i32, [_vp, _vp, _vp, _vp]),
+    "b200gym_walker_get_terrain": (_i32, [_vp, _vp, _vp, _vp, _vp]),
     "b200gym_p2p_create": (_i32, [_vp, _i32, _i32, _vp, _vp]),
     "b200gym_p2p_connect": (_i32, [_vp, _vp]),
     "b200gym_step_p2p": (_i32, [_vp, _vp, _i32, _vp, _vp, ctypes.POINTER(_i32)]),

@@ -98,10 +98,10 @@ static int fail(const b200gym *h, const char *fmt, ...) {
             return fail(h, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
     } while (0)
 
-static const int k_obs_dim[B200GYM_NUM_KINDS] = {4, 2, 2, 3, 6, 8, 24, 8};
-static const int k_act_dim[B200GYM_NUM_KINDS] = {0, 0, 1, 1, 0, 0, 4, 2};
-static const int k_nact[B200GYM_NUM_KINDS] = {2, 3, 0, 0, 3, 4, 0, 0};
-static const int k_state_dim[B200GYM_NUM_KINDS] = {4, 2, 2, 2, 4, 0, 0, 0};
+static const int k_obs_dim[B200GYM_NUM_KINDS] = {4, 2, 2, 3, 6, 8, 24, 8, 24};
+static const int k_act_dim[B200GYM_NUM_KINDS] = {0, 0, 1, 1, 0, 0, 4, 2, 4};
+static const int k_nact[B200GYM_NUM_KINDS] = {2, 3, 0, 0, 3, 4, 0, 0, 0};
+static const int k_state_dim[B200GYM_NUM_KINDS] = {4, 2, 2, 2, 4, 0, 0, 0, 0};
 
 static bool kind_ok(int k) { return k >= 0 && k < B200GYM_NUM_KINDS; }
 
@@ -678,6 +678,7 @@ static int lunar_upload_consts(b200gym *h) {
 }
 
 // ---- BipedalWalker-v3 (walker.cuh): one thread per env --------------------------------------------
+template <bool HC>
 __global__ void __launch_bounds__(kLunarThreads) walker_step_kernel(const StepArgs a) {
     const int64_t j = (int64_t)blockIdx.x * kLunarThreads + threadIdx.x;
     if (j >= a.count) return;
@@ -686,27 +687,28 @@ __global__ void __launch_bounds__(kLunarThreads) walker_step_kernel(const StepAr
     const float action[4] = {av.x, av.y, av.z, av.w};
     walker::World W;
     walker::Rng rng;
-    walker::load_world(W, a.lunar_rec, a.n, i, rng);
+    walker::load_world(W, a.lunar_rec, a.n, i, rng, HC);
     int32_t elapsed = a.elapsed[i];
     float obs[24];
     double reward;
     bool terminated;
-    walker::env_step(W, action, false, walker::V(0.0f, 0.0f), obs, reward, terminated);
+    walker::env_step<HC>(W, action, false, walker::V(0.0f, 0.0f), obs, reward, terminated);
     elapsed += 1;                                                        // time_limit.py:51
     const bool truncated = (a.max_steps > 0) && (elapsed >= a.max_steps);
     store_scalars_all(a, i, reward, terminated ? 1 : 0, truncated ? 1 : 0);
     if ((terminated || truncated) && a.autoreset) {                      // sync_vector_env.py:152-156
         if (a.final_obs) store_row<24>(a.final_obs, i, obs);
         rng.g = pcg64_load(a.rng + 4 * i);
-        walker::env_reset(W, rng, obs);
+        walker::env_reset<HC>(W, rng, obs);
         pcg64_store(a.rng + 4 * i, rng.g);
         elapsed = 0;
     }
-    walker::store_world(W, a.lunar_rec, a.n, i, rng);
+    walker::store_world(W, a.lunar_rec, a.n, i, rng, HC);
     a.elapsed[i] = elapsed;
     store_obs_all<24>(a, i, obs);
 }
 
+template <bool HC>
 __global__ void __launch_bounds__(kLunarThreads) walker_reset_kernel(uint32_t *rec, int32_t *elapsed, uint64_t *rng,
                                                                      const uint8_t *mask, float *obs, int64_t n) {
     const int64_t i = (int64_t)blockIdx.x * kLunarThreads + threadIdx.x;
@@ -720,8 +722,9 @@ __global__ void __launch_bounds__(kLunarThreads) walker_reset_kernel(uint32_t *r
     r.val32 = rec[(int64_t)(walker::W_RNG32 + 1) * n + i];
     r.g = pcg64_load(rng + 4 * i);
     float o[24];
-    walker::env_reset(W, r, o);
-    walker::store_world(W, rec, n, i, r);
+    W.np = 0; W.p_lo = 0; W.p_hi = -1;
+    walker::env_reset<HC>(W, r, o);
+    walker::store_world(W, rec, n, i, r, HC);
     pcg64_store(rng + 4 * i, r.g);
     elapsed[i] = 0;
     if (obs) store_row<24>(obs, i, o);
@@ -733,6 +736,18 @@ __global__ void walker_clear_rng32_kernel(uint32_t *rec, const uint8_t *mask, in
     if (i >= n || (mask && !mask[i])) return;
     rec[(int64_t)walker::W_RNG32 * n + i] = 0u;
     rec[(int64_t)(walker::W_RNG32 + 1) * n + i] = 0u;
+}
+
+// terrain heights [n][200] and (hardcore) obstacle boxes [n][40][4] = {x0, ylo, x1, yhi} + their number [n]
+__global__ void walker_terrain_kernel(const uint32_t *rec, float *terrain, float *polys, int32_t *npoly, int64_t n, int hardcore) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    for (int k = 0; k < walker::kTerrain; k++) terrain[i * walker::kTerrain + k] = __uint_as_float(rec[(int64_t)(walker::W_TERRAIN + k) * n + i]);
+    if (!polys || !npoly) return;
+    const int np = hardcore ? (int)rec[(int64_t)walker::W_NPOLY * n + i] : 0;
+    npoly[i] = np;
+    for (int k = 0; k < 4 * walker::NP; k++)
+        polys[i * 4 * walker::NP + k] = k < 4 * np ? __uint_as_float(rec[(int64_t)(walker::W_POLY + k) * n + i]) : 0.0f;
 }
 
 __global__ void walker_bodies_kernel(const uint32_t *rec, float *out, int32_t *flags, int64_t n) {
@@ -1037,10 +1052,13 @@ static int launch_step(b200gym *h, const StepArgs &a, int action_dtype, cudaStre
         CK(h, cudaGetLastError());
         return 0;
     }
-    case B200GYM_BIPEDALWALKER: {
+    case B200GYM_BIPEDALWALKER:
+    case B200GYM_BIPEDALWALKER_HARDCORE: {
         if (action_dtype != B200GYM_ACT_F32) return fail(h, "Box env needs float32 actions (got dtype code %d)", action_dtype);
         if ((uintptr_t)a.actions % 16 != 0) return fail(h, "BipedalWalker actions must be 16-byte aligned");
-        walker_step_kernel<<<(unsigned)((a.count + kLunarThreads - 1) / kLunarThreads), kLunarThreads, 0, st>>>(a);
+        const unsigned grid = (unsigned)((a.count + kLunarThreads - 1) / kLunarThreads);
+        if (h->cfg.kind == B200GYM_BIPEDALWALKER_HARDCORE) walker_step_kernel<true><<<grid, kLunarThreads, 0, st>>>(a);
+        else walker_step_kernel<false><<<grid, kLunarThreads, 0, st>>>(a);
         CK(h, cudaGetLastError());
         return 0;
     }
@@ -1070,7 +1088,11 @@ static int launch_reset(b200gym *h, const uint8_t *mask, const double *bounds, f
             h->lunar_rec, h->elapsed, h->rng, mask, obs, h->n, h->lunar_opts);
         break;
     case B200GYM_BIPEDALWALKER:
-        walker_reset_kernel<<<(unsigned)((h->n + kLunarThreads - 1) / kLunarThreads), kLunarThreads, 0, st>>>(
+        walker_reset_kernel<false><<<(unsigned)((h->n + kLunarThreads - 1) / kLunarThreads), kLunarThreads, 0, st>>>(
+            h->lunar_rec, h->elapsed, h->rng, mask, obs, h->n);
+        break;
+    case B200GYM_BIPEDALWALKER_HARDCORE:
+        walker_reset_kernel<true><<<(unsigned)((h->n + kLunarThreads - 1) / kLunarThreads), kLunarThreads, 0, st>>>(
             h->lunar_rec, h->elapsed, h->rng, mask, obs, h->n);
         break;
     default: return fail(h, "bad kind %d", h->cfg.kind);
@@ -1142,7 +1164,7 @@ extern "C" int b200gym_create(const b200gym_config *cfg, int64_t num_envs, int d
             return 1;
         }
     h->is_lunar = cfg->kind == B200GYM_LUNARLANDER || cfg->kind == B200GYM_LUNARLANDER_CONT;
-    h->is_walker = cfg->kind == B200GYM_BIPEDALWALKER;
+    h->is_walker = cfg->kind == B200GYM_BIPEDALWALKER || cfg->kind == B200GYM_BIPEDALWALKER_HARDCORE;
     if (h->is_lunar) {  // LunarLander.__init__ arguments (lunar_lander.py:194-233)
         h->lunar_opts.continuous = cfg->kind == B200GYM_LUNARLANDER_CONT;
         h->lunar_opts.wind = (cfg->flags & B200GYM_LUNAR_ENABLE_WIND) != 0;
@@ -1152,7 +1174,8 @@ extern "C" int b200gym_create(const b200gym_config *cfg, int64_t num_envs, int d
     }
     if (h->is_lunar || h->is_walker) {
         const bool lun = h->is_lunar;
-        const size_t words = lun ? lunar::kWords : walker::kWords;
+        const size_t words = lun ? lunar::kWords
+                                 : (cfg->kind == B200GYM_BIPEDALWALKER_HARDCORE ? walker::kWordsHC : walker::kWords);
         if (cudaMalloc(&h->lunar_rec, sizeof(uint32_t) * words * n) != cudaSuccess ||
             cudaMemset(h->lunar_rec, 0, sizeof(uint32_t) * words * n) != cudaSuccess ||
             (lun ? lunar_upload_consts(h) : walker_upload_consts(h))) {
@@ -1216,7 +1239,7 @@ extern "C" int b200gym_seed_range(b200gym_t *h, const uint32_t base_words[4], in
     seed_range_kernel<<<blocks_for(h->n), kThreads, 0, (cudaStream_t)stream>>>(
         h->rng, h->n, base_words[0], base_words[1], base_words[2], base_words[3], (uint64_t)first_index);
     CK(h, cudaGetLastError());
-    if (h->cfg.kind == B200GYM_BIPEDALWALKER) {
+    if (h->is_walker) {
         walker_clear_rng32_kernel<<<blocks_for(h->n), kThreads, 0, (cudaStream_t)stream>>>(h->lunar_rec, nullptr, h->n);
         CK(h, cudaGetLastError());
     }
@@ -1237,7 +1260,7 @@ extern "C" int b200gym_seed_each(b200gym_t *h, const uint32_t *ent_host, const u
     }
     if (e == cudaSuccess) {
         seed_each_kernel<<<blocks_for(h->n), kThreads, 0, st>>>(h->rng, h->n, d_ent, d_mask);
-        if (h->cfg.kind == B200GYM_BIPEDALWALKER)
+        if (h->is_walker)
             walker_clear_rng32_kernel<<<blocks_for(h->n), kThreads, 0, st>>>(h->lunar_rec, d_mask, h->n);
         e = cudaGetLastError();
     }
@@ -1661,9 +1684,19 @@ extern "C" int b200gym_lunar_wind_idx(b200gym_t *h, int32_t *wind_idx_host, int3
 
 extern "C" int b200gym_walker_get_bodies(b200gym_t *h, float *bodies_dev, int32_t *flags_dev, void *stream) {
     if (!h || !bodies_dev || !flags_dev) return fail(h, "b200gym_walker_get_bodies: null argument");
-    if (h->cfg.kind != B200GYM_BIPEDALWALKER) return fail(h, "b200gym_walker_get_bodies: not a BipedalWalker handle");
+    if (!h->is_walker) return fail(h, "b200gym_walker_get_bodies: not a BipedalWalker handle");
     DeviceGuard guard(h->device);
     walker_bodies_kernel<<<blocks_for(h->n), kThreads, 0, (cudaStream_t)stream>>>(h->lunar_rec, bodies_dev, flags_dev, h->n);
+    CK(h, cudaGetLastError());
+    return 0;
+}
+
+extern "C" int b200gym_walker_get_terrain(b200gym_t *h, float *terrain_dev, float *polys_dev, int32_t *npoly_dev, void *stream) {
+    if (!h || !terrain_dev) return fail(h, "b200gym_walker_get_terrain: null argument");
+    if (!h->is_walker) return fail(h, "b200gym_walker_get_terrain: not a BipedalWalker handle");
+    DeviceGuard guard(h->device);
+    walker_terrain_kernel<<<blocks_for(h->n), kThreads, 0, (cudaStream_t)stream>>>(
+        h->lunar_rec, terrain_dev, polys_dev, npoly_dev, h->n, h->cfg.kind == B200GYM_BIPEDALWALKER_HARDCORE);
     CK(h, cudaGetLastError());
     return 0;
 }

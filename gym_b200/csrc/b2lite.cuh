@@ -232,6 +232,136 @@ __device__ __noinline__ void collide_edge_polygon(Manifold &m, v2 v1, v2 v2_, co
     m.pointCount = pc;
 }
 
+// ---- b2CollidePolygons (Box2D 2.3.1+: brute-force b2FindMaxSeparation), polygon A = a static 4-gon at the
+// identity transform (BipedalWalkerHardcore's stumps, stair steps, pit walls), polygon B = a body's fixture ----
+struct StaticBox { v2 verts[4], normals[4]; };
+
+// b2PolygonShape::Set on the corners of an axis-aligned box: hull from the right-most lowest corner, CCW
+LD void static_box(StaticBox &s, float x0, float ylo, float x1, float yhi) {
+    s.verts[0] = V(x1, ylo); s.verts[1] = V(x1, yhi); s.verts[2] = V(x0, yhi); s.verts[3] = V(x0, ylo);
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+        const v2 edge = sub(s.verts[(i + 1) & 3], s.verts[i]);
+        const v2 nr = crs_vs(edge, 1.0f);
+        const float len = sqrtf(nr.x * nr.x + nr.y * nr.y);
+        const float inv = 1.0f / len;
+        s.normals[i] = V(inv * nr.x, inv * nr.y);
+    }
+}
+
+LD v2 rmulT(rot q, v2 v) { return V(q.c * v.x + q.s * v.y, -q.s * v.x + q.c * v.y); }
+LD xform xf_mulT(const xform &A, const xform &B) {  // b2MulT(A, B)
+    xform C;
+    C.q.s = A.q.c * B.q.s - A.q.s * B.q.c;
+    C.q.c = A.q.c * B.q.c + A.q.s * B.q.s;
+    C.p = rmulT(A.q, sub(B.p, A.p));
+    return C;
+}
+
+LD float find_max_separation(int &edgeIndex, int count1, const v2 *n1s, const v2 *v1s, const xform &xf1, int count2,
+                             const v2 *v2s, const xform &xf2) {
+    const xform xf = xf_mulT(xf2, xf1);
+    int bestIndex = 0;
+    float maxSeparation = -kFltMax;
+    for (int i = 0; i < count1; i++) {
+        const v2 n = rmul(xf.q, n1s[i]);
+        const v2 v1 = xmul(xf, v1s[i]);
+        float si = kFltMax;
+        for (int j = 0; j < count2; j++) { const float sij = dot(n, sub(v2s[j], v1)); if (sij < si) si = sij; }
+        if (si > maxSeparation) { maxSeparation = si; bestIndex = i; }
+    }
+    edgeIndex = bestIndex;
+    return maxSeparation;
+}
+
+__device__ __noinline__ void collide_polygons(Manifold &m, const StaticBox &A, const ShapeConst &sh, const xform &xfB) {
+    xform xfA;
+    xfA.p = V(0.0f, 0.0f); xfA.q.s = 0.0f; xfA.q.c = 1.0f;
+    m.pointCount = 0;
+    const float totalRadius = kPolygonRadius + kPolygonRadius;
+    int edgeA = 0, edgeB = 0;
+    const float separationA = find_max_separation(edgeA, 4, A.normals, A.verts, xfA, sh.count, sh.verts, xfB);
+    if (separationA > totalRadius) return;
+    const float separationB = find_max_separation(edgeB, sh.count, sh.normals, sh.verts, xfB, 4, A.verts, xfA);
+    if (separationB > totalRadius) return;
+    const v2 *verts1, *normals1, *verts2, *normals2;
+    int count1, count2, edge1;
+    bool flip;
+    xform xf1, xf2;
+    const float k_tol = 0.1f * kLinearSlop;
+    if (separationB > separationA + k_tol) {
+        verts1 = sh.verts; normals1 = sh.normals; count1 = sh.count; verts2 = A.verts; normals2 = A.normals; count2 = 4;
+        xf1 = xfB; xf2 = xfA; edge1 = edgeB; m.type = 1; flip = true;
+    } else {
+        verts1 = A.verts; normals1 = A.normals; count1 = 4; verts2 = sh.verts; normals2 = sh.normals; count2 = sh.count;
+        xf1 = xfA; xf2 = xfB; edge1 = edgeA; m.type = 0; flip = false;
+    }
+    ClipV ie[2];
+    {   // b2FindIncidentEdge
+        const v2 normal1 = rmulT(xf2.q, rmul(xf1.q, normals1[edge1]));
+        int index = 0;
+        float minDot = kFltMax;
+        for (int i = 0; i < count2; i++) { const float d = dot(normal1, normals2[i]); if (d < minDot) { minDot = d; index = i; } }
+        const int i1 = index, i2 = i1 + 1 < count2 ? i1 + 1 : 0;
+        ie[0].v = xmul(xf2, verts2[i1]); ie[0].id = make_id((uint32_t)edge1, (uint32_t)i1, 1u, 0u);
+        ie[1].v = xmul(xf2, verts2[i2]); ie[1].id = make_id((uint32_t)edge1, (uint32_t)i2, 1u, 0u);
+    }
+    const int iv1 = edge1, iv2 = edge1 + 1 < count1 ? edge1 + 1 : 0;
+    v2 v11 = verts1[iv1], v12 = verts1[iv2];
+    v2 localTangent = sub(v12, v11);
+    {
+        const float len = sqrtf(localTangent.x * localTangent.x + localTangent.y * localTangent.y);
+        if (len >= 1.1920929e-07f) { const float inv = 1.0f / len; localTangent.x *= inv; localTangent.y *= inv; }
+    }
+    const v2 localNormal = crs_vs(localTangent, 1.0f);
+    const v2 planePoint = scl(0.5f, add(v11, v12));
+    const v2 tangent = rmul(xf1.q, localTangent);
+    const v2 normal = crs_vs(tangent, 1.0f);
+    v11 = xmul(xf1, v11); v12 = xmul(xf1, v12);
+    const float frontOffset = dot(normal, v11);
+    const float sideOffset1 = -dot(tangent, v11) + totalRadius;
+    const float sideOffset2 = dot(tangent, v12) + totalRadius;
+    ClipV c1[2], c2[2];
+    if (clip_segment(c1, ie, neg(tangent), sideOffset1, iv1) < 2) return;
+    if (clip_segment(c2, c1, tangent, sideOffset2, iv2) < 2) return;
+    m.localNormal = localNormal;
+    m.localPoint = planePoint;
+    int pc = 0;
+    for (int i = 0; i < 2; i++) {
+        const float separation = dot(normal, c2[i].v) - frontOffset;
+        if (separation <= totalRadius) {
+            MPoint &cp = m.pts[pc];
+            cp.localPoint = xmulT(xf2, c2[i].v);
+            const uint32_t id = c2[i].id;
+            cp.id = flip ? make_id((id >> 8) & 0xff, id & 0xff, (id >> 24) & 0xff, (id >> 16) & 0xff) : id;
+            pc++;
+        }
+    }
+    m.pointCount = pc;
+}
+
+// b2PolygonShape::RayCast against a static box at the identity transform
+LD bool static_box_raycast(const StaticBox &s, v2 p1_, v2 p2_, float maxFraction, float &t_out) {
+    rot qi;
+    qi.s = 0.0f; qi.c = 1.0f;
+    const v2 p1 = rmulT(qi, sub(p1_, V(0.0f, 0.0f))), p2 = rmulT(qi, sub(p2_, V(0.0f, 0.0f)));
+    const v2 d = sub(p2, p1);
+    float lower = 0.0f, upper = maxFraction;
+    int index = -1;
+    for (int i = 0; i < 4; i++) {
+        const float numerator = dot(s.normals[i], sub(s.verts[i], p1));
+        const float denominator = dot(s.normals[i], d);
+        if (denominator == 0.0f) { if (numerator < 0.0f) return false; }
+        else {
+            if (denominator < 0.0f && numerator < lower * denominator) { lower = numerator / denominator; index = i; }
+            else if (denominator > 0.0f && numerator < upper * denominator) upper = numerator / denominator;
+        }
+        if (upper < lower) return false;
+    }
+    if (index >= 0) { t_out = lower; return true; }
+    return false;
+}
+
 // ---- constraints ---------------------------------------------------------------------------------
 struct VCP { v2 rB; float nI, tI, normalMass, tangentMass; };
 struct VC {
@@ -384,13 +514,14 @@ __device__ __noinline__ bool joint_solve_position(const Joint &j, const JointDef
 
 // ---- b2World::Step(1/50, 180, 60) for one env ------------------------------------------------------
 // Scene supplies: NB, NJ, kSlots, kMaxVC, World (with b[], j[], flags, slot_*), shape(b), jdef(k),
-// body_order(k), joint_order(k), edge(W, e, v1, v2, friction), edge_range(W, lox, hix, lo, hi),
-// on_event(W, body, begin).  `force0` / `torque0` are the force and torque accumulated on body 0 before the
+// body_order(k), joint_order(k), edge(W, e, v1, v2, friction), edge_range(W, lox, hix, lo, hi), NP (+ poly(W, p,
+// x0, ylo, x1, yhi, friction), poly_range(W, lox, hix, lo, hi) when NP > 0), on_event(W, body, begin).  `force0` / `torque0` are the force and torque accumulated on body 0 before the
 // step (b2Body::ApplyForceToCenter / ApplyTorque), `gravity_y` the world's gravity (0, gravity_y).
 template <typename Scene>
 __device__ __noinline__ void world_step(typename Scene::World &W, v2 force0, float torque0, float gravity_y,
                                         bool &island_awake) {
     constexpr int NB = Scene::NB, NJ = Scene::NJ, kSlots = Scene::kSlots, kMaxVC = Scene::kMaxVC;
+    constexpr int NE = Scene::NE, NP = Scene::NP, NF = NE + NP;
     const float dt = (float)(1.0 / 50);
     const float inv_dt0 = (W.flags & kFlagStepped) ? 1.0f / dt : 0.0f;
     const float dtRatio = inv_dt0 * dt;
@@ -409,29 +540,47 @@ __device__ __noinline__ void world_step(typename Scene::World &W, v2 force0, flo
             lox = fmin_(lox, p.x); loy = fmin_(loy, p.y); hix = fmax_(hix, p.x); hiy = fmax_(hiy, p.y);
         }
         const float ext = kPolygonRadius + kAabbExtension;
-        // candidate edges: those the scene says can overlap the AABB, widened to every edge this body
-        // was touching last step (so that leaving it raises EndContact), visited in descending order
-        int e_lo, e_hi;
+        // candidate ground fixtures: those the scene says can overlap the AABB, widened to every fixture this
+        // body was touching last step (so that leaving it raises EndContact).  Fixture index f: edges 0..NE-1,
+        // static polygons NE..NE+NP-1; visited in descending f (polygons first, then edges).
+        int e_lo, e_hi, p_lo = 0, p_hi = -1;
         Scene::edge_range(W, lox - ext, hix + ext, e_lo, e_hi);
+        if constexpr (NP > 0) Scene::poly_range(W, lox - ext, hix + ext, p_lo, p_hi);
         for (int s = 0; s < kSlots; s++)
-            if ((W.slot_key[s] >> 16) && (int)((W.slot_key[s] & 0xffffu) / Scene::NE) == b) {
-                const int pe = (int)((W.slot_key[s] & 0xffffu) % Scene::NE);
-                e_lo = pe < e_lo ? pe : e_lo;
-                e_hi = pe > e_hi ? pe : e_hi;
+            if ((W.slot_key[s] >> 16) && (int)((W.slot_key[s] & 0xffffu) / NF) == b) {
+                const int pf = (int)((W.slot_key[s] & 0xffffu) % NF);
+                if (pf < NE) { e_lo = pf < e_lo ? pf : e_lo; e_hi = pf > e_hi ? pf : e_hi; }
+                else if (p_hi < p_lo) { p_lo = p_hi = pf - NE; }
+                else { p_lo = pf - NE < p_lo ? pf - NE : p_lo; p_hi = pf - NE > p_hi ? pf - NE : p_hi; }
             }
-        for (int e = e_hi; e >= e_lo; e--) {
-            const int pair = b * Scene::NE + e;
+        for (int f = (NP > 0 && p_hi >= p_lo) ? NE + p_hi : e_hi; f >= e_lo;) {
+            const int pair = b * NF + f;
             bool was = false;
             for (int s = 0; s < kSlots; s++) was = was || ((W.slot_key[s] >> 16) && (int)(W.slot_key[s] & 0xffffu) == pair);
-            v2 v1, v2_;
             float efric;
-            Scene::edge(W, e, v1, v2_, efric);
-            const float elox = fmin_(v1.x, v2_.x) - ext, ehix = fmax_(v1.x, v2_.x) + ext;
-            const float eloy = fmin_(v1.y, v2_.y) - ext, ehiy = fmax_(v1.y, v2_.y) + ext;
             Manifold m;
             m.pointCount = 0;
-            if (!(lox - ext > ehix || elox > hix + ext || loy - ext > ehiy || eloy > hiy + ext))
-                collide_edge_polygon(m, v1, v2_, sh, W.b[b].xf);
+            if (NP > 0 && f >= NE) {
+                if constexpr (NP > 0) {
+                    float x0, ylo, x1, yhi;
+                    Scene::poly(W, f - NE, x0, ylo, x1, yhi, efric);
+                    if (!(lox - ext > x1 + ext || x0 - ext > hix + ext || loy - ext > yhi + ext || ylo - ext > hiy + ext)) {
+                        StaticBox sb;
+                        static_box(sb, x0, ylo, x1, yhi);
+                        collide_polygons(m, sb, sh, W.b[b].xf);
+                    }
+                }
+            } else {
+                v2 v1, v2_;
+                Scene::edge(W, f, v1, v2_, efric);
+                const float elox = fmin_(v1.x, v2_.x) - ext, ehix = fmax_(v1.x, v2_.x) + ext;
+                const float eloy = fmin_(v1.y, v2_.y) - ext, ehiy = fmax_(v1.y, v2_.y) + ext;
+                if (!(lox - ext > ehix || elox > hix + ext || loy - ext > ehiy || eloy > hiy + ext))
+                    collide_edge_polygon(m, v1, v2_, sh, W.b[b].xf);
+            }
+            const int e = f;
+            f--;
+            if (f > e_hi && f < NE + p_lo) f = e_hi;   // from the lowest candidate polygon down to the highest candidate edge
             const bool touching = m.pointCount > 0;
             if (touching != was) Scene::on_event(W, b, touching);  // Begin/EndContact listener
             if (!touching) continue;
@@ -626,7 +775,7 @@ __device__ __noinline__ void world_step(typename Scene::World &W, v2 force0, flo
     for (int s = 0; s < kSlots; s++) W.slot_key[s] = 0u;
     for (int ci = 0; ci < nvc; ci++) {
         const VC &k = vc[ci];
-        W.slot_key[ci] = (uint32_t)(k.body * Scene::NE + k.edge) | ((uint32_t)(k.mPointCount + 1) << 16);
+        W.slot_key[ci] = (uint32_t)(k.body * NF + k.edge) | ((uint32_t)(k.mPointCount + 1) << 16);
         for (int p = 0; p < 2; p++) {
             W.slot_id[ci][p] = ids[ci][p];
             // points dropped by the condition-number fallback keep the impulse they were given

@@ -60,6 +60,7 @@ struct World : WorldBase<NB, NJ, kSlots> {
 
 struct Scene {
     static constexpr int NB = lunar::NB, NJ = lunar::NJ, NE = lunar::NE, kSlots = lunar::kSlots, kMaxVC = 8;
+    static constexpr int NP = 0;   // no static polygons in this scene
     using World = lunar::World;
     LD static const ShapeConst &shape(int b) { return kC.shape[b == 0 ? 0 : 1]; }
     LD static const JointDef &jdef(int k) { return kC.jd[k]; }

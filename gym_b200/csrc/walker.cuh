@@ -1,10 +1,12 @@
-// walker.cuh -- BipedalWalker-v3 on the device (scene + environment logic on top of b2lite.cuh).
+// walker.cuh -- BipedalWalker-v3 / BipedalWalkerHardcore-v3 on the device (scene + environment logic on top of
+// b2lite.cuh).
 //
 // Reference: gym/envs/box2d/bipedal_walker.py (reset :425-515, _generate_terrain :277-402,
 // _generate_clouds :404-423, step :517-606, ContactDetector :80-98, LidarCallback :504-510).
 // Scene: hull (5-gon, density 5) + two upper and two lower leg boxes (density 1), four revolute
 // joints (hips, knees; limits + motors whose speed/torque the action sets every step), 199
-// static terrain edges (friction 2.5), 10 lidar rays.  Non-hardcore terrain only.
+// static terrain edges (friction 2.5), 10 lidar rays; hardcore=True (template parameter HC) adds up to 39 static
+// boxes -- stumps, stair steps, pit walls (:300-373) -- that collide (b2CollidePolygons) and stop the lidar.
 #pragma once
 #include <cstdint>
 
@@ -40,20 +42,47 @@ constexpr int W_RNG32 = 58;     // numpy's buffered next_uint32: {has_uint32, ui
 constexpr int W_SLOT = 60;      // kSlots x {key, id0, nI0, tI0, id1, nI1, tI1}
 constexpr int W_TERRAIN = W_SLOT + 7 * kSlots;  // terrain_y[200] (read on demand, written by reset)
 constexpr int kWords = W_TERRAIN + kTerrain;    // 330
+// hardcore only: the obstacle boxes, in creation (ascending x) order
+constexpr int NP = 40;                          // at most 39 can be generated on 200 segments
+constexpr int W_NPOLY = kWords;                 // number of boxes
+constexpr int W_POLY = W_NPOLY + 1;             // NP x {x0, ylo, x1, yhi}
+constexpr int kWordsHC = W_POLY + 4 * NP;       // 491
 
 struct World : WorldBase<NB, NJ, kSlots> {
     double prev_shaping;
     uint32_t *terrain;        // &rec[W_TERRAIN * n + i]; element k lives at terrain[k * n]
     int64_t n;
+    int np, p_lo, p_hi;       // hardcore: boxes in use; the window of boxes near the walker this step
 };
 
 LD float terrain_x(int k) { return (float)((double)k * (14 / 30.0)); }          // i * TERRAIN_STEP
 // plain (coherent) load: an autoreset in the same kernel rewrites the terrain this thread then reads
 LD float terrain_y(const World &W, int k) { return __uint_as_float(W.terrain[(int64_t)k * W.n]); }
+LD float poly_word(const World &W, int p, int k) {
+    return __uint_as_float(W.terrain[(int64_t)(W_POLY - W_TERRAIN + 4 * p + k) * W.n]);
+}
+// boxes whose x-extent meets [lo_x, hi_x]: they are sorted by x and disjoint in x
+LD void poly_window(const World &W, float lo_x, float hi_x, int &lo, int &hi) {
+    lo = 0; hi = -1;
+    bool any = false;
+    for (int p = 0; p < W.np; p++) {
+        const float x0 = poly_word(W, p, 0), x1 = poly_word(W, p, 2);
+        if (x1 >= lo_x && x0 <= hi_x) { if (!any) { lo = p; any = true; } hi = p; }
+    }
+}
 
-struct Scene {
+template <bool HC>
+struct SceneT {
     static constexpr int NB = walker::NB, NJ = walker::NJ, NE = walker::NE, kSlots = walker::kSlots, kMaxVC = 10;
+    static constexpr int NP = HC ? walker::NP : 0;
     using World = walker::World;
+    // fd_polygon: friction 2.5 (bipedal_walker.py:180-184)
+    LD static void poly(const World &W, int p, float &x0, float &ylo, float &x1, float &yhi, float &friction) {
+        x0 = poly_word(W, p, 0); ylo = poly_word(W, p, 1); x1 = poly_word(W, p, 2); yhi = poly_word(W, p, 3);
+        friction = 2.5f;
+    }
+    // the window computed once per step around the whole walker (every body lies inside it)
+    LD static void poly_range(const World &W, float, float, int &lo, int &hi) { lo = W.p_lo; hi = W.p_hi; }
     LD static const ShapeConst &shape(int b) { return kC.shape[b == 0 ? 0 : ((b & 1) ? 1 : 2)]; }
     LD static const JointDef &jdef(int k) { return kC.jd[k]; }
     // b2World::Solve's depth-first island walk from the newest body: lower(+1), leg(+1), hull, leg(-1), lower(-1);
@@ -85,6 +114,7 @@ struct Scene {
         }
     }
 };
+using Scene = SceneT<false>;
 
 // numpy Generator with the 32-bit cache that Generator.integers() uses
 struct Rng { Pcg64 g; uint32_t has32, val32; };
@@ -134,6 +164,7 @@ LD float sgnf(float a) { return a > 0.0f ? 1.0f : (a < 0.0f ? -1.0f : 0.0f); }
 LD float clip01_abs(float a) { float x = fabsf(a); x = x < 0.0f ? 0.0f : x; return x > 1.0f ? 1.0f : x; }
 
 // bipedal_walker.py:517-606
+template <bool HC>
 __device__ __noinline__ void env_step(World &W, const float (&action)[4], bool from_reset, v2 hull_force, float (&obs)[24],
                                       double &reward, bool &terminated) {
     const double SCALE = 30.0, FPS = 50;
@@ -143,11 +174,17 @@ __device__ __noinline__ void env_step(World &W, const float (&action)[4], bool f
         W.j[k].maxMotorTorque = 80.0f * clip01_abs(action[k]);
     }
     bool awake;
-    world_step<Scene>(W, hull_force, 0.0f, -10.0f, awake);                                     // :545
+    if constexpr (HC) {
+        // every body stays within two leg lengths (2 x 34/30 m) of the hull: one window of boxes for all of them
+        poly_window(W, W.b[0].c.x - 4.0f, W.b[0].c.x + 4.0f, W.p_lo, W.p_hi);
+    }
+    world_step<SceneT<HC>>(W, hull_force, 0.0f, -10.0f, awake);                  // :545
     const Body &H = W.b[0];
     const double posx = (double)H.xf.p.x, posy = (double)H.xf.p.y;
     double st[24];
     const float step = (float)(14 / 30.0);
+    int lp_lo = 0, lp_hi = -1;
+    if constexpr (HC) poly_window(W, (float)posx - 0.5f, (float)posx + 6.0f, lp_lo, lp_hi);   // LIDAR_RANGE = 160/30
     for (int i = 0; i < 10; i++) {                                               // :550-557
         // math.sin / math.cos(1.5 * i / 10.0): compile-time constants, spelled out so that the device uses
         // the host libm's values
@@ -168,6 +205,14 @@ __device__ __noinline__ void env_step(World &W, const float (&action)[4], bool f
             float t;
             if (edge_raycast(V(terrain_x(e), terrain_y(W, e)), V(terrain_x(e + 1), terrain_y(W, e + 1)), p1, p2,
                              maxFraction, t)) { frac = t; maxFraction = t; }
+        }
+        if constexpr (HC) {   // LidarCallback accepts every fixture with categoryBits & 1: the boxes too (:504-510)
+            for (int q = lp_lo; q <= lp_hi; q++) {
+                StaticBox sb;
+                static_box(sb, poly_word(W, q, 0), poly_word(W, q, 1), poly_word(W, q, 2), poly_word(W, q, 3));
+                float t;
+                if (static_box_raycast(sb, p1, p2, maxFraction, t)) { frac = t; maxFraction = t; }
+            }
         }
         st[14 + i] = (double)frac;
     }
@@ -209,31 +254,72 @@ __device__ __noinline__ void env_step(World &W, const float (&action)[4], bool f
 }
 
 // bipedal_walker.py:425-515 (W.terrain / W.n must be bound to this env's record)
+template <bool HC>
 __device__ __noinline__ void env_reset(World &W, Rng &rng, float (&obs)[24]) {
     uint32_t *terrain_out = W.terrain;
     const double SCALE = 30.0;
-    const double TERRAIN_HEIGHT = 400 / SCALE / 4;
+    const double TERRAIN_HEIGHT = 400 / SCALE / 4, TERRAIN_STEP = 14 / SCALE;
     const uint32_t stepped = W.flags & kFlagStepped;
-    {   // _generate_terrain(hardcore=False) :277-402
-        double velocity = 0.0, y = TERRAIN_HEIGHT;
-        int counter = 20;
+    {   // _generate_terrain(hardcore) :277-402
+        enum { GRASS = 0, STUMP, STAIRS, PIT, STATES };
+        int state = GRASS;
+        double velocity = 0.0, y = TERRAIN_HEIGHT, original_y = 0;
+        long long counter = 20, stair_steps = 0, stair_width = 0, stair_height = 0;
         bool oneshot = false;
+        int np = 0;
+        auto box = [&](double x0, double ylo, double x1, double yhi) {   // CreateStaticBody(fixtures=fd_polygon)
+            const int64_t base = (int64_t)(W_POLY - W_TERRAIN + 4 * np) * W.n;
+            terrain_out[base] = __float_as_uint((float)x0);
+            terrain_out[base + W.n] = __float_as_uint((float)ylo);
+            terrain_out[base + 2 * W.n] = __float_as_uint((float)x1);
+            terrain_out[base + 3 * W.n] = __float_as_uint((float)yhi);
+            np++;
+        };
         for (int i = 0; i < kTerrain; i++) {
-            if (!oneshot) {
+            const double x = i * TERRAIN_STEP;
+            if (state == GRASS && !oneshot) {
                 const double d = TERRAIN_HEIGHT - y;
                 const double sgn = d > 0 ? 1.0 : (d < 0 ? -1.0 : 0.0);
                 velocity = 0.8 * velocity + 0.01 * sgn;                          // :296
                 if (i > 20) velocity += bgym::pcg64_uniform(rng.g, -1, 1) / SCALE;  // :297-298
                 y += velocity;
+            } else if (HC && state == PIT && oneshot) {                          // :301-323
+                counter = integers(rng, 3, 5);
+                box(x, y - 4 * TERRAIN_STEP, x + TERRAIN_STEP, y);
+                box(x + TERRAIN_STEP * counter, y - 4 * TERRAIN_STEP, x + TERRAIN_STEP + TERRAIN_STEP * counter, y);
+                counter += 2;
+                original_y = y;
+            } else if (HC && state == PIT && !oneshot) {                         // :325-328
+                y = original_y;
+                if (counter > 1) y -= 4 * TERRAIN_STEP;
+            } else if (HC && state == STUMP && oneshot) {                        // :330-341
+                counter = integers(rng, 1, 3);
+                box(x, y, x + counter * TERRAIN_STEP, y + counter * TERRAIN_STEP);
+            } else if (HC && state == STAIRS && oneshot) {                       // :343-371
+                stair_height = bgym::pcg64_next_double(rng.g) > 0.5 ? +1 : -1;
+                stair_width = integers(rng, 4, 5);
+                stair_steps = integers(rng, 3, 5);
+                original_y = y;
+                for (long long st = 0; st < stair_steps; st++)
+                    box(x + (st * stair_width) * TERRAIN_STEP, y + (-1 + st * stair_height) * TERRAIN_STEP,
+                        x + ((1 + st) * stair_width) * TERRAIN_STEP, y + (st * stair_height) * TERRAIN_STEP);
+                counter = stair_steps * stair_width;
+            } else if (HC && state == STAIRS && !oneshot) {                      // :373-376
+                const long long sq = stair_steps * stair_width - counter - stair_height;
+                const double nn = (double)sq / (double)stair_width;
+                y = original_y + (nn * stair_height) * TERRAIN_STEP;
             }
             oneshot = false;
             terrain_out[(int64_t)i * W.n] = __float_as_uint((float)y);
             counter -= 1;
             if (counter == 0) {
-                counter = (int)integers(rng, 10 / 2, 10);                        // :379
-                oneshot = true;                                                  // :384-385
+                counter = integers(rng, 10 / 2, 10);                             // :379
+                if (HC && state == GRASS) state = (int)integers(rng, 1, STATES); // :380-382
+                else state = GRASS;                                              // :383-385
+                oneshot = true;
             }
         }
+        W.np = np;
     }
     for (int i = 0; i < kTerrain / 20; i++) {   // _generate_clouds :404-423 (cosmetic, consumes the stream)
         (void)bgym::pcg64_next64(rng.g);
@@ -262,7 +348,7 @@ __device__ __noinline__ void env_reset(World &W, Rng &rng, float (&obs)[24]) {
     const float zero[4] = {0.0f, 0.0f, 0.0f, 0.0f};
     double r;
     bool t;
-    env_step(W, zero, true, V((float)fx, 0.0f), obs, r, t);                      // :515
+    env_step<HC>(W, zero, true, V((float)fx, 0.0f), obs, r, t);                  // :515
 }
 
 // ---- HBM <-> registers/local ---------------------------------------------------------------------
@@ -271,7 +357,7 @@ LD void bind_world(World &W, uint32_t *rec, int64_t n, int64_t i) {
     W.n = n;
 }
 
-LD void load_world(World &W, uint32_t *rec, int64_t n, int64_t i, Rng &rng) {
+LD void load_world(World &W, uint32_t *rec, int64_t n, int64_t i, Rng &rng, bool hardcore = false) {
     auto ld = [&](int k) { return rec[(int64_t)k * n + i]; };
     for (int b = 0; b < NB; b++) {
         Body &B = W.b[b];
@@ -301,9 +387,11 @@ LD void load_world(World &W, uint32_t *rec, int64_t n, int64_t i, Rng &rng) {
         }
     }
     bind_world(W, rec, n, i);
+    W.np = hardcore ? (int)ld(W_NPOLY) : 0;
+    W.p_lo = 0; W.p_hi = -1;
 }
 
-LD void store_world(const World &W, uint32_t *rec, int64_t n, int64_t i, const Rng &rng) {
+LD void store_world(const World &W, uint32_t *rec, int64_t n, int64_t i, const Rng &rng, bool hardcore = false) {
     auto st = [&](int k, uint32_t v) { rec[(int64_t)k * n + i] = v; };
     for (int b = 0; b < NB; b++) {
         const Body &B = W.b[b];
@@ -321,6 +409,7 @@ LD void store_world(const World &W, uint32_t *rec, int64_t n, int64_t i, const R
     const unsigned long long ps = (unsigned long long)__double_as_longlong(W.prev_shaping);
     st(W_SHAPING, (uint32_t)ps); st(W_SHAPING + 1, (uint32_t)(ps >> 32));
     st(W_RNG32, rng.has32); st(W_RNG32 + 1, rng.val32);
+    if (hardcore) st(W_NPOLY, (uint32_t)W.np);
     for (int s = 0; s < kSlots; s++) {
         st(W_SLOT + 7 * s, W.slot_key[s]);
         for (int p = 0; p < 2; p++) {

@@ -118,6 +118,9 @@ KINDS = {
     _lib.KIND_BIPEDALWALKER: KindInfo(
         "BipedalWalker", _walker_spaces, {}, ("low", "high"), (0.0, 0.0), dict(hardcore=False),
         {"render_modes": [], "render_fps": 50}),
+    _lib.KIND_BIPEDALWALKER_HARDCORE: KindInfo(
+        "BipedalWalker", _walker_spaces, {}, ("low", "high"), (0.0, 0.0), dict(hardcore=True),
+        {"render_modes": [], "render_fps": 50}),
 }
 
 
@@ -135,7 +138,8 @@ def parse_reset_bounds(kind, options):
     low/high kinds follow maybe_parse_reset_bounds (classic_control/utils.py:17-46);
     Pendulum follows pendulum.py:143-152 (x_init / y_init, symmetric limits).
     """
-    if options is None or kind in (_lib.KIND_LUNARLANDER, _lib.KIND_LUNARLANDER_CONT, _lib.KIND_BIPEDALWALKER):
+    if options is None or kind in (_lib.KIND_LUNARLANDER, _lib.KIND_LUNARLANDER_CONT, _lib.KIND_BIPEDALWALKER,
+                                   _lib.KIND_BIPEDALWALKER_HARDCORE):
         # their reset() ignores options
         return None
     info = KINDS[kind]
@@ -158,6 +162,9 @@ def resolve_variant(kind, kwargs):
             kind = _lib.KIND_LUNARLANDER_CONT if kwargs["continuous"] else _lib.KIND_LUNARLANDER
         if kwargs.get("enable_wind", False):
             flags |= _lib.LUNAR_ENABLE_WIND
+    if kind in (_lib.KIND_BIPEDALWALKER, _lib.KIND_BIPEDALWALKER_HARDCORE) and "hardcore" in kwargs:
+        # gym/envs/__init__.py:79-85 registers hardcore=True as BipedalWalkerHardcore-v3
+        kind = _lib.KIND_BIPEDALWALKER_HARDCORE if kwargs["hardcore"] else _lib.KIND_BIPEDALWALKER
     return kind, flags
 
 
@@ -185,14 +192,12 @@ def resolve_params(kind, kwargs):
             warnings.warn("WARN: turbulence_power value is recommended to be between 0.0 and 2.0, "
                           f"(current value: {turbulence_power})")
         return [gravity, wind_power, turbulence_power, 0.0]
-    if kind == _lib.KIND_BIPEDALWALKER:
-        for key, value in kwargs.items():
+    if kind in (_lib.KIND_BIPEDALWALKER, _lib.KIND_BIPEDALWALKER_HARDCORE):
+        for key, value in kwargs.items():   # BipedalWalker.__init__(render_mode, hardcore), bipedal_walker.py:167
             if key == "render_mode" and value is None:
                 continue
             if key != "hardcore":
                 raise TypeError(f"BipedalWalker got an unexpected keyword argument '{key}'")
-            if value:
-                raise NotImplementedError("gym_b200 BipedalWalker supports only hardcore=False")
         return params
     for key, (slot, default) in info.kwargs.items():
         params[slot] = float(default)

@@ -94,3 +94,5 @@ register("LunarLanderContinuous-v2", _lib.KIND_LUNARLANDER_CONT, "gym.envs.box2d
          reward_threshold=200, max_episode_steps=1000, continuous=True)
 register("BipedalWalker-v3", _lib.KIND_BIPEDALWALKER, "gym.envs.box2d.bipedal_walker:BipedalWalker",
          reward_threshold=300, max_episode_steps=1600)
+register("BipedalWalkerHardcore-v3", _lib.KIND_BIPEDALWALKER_HARDCORE, "gym.envs.box2d.bipedal_walker:BipedalWalker",
+         reward_threshold=300, max_episode_steps=2000, hardcore=True)

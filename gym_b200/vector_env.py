@@ -539,6 +539,20 @@ class B200VectorEnv:
             return self.max_episode_steps
         raise AttributeError(f"'{self._info.name}' env has no attribute '{name}' in gym_b200")
 
+    def walker_terrain(self):
+        """BipedalWalker* only: (terrain_y float32 (N, 200); obstacle boxes float32 (N, 40, 4) = {x0, y_low, x1,
+        y_high} in creation order; number of boxes int32 (N,)) -- `env.terrain_y` and the hardcore `fd_polygon`
+        bodies of the reference (bipedal_walker.py:309-316,336,365,377)."""
+        self._assert_open("walker_terrain")
+        torch = _torch()
+        terrain = torch.empty((self.num_envs, 200), dtype=torch.float32, device=self.device)
+        polys = torch.empty((self.num_envs, 40, 4), dtype=torch.float32, device=self.device)
+        npoly = torch.empty((self.num_envs,), dtype=torch.int32, device=self.device)
+        _lib.check(self._lib.b200gym_walker_get_terrain(self._handle, ctypes.c_void_p(terrain.data_ptr()),
+                                                        ctypes.c_void_p(polys.data_ptr()), ctypes.c_void_p(npoly.data_ptr()),
+                                                        self._stream()), self._handle)
+        return terrain, polys, npoly
+
     def get_attr(self, name):
         return self.call(name)
 

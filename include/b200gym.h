@@ -44,7 +44,9 @@ enum b200gym_kind {
                                      re-derived in csrc/b2lite.cuh */
     B200GYM_LUNARLANDER_CONT = 7, /* LunarLanderContinuous-v2 = LunarLander(continuous=True), gym/envs/__init__.py:71-77,
                                      lunar_lander.py:152-160,479-481,496-533: Box(2) float32 actions */
-    B200GYM_NUM_KINDS = 8
+    B200GYM_BIPEDALWALKER_HARDCORE = 8, /* BipedalWalkerHardcore-v3 = BipedalWalker(hardcore=True), gym/envs/__init__.py:79-85,
+                                     bipedal_walker.py:300-373: stumps, stairs and pits as static polygons */
+    B200GYM_NUM_KINDS = 9
 };
 
 /* b200gym_config.flags */
@@ -214,6 +216,10 @@ int b200gym_lunar_wind_idx(b200gym_t *h, int32_t *wind_idx_host, int32_t *torque
 /* BipedalWalker: float32 [n][30] = 5 x {c.x, c.y, angle, v.x, v.y, omega} (hull, leg(-1), lower(-1), leg(+1),
  * lower(+1)) and int32 [n][4] = {game_over, legs[1] contact, legs[3] contact, #touching contacts}. */
 int b200gym_walker_get_bodies(b200gym_t *h, float *bodies_dev, int32_t *flags_dev, void *stream);
+/* BipedalWalker*: what `env.terrain_y` (bipedal_walker.py:377) and the `fd_polygon` static bodies of the hardcore
+ * terrain (:309-316,336,365) hold: float32 terrain_dev[n][200]; polys_dev[n][40][4] = {x0, y_low, x1, y_high} of each
+ * obstacle box in creation order (unused rows 0) and int32 npoly_dev[n] (both may be NULL). */
+int b200gym_walker_get_terrain(b200gym_t *h, float *terrain_dev, float *polys_dev, int32_t *npoly_dev, void *stream);
 
 /*
  * Multi-GPU: fused step + all-gather over NVLink peer memory.

@@ -1,4 +1,4 @@
-"""BipedalWalker-v3 on the GPU against the CPU oracle (oracle/walker_oracle.c).  `pytest -m gpu`.
+"""BipedalWalker-v3 / BipedalWalkerHardcore-v3 on the GPU against the CPU oracle (oracle/walker_oracle.c).  `pytest -m gpu`.
 
 PARITY UNPINNED w.r.t. the real reference (no Box2D here).  Checked: the generic C implementation
 and the specialised CUDA one agree bit for bit (observations incl. lidar, rewards, flags, terrain,
@@ -78,8 +78,8 @@ def test_invariants_and_api():
         assert bool((r[~te] > -30).all())       # shaping deltas: a few points per step at most
         total_term += int(te.sum())
     assert total_term > N
-    with pytest.raises(NotImplementedError):
-        gym_b200.vector.make("BipedalWalker-v3", 4, hardcore=True)
+    with pytest.raises(TypeError):
+        gym_b200.vector.make("BipedalWalker-v3", 4, continuous=True)
     env.close()
     single = gym_b200.make("BipedalWalker-v3")
     s, _ = single.reset(seed=3)
@@ -87,3 +87,100 @@ def test_invariants_and_api():
     s2, r, term, trunc, _ = single.step(np.array([0.5, -0.5, 1.0, 0.0], dtype=np.float32))
     assert s2.shape == (24,) and isinstance(r, float) and term is False
     single.close()
+
+
+def _compare_step(t, got, want):
+    o, r, te, tr, info = got
+    ro, rr, rte, rtr, rfo = want
+    assert np.array_equal(te.cpu().numpy(), rte), f"step {t}: terminated"
+    assert np.array_equal(tr.cpu().numpy(), rtr), f"step {t}: truncated"
+    o_h = o.cpu().numpy()
+    if not np.array_equal(o_h, ro):
+        bad = np.argwhere(o_h != ro)
+        raise AssertionError(f"step {t}: {len(bad)} observation values differ, first {bad[0]} "
+                             f"got {o_h[tuple(bad[0])]!r} want {ro[tuple(bad[0])]!r}")
+    assert np.array_equal(r.cpu().numpy(), rr), f"step {t}: reward"
+    done = rte | rtr
+    if done.any():
+        assert np.array_equal(info["final_observation"].cpu().numpy()[done], rfo[done])
+    return done
+
+
+@pytest.mark.parametrize("env_id,hardcore", [("BipedalWalker-v3", False), ("BipedalWalkerHardcore-v3", True)])
+def test_demo_gait_bit_exact_against_oracle(env_id, hardcore):
+    """The reference's demo controller (bipedal_walker.py:775-854) drives every env: the walkers cross the course
+    (plain) or run into the stumps / stairs / pits (hardcore: polygon-polygon manifolds, boxes seen by the lidar),
+    and the kernel still agrees with the CPU oracle bit for bit."""
+    import gym_b200
+    import torch
+    from oracle.oracle import OracleWalker, WalkerHeuristic
+    N, T, seed = 96, 700, 40
+    env = gym_b200.vector.make(env_id, N)
+    assert env.max_episode_steps == (2000 if hardcore else 1600)
+    assert env.get_attr("hardcore") == (hardcore,) * N
+    orc = OracleWalker(N, hardcore=hardcore, max_episode_steps=env.max_episode_steps)
+    obs, _ = env.reset(seed=seed)
+    ref = orc.reset(seed=seed)
+    assert np.array_equal(obs.cpu().numpy(), ref)
+    terrain, polys, npoly = env.walker_terrain()
+    for i in range(N):
+        assert np.array_equal(terrain[i].cpu().numpy(), orc.terrain(i))
+        want = orc.polys(i)
+        assert int(npoly[i]) == len(want) and np.array_equal(polys[i, :len(want)].cpu().numpy(), want)
+    assert bool((npoly > 8).all()) if hardcore else bool((npoly == 0).all())
+    gaits = [WalkerHeuristic() for _ in range(N)]
+    a = np.zeros((N, 4), dtype=np.float32)
+    n_done, min_lidar, far = 0, 1.0, 0.0
+    for t in range(T):
+        got = env.step(torch.as_tensor(a, device=env.device))
+        want = orc.step(a)
+        done = _compare_step(t, got, want)
+        n_done += int(done.sum())
+        min_lidar = min(min_lidar, float(want[0][:, 14:].min()))
+        for i in range(N):
+            if done[i]:
+                gaits[i] = WalkerHeuristic()
+                a[i] = 0.0
+            else:
+                a[i] = gaits[i](want[0][i])
+        if t % 50 == 0:
+            bodies, _ = env.walker_bodies()
+            far = max(far, float(bodies[:, 0, 0].max()))
+    if hardcore:
+        assert n_done >= N // 2 and min_lidar < 0.4      # the gait falls at the obstacles
+        assert far > 9.0                                   # ... having walked up to them (first obstacle at x >= 9.33)
+    else:
+        assert far > 30.0                                  # a third of the course in 700 steps
+    bodies, flags = env.walker_bodies()
+    for i in (0, N // 2, N - 1):
+        ob, of = orc.bodies(i)
+        assert np.array_equal(bodies[i].cpu().numpy(), ob)
+        assert flags[i].tolist() == of.tolist()
+    env.close()
+    orc.close()
+
+
+def test_hardcore_random_actions_bit_exact_and_kwarg_selects_the_variant():
+    """BipedalWalker-v3 with hardcore=True is BipedalWalkerHardcore-v3 minus the registry's TimeLimit
+    (gym/envs/__init__.py:70-85); random torques, many resets (fresh obstacle layouts)."""
+    import gym_b200
+    import torch
+    from oracle.oracle import OracleWalker
+    N, T, seed = 512, 250, 77
+    env = gym_b200.vector.make("BipedalWalker-v3", N, hardcore=True)
+    assert env.max_episode_steps == 1600
+    orc = OracleWalker(N, hardcore=True, max_episode_steps=1600)
+    assert np.array_equal(env.reset(seed=seed)[0].cpu().numpy(), orc.reset(seed=seed))
+    rng = np.random.default_rng(6)
+    n_term = 0
+    for t in range(T):
+        a = rng.uniform(-1.2, 1.2, size=(N, 4)).astype(np.float32)
+        done = _compare_step(t, env.step(torch.as_tensor(a, device=env.device)), orc.step(a))
+        n_term += int(done.sum())
+    assert n_term > N
+    terrain, polys, npoly = env.walker_terrain()
+    for i in (0, 100, N - 1):
+        want = orc.polys(i)
+        assert int(npoly[i]) == len(want) and np.array_equal(polys[i, :len(want)].cpu().numpy(), want)
+    env.close()
+    orc.close()

@@ -34,10 +34,10 @@ def test_library_builds_and_exports_every_declared_symbol():
 def test_shape_queries_need_no_device():
     lib = _lib.load()
     assert lib.b200gym_version() == 1
-    assert [lib.b200gym_obs_dim(k) for k in range(8)] == [4, 2, 2, 3, 6, 8, 24, 8]
-    assert [lib.b200gym_act_dim(k) for k in range(8)] == [0, 0, 1, 1, 0, 0, 4, 2]
-    assert [lib.b200gym_num_actions(k) for k in range(8)] == [2, 3, 0, 0, 3, 4, 0, 0]
-    assert [lib.b200gym_state_dim(k) for k in range(8)] == [4, 2, 2, 2, 4, 0, 0, 0]
+    assert [lib.b200gym_obs_dim(k) for k in range(9)] == [4, 2, 2, 3, 6, 8, 24, 8, 24]
+    assert [lib.b200gym_act_dim(k) for k in range(9)] == [0, 0, 1, 1, 0, 0, 4, 2, 4]
+    assert [lib.b200gym_num_actions(k) for k in range(9)] == [2, 3, 0, 0, 3, 4, 0, 0, 0]
+    assert [lib.b200gym_state_dim(k) for k in range(9)] == [4, 2, 2, 2, 4, 0, 0, 0, 0]
     assert lib.b200gym_obs_dim(99) == -1
 
 
@@ -80,11 +80,13 @@ def test_registry_matches_reference_table():
     # gym/envs/__init__.py:11-60
     want = {"CartPole-v0": (200, 195.0), "CartPole-v1": (500, 475.0), "MountainCar-v0": (200, -110.0),
             "MountainCarContinuous-v0": (999, 90.0), "Pendulum-v1": (200, None), "Acrobot-v1": (500, -100.0),
-            "LunarLander-v2": (1000, 200), "LunarLanderContinuous-v2": (1000, 200), "BipedalWalker-v3": (1600, 300)}
+            "LunarLander-v2": (1000, 200), "LunarLanderContinuous-v2": (1000, 200), "BipedalWalker-v3": (1600, 300),
+            "BipedalWalkerHardcore-v3": (2000, 300)}
     for env_id, (steps, thr) in want.items():
         s = gym_b200.spec(env_id)
         assert s.max_episode_steps == steps and s.reward_threshold == thr
     assert gym_b200.spec("LunarLanderContinuous-v2").kwargs == {"continuous": True}   # gym/envs/__init__.py:62-68
+    assert gym_b200.spec("BipedalWalkerHardcore-v3").kwargs == {"hardcore": True}     # gym/envs/__init__.py:79-85
     assert gym_b200.spec("CartPole").id == "CartPole-v1"  # unversioned -> latest (registration.py:548-570)
     with pytest.raises(error.VersionNotFound):
         gym_b200.spec("CartPole-v7")
@@ -113,6 +115,12 @@ def test_lunar_lander_constructor_variants_resolve_like_the_reference():
         envs.resolve_params(K, {"turbulence_power": 2.5})
     with pytest.raises(TypeError):
         envs.resolve_params(K, {"hardcore": True})
+    W = _lib.KIND_BIPEDALWALKER
+    assert envs.resolve_variant(W, {"hardcore": True}) == (_lib.KIND_BIPEDALWALKER_HARDCORE, 0)
+    assert envs.resolve_variant(_lib.KIND_BIPEDALWALKER_HARDCORE, {"hardcore": False}) == (W, 0)
+    assert envs.resolve_variant(_lib.KIND_BIPEDALWALKER_HARDCORE, {}) == (_lib.KIND_BIPEDALWALKER_HARDCORE, 0)
+    with pytest.raises(TypeError):
+        envs.resolve_params(W, {"gravity": -5.0})
     obs_space, act_space = envs.KINDS[_lib.KIND_LUNARLANDER_CONT].spaces(None)
     assert act_space.shape == (2,) and act_space.dtype == np.float32
     assert float(act_space.low.min()) == -1.0 and float(act_space.high.max()) == 1.0 and obs_space.shape == (8,)

@@ -43,6 +43,8 @@ BYTES_PER_ENV_STEP = {"CartPole-v1": 106, "CartPole-v0": 106, "Pendulum-v1": 16 
                       "LunarLander-v2": 101 * 4 * 2 + 32 + 16 + 8 + 8 + 32 + 8 + 2,
                       # BipedalWalker: 130-word record r+w (the 200 terrain words are read on demand), action, outputs
                       "BipedalWalker-v3": 130 * 4 * 2 + 8 + 16 + 96 + 8 + 2}
+BYTES_PER_ENV_STEP["LunarLanderContinuous-v2"] = BYTES_PER_ENV_STEP["LunarLander-v2"]
+BYTES_PER_ENV_STEP["BipedalWalkerHardcore-v3"] = BYTES_PER_ENV_STEP["BipedalWalker-v3"] + 4
 # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed ncu --set full capture (2^20 envs)
 NCU_DRAM_BYTES_PER_LAUNCH = {"CartPole-v1": 56.20e6 + 25.84e6}
 FALLBACK_HBM_GBS = 6650.0  # /opt/skills/guides/B200_PROFILING.md fallback
@@ -136,6 +138,8 @@ def host_threads():
 
 
 def random_actions_np(env_id, n, rng):
+    if env_id.startswith("LunarLanderContinuous"):
+        return rng.uniform(-1.0, 1.0, size=(n, 2)).astype(np.float32)
     if env_id.startswith("LunarLander"):
         return rng.integers(0, 4, size=n).astype(np.int64)
     if env_id.startswith("BipedalWalker"):
@@ -153,8 +157,8 @@ def cpu_oracle_throughput(env_id, n, seconds, threads, min_steps=3):
     from oracle.oracle import OracleLunar, OracleVec, OracleWalker
     rng = np.random.default_rng(0)
     lunar = env_id.startswith(("LunarLander", "BipedalWalker"))
-    v = OracleLunar(n) if env_id.startswith("LunarLander") else (
-        OracleWalker(n) if env_id.startswith("BipedalWalker") else OracleVec(env_id, n))
+    v = OracleLunar(n, continuous="Continuous" in env_id) if env_id.startswith("LunarLander") else (
+        OracleWalker(n, hardcore="Hardcore" in env_id) if env_id.startswith("BipedalWalker") else OracleVec(env_id, n))
     v.reset(seed=0)
     pool = [random_actions_np(env_id, n, rng) for _ in range(4)]
     kw = {} if lunar else {"nthreads": threads}

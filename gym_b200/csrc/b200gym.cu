@@ -679,7 +679,7 @@ static int lunar_upload_consts(b200gym *h) {
 
 // ---- BipedalWalker-v3 (walker.cuh): one thread per env --------------------------------------------
 template <bool HC>
-__global__ void __launch_bounds__(kLunarThreads) walker_step_kernel(const StepArgs a) {
+__global__ void __launch_bounds__(kLunarThreads, 4) walker_step_kernel(const StepArgs a) {
     const int64_t j = (int64_t)blockIdx.x * kLunarThreads + threadIdx.x;
     if (j >= a.count) return;
     const int64_t i = a.first + j;

@@ -22,6 +22,7 @@
 // implementation can be matched bit for bit.
 #pragma once
 #include <cstdint>
+#include <type_traits>
 
 namespace b2l {
 
@@ -362,6 +363,15 @@ LD bool static_box_raycast(const StaticBox &s, v2 p1_, v2 p2_, float maxFraction
     return false;
 }
 
+// compile-time loop: f(std::integral_constant<int, I>{}) for I in [I0, N)
+template <int I, int N, typename F>
+__device__ __forceinline__ void static_for(F &&f) {
+    if constexpr (I < N) {
+        f(std::integral_constant<int, I>{});
+        static_for<I + 1, N>(static_cast<F &&>(f));
+    }
+}
+
 // ---- constraints ---------------------------------------------------------------------------------
 struct VCP { v2 rB; float nI, tI, normalMass, tangentMass; };
 struct VC {
@@ -426,7 +436,7 @@ LD void joint_init(Joint &j, JTemp &t, const JointDef &d, const ShapeConst &A, c
     sB.w += iB * (crs(rB, P) + j.motorImpulse + j.imp[2]);
 }
 
-__device__ __noinline__ void joint_solve_velocity(Joint &j, const JTemp &t, const ShapeConst &A, const ShapeConst &B, BState &sA,
+LD void joint_solve_velocity(Joint &j, const JTemp &t, const ShapeConst &A, const ShapeConst &B, BState &sA,
                                                   BState &sB, float dt) {
     const float mA = A.invMass, mB = B.invMass, iA = A.invI, iB = B.invI;
     v2 vA = sA.v, vB = sB.v;
@@ -471,7 +481,7 @@ __device__ __noinline__ void joint_solve_velocity(Joint &j, const JTemp &t, cons
     sA.v = vA; sA.w = wA; sB.v = vB; sB.w = wB;
 }
 
-__device__ __noinline__ bool joint_solve_position(const Joint &j, const JointDef &d, const ShapeConst &A, const ShapeConst &B,
+LD bool joint_solve_position(const Joint &j, const JointDef &d, const ShapeConst &A, const ShapeConst &B,
                                                   BState &sA, BState &sB) {
     const float mA = A.invMass, mB = B.invMass, iA = A.invI, iB = B.invI;
     v2 cA = sA.c, cB = sB.c;
@@ -514,7 +524,7 @@ __device__ __noinline__ bool joint_solve_position(const Joint &j, const JointDef
 
 // ---- b2World::Step(1/50, 180, 60) for one env ------------------------------------------------------
 // Scene supplies: NB, NJ, kSlots, kMaxVC, World (with b[], j[], flags, slot_*), shape(b), jdef(k),
-// body_order(k), joint_order(k), edge(W, e, v1, v2, friction), edge_range(W, lox, hix, lo, hi), NP (+ poly(W, p,
+// body_order(k), joint_order(k), joint_body_a(k), joint_body_b(k) (all constexpr), edge(W, e, v1, v2, friction), edge_range(W, lox, hix, lo, hi), NP (+ poly(W, p,
 // x0, ylo, x1, yhi, friction), poly_range(W, lox, hix, lo, hi) when NP > 0), on_event(W, body, begin).  `force0` / `torque0` are the force and torque accumulated on body 0 before the
 // step (b2Body::ApplyForceToCenter / ApplyTorque), `gravity_y` the world's gravity (0, gravity_y).
 template <typename Scene>
@@ -530,6 +540,8 @@ __device__ __noinline__ void world_step(typename Scene::World &W, v2 force0, flo
     // --- Collide + begin/end events; touching pairs become velocity constraints in island order
     VC vc[kMaxVC];
     int nvc = 0;
+    int cend[NB];   // contacts of island position oi: vc[cend[oi - 1] .. cend[oi])
+#pragma unroll
     for (int oi = 0; oi < NB; oi++) {
         const int b = Scene::body_order(oi);
         const ShapeConst &sh = Scene::shape(b);
@@ -607,11 +619,17 @@ __device__ __noinline__ void world_step(typename Scene::World &W, v2 force0, flo
                 }
             }
         }
+        cend[oi] = nvc;
     }
 
+    // From here on every body / joint index is a compile-time constant (static_for over the scene's island
+    // order), so st[], jn[], jt[] live in registers for the whole 180 + 60 iteration solve; only the contact
+    // constraints (their number is data dependent) stay in local memory.  Contacts were appended body by body
+    // in island order: those of island position oi are vc[cbeg(oi) .. cend[oi]).
     // --- integrate velocities
     BState st[NB];
-    for (int i = 0; i < NB; i++) {
+    static_for<0, NB>([&](auto I) {
+        constexpr int i = decltype(I)::value;
         const ShapeConst &sh = Scene::shape(i);
         v2 v = W.b[i].v;
         float w = W.b[i].w;
@@ -621,155 +639,166 @@ __device__ __noinline__ void world_step(typename Scene::World &W, v2 force0, flo
         v = scl(1.0f / (1.0f + dt * 0.0f), v);
         w = w * (1.0f / (1.0f + dt * 0.0f));
         st[i].c = W.b[i].c; st[i].a = W.b[i].a; st[i].v = v; st[i].w = w;
-    }
+    });
+    Joint jn[NJ];
+    static_for<0, NJ>([&](auto K) { constexpr int k = decltype(K)::value; jn[k] = W.j[k]; });
     // --- InitializeVelocityConstraints (+ remember the feature ids for the new store)
     uint32_t ids[kMaxVC][2];
-    for (int ci = 0; ci < nvc; ci++) {
-        VC &k = vc[ci];
-        const ShapeConst &sh = Scene::shape(k.body);
-        const BState &sB = st[k.body];
+    static_for<0, NB>([&](auto OI) {
+        constexpr int oi = decltype(OI)::value, body = Scene::body_order(oi);
+        const ShapeConst &sh = Scene::shape(body);
+        const BState &sB = st[body];
         const float mB = sh.invMass, iB = sh.invI;
-        ids[ci][0] = __float_as_uint(k.p[0].normalMass);
-        ids[ci][1] = k.pointCount > 1 ? __float_as_uint(k.p[1].normalMass) : 0u;
-        xform xfB;
-        xfB.q = rot_of(sB.a);
-        xfB.p = sub(sB.c, rmul(xfB.q, sh.localCenter));
-        v2 pts[2];
-        xform xfA;  // the moon: identity transform (kept as explicit arithmetic, like Box2D does)
-        xfA.p = V(0.0f, 0.0f); xfA.q.s = 0.0f; xfA.q.c = 1.0f;
-        if (k.mType == 0) {  // b2WorldManifold::Initialize, e_faceA
-            k.normal = rmul(xfA.q, k.localNormal);
-            const v2 plane = xmul(xfA, k.localPoint);
-            for (int p = 0; p < k.pointCount; p++) {
-                const v2 clip = xmul(xfB, k.lp[p]);
-                const v2 cA = add(clip, scl(kPolygonRadius - dot(sub(clip, plane), k.normal), k.normal));
-                const v2 cB = sub(clip, scl(kPolygonRadius, k.normal));
-                pts[p] = scl(0.5f, add(cA, cB));
-            }
-        } else {             // e_faceB
-            v2 nrm = rmul(xfB.q, k.localNormal);
-            const v2 plane = xmul(xfB, k.localPoint);
-            for (int p = 0; p < k.pointCount; p++) {
-                const v2 clip = xmul(xfA, k.lp[p]);
-                const v2 cB = add(clip, scl(kPolygonRadius - dot(sub(clip, plane), nrm), nrm));
-                const v2 cA = sub(clip, scl(kPolygonRadius, nrm));
-                pts[p] = scl(0.5f, add(cA, cB));
-            }
-            k.normal = neg(nrm);
-        }
-        for (int p = 0; p < k.pointCount; p++) {
-            VCP &cp = k.p[p];
-            cp.rB = sub(pts[p], sB.c);
-            const float rnB = crs(cp.rB, k.normal);
-            const float kN = mB + iB * rnB * rnB;
-            cp.normalMass = kN > 0.0f ? 1.0f / kN : 0.0f;
-            const v2 tangent = crs_vs(k.normal, 1.0f);
-            const float rtB = crs(cp.rB, tangent);
-            const float kT = mB + iB * rtB * rtB;
-            cp.tangentMass = kT > 0.0f ? 1.0f / kT : 0.0f;
-        }
-        if (k.pointCount == 2) {
-            const float rn1B = crs(k.p[0].rB, k.normal), rn2B = crs(k.p[1].rB, k.normal);
-            const float k11 = mB + iB * rn1B * rn1B, k22 = mB + iB * rn2B * rn2B, k12 = mB + iB * rn1B * rn2B;
-            if (k11 * k11 < 1000.0f * (k11 * k22 - k12 * k12)) {
-                k.k11 = k11; k.k12 = k12; k.k22 = k22;
-                float det = k11 * k22 - k12 * k12;
-                if (det != 0.0f) det = 1.0f / det;
-                k.n11 = det * k22; k.n12 = -det * k12; k.n22 = det * k11;
-            } else k.pointCount = 1;
-        }
-    }
-    // --- WarmStart
-    for (int ci = 0; ci < nvc; ci++) {
-        VC &k = vc[ci];
-        const ShapeConst &sh = Scene::shape(k.body);
-        BState &sB = st[k.body];
-        const v2 tangent = crs_vs(k.normal, 1.0f);
-        for (int p = 0; p < k.pointCount; p++) {
-            const v2 P = add(scl(k.p[p].nI, k.normal), scl(k.p[p].tI, tangent));
-            sB.w += sh.invI * crs(k.p[p].rB, P);
-            sB.v = add(sB.v, scl(sh.invMass, P));
-        }
-    }
-    // --- joints in island order
-    JTemp jt[NJ];
-    for (int q = 0; q < NJ; q++) {
-        const int k = Scene::joint_order(q);
-        const JointDef &d = Scene::jdef(k);
-        joint_init(W.j[k], jt[k], d, Scene::shape(d.bodyA), Scene::shape(d.bodyB), st[d.bodyA], st[d.bodyB], dtRatio);
-    }
-
-    // --- 180 velocity iterations
-    for (int it = 0; it < 180; it++) {
-        for (int q = 0; q < NJ; q++) {
-            const int k = Scene::joint_order(q);
-            const JointDef &d = Scene::jdef(k);
-            joint_solve_velocity(W.j[k], jt[k], Scene::shape(d.bodyA), Scene::shape(d.bodyB), st[d.bodyA], st[d.bodyB], dt);
-        }
-        for (int ci = 0; ci < nvc; ci++) {
+        for (int ci = oi == 0 ? 0 : cend[oi == 0 ? 0 : oi - 1]; ci < cend[oi]; ci++) {
             VC &k = vc[ci];
-            const ShapeConst &sh = Scene::shape(k.body);
-            const float mB = sh.invMass, iB = sh.invI;
-            v2 vB = st[k.body].v;
-            float wB = st[k.body].w;
-            const v2 normal = k.normal, tangent = crs_vs(normal, 1.0f);
+            ids[ci][0] = __float_as_uint(k.p[0].normalMass);
+            ids[ci][1] = k.pointCount > 1 ? __float_as_uint(k.p[1].normalMass) : 0u;
+            xform xfB;
+            xfB.q = rot_of(sB.a);
+            xfB.p = sub(sB.c, rmul(xfB.q, sh.localCenter));
+            v2 pts[2];
+            xform xfA;  // the ground body: identity transform (kept as explicit arithmetic, like Box2D does)
+            xfA.p = V(0.0f, 0.0f); xfA.q.s = 0.0f; xfA.q.c = 1.0f;
+            if (k.mType == 0) {  // b2WorldManifold::Initialize, e_faceA
+                k.normal = rmul(xfA.q, k.localNormal);
+                const v2 plane = xmul(xfA, k.localPoint);
+                for (int p = 0; p < k.pointCount; p++) {
+                    const v2 clip = xmul(xfB, k.lp[p]);
+                    const v2 cA = add(clip, scl(kPolygonRadius - dot(sub(clip, plane), k.normal), k.normal));
+                    const v2 cB = sub(clip, scl(kPolygonRadius, k.normal));
+                    pts[p] = scl(0.5f, add(cA, cB));
+                }
+            } else {             // e_faceB
+                v2 nrm = rmul(xfB.q, k.localNormal);
+                const v2 plane = xmul(xfB, k.localPoint);
+                for (int p = 0; p < k.pointCount; p++) {
+                    const v2 clip = xmul(xfA, k.lp[p]);
+                    const v2 cB = add(clip, scl(kPolygonRadius - dot(sub(clip, plane), nrm), nrm));
+                    const v2 cA = sub(clip, scl(kPolygonRadius, nrm));
+                    pts[p] = scl(0.5f, add(cA, cB));
+                }
+                k.normal = neg(nrm);
+            }
             for (int p = 0; p < k.pointCount; p++) {
                 VCP &cp = k.p[p];
-                const v2 dv = add(vB, crs_sv(wB, cp.rB));
-                const float vt = dot(dv, tangent) - 0.0f;
-                float lambda = cp.tangentMass * (-vt);
-                const float maxF = k.friction * cp.nI;
-                const float newImp = clampf(cp.tI + lambda, -maxF, maxF);
-                lambda = newImp - cp.tI;
-                cp.tI = newImp;
-                const v2 P = scl(lambda, tangent);
-                vB = add(vB, scl(mB, P)); wB += iB * crs(cp.rB, P);
+                cp.rB = sub(pts[p], sB.c);
+                const float rnB = crs(cp.rB, k.normal);
+                const float kN = mB + iB * rnB * rnB;
+                cp.normalMass = kN > 0.0f ? 1.0f / kN : 0.0f;
+                const v2 tangent = crs_vs(k.normal, 1.0f);
+                const float rtB = crs(cp.rB, tangent);
+                const float kT = mB + iB * rtB * rtB;
+                cp.tangentMass = kT > 0.0f ? 1.0f / kT : 0.0f;
             }
-            if (k.pointCount == 1) {
-                VCP &cp = k.p[0];
-                const v2 dv = add(vB, crs_sv(wB, cp.rB));
-                const float vn = dot(dv, normal);
-                float lambda = -cp.normalMass * (vn - 0.0f);
-                const float newImp = fmax_(cp.nI + lambda, 0.0f);
-                lambda = newImp - cp.nI;
-                cp.nI = newImp;
-                const v2 P = scl(lambda, normal);
-                vB = add(vB, scl(mB, P)); wB += iB * crs(cp.rB, P);
-            } else {
-                VCP &c1 = k.p[0], &c2 = k.p[1];
-                const v2 a = V(c1.nI, c2.nI);
-                const v2 dv1 = add(vB, crs_sv(wB, c1.rB)), dv2 = add(vB, crs_sv(wB, c2.rB));
-                float vn1 = dot(dv1, normal), vn2 = dot(dv2, normal);
-                v2 b = V(vn1 - 0.0f, vn2 - 0.0f);
-                b = sub(b, V(k.k11 * a.x + k.k12 * a.y, k.k12 * a.x + k.k22 * a.y));
-                v2 x;
-                bool solved = false;
-                x = V(-(k.n11 * b.x + k.n12 * b.y), -(k.n12 * b.x + k.n22 * b.y));
-                if (x.x >= 0.0f && x.y >= 0.0f) solved = true;
-                if (!solved) {
-                    x.x = -c1.normalMass * b.x; x.y = 0.0f;
-                    vn2 = k.k12 * x.x + b.y;
-                    if (x.x >= 0.0f && vn2 >= 0.0f) solved = true;
-                }
-                if (!solved) {
-                    x.x = 0.0f; x.y = -c2.normalMass * b.y;
-                    vn1 = k.k12 * x.y + b.x;
-                    if (x.y >= 0.0f && vn1 >= 0.0f) solved = true;
-                }
-                if (!solved) {
-                    x.x = 0.0f; x.y = 0.0f;
-                    if (b.x >= 0.0f && b.y >= 0.0f) solved = true;
-                }
-                if (solved) {
-                    const v2 d = sub(x, a);
-                    const v2 P1 = scl(d.x, normal), P2 = scl(d.y, normal);
-                    vB = add(vB, scl(mB, add(P1, P2)));
-                    wB += iB * (crs(c1.rB, P1) + crs(c2.rB, P2));
-                    c1.nI = x.x; c2.nI = x.y;
-                }
+            if (k.pointCount == 2) {
+                const float rn1B = crs(k.p[0].rB, k.normal), rn2B = crs(k.p[1].rB, k.normal);
+                const float k11 = mB + iB * rn1B * rn1B, k22 = mB + iB * rn2B * rn2B, k12 = mB + iB * rn1B * rn2B;
+                if (k11 * k11 < 1000.0f * (k11 * k22 - k12 * k12)) {
+                    k.k11 = k11; k.k12 = k12; k.k22 = k22;
+                    float det = k11 * k22 - k12 * k12;
+                    if (det != 0.0f) det = 1.0f / det;
+                    k.n11 = det * k22; k.n12 = -det * k12; k.n22 = det * k11;
+                } else k.pointCount = 1;
             }
-            st[k.body].v = vB; st[k.body].w = wB;
         }
+    });
+    // --- WarmStart
+    static_for<0, NB>([&](auto OI) {
+        constexpr int oi = decltype(OI)::value, body = Scene::body_order(oi);
+        const ShapeConst &sh = Scene::shape(body);
+        BState &sB = st[body];
+        for (int ci = oi == 0 ? 0 : cend[oi == 0 ? 0 : oi - 1]; ci < cend[oi]; ci++) {
+            VC &k = vc[ci];
+            const v2 tangent = crs_vs(k.normal, 1.0f);
+            for (int p = 0; p < k.pointCount; p++) {
+                const v2 P = add(scl(k.p[p].nI, k.normal), scl(k.p[p].tI, tangent));
+                sB.w += sh.invI * crs(k.p[p].rB, P);
+                sB.v = add(sB.v, scl(sh.invMass, P));
+            }
+        }
+    });
+    // --- joints in island order
+    JTemp jt[NJ];
+    static_for<0, NJ>([&](auto Q) {
+        constexpr int k = Scene::joint_order(decltype(Q)::value), bA = Scene::joint_body_a(k), bB = Scene::joint_body_b(k);
+        joint_init(jn[k], jt[k], Scene::jdef(k), Scene::shape(bA), Scene::shape(bB), st[bA], st[bB], dtRatio);
+    });
+
+    // --- 180 velocity iterations
+#pragma unroll 1
+    for (int it = 0; it < 180; it++) {
+        static_for<0, NJ>([&](auto Q) {
+            constexpr int k = Scene::joint_order(decltype(Q)::value), bA = Scene::joint_body_a(k), bB = Scene::joint_body_b(k);
+            joint_solve_velocity(jn[k], jt[k], Scene::shape(bA), Scene::shape(bB), st[bA], st[bB], dt);
+        });
+        if (nvc == 0) continue;
+        static_for<0, NB>([&](auto OI) {
+            constexpr int oi = decltype(OI)::value, body = Scene::body_order(oi);
+            const ShapeConst &sh = Scene::shape(body);
+            const float mB = sh.invMass, iB = sh.invI;
+            for (int ci = oi == 0 ? 0 : cend[oi == 0 ? 0 : oi - 1]; ci < cend[oi]; ci++) {
+                VC &k = vc[ci];
+                v2 vB = st[body].v;
+                float wB = st[body].w;
+                const v2 normal = k.normal, tangent = crs_vs(normal, 1.0f);
+                for (int p = 0; p < k.pointCount; p++) {
+                    VCP &cp = k.p[p];
+                    const v2 dv = add(vB, crs_sv(wB, cp.rB));
+                    const float vt = dot(dv, tangent) - 0.0f;
+                    float lambda = cp.tangentMass * (-vt);
+                    const float maxF = k.friction * cp.nI;
+                    const float newImp = clampf(cp.tI + lambda, -maxF, maxF);
+                    lambda = newImp - cp.tI;
+                    cp.tI = newImp;
+                    const v2 P = scl(lambda, tangent);
+                    vB = add(vB, scl(mB, P)); wB += iB * crs(cp.rB, P);
+                }
+                if (k.pointCount == 1) {
+                    VCP &cp = k.p[0];
+                    const v2 dv = add(vB, crs_sv(wB, cp.rB));
+                    const float vn = dot(dv, normal);
+                    float lambda = -cp.normalMass * (vn - 0.0f);
+                    const float newImp = fmax_(cp.nI + lambda, 0.0f);
+                    lambda = newImp - cp.nI;
+                    cp.nI = newImp;
+                    const v2 P = scl(lambda, normal);
+                    vB = add(vB, scl(mB, P)); wB += iB * crs(cp.rB, P);
+                } else {
+                    VCP &c1 = k.p[0], &c2 = k.p[1];
+                    const v2 a = V(c1.nI, c2.nI);
+                    const v2 dv1 = add(vB, crs_sv(wB, c1.rB)), dv2 = add(vB, crs_sv(wB, c2.rB));
+                    float vn1 = dot(dv1, normal), vn2 = dot(dv2, normal);
+                    v2 b = V(vn1 - 0.0f, vn2 - 0.0f);
+                    b = sub(b, V(k.k11 * a.x + k.k12 * a.y, k.k12 * a.x + k.k22 * a.y));
+                    v2 x;
+                    bool solved = false;
+                    x = V(-(k.n11 * b.x + k.n12 * b.y), -(k.n12 * b.x + k.n22 * b.y));
+                    if (x.x >= 0.0f && x.y >= 0.0f) solved = true;
+                    if (!solved) {
+                        x.x = -c1.normalMass * b.x; x.y = 0.0f;
+                        vn2 = k.k12 * x.x + b.y;
+                        if (x.x >= 0.0f && vn2 >= 0.0f) solved = true;
+                    }
+                    if (!solved) {
+                        x.x = 0.0f; x.y = -c2.normalMass * b.y;
+                        vn1 = k.k12 * x.y + b.x;
+                        if (x.y >= 0.0f && vn1 >= 0.0f) solved = true;
+                    }
+                    if (!solved) {
+                        x.x = 0.0f; x.y = 0.0f;
+                        if (b.x >= 0.0f && b.y >= 0.0f) solved = true;
+                    }
+                    if (solved) {
+                        const v2 d = sub(x, a);
+                        const v2 P1 = scl(d.x, normal), P2 = scl(d.y, normal);
+                        vB = add(vB, scl(mB, add(P1, P2)));
+                        wB += iB * (crs(c1.rB, P1) + crs(c2.rB, P2));
+                        c1.nI = x.x; c2.nI = x.y;
+                    }
+                }
+                st[body].v = vB; st[body].w = wB;
+            }
+        });
     }
     // --- StoreImpulses: rebuild the warm-start store from this step's touching contacts
     for (int s = 0; s < kSlots; s++) W.slot_key[s] = 0u;
@@ -784,7 +813,8 @@ __device__ __noinline__ void world_step(typename Scene::World &W, v2 force0, flo
         }
     }
     // --- integrate positions
-    for (int i = 0; i < NB; i++) {
+    static_for<0, NB>([&](auto I) {
+        constexpr int i = decltype(I)::value;
         v2 v = st[i].v;
         float w = st[i].w;
         const v2 tr = scl(dt, v);
@@ -794,68 +824,74 @@ __device__ __noinline__ void world_step(typename Scene::World &W, v2 force0, flo
         st[i].c = add(st[i].c, scl(dt, v));
         st[i].a = st[i].a + dt * w;
         st[i].v = v; st[i].w = w;
-    }
+    });
     // --- <= 60 position iterations
     bool positionSolved = false;
+#pragma unroll 1
     for (int it = 0; it < 60; it++) {
         float minSep = 0.0f;
-        for (int ci = 0; ci < nvc; ci++) {
-            const VC &k = vc[ci];
-            const ShapeConst &sh = Scene::shape(k.body);
-            const float mB = sh.invMass, iB = sh.invI;
-            v2 cB = st[k.body].c;
-            float aB = st[k.body].a;
-            for (int p = 0; p < k.mPointCount; p++) {
-                xform xfB;
-                xfB.q = rot_of(aB);
-                xfB.p = sub(cB, rmul(xfB.q, sh.localCenter));
-                v2 normal, point;
-                float separation;
-                if (k.mType == 0) {
-                    normal = k.localNormal;
-                    const v2 clip = xmul(xfB, k.lp[p]);
-                    separation = dot(sub(clip, k.localPoint), normal) - kPolygonRadius - kPolygonRadius;
-                    point = clip;
-                } else {
-                    normal = rmul(xfB.q, k.localNormal);
-                    const v2 plane = xmul(xfB, k.localPoint);
-                    const v2 clip = k.lp[p];
-                    separation = dot(sub(clip, plane), normal) - kPolygonRadius - kPolygonRadius;
-                    point = clip;
-                    normal = neg(normal);
+        if (nvc != 0)
+            static_for<0, NB>([&](auto OI) {
+                constexpr int oi = decltype(OI)::value, body = Scene::body_order(oi);
+                const ShapeConst &sh = Scene::shape(body);
+                const float mB = sh.invMass, iB = sh.invI;
+                for (int ci = oi == 0 ? 0 : cend[oi == 0 ? 0 : oi - 1]; ci < cend[oi]; ci++) {
+                    const VC &k = vc[ci];
+                    v2 cB = st[body].c;
+                    float aB = st[body].a;
+                    for (int p = 0; p < k.mPointCount; p++) {
+                        xform xfB;
+                        xfB.q = rot_of(aB);
+                        xfB.p = sub(cB, rmul(xfB.q, sh.localCenter));
+                        v2 normal, point;
+                        float separation;
+                        if (k.mType == 0) {
+                            normal = k.localNormal;
+                            const v2 clip = xmul(xfB, k.lp[p]);
+                            separation = dot(sub(clip, k.localPoint), normal) - kPolygonRadius - kPolygonRadius;
+                            point = clip;
+                        } else {
+                            normal = rmul(xfB.q, k.localNormal);
+                            const v2 plane = xmul(xfB, k.localPoint);
+                            const v2 clip = k.lp[p];
+                            separation = dot(sub(clip, plane), normal) - kPolygonRadius - kPolygonRadius;
+                            point = clip;
+                            normal = neg(normal);
+                        }
+                        const v2 rB = sub(point, cB);
+                        minSep = fmin_(minSep, separation);
+                        const float C = clampf(kBaumgarte * (separation + kLinearSlop), -kMaxLinearCorrection, 0.0f);
+                        const float rnB = crs(rB, normal);
+                        const float K = mB + iB * rnB * rnB;
+                        const float impulse = K > 0.0f ? -C / K : 0.0f;
+                        const v2 P = scl(impulse, normal);
+                        cB = add(cB, scl(mB, P));
+                        aB += iB * crs(rB, P);
+                    }
+                    st[body].c = cB; st[body].a = aB;
                 }
-                const v2 rB = sub(point, cB);
-                minSep = fmin_(minSep, separation);
-                const float C = clampf(kBaumgarte * (separation + kLinearSlop), -kMaxLinearCorrection, 0.0f);
-                const float rnB = crs(rB, normal);
-                const float K = mB + iB * rnB * rnB;
-                const float impulse = K > 0.0f ? -C / K : 0.0f;
-                const v2 P = scl(impulse, normal);
-                cB = add(cB, scl(mB, P));
-                aB += iB * crs(rB, P);
-            }
-            st[k.body].c = cB; st[k.body].a = aB;
-        }
+            });
         const bool contactsOkay = minSep >= -3.0f * kLinearSlop;
         bool jointsOkay = true;
-        for (int q = 0; q < NJ; q++) {
-            const int k = Scene::joint_order(q);
-            const JointDef &d = Scene::jdef(k);
-            const bool ok = joint_solve_position(W.j[k], d, Scene::shape(d.bodyA), Scene::shape(d.bodyB), st[d.bodyA], st[d.bodyB]);
+        static_for<0, NJ>([&](auto Q) {
+            constexpr int k = Scene::joint_order(decltype(Q)::value), bA = Scene::joint_body_a(k), bB = Scene::joint_body_b(k);
+            const bool ok = joint_solve_position(jn[k], Scene::jdef(k), Scene::shape(bA), Scene::shape(bB), st[bA], st[bB]);
             jointsOkay = jointsOkay && ok;
-        }
+        });
         if (contactsOkay && jointsOkay) { positionSolved = true; break; }
     }
     // --- copy back, sleep management
     float minSleep = kFltMax;
     const float linTol = kLinearSleepTol * kLinearSleepTol, angTol = kAngularSleepTol * kAngularSleepTol;
-    for (int i = 0; i < NB; i++) {
+    static_for<0, NJ>([&](auto K) { constexpr int k = decltype(K)::value; W.j[k] = jn[k]; });
+    static_for<0, NB>([&](auto I) {
+        constexpr int i = decltype(I)::value;
         Body &b = W.b[i];
         b.c = st[i].c; b.a = st[i].a; b.v = st[i].v; b.w = st[i].w;
         sync_xf(b, Scene::shape(i));
         if (b.w * b.w > angTol || dot(b.v, b.v) > linTol) { b.sleepTime = 0.0f; minSleep = 0.0f; }
         else { b.sleepTime += dt; minSleep = fmin_(minSleep, b.sleepTime); }
-    }
+    });
     island_awake = true;
     if (minSleep >= kTimeToSleep && positionSolved) {
         island_awake = false;
@@ -863,7 +899,6 @@ __device__ __noinline__ void world_step(typename Scene::World &W, v2 force0, flo
     }
     W.flags |= kFlagStepped;
 }
-
 
 #undef LD
 }  // namespace b2l

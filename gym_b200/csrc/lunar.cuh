@@ -65,8 +65,11 @@ struct Scene {
     LD static const ShapeConst &shape(int b) { return kC.shape[b == 0 ? 0 : 1]; }
     LD static const JointDef &jdef(int k) { return kC.jd[k]; }
     // b2World::Solve's depth-first island walk starts at the newest body: leg(+1), lander, leg(-1)
-    LD static int body_order(int k) { return k == 0 ? 2 : (k == 1 ? 0 : 1); }
-    LD static int joint_order(int k) { return 1 - k; }
+    __host__ __device__ static constexpr int body_order(int k) { return k == 0 ? 2 : (k == 1 ? 0 : 1); }
+    __host__ __device__ static constexpr int joint_order(int k) { return 1 - k; }
+    // joint k ties the lander (body 0) to leg k (body k + 1); the runtime JointDef holds the same indices
+    __host__ __device__ static constexpr int joint_body_a(int) { return 0; }
+    __host__ __device__ static constexpr int joint_body_b(int k) { return k + 1; }
     LD static void edge(const World &W, int e, v2 &v1, v2 &v2_, float &friction) {
         if (e == 0) { v1 = V(0.0f, 0.0f); v2_ = V(kC.world_w, 0.0f); friction = 0.2f; }
         else { v1 = V(kC.chunk_x[e - 1], W.terrain[e - 1]); v2_ = V(kC.chunk_x[e], W.terrain[e]); friction = 0.1f; }

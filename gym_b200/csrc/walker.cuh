@@ -87,8 +87,11 @@ struct SceneT {
     LD static const JointDef &jdef(int k) { return kC.jd[k]; }
     // b2World::Solve's depth-first island walk from the newest body: lower(+1), leg(+1), hull, leg(-1), lower(-1);
     // joints in discovery order: knee(+1), hip(+1), hip(-1), knee(-1)
-    LD static int body_order(int k) { const int o[NB] = {4, 3, 0, 1, 2}; return o[k]; }
-    LD static int joint_order(int k) { const int o[NJ] = {3, 2, 0, 1}; return o[k]; }
+    __host__ __device__ static constexpr int body_order(int k) { return k == 0 ? 4 : (k == 1 ? 3 : (k == 2 ? 0 : (k == 3 ? 1 : 2))); }
+    __host__ __device__ static constexpr int joint_order(int k) { return k == 0 ? 3 : (k == 1 ? 2 : (k == 2 ? 0 : 1)); }
+    // hips (0, 2) tie the hull to the upper legs (1, 3); knees (1, 3) tie the upper to the lower legs (2, 4)
+    __host__ __device__ static constexpr int joint_body_a(int k) { return k == 0 ? 0 : (k == 1 ? 1 : (k == 2 ? 0 : 3)); }
+    __host__ __device__ static constexpr int joint_body_b(int k) { return k + 1; }
     LD static void edge(const World &W, int e, v2 &v1, v2 &v2_, float &friction) {
         v1 = V(terrain_x(e), terrain_y(W, e));
         v2_ = V(terrain_x(e + 1), terrain_y(W, e + 1));

@@ -18,6 +18,8 @@
 // Built for sm_100a only, with -fmad=false (see envs.cuh).
 #include <cuda_runtime.h>
 
+#include <algorithm>
+
 #include <cstdarg>
 #include <cstdio>
 #include <cstdlib>
@@ -54,6 +56,12 @@ struct b200gym {
     int kernel_choice = 0;                  // 0: kernel A (default: fastest measured), 1: kernel B (TMA-staged tiles);
                                             // B200GYM_KERNEL=a|b overrides
     int block_a = 256;                      // CTA size of kernel A (B200GYM_BLOCK_A=64|128|256, tuning runs)
+    int box2d_block = 128;                  // LunarLander step kernel: CTA size (B200GYM_BOX2D_BLOCK=128|256, tuning runs)
+    int box2d_defer = 0;                    // Box2D tasks: 1 = the autoresets of a step run in a second, compacted
+                                            // kernel (B200GYM_BOX2D_DEFER=1).  Measured neutral at 2^16 envs (the step
+                                            // is bound by its slowest warps, not by reset work), so inline is the default
+    int32_t *reset_list = nullptr;          // [n] env offsets to reset, filled per launch range
+    int32_t *reset_count = nullptr;         // [kResetSlots] one counter per concurrently running launch range
     // fused all-gather over peer memory (b200gym_p2p_*)
     struct {
         int world = 0, rank = 0;
@@ -141,6 +149,10 @@ struct StepArgs {
     int32_t autoreset;
     double param0;
     lunar::Opts lunar_opts;   // LunarLander constructor variants (uniform over the batch)
+    // Box2D tasks: envs whose episode ended in this launch are appended here (offset from `first`) and reset by
+    // the *_reset_list_kernel that follows on the stream; nullptr: reset inline
+    int32_t *reset_list;
+    int32_t *reset_count;
     // fused all-gather (multi-GPU): every result is ALSO stored into the same rows of the peers'
     // gather buffers over NVLink (peer-mapped pointers, slice offset already applied)
     int32_t npeer;
@@ -495,10 +507,13 @@ __global__ void __launch_bounds__(kThreads) state_set_kernel(double *soa, const 
 
 // ---- LunarLander-v2 (lunar.cuh): one thread per env, the whole b2World::Step in registers/local ----
 constexpr int kLunarThreads = 128;
+constexpr int kResetSlots = 64;   // launch ranges of one handle that may be in flight at once (host path: <= 64 chunks)
+
+constexpr int kLunarMaxThreads = 256;
 
 template <typename ActT, bool CONT>
-__global__ void __launch_bounds__(kLunarThreads) lunar_step_kernel(const StepArgs a) {
-    const int64_t j = (int64_t)blockIdx.x * kLunarThreads + threadIdx.x;
+__global__ void __launch_bounds__(kLunarMaxThreads, 2) lunar_step_kernel(const StepArgs a) {
+    const int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (j >= a.count) return;
     const int64_t i = a.first + j;
     long long act = 0;
@@ -526,15 +541,43 @@ __global__ void __launch_bounds__(kLunarThreads) lunar_step_kernel(const StepArg
     elapsed += 1;                                                        // time_limit.py:51
     const bool truncated = (a.max_steps > 0) && (elapsed >= a.max_steps);
     store_scalars_all(a, i, reward, terminated ? 1 : 0, truncated ? 1 : 0);
+    bool deferred = false;
     if ((terminated || truncated) && a.autoreset) {                      // sync_vector_env.py:152-156
         if (a.final_obs) store_row<8>(a.final_obs, i, obs);
-        lunar::env_reset(W, g, O, obs);
-        elapsed = 0;
+        if (a.reset_list) {  // the new episode is drawn by lunar_reset_list_kernel, in warps full of resetting envs
+            a.reset_list[a.first + atomicAdd(a.reset_count, 1)] = (int32_t)j;
+            deferred = true;
+        } else {
+            lunar::env_reset(W, g, O, obs);
+            elapsed = 0;
+        }
     }
     lunar::store_world(W, a.lunar_rec, a.n, i, O.wind != 0);
     pcg64_store(a.rng + 4 * i, g);
     a.elapsed[i] = elapsed;
-    store_obs_all<8>(a, i, obs);
+    if (!deferred) store_obs_all<8>(a, i, obs);
+}
+
+// The autoresets of one step, compacted: a lone finishing env would otherwise keep its whole warp waiting through
+// a full reset() (terrain draw + the embedded world step) with one active lane.  Same per-env arithmetic and RNG
+// stream as the inline path.
+__global__ void __launch_bounds__(kLunarThreads) lunar_reset_list_kernel(const StepArgs a) {
+    const int cnt = *a.reset_count;
+    const lunar::Opts &O = a.lunar_opts;
+    for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < cnt; idx += gridDim.x * blockDim.x) {
+        const int64_t i = a.first + a.reset_list[a.first + idx];
+        lunar::World W;
+        W.flags = a.lunar_rec[(int64_t)lunar::W_FLAGS * a.n + i] & 16u;
+        W.wind_idx = O.wind ? (int32_t)a.lunar_rec[(int64_t)lunar::W_WIND * a.n + i] : 0;
+        W.torque_idx = O.wind ? (int32_t)a.lunar_rec[(int64_t)(lunar::W_WIND + 1) * a.n + i] : 0;
+        Pcg64 g = pcg64_load(a.rng + 4 * i);
+        float obs[8];
+        lunar::env_reset(W, g, O, obs);
+        lunar::store_world(W, a.lunar_rec, a.n, i, O.wind != 0);
+        pcg64_store(a.rng + 4 * i, g);
+        a.elapsed[i] = 0;
+        store_obs_all<8>(a, i, obs);
+    }
 }
 
 __global__ void __launch_bounds__(kLunarThreads) lunar_reset_kernel(uint32_t *rec, int32_t *elapsed, uint64_t *rng,
@@ -696,16 +739,44 @@ __global__ void __launch_bounds__(kLunarThreads, 4) walker_step_kernel(const Ste
     elapsed += 1;                                                        // time_limit.py:51
     const bool truncated = (a.max_steps > 0) && (elapsed >= a.max_steps);
     store_scalars_all(a, i, reward, terminated ? 1 : 0, truncated ? 1 : 0);
+    bool deferred = false;
     if ((terminated || truncated) && a.autoreset) {                      // sync_vector_env.py:152-156
         if (a.final_obs) store_row<24>(a.final_obs, i, obs);
-        rng.g = pcg64_load(a.rng + 4 * i);
-        walker::env_reset<HC>(W, rng, obs);
-        pcg64_store(a.rng + 4 * i, rng.g);
-        elapsed = 0;
+        if (a.reset_list) {  // drawn by walker_reset_list_kernel (see lunar_reset_list_kernel)
+            a.reset_list[a.first + atomicAdd(a.reset_count, 1)] = (int32_t)j;
+            deferred = true;
+        } else {
+            rng.g = pcg64_load(a.rng + 4 * i);
+            walker::env_reset<HC>(W, rng, obs);
+            pcg64_store(a.rng + 4 * i, rng.g);
+            elapsed = 0;
+        }
     }
     walker::store_world(W, a.lunar_rec, a.n, i, rng, HC);
     a.elapsed[i] = elapsed;
-    store_obs_all<24>(a, i, obs);
+    if (!deferred) store_obs_all<24>(a, i, obs);
+}
+
+template <bool HC>
+__global__ void __launch_bounds__(kLunarThreads, 4) walker_reset_list_kernel(const StepArgs a) {
+    const int cnt = *a.reset_count;
+    for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < cnt; idx += gridDim.x * blockDim.x) {
+        const int64_t i = a.first + a.reset_list[a.first + idx];
+        walker::World W;
+        walker::Rng r;
+        walker::bind_world(W, a.lunar_rec, a.n, i);
+        W.flags = a.lunar_rec[(int64_t)walker::W_FLAGS * a.n + i] & b2l::kFlagStepped;
+        r.has32 = a.lunar_rec[(int64_t)walker::W_RNG32 * a.n + i];
+        r.val32 = a.lunar_rec[(int64_t)(walker::W_RNG32 + 1) * a.n + i];
+        r.g = pcg64_load(a.rng + 4 * i);
+        W.np = 0; W.p_lo = 0; W.p_hi = -1;
+        float obs[24];
+        walker::env_reset<HC>(W, r, obs);
+        walker::store_world(W, a.lunar_rec, a.n, i, r, HC);
+        pcg64_store(a.rng + 4 * i, r.g);
+        a.elapsed[i] = 0;
+        store_obs_all<24>(a, i, obs);
+    }
 }
 
 template <bool HC>
@@ -1034,31 +1105,51 @@ static int launch_step(b200gym *h, const StepArgs &a, int action_dtype, cudaStre
     case B200GYM_MOUNTAINCAR_CONT: return launch_step_kind<B200GYM_MOUNTAINCAR_CONT>(h, a, action_dtype, st);
     case B200GYM_PENDULUM: return launch_step_kind<B200GYM_PENDULUM>(h, a, action_dtype, st);
     case B200GYM_ACROBOT: return launch_step_kind<B200GYM_ACROBOT>(h, a, action_dtype, st);
-    case B200GYM_LUNARLANDER: {
-        const unsigned grid = (unsigned)((a.count + kLunarThreads - 1) / kLunarThreads);
-        switch (action_dtype) {
-        case B200GYM_ACT_I64: lunar_step_kernel<long long, false><<<grid, kLunarThreads, 0, st>>>(a); break;
-        case B200GYM_ACT_I32: lunar_step_kernel<int, false><<<grid, kLunarThreads, 0, st>>>(a); break;
-        case B200GYM_ACT_U8: lunar_step_kernel<unsigned char, false><<<grid, kLunarThreads, 0, st>>>(a); break;
-        default: return fail(h, "Discrete env needs an integer action dtype (got code %d)", action_dtype);
-        }
-        CK(h, cudaGetLastError());
-        return 0;
-    }
-    case B200GYM_LUNARLANDER_CONT: {
-        if (action_dtype != B200GYM_ACT_F32) return fail(h, "Box env needs float32 actions (got dtype code %d)", action_dtype);
-        if ((uintptr_t)a.actions % 8 != 0) return fail(h, "LunarLanderContinuous actions must be 8-byte aligned");
-        lunar_step_kernel<float, true><<<(unsigned)((a.count + kLunarThreads - 1) / kLunarThreads), kLunarThreads, 0, st>>>(a);
-        CK(h, cudaGetLastError());
-        return 0;
-    }
+    case B200GYM_LUNARLANDER:
+    case B200GYM_LUNARLANDER_CONT:
     case B200GYM_BIPEDALWALKER:
     case B200GYM_BIPEDALWALKER_HARDCORE: {
-        if (action_dtype != B200GYM_ACT_F32) return fail(h, "Box env needs float32 actions (got dtype code %d)", action_dtype);
-        if ((uintptr_t)a.actions % 16 != 0) return fail(h, "BipedalWalker actions must be 16-byte aligned");
-        const unsigned grid = (unsigned)((a.count + kLunarThreads - 1) / kLunarThreads);
-        if (h->cfg.kind == B200GYM_BIPEDALWALKER_HARDCORE) walker_step_kernel<true><<<grid, kLunarThreads, 0, st>>>(a);
-        else walker_step_kernel<false><<<grid, kLunarThreads, 0, st>>>(a);
+        StepArgs b = a;
+        const bool defer = h->cfg.autoreset && h->box2d_defer && h->reset_list;
+        if (defer) {   // the caller may have picked a counter slot (one per concurrently running range)
+            b.reset_list = h->reset_list;
+            if (!b.reset_count) b.reset_count = h->reset_count;
+            CK(h, cudaMemsetAsync(b.reset_count, 0, sizeof(int32_t), st));
+        } else {
+            b.reset_list = nullptr; b.reset_count = nullptr;
+        }
+        // at most this many CTAs of the compacted reset kernel (it strides over the list)
+        const unsigned rgrid = (unsigned)std::min<int64_t>((b.count + kLunarThreads - 1) / kLunarThreads, 2 * h->sm_count);
+        if (h->is_lunar) {
+            const int bs = h->box2d_block;
+            const unsigned grid = (unsigned)((b.count + bs - 1) / bs);
+            if (h->cfg.kind == B200GYM_LUNARLANDER_CONT) {
+                if (action_dtype != B200GYM_ACT_F32) return fail(h, "Box env needs float32 actions (got dtype code %d)", action_dtype);
+                if ((uintptr_t)b.actions % 8 != 0) return fail(h, "LunarLanderContinuous actions must be 8-byte aligned");
+                lunar_step_kernel<float, true><<<grid, bs, 0, st>>>(b);
+            } else {
+                switch (action_dtype) {
+                case B200GYM_ACT_I64: lunar_step_kernel<long long, false><<<grid, bs, 0, st>>>(b); break;
+                case B200GYM_ACT_I32: lunar_step_kernel<int, false><<<grid, bs, 0, st>>>(b); break;
+                case B200GYM_ACT_U8: lunar_step_kernel<unsigned char, false><<<grid, bs, 0, st>>>(b); break;
+                default: return fail(h, "Discrete env needs an integer action dtype (got code %d)", action_dtype);
+                }
+            }
+            CK(h, cudaGetLastError());
+            if (defer) lunar_reset_list_kernel<<<rgrid, kLunarThreads, 0, st>>>(b);
+        } else {
+            if (action_dtype != B200GYM_ACT_F32) return fail(h, "Box env needs float32 actions (got dtype code %d)", action_dtype);
+            if ((uintptr_t)b.actions % 16 != 0) return fail(h, "BipedalWalker actions must be 16-byte aligned");
+            const unsigned grid = (unsigned)((b.count + kLunarThreads - 1) / kLunarThreads);
+            const bool hc = h->cfg.kind == B200GYM_BIPEDALWALKER_HARDCORE;
+            if (hc) walker_step_kernel<true><<<grid, kLunarThreads, 0, st>>>(b);
+            else walker_step_kernel<false><<<grid, kLunarThreads, 0, st>>>(b);
+            CK(h, cudaGetLastError());
+            if (defer) {
+                if (hc) walker_reset_list_kernel<true><<<rgrid, kLunarThreads, 0, st>>>(b);
+                else walker_reset_list_kernel<false><<<rgrid, kLunarThreads, 0, st>>>(b);
+            }
+        }
         CK(h, cudaGetLastError());
         return 0;
     }
@@ -1149,6 +1240,10 @@ extern "C" int b200gym_create(const b200gym_config *cfg, int64_t num_envs, int d
         const char *kc = getenv("B200GYM_KERNEL");
         if (kc && (kc[0] == 'a' || kc[0] == 'b')) h->kernel_choice = kc[0] - 'a';
         if (fs && fs[0] == '1') h->kernel_choice = 0;
+        const char *bb = getenv("B200GYM_BOX2D_BLOCK");
+        if (bb && (atoi(bb) == 128 || atoi(bb) == 256)) h->box2d_block = atoi(bb);
+        const char *bdf = getenv("B200GYM_BOX2D_DEFER");
+        if (bdf && (bdf[0] == '0' || bdf[0] == '1')) h->box2d_defer = bdf[0] - '0';
         const char *ba = getenv("B200GYM_BLOCK_A");
         if (ba && (atoi(ba) == 64 || atoi(ba) == 128 || atoi(ba) == 256)) h->block_a = atoi(ba);
     }
@@ -1178,6 +1273,9 @@ extern "C" int b200gym_create(const b200gym_config *cfg, int64_t num_envs, int d
                                  : (cfg->kind == B200GYM_BIPEDALWALKER_HARDCORE ? walker::kWordsHC : walker::kWords);
         if (cudaMalloc(&h->lunar_rec, sizeof(uint32_t) * words * n) != cudaSuccess ||
             cudaMemset(h->lunar_rec, 0, sizeof(uint32_t) * words * n) != cudaSuccess ||
+            cudaMalloc((void **)&h->reset_list, sizeof(int32_t) * n) != cudaSuccess ||
+            cudaMalloc((void **)&h->reset_count, sizeof(int32_t) * kResetSlots) != cudaSuccess ||
+            cudaMemset(h->reset_count, 0, sizeof(int32_t) * kResetSlots) != cudaSuccess ||
             (lun ? lunar_upload_consts(h) : walker_upload_consts(h))) {
             fail(nullptr, "b200gym_create: Box2D-task state allocation failed");
             b200gym_destroy(h);
@@ -1223,6 +1321,8 @@ extern "C" void b200gym_destroy(b200gym_t *h) {
     cudaFree(h->rng);
     cudaFree(h->invalid);
     cudaFree(h->lunar_rec);
+    cudaFree(h->reset_list);
+    cudaFree(h->reset_count);
     if (h->p2p.base) {
         for (int r = 0; r < h->p2p.world; r++)
             if (r != h->p2p.rank && h->p2p.peer[r]) cudaIpcCloseMemHandle(h->p2p.peer[r]);
@@ -1288,6 +1388,7 @@ static StepArgs make_args(b200gym *h, const void *actions, float *obs, double *r
     a.n = h->n; a.first = 0; a.count = h->n;
     a.max_steps = h->cfg.max_episode_steps; a.autoreset = h->cfg.autoreset; a.param0 = h->cfg.param[0];
     a.lunar_opts = h->lunar_opts;
+    a.reset_list = nullptr; a.reset_count = nullptr;
     a.npeer = 0;
     return a;
 }
@@ -1579,6 +1680,7 @@ extern "C" int b200gym_step_host(b200gym_t *h, const void *actions_host, int act
                               cudaMemcpyHostToDevice, st));
         a.first = lo;
         a.count = cnt;
+        a.reset_count = h->reset_count ? h->reset_count + (c % kResetSlots) : nullptr;
         if (launch_step(h, a, action_dtype, st)) return 1;
         CK(h, cudaMemcpyAsync((char *)obs_host + lo * osz, (char *)h->dio.obs + lo * osz, cnt * osz,
                               cudaMemcpyDeviceToHost, st));

@@ -269,3 +269,40 @@ def test_wind_indices_default_to_numpy_global_generator():
     w, t = env.lunar_wind_idx()
     assert w.tolist() == want[0::2] and t.tolist() == want[1::2]
     env.close()
+
+
+@pytest.mark.parametrize("env_id", ["LunarLander-v2", "BipedalWalkerHardcore-v3"])
+def test_compacted_autoreset_kernel_equals_inline_reset(env_id, monkeypatch):
+    """B200GYM_BOX2D_DEFER=1: the episodes that end in a step are restarted by a second, compacted kernel
+    (*_reset_list_kernel).  Same results as the inline reset, on the device path and on the chunked host path."""
+    import gym_b200
+    import torch
+    N, T = 3000, 220
+    monkeypatch.setenv("B200GYM_BOX2D_DEFER", "0")
+    inline = gym_b200.vector.make(env_id, N)
+    monkeypatch.setenv("B200GYM_BOX2D_DEFER", "1")
+    monkeypatch.setenv("B200GYM_HOST_CHUNKS", "3")
+    deferred = gym_b200.vector.make(env_id, N)
+    host = gym_b200.vector.make(env_id, N, backend="numpy")
+    o0, _ = inline.reset(seed=9)
+    o1, _ = deferred.reset(seed=9)
+    o2, _ = host.reset(seed=9)
+    assert torch.equal(o0, o1) and np.array_equal(o0.cpu().numpy(), o2)
+    gen = torch.Generator(device="cuda").manual_seed(4)
+    n_done = 0
+    for t in range(T):
+        if inline.discrete:
+            a = torch.randint(0, 4, (N,), device="cuda", generator=gen)
+        else:
+            a = torch.rand((N, 4), device="cuda", generator=gen) * 2 - 1
+        r0, r1, r2 = inline.step(a), deferred.step(a), host.step(a.cpu().numpy())
+        for k in range(4):
+            assert torch.equal(r0[k], r1[k]), f"step {t}, output {k}: device path"
+            assert np.array_equal(r0[k].cpu().numpy(), r2[k]), f"step {t}, output {k}: host path"
+        done = r0[2] | r0[3]
+        if bool(done.any()):
+            assert torch.equal(r0[4]["final_observation"][done], r1[4]["final_observation"][done])
+        n_done += int(done.sum())
+    assert n_done > N // 2
+    for e in (inline, deferred, host):
+        e.close()

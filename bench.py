@@ -376,7 +376,8 @@ def run_b200(args):
         v, cpu_steps, cpu_el = cpu_oracle_throughput(args.env, n, args.cpu_seconds, threads)
         cpu = {"value": v, "unit": "env-steps/s", "cores": threads, "kind": "port",
                "sample": f"{cpu_steps} vector steps of 2^{args.log2_envs} envs ({cpu_el:.1f} s) of the same workload, "
-                         "oracle/gym_oracle.c with one pthread per host core"}
+                         + ("the single-threaded C oracle of the Box2D task (oracle/lunar_oracle.c / walker_oracle.c)"
+                            if threads == 1 else "oracle/gym_oracle.c with one pthread per host core")}
 
     if rank == 0:
         peak, peak_src = measured_hbm_peak()
@@ -385,8 +386,10 @@ def run_b200(args):
         line = {
             "metric": "env-steps/sec", "value": value, "unit": "env-steps/s", "n_gpus": world, "steps": K,
             "warmup": W, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": f"{args.env} num_envs=2^{args.log2_envs} per GPU x {world} GPU(s), random int64 "
+            "vs_baseline": None, "dtype": "f32" if args.env.startswith(("LunarLander", "BipedalWalker")) else "f64",
+            "data": "synthetic",
+            "config": {"workload": f"{args.env} num_envs=2^{args.log2_envs} per GPU x {world} GPU(s), random "
+                                   f"{'int64' if inner.discrete else 'float32'} "
                                    "actions resident in HBM, fused step+TimeLimit+autoreset"
                                    + ((", all-gather of (obs,reward,terminated,truncated) per step fused into the "
                                        "step kernel (NVLink peer stores + flag exchange)" if gather == "p2p" else

@@ -881,7 +881,7 @@ static int walker_upload_consts(b200gym *h) {
 __global__ void __launch_bounds__(kThreads) episode_stats_kernel(const double *reward, const uint8_t *term,
                                                                 const uint8_t *trunc, float *ret_acc, int32_t *len_acc,
                                                                 float *ep_r, int32_t *ep_l, uint8_t *ep_mask,
-                                                                float *ring_r, int32_t *ring_l,
+                                                                unsigned long long *ring,
                                                                 unsigned long long *counter, int ring_size, int64_t n) {
     const int64_t i = (int64_t)blockIdx.x * kThreads + threadIdx.x;
     if (i >= n) return;
@@ -894,9 +894,11 @@ __global__ void __launch_bounds__(kThreads) episode_stats_kernel(const double *r
         ep_r[i] = ret;
         ep_l[i] = len;
         if (ring_size > 0) {
+            // one 64-bit store per episode {length : return bits}: when more than ring_size episodes finish in one
+            // step several of them land on the same slot, and a slot must never mix two episodes
             const unsigned long long slot = atomicAdd(counter, 1ULL);
-            ring_r[slot % (unsigned long long)ring_size] = ret;
-            ring_l[slot % (unsigned long long)ring_size] = len;
+            ring[slot % (unsigned long long)ring_size] =
+                ((unsigned long long)(uint32_t)len << 32) | (unsigned long long)__float_as_uint(ret);
         } else atomicAdd(counter, 1ULL);
         ret_acc[i] = 0.0f;
         len_acc[i] = 0;
@@ -1538,14 +1540,14 @@ extern "C" int b200gym_step_p2p(b200gym_t *h, const void *actions_dev, int actio
 // ---- stateless device utilities for the vector-aware wrappers -----------------------
 extern "C" int b200gym_episode_stats(const double *reward_dev, const uint8_t *terminated_dev, const uint8_t *truncated_dev,
                                      float *return_acc_dev, int32_t *length_acc_dev, float *episode_r_dev,
-                                     int32_t *episode_l_dev, uint8_t *episode_mask_dev, float *ring_r_dev,
-                                     int32_t *ring_l_dev, uint64_t *counter_dev, int ring_size, int64_t n, void *stream) {
+                                     int32_t *episode_l_dev, uint8_t *episode_mask_dev, uint64_t *ring_dev,
+                                     uint64_t *counter_dev, int ring_size, int64_t n, void *stream) {
     if (!reward_dev || !terminated_dev || !truncated_dev || !return_acc_dev || !length_acc_dev || !episode_r_dev ||
-        !episode_l_dev || !episode_mask_dev || !counter_dev || n <= 0 || (ring_size > 0 && (!ring_r_dev || !ring_l_dev)))
+        !episode_l_dev || !episode_mask_dev || !counter_dev || n <= 0 || (ring_size > 0 && !ring_dev))
         return fail(nullptr, "b200gym_episode_stats: bad argument");
     episode_stats_kernel<<<blocks_for(n), kThreads, 0, (cudaStream_t)stream>>>(
         reward_dev, terminated_dev, truncated_dev, return_acc_dev, length_acc_dev, episode_r_dev, episode_l_dev,
-        episode_mask_dev, ring_r_dev, ring_l_dev, (unsigned long long *)counter_dev, ring_size, n);
+        episode_mask_dev, (unsigned long long *)ring_dev, (unsigned long long *)counter_dev, ring_size, n);
     CK(nullptr, cudaGetLastError());
     return 0;
 }

@@ -69,8 +69,8 @@ class RecordEpisodeStatistics(VectorWrapper):
         self._ep_r = [torch.zeros(n, dtype=torch.float32, device=dev) for _ in range(2)]
         self._ep_l = [torch.zeros(n, dtype=torch.int32, device=dev) for _ in range(2)]
         self._ep_m = [torch.zeros(n, dtype=torch.bool, device=dev) for _ in range(2)]
-        self._ring_r = torch.zeros(max(self.deque_size, 1), dtype=torch.float32, device=dev)
-        self._ring_l = torch.zeros(max(self.deque_size, 1), dtype=torch.int32, device=dev)
+        # one int64 word per slot: length << 32 | float32 bits of the return (written with a single store)
+        self._ring = torch.zeros(max(self.deque_size, 1), dtype=torch.int64, device=dev)
         self._counter = torch.zeros(1, dtype=torch.int64, device=dev)
         self._flip = 0
 
@@ -87,7 +87,7 @@ class RecordEpisodeStatistics(VectorWrapper):
         env = self.env.unwrapped
         _lib.check(env._lib.b200gym_episode_stats(
             _p(rew), _p(term), _p(trunc), _p(self.episode_returns), _p(self.episode_lengths), _p(self._ep_r[k]),
-            _p(self._ep_l[k]), _p(self._ep_m[k]), _p(self._ring_r), _p(self._ring_l), _p(self._counter),
+            _p(self._ep_l[k]), _p(self._ep_m[k]), _p(self._ring), _p(self._counter),
             self.deque_size, self.num_envs, env._stream()))
         infos["episode"] = {"r": self._ep_r[k], "l": self._ep_l[k], "t": round(time.perf_counter() - self.t0, 6)}
         infos["_episode"] = self._ep_m[k]
@@ -97,20 +97,22 @@ class RecordEpisodeStatistics(VectorWrapper):
     def episode_count(self):
         return int(self._counter.item())
 
-    def _queue(self, ring):
+    def _queue(self, returns):
         count = self.episode_count
         k = min(count, self.deque_size)
-        vals = ring.cpu().numpy()
+        words = self._ring.cpu().numpy().view(np.uint64)
+        vals = (words & np.uint64(0xFFFFFFFF)).astype(np.uint32).view(np.float32) if returns else \
+            (words >> np.uint64(32)).astype(np.int32)
         order = [(count - k + j) % max(self.deque_size, 1) for j in range(k)]
         return deque((vals[i].item() for i in order), maxlen=self.deque_size)
 
     @property
     def return_queue(self):
-        return self._queue(self._ring_r)
+        return self._queue(True)
 
     @property
     def length_queue(self):
-        return self._queue(self._ring_l)
+        return self._queue(False)
 
 
 class _RunningMeanStd:

@@ -259,12 +259,16 @@ int b200gym_step_p2p(b200gym_t *h, const void *actions_dev, int action_dtype, fl
  *
  * b200gym_episode_stats replaces RecordEpisodeStatistics.step's Python loop over the batch
  * (gym/wrappers/record_episode_statistics.py:103-151): float32 return / int32 length accumulators,
- * infos["episode"]["r"/"l"] rows + `_episode` mask for finishing envs, and a ring of the last
- * `ring_size` finished episodes (return_queue / length_queue); *counter_dev counts finished episodes.
+ * infos["episode"]["r"/"l"] rows + `_episode` mask for finishing envs, and a ring of `ring_size`
+ * recently finished episodes (return_queue / length_queue); *counter_dev counts finished episodes.
+ * ring_dev[k] = (uint64)length << 32 | float32 bits of the return, written with one store per episode
+ * into slot (episode number mod ring_size); episodes that finish in the same step are numbered in no
+ * particular order (the reference appends them in env order), and when more than ring_size finish at once
+ * the ring keeps an arbitrary ring_size of them.
  */
 int b200gym_episode_stats(const double *reward_dev, const uint8_t *terminated_dev, const uint8_t *truncated_dev,
                           float *return_acc_dev, int32_t *length_acc_dev, float *episode_r_dev, int32_t *episode_l_dev,
-                          uint8_t *episode_mask_dev, float *ring_r_dev, int32_t *ring_l_dev, uint64_t *counter_dev,
+                          uint8_t *episode_mask_dev, uint64_t *ring_dev, uint64_t *counter_dev,
                           int ring_size, int64_t n, void *stream);
 /*
  * NormalizeObservation (gym/wrappers/normalize.py:50-95): fold this batch into the running mean /

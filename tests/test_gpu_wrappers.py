@@ -43,9 +43,10 @@ def test_record_episode_statistics():
     assert env.episode_count == len(finished) > N
     rq, lq = env.return_queue, env.length_queue
     assert len(rq) == 64 and len(lq) == 64
-    # CartPole returns equal lengths (reward 1 per step); the ring holds finished episodes
+    # CartPole returns equal lengths (reward 1 per step); every ring slot holds ONE finished episode even though
+    # ~190 episodes finish per step here and several of them land on the same slot (64-bit packed store)
     assert all(float(a) == float(b) for a, b in zip(rq, lq))
-    assert set(lq) <= set(l for _, l in finished)
+    assert set(zip(rq, lq)) <= set(finished)
     env.close()
 
 

@@ -11,7 +11,7 @@ single-env agents run unchanged; the throughput path is ``B200VectorEnv``.
 """
 import numpy as np
 
-from gym_b200 import error
+from gym_b200 import _lib, error
 from gym_b200.vector_env import B200VectorEnv
 
 
@@ -45,7 +45,8 @@ class B200Env:
         info = {}
         if self._autoreset and "final_observation" in infos:
             info = {"final_observation": infos["final_observation"][0], "final_info": infos["final_info"][0]}
-        reward = rew[0] if self.spec.kind == 3 else float(rew[0])  # Pendulum returns np.float64 (pendulum.py:139)
+        # Pendulum returns np.float64 (pendulum.py:139); `spec` may have been replaced by gym.make (registration.py:657)
+        reward = rew[0] if v.kind == _lib.KIND_PENDULUM else float(rew[0])
         return obs[0], reward, bool(term[0]), bool(trunc[0]), info
 
     @property

@@ -89,3 +89,29 @@ def test_space_objects_sample_like_the_reference(gym):
         assert np.array_equal(mb.sample(), rb.sample())
         assert type(mb).__name__ == type(rb).__name__ and mb.shape == rb.shape and mb.dtype == rb.dtype
         ref.close()
+
+
+def test_plugin_registers_engine_ids_in_the_real_registry(gym):
+    """gym/envs/registration.py:266-309,434-499: the ids resolve through gym's own registry and gym.make
+    reaches the engine's constructor (which refuses to run without a B200: no CPU fallback)."""
+    import gym_b200
+    from gym_b200 import error, plugin
+    ids = plugin.register_all()
+    assert "B200/CartPole-v1" in ids and "B200/BipedalWalkerHardcore-v3" in ids
+    for env_id in ids:
+        s = gym.spec(env_id)
+        assert s.namespace == "B200" and s.entry_point == "gym_b200.plugin:make_env"
+        assert s.max_episode_steps is None and s.order_enforce is False and s.disable_env_checker is True
+        assert s.kwargs == {"env_id": env_id.split("/", 1)[1]}
+        assert s.reward_threshold == gym_b200.spec(s.kwargs["env_id"]).reward_threshold
+    # the reference's own ids are untouched
+    assert gym.spec("CartPole-v1").entry_point == "gym.envs.classic_control.cartpole:CartPoleEnv"
+    import torch
+    if not torch.cuda.is_available():
+        with pytest.raises(error.DependencyNotInstalled):
+            gym.make("B200/CartPole-v1")
+    else:
+        env = gym.make("B200/CartPole-v1")
+        obs, info = env.reset(seed=0)
+        assert obs.shape == (4,) and env.spec.id == "B200/CartPole-v1"
+        env.close()

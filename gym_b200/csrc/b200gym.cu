@@ -321,6 +321,92 @@ __global__ void __launch_bounds__(kThreads, Tuning<KIND>::kMinCtas) step_kernel(
         reset_env<KIND>(a, a.first + (int64_t)blockIdx.x * blockDim.x + reset_list[threadIdx.x]);
 }
 
+// --- kernel C: two adjacent envs per thread, 16-byte accesses ---------------------------------
+// The step is latency-bound (one dependent float64 chain per env, long-scoreboard stalls on the loads): thread t
+// of a CTA owns envs 2t and 2t+1 of a 512-env tile, so every state row / action / counter arrives as ONE 16-byte
+// (8-byte) load for two envs, the two float64 chains interleave in the pipe (ILP 2), and the results leave as
+// 16-byte stores -- half the memory instructions per env and twice the bytes in flight per warp.  A finishing env
+// is stored like any other (post-step state, terminal observation) and then re-drawn by phase 2, after the CTA
+// barrier: the later store wins.  Needs an even SoA stride, an even range start and 16-byte aligned buffers;
+// anything else (and the odd last env) goes through kernel A.
+template <typename T> struct Pair;
+template <> struct Pair<long long> { using type = longlong2; };
+template <> struct Pair<int> { using type = int2; };
+template <> struct Pair<unsigned char> { using type = uchar2; };
+template <> struct Pair<float> { using type = float2; };
+
+template <int KIND, typename ActT>
+__global__ void __launch_bounds__(kThreads, 4) step_kernel_pair(const StepArgs a) {
+    using E = Env<KIND>;
+    __shared__ int reset_list[2 * kThreads];
+    __shared__ int reset_count;
+    if (threadIdx.x == 0) reset_count = 0;
+    __syncthreads();
+    const int64_t j = 2 * ((int64_t)blockIdx.x * kThreads + threadIdx.x);   // first env of the pair, even
+    if (j < a.count) {                                                      // a.count is even here
+        const int64_t i = a.first + j;
+        double s0[E::S], s1[E::S];
+#pragma unroll
+        for (int k = 0; k < E::S; k++) {
+            const double2 v = *reinterpret_cast<const double2 *>(a.state + k * a.n + i);
+            s0[k] = v.x; s1[k] = v.y;
+        }
+        const int2 el = *reinterpret_cast<const int2 *>(a.elapsed + i);
+        const typename Pair<ActT>::type av = __ldg(reinterpret_cast<const typename Pair<ActT>::type *>(a.actions) + (i >> 1));
+        int act0 = 0, act1 = 0;
+        float f0 = 0.0f, f1 = 0.0f;
+        bool valid = true;
+        if constexpr (E::A == 0) {
+            const long long l0 = (long long)av.x, l1 = (long long)av.y;
+            valid = l0 >= 0 && l0 < E::NACT && l1 >= 0 && l1 < E::NACT;
+            act0 = (int)l0; act1 = (int)l1;
+        } else {
+            f0 = (float)av.x; f1 = (float)av.y;
+        }
+        if (!valid) {
+            // rare error path (the reference raises): per env, exactly as kernel A
+            if (advance_env<KIND>(a, i, s0, el.x, (long long)av.x, 0.0f)) reset_list[atomicAdd(&reset_count, 1)] = 2 * threadIdx.x;
+            if (advance_env<KIND>(a, i + 1, s1, el.y, (long long)av.y, 0.0f)) reset_list[atomicAdd(&reset_count, 1)] = 2 * threadIdx.x + 1;
+        } else {
+            float o0[E::D], o1[E::D];
+            double r0, r1;
+            bool t0, t1;
+            E::step(s0, el.x == 0, act0, f0, a.param0, o0, r0, t0);
+            E::step(s1, el.y == 0, act1, f1, a.param0, o1, r1, t1);
+            const int e0 = el.x + 1, e1 = el.y + 1;                                  // time_limit.py:51
+            const bool u0 = (a.max_steps > 0) && (e0 >= a.max_steps), u1 = (a.max_steps > 0) && (e1 >= a.max_steps);
+#pragma unroll
+            for (int k = 0; k < E::S; k++) *reinterpret_cast<double2 *>(a.state + k * a.n + i) = make_double2(s0[k], s1[k]);
+            *reinterpret_cast<int2 *>(a.elapsed + i) = make_int2(e0, e1);
+            const uchar2 tt = make_uchar2(t0 ? 1 : 0, t1 ? 1 : 0), uu = make_uchar2(u0 ? 1 : 0, u1 ? 1 : 0);
+            *reinterpret_cast<double2 *>(a.reward + i) = make_double2(r0, r1);
+            *reinterpret_cast<uchar2 *>(a.terminated + i) = tt;
+            *reinterpret_cast<uchar2 *>(a.truncated + i) = uu;
+            store_row<E::D>(a.obs, i, o0);
+            store_row<E::D>(a.obs, i + 1, o1);
+            for (int p = 0; p < a.npeer; p++) {
+                *reinterpret_cast<double2 *>(a.peer_reward[p] + i) = make_double2(r0, r1);
+                *reinterpret_cast<uchar2 *>(a.peer_term[p] + i) = tt;
+                *reinterpret_cast<uchar2 *>(a.peer_trunc[p] + i) = uu;
+                store_row<E::D>(a.peer_obs[p], i, o0);
+                store_row<E::D>(a.peer_obs[p], i + 1, o1);
+            }
+            if (t0 || u0) {                                                          // sync_vector_env.py:152-156
+                if (a.final_obs) store_row<E::D>(a.final_obs, i, o0);
+                reset_list[atomicAdd(&reset_count, 1)] = 2 * threadIdx.x;
+            }
+            if (t1 || u1) {
+                if (a.final_obs) store_row<E::D>(a.final_obs, i + 1, o1);
+                reset_list[atomicAdd(&reset_count, 1)] = 2 * threadIdx.x + 1;
+            }
+        }
+    }
+    __syncthreads();
+    const int cnt = reset_count;
+    for (int q = threadIdx.x; q < cnt; q += kThreads)
+        reset_env<KIND>(a, a.first + 2 * (int64_t)blockIdx.x * kThreads + reset_list[q]);
+}
+
 // --- kernel B: persistent CTAs, TMA-staged inputs -------------------------------------
 // Persistent grid (SMs x occupancy CTAs), one thread per env of a 256-env tile, tiles strided
 // by gridDim.x.  Each CTA owns a ring of kStages shared-memory stages; one elected thread keeps
@@ -1072,6 +1158,25 @@ static int launch_step_typed(b200gym *h, const StepArgs &a, cudaStream_t st) {
         CK(h, cudaGetLastError());
         done = tiles * kThreads;
     }
+    // kernel C (pairs): autoreset mode only (no per-env `flags` bookkeeping), 16-byte aligned everything
+    if (KIND != B200GYM_ACROBOT /* 2 x RK4 state does not fit 64 registers */ && done == 0 && h->kernel_choice == 2 &&
+        a.autoreset && (a.n % 2 == 0) && (a.first % 2 == 0) && a.count >= 2 &&
+        (uintptr_t)a.state % 16 == 0 && (uintptr_t)a.elapsed % 8 == 0 && (uintptr_t)a.actions % 16 == 0 &&
+        (uintptr_t)a.reward % 16 == 0 && (uintptr_t)a.obs % 16 == 0 && (uintptr_t)a.terminated % 2 == 0 &&
+        (uintptr_t)a.truncated % 2 == 0) {
+        bool peers_ok = true;
+        for (int p = 0; p < a.npeer; p++)
+            peers_ok = peers_ok && (uintptr_t)a.peer_reward[p] % 16 == 0 && (uintptr_t)a.peer_obs[p] % 16 == 0 &&
+                       (uintptr_t)a.peer_term[p] % 2 == 0 && (uintptr_t)a.peer_trunc[p] % 2 == 0;
+        if (peers_ok) {
+            StepArgs t = a;
+            t.count = a.count & ~(int64_t)1;
+            const int64_t pairs = t.count / 2;
+            step_kernel_pair<KIND, ActT><<<(unsigned)((pairs + kThreads - 1) / kThreads), kThreads, 0, st>>>(t);
+            CK(h, cudaGetLastError());
+            done = t.count;
+        }
+    }
     if (done < a.count) {
         StepArgs t = a;
         t.first = a.first + done;
@@ -1240,7 +1345,7 @@ extern "C" int b200gym_create(const b200gym_config *cfg, int64_t num_envs, int d
     {
         const char *fs = getenv("B200GYM_SIMPLE_KERNEL");
         const char *kc = getenv("B200GYM_KERNEL");
-        if (kc && (kc[0] == 'a' || kc[0] == 'b')) h->kernel_choice = kc[0] - 'a';
+        if (kc && (kc[0] == 'a' || kc[0] == 'b' || kc[0] == 'c')) h->kernel_choice = kc[0] - 'a';
         if (fs && fs[0] == '1') h->kernel_choice = 0;
         const char *bb = getenv("B200GYM_BOX2D_BLOCK");
         if (bb && (atoi(bb) == 128 || atoi(bb) == 256)) h->box2d_block = atoi(bb);

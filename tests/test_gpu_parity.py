@@ -321,19 +321,20 @@ def test_state_roundtrip_and_teacher_forcing(oracle_mod):
 
 @pytest.mark.parametrize("env_id", ENV_IDS)
 def test_tma_pipelined_kernels_equal_simple_kernel(env_id, monkeypatch):
-    """Kernel B (persistent CTAs, cp.async.bulk-staged 256-env tiles) against kernel A (plain loads):
-    same arithmetic, so every output and the persistent state must be bit-identical.  N gives the TMA
-    kernel full tiles plus a ragged tail that falls back to kernel A in the same step."""
+    """Kernel B (persistent CTAs, cp.async.bulk-staged 256-env tiles) and kernel C (two envs per thread, 16-byte
+    accesses) against kernel A (plain loads): same arithmetic, so every output and the persistent state must be
+    bit-identical.  N gives the TMA kernel full tiles plus a ragged tail that falls back to kernel A in the same
+    step; the wild actions drive kernel C through its per-env error path."""
     import gym_b200
     torch = _torch()
     N, T = 148 * 256 * 2 + 178, 70
     envs = {}
-    for k in ("a", "b"):
+    for k in ("a", "b", "c"):
         monkeypatch.setenv("B200GYM_KERNEL", k)
         envs[k] = gym_b200.vector.make(env_id, N, max_episode_steps=40)
     monkeypatch.delenv("B200GYM_KERNEL")
     obs = {k: e.reset(seed=99)[0] for k, e in envs.items()}
-    assert torch.equal(obs["a"], obs["b"])
+    assert torch.equal(obs["a"], obs["b"]) and torch.equal(obs["a"], obs["c"])
     ea = envs["a"]
     acts = torch.as_tensor(_actions(env_id, np.random.default_rng(11), T, N, wild=True), device=ea.device)
     dtypes = [torch.int64, torch.int32, torch.uint8] if ea.discrete else [torch.float32]
@@ -342,7 +343,7 @@ def test_tma_pipelined_kernels_equal_simple_kernel(env_id, monkeypatch):
         a = acts[t].to(dtypes[t % len(dtypes)])
         ra = ea.step(a)
         m = ra[4]["_final_observation"]
-        for k in ("b",):
+        for k in ("b", "c"):
             rb = envs[k].step(a)
             for x, y in zip(ra[:4], rb[:4]):
                 assert torch.equal(x, y), f"kernel {k} step {t}"
@@ -350,7 +351,7 @@ def test_tma_pipelined_kernels_equal_simple_kernel(env_id, monkeypatch):
             assert torch.equal(ra[4]["final_observation"][m], rb[4]["final_observation"][m])
         n_done += int(m.sum())
     assert n_done >= N
-    for k in ("b",):
+    for k in ("b", "c"):
         for x, y in zip(ea.get_state(), envs[k].get_state()):
             assert torch.equal(x, y), f"kernel {k} state"
     for e in envs.values():

@@ -366,3 +366,86 @@ def test_hardcore_obstacles_are_solid_and_seen_by_the_lidar():
     # restatement; resting contacts stay within the solver's 0.005 slop + 0.01 skin)
     assert deepest < 0.15, deepest
     assert min_lidar < 0.35
+
+
+# ---------------------------------------------------------------------------------------------------------
+# physics invariants of the re-derived solver (independent of any Box2D implementation detail)
+# ---------------------------------------------------------------------------------------------------------
+def _poly_area(pts):
+    x, y = np.asarray(pts, dtype=np.float64).T
+    return 0.5 * abs(np.dot(x, np.roll(y, -1)) - np.dot(y, np.roll(x, -1)))
+
+
+def _lunar_masses():
+    """density x area of the fixtures of lunar_lander.py:354-368,379-398 (lander density 5, legs density 1)."""
+    S = 30.0
+    lander = _poly_area([(-14 / S, 17 / S), (-17 / S, 0), (-17 / S, -10 / S), (17 / S, -10 / S), (17 / S, 0), (14 / S, 17 / S)])
+    leg = (2 * 2 / S) * (2 * 8 / S)
+    return np.array([5.0 * lander, 1.0 * leg, 1.0 * leg])
+
+
+def test_free_flight_conserves_momentum_up_to_gravity():
+    """Joint impulses are internal: in free flight the linear momentum of lander + legs changes by exactly
+    M g dt per step and nothing else (no engines: action 0; no wind)."""
+    m = _lunar_masses()
+    M = m.sum()
+    for g in (-10.0, -4.0):
+        e = orc.OracleLunar(1, gravity=g)
+        e.reset(seed=6)
+        b0 = e.bodies(0)[0].astype(np.float64)
+        px0, py0 = float(m @ b0[:, 3]), float(m @ b0[:, 4])
+        for k in range(1, 26):
+            o = e.step(np.asarray([0]))[0][0]
+            assert o[6] == 0 and o[7] == 0, "still in the air"
+            b = e.bodies(0)[0].astype(np.float64)
+            px, py = float(m @ b[:, 3]), float(m @ b[:, 4])
+            assert abs(px - px0) < 2e-3 * M, (k, px - px0)                        # float32 solver round-off only
+            assert abs((py - py0) - M * g * k / 50.0) < 2e-3 * M, (k, py - py0, M * g * k / 50.0)
+
+
+def test_leg_joints_respect_their_limits_and_anchors():
+    """The revolute joints hold: leg angles stay within [lower, upper] up to the solver's angular slop + one step of
+    motion, and each leg's anchor keeps its distance to the lander's centre (the lander-side anchor is a fixed point
+    of the lander) up to the linear slop, over a whole heuristic episode including the landing impacts."""
+    e = orc.OracleLunar(1)
+    s = e.reset(seed=1)[0]
+    S = 30.0
+    worst_angle = worst_anchor = 0.0
+    d0 = {}
+    for t in range(600):
+        obs, r, te, tr, fo = e.step(np.asarray([orc.lunar_heuristic(s)]))
+        if te[0] or tr[0]:
+            break
+        b = e.bodies(0)[0].astype(np.float64)
+        for li, i in ((1, -1), (2, +1)):
+            rel = b[li, 2] - b[0, 2]
+            lo, hi = (0.4, 0.9) if i == -1 else (-0.9, -0.4)          # lunar_lander.py:405-412
+            worst_angle = max(worst_angle, lo - rel, rel - hi)
+            ca, sa = np.cos(b[li, 2]), np.sin(b[li, 2])
+            ax, ay = i * 20 / S, 18 / S                               # localAnchorB, :402-404
+            anchor = np.array([b[li, 0] + ca * ax - sa * ay, b[li, 1] + sa * ax + ca * ay])
+            d = float(np.hypot(*(anchor - b[0, :2])))
+            worst_anchor = max(worst_anchor, abs(d - d0.setdefault(li, d)))
+        s = obs[0]
+    assert t > 100
+    assert worst_angle < 0.08, worst_angle          # 2 deg slop + impacts (the limit is soft within one step)
+    assert worst_anchor < 0.02, worst_anchor
+
+
+def test_landed_lander_comes_to_rest_and_sleeps():
+    """A lander that has landed ends its episode through `not self.lander.awake` (+100, lunar_lander.py:594-596):
+    the island has to fall below the sleep tolerances for 0.5 s while resting on two leg contacts."""
+    e = orc.OracleLunar(1)
+    s = e.reset(seed=1)[0]
+    last = None
+    for t in range(1000):
+        obs, r, te, tr, fo = e.step(np.asarray([orc.lunar_heuristic(s)]))
+        if te[0] or tr[0]:
+            last = (float(r[0]), fo[0].copy())
+            break
+        s = obs[0]
+    assert last is not None and last[0] == 100.0
+    final = last[1]
+    assert final[6] == 1.0 and final[7] == 1.0                      # both legs on the ground
+    assert abs(final[2]) < 0.01 and abs(final[3]) < 0.01 and abs(final[5]) < 0.01
+    assert abs(final[0]) < 0.3 and abs(final[4]) < 0.2               # on the pad, upright

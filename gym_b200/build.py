@@ -30,7 +30,7 @@ def _nvcc():
 
 
 def sources():
-    return [os.path.join(CSRC, f) for f in sorted(os.listdir(CSRC)) if f.endswith((".cu", ".cuh"))] + [
+    return [os.path.join(CSRC, f) for f in sorted(os.listdir(CSRC)) if f.endswith((".cu", ".cuh", ".h"))] + [
         os.path.join(os.path.dirname(_HERE), "include", "b200gym.h")]
 
 

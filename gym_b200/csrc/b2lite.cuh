@@ -24,6 +24,14 @@
 #include <cstdint>
 #include <type_traits>
 
+// An optimisation barrier that makes a float opaque to the compiler (it must then live in a register instead of
+// being recomputed); a no-op for the host build of this header that tests/hostsim uses.
+#ifdef __CUDA_ARCH__
+#define B2L_KEEP_IN_REGISTER(x) asm volatile("" : "+f"(x))
+#else
+#define B2L_KEEP_IN_REGISTER(x) ((void)0)
+#endif
+
 namespace b2l {
 
 #define LD __device__ __forceinline__
@@ -427,7 +435,7 @@ LD void joint_init(Joint &j, JTemp &t, const JointDef &d, const ShapeConst &A, c
 #pragma unroll
     for (int c = 0; c < 3; c++)
 #pragma unroll
-        for (int r = c; r < 3; r++) { asm volatile("" : "+f"(t.K[c][r])); t.K[r][c] = t.K[c][r]; }
+        for (int r = c; r < 3; r++) { B2L_KEEP_IN_REGISTER(t.K[c][r]); t.K[r][c] = t.K[c][r]; }
     const float jointAngle = sB.a - sA.a - 0.0f;
     const float lower = d.lower, upper = d.upper;
     if (fabsf(upper - lower) < 2.0f * kAngularSlop) j.limitState = 3;

@@ -1,0 +1,208 @@
+// hostsim.cpp -- the device solver source of the Box2D tasks, compiled for the CPU.
+//
+// TEST INFRASTRUCTURE (never shipped, never imported by gym_b200/): includes gym_b200/csrc/{rng,b2lite,lunar,
+// walker}.cuh and box2d_consts.h through tests/hostsim/cuda_shim.h and drives them with plain loops that mirror the
+// bodies of lunar_step_kernel / walker_step_kernel / *_reset_kernel in gym_b200/csrc/b200gym.cu (same record layout,
+// same load -> env_step -> TimeLimit -> autoreset -> store sequence).  tests/test_hostsim_cpu.py compares it bit for
+// bit with the C oracle, so the `-m "not gpu"` suite exercises the code the kernels run: solver, scenes, record
+// packing, host-computed constants, numpy-compatible RNG.
+#include "cuda_shim.h"
+
+#include <cstdlib>
+#include <vector>
+
+#include "../../gym_b200/csrc/rng.cuh"
+#include "../../gym_b200/csrc/box2d_consts.h"
+
+using bgym::Pcg64;
+
+namespace {
+
+struct Sim {
+    int kind = 0;            // enum b200gym_kind: 5 lunar, 7 lunar continuous, 6 walker, 8 walker hardcore
+    int64_t n = 0;
+    int max_steps = 0;
+    lunar::Opts opts{};
+    std::vector<uint32_t> rec;       // [words][n]
+    std::vector<uint64_t> rng;       // [n][4]
+    std::vector<int32_t> elapsed;
+    bool lunar() const { return kind == 5 || kind == 7; }
+    bool hardcore() const { return kind == 8; }
+};
+
+bool g_consts_ready = false;
+void ensure_consts() {
+    if (g_consts_ready) return;
+    b2l_host::lunar_consts(lunar::kC);
+    b2l_host::walker_consts(walker::kC);
+    g_consts_ready = true;
+}
+
+void lunar_reset_env(Sim &S, int64_t i, float *obs) {     // lunar_reset_kernel
+    lunar::World W;
+    W.flags = S.rec[(int64_t)lunar::W_FLAGS * S.n + i] & 16u;
+    W.wind_idx = S.opts.wind ? (int32_t)S.rec[(int64_t)lunar::W_WIND * S.n + i] : 0;
+    W.torque_idx = S.opts.wind ? (int32_t)S.rec[(int64_t)(lunar::W_WIND + 1) * S.n + i] : 0;
+    Pcg64 g = bgym::pcg64_load(&S.rng[4 * i]);
+    float o[8];
+    lunar::env_reset(W, g, S.opts, o);
+    lunar::store_world(W, S.rec.data(), S.n, i, S.opts.wind != 0);
+    bgym::pcg64_store(&S.rng[4 * i], g);
+    S.elapsed[i] = 0;
+    if (obs) std::memcpy(obs + 8 * i, o, sizeof o);
+}
+
+template <bool HC>
+void walker_reset_env(Sim &S, int64_t i, float *obs) {    // walker_reset_kernel<HC>
+    walker::World W;
+    walker::Rng r;
+    walker::bind_world(W, S.rec.data(), S.n, i);
+    W.flags = S.rec[(int64_t)walker::W_FLAGS * S.n + i] & b2l::kFlagStepped;
+    r.has32 = S.rec[(int64_t)walker::W_RNG32 * S.n + i];
+    r.val32 = S.rec[(int64_t)(walker::W_RNG32 + 1) * S.n + i];
+    r.g = bgym::pcg64_load(&S.rng[4 * i]);
+    W.np = 0; W.p_lo = 0; W.p_hi = -1;
+    float o[24];
+    walker::env_reset<HC>(W, r, o);
+    walker::store_world(W, S.rec.data(), S.n, i, r, HC);
+    bgym::pcg64_store(&S.rng[4 * i], r.g);
+    S.elapsed[i] = 0;
+    if (obs) std::memcpy(obs + 24 * i, o, sizeof o);
+}
+
+template <bool HC>
+void walker_step_env(Sim &S, int64_t i, const float *act, float *obs_out, double *reward, uint8_t *term, uint8_t *trunc,
+                     float *final_obs) {                  // walker_step_kernel<HC>
+    const float action[4] = {act[4 * i], act[4 * i + 1], act[4 * i + 2], act[4 * i + 3]};
+    walker::World W;
+    walker::Rng rng;
+    walker::load_world(W, S.rec.data(), S.n, i, rng, HC);
+    int32_t elapsed = S.elapsed[i];
+    float obs[24];
+    double r;
+    bool terminated;
+    walker::env_step<HC>(W, action, false, walker::V(0.0f, 0.0f), obs, r, terminated);
+    elapsed += 1;
+    const bool truncated = (S.max_steps > 0) && (elapsed >= S.max_steps);
+    reward[i] = r; term[i] = terminated ? 1 : 0; trunc[i] = truncated ? 1 : 0;
+    if (terminated || truncated) {
+        if (final_obs) std::memcpy(final_obs + 24 * i, obs, sizeof obs);
+        rng.g = bgym::pcg64_load(&S.rng[4 * i]);
+        walker::env_reset<HC>(W, rng, obs);
+        bgym::pcg64_store(&S.rng[4 * i], rng.g);
+        elapsed = 0;
+    }
+    walker::store_world(W, S.rec.data(), S.n, i, rng, HC);
+    S.elapsed[i] = elapsed;
+    std::memcpy(obs_out + 24 * i, obs, sizeof obs);
+}
+
+}  // namespace
+
+extern "C" {
+
+void *hs_create(int kind, int64_t n, int max_steps, int wind, double gravity, double wind_power, double turbulence_power) {
+    if (n <= 0 || kind < 5 || kind > 8) return nullptr;
+    ensure_consts();
+    Sim *S = new Sim();
+    S->kind = kind; S->n = n; S->max_steps = max_steps;
+    S->opts.continuous = kind == 7; S->opts.wind = wind != 0; S->opts.gravity = (float)gravity;
+    S->opts.wind_power = wind_power; S->opts.turbulence_power = turbulence_power;
+    const size_t words = S->lunar() ? lunar::kWords : (S->hardcore() ? walker::kWordsHC : walker::kWords);
+    S->rec.assign(words * (size_t)n, 0u);
+    S->rng.assign(4 * (size_t)n, 0ull);
+    S->elapsed.assign((size_t)n, 0);
+    return S;
+}
+void hs_destroy(void *h) { delete (Sim *)h; }
+
+void hs_seed_range(void *h, const uint32_t base[4], int64_t first) {   // seed_range_kernel (+ walker_clear_rng32_kernel)
+    Sim &S = *(Sim *)h;
+    using bgym::u128;
+    const u128 b = ((u128)base[3] << 96) | ((u128)base[2] << 64) | ((u128)base[1] << 32) | (u128)base[0];
+    for (int64_t i = 0; i < S.n; i++) {
+        const u128 seed = b + (u128)(uint64_t)(first + i);
+        const uint32_t ent[4] = {(uint32_t)seed, (uint32_t)(seed >> 32), (uint32_t)(seed >> 64), (uint32_t)(seed >> 96)};
+        Pcg64 g;
+        bgym::pcg64_from_entropy(g, ent);
+        bgym::pcg64_store_full(&S.rng[4 * i], g);
+        if (!S.lunar()) { S.rec[(int64_t)walker::W_RNG32 * S.n + i] = 0u; S.rec[(int64_t)(walker::W_RNG32 + 1) * S.n + i] = 0u; }
+    }
+}
+
+void hs_set_wind_idx(void *h, const int32_t *wind, const int32_t *torque) {
+    Sim &S = *(Sim *)h;
+    for (int64_t i = 0; i < S.n; i++) {
+        S.rec[(int64_t)lunar::W_WIND * S.n + i] = (uint32_t)wind[i];
+        S.rec[(int64_t)(lunar::W_WIND + 1) * S.n + i] = (uint32_t)torque[i];
+    }
+}
+void hs_get_wind_idx(void *h, int32_t *wind, int32_t *torque) {
+    Sim &S = *(Sim *)h;
+    for (int64_t i = 0; i < S.n; i++) {
+        wind[i] = (int32_t)S.rec[(int64_t)lunar::W_WIND * S.n + i];
+        torque[i] = (int32_t)S.rec[(int64_t)(lunar::W_WIND + 1) * S.n + i];
+    }
+}
+
+void hs_reset(void *h, float *obs) {
+    Sim &S = *(Sim *)h;
+    for (int64_t i = 0; i < S.n; i++) {
+        if (S.lunar()) lunar_reset_env(S, i, obs);
+        else if (S.hardcore()) walker_reset_env<true>(S, i, obs);
+        else walker_reset_env<false>(S, i, obs);
+    }
+}
+
+// actions: int64 [n] (kind 5) or float32 [n][2] (kind 7) or float32 [n][4] (kinds 6, 8); returns #invalid actions
+int64_t hs_step(void *h, const void *actions, float *obs_out, double *reward, uint8_t *term, uint8_t *trunc, float *final_obs) {
+    Sim &S = *(Sim *)h;
+    int64_t invalid = 0;
+    for (int64_t i = 0; i < S.n; i++) {
+        if (!S.lunar()) {
+            if (S.hardcore()) walker_step_env<true>(S, i, (const float *)actions, obs_out, reward, term, trunc, final_obs);
+            else walker_step_env<false>(S, i, (const float *)actions, obs_out, reward, term, trunc, final_obs);
+            continue;
+        }
+        // lunar_step_kernel<ActT, CONT>
+        long long act = 0;
+        float ca0 = 0.0f, ca1 = 0.0f;
+        if (S.kind == 7) { ca0 = ((const float *)actions)[2 * i]; ca1 = ((const float *)actions)[2 * i + 1]; }
+        else {
+            act = ((const int64_t *)actions)[i];
+            if (act < 0 || act > 3) { invalid++; continue; }
+        }
+        lunar::World W;
+        lunar::load_world(W, S.rec.data(), S.n, i, S.opts.wind != 0);
+        Pcg64 g = bgym::pcg64_load(&S.rng[4 * i]);
+        int32_t elapsed = S.elapsed[i];
+        float obs[8];
+        double r;
+        bool terminated;
+        lunar::env_step(W, g, S.opts, (int)act, ca0, ca1, lunar::V(0.0f, 0.0f), obs, r, terminated);
+        elapsed += 1;
+        const bool truncated = (S.max_steps > 0) && (elapsed >= S.max_steps);
+        reward[i] = r; term[i] = terminated ? 1 : 0; trunc[i] = truncated ? 1 : 0;
+        if (terminated || truncated) {
+            if (final_obs) std::memcpy(final_obs + 8 * i, obs, sizeof obs);
+            lunar::env_reset(W, g, S.opts, obs);
+            elapsed = 0;
+        }
+        lunar::store_world(W, S.rec.data(), S.n, i, S.opts.wind != 0);
+        bgym::pcg64_store(&S.rng[4 * i], g);
+        S.elapsed[i] = elapsed;
+        std::memcpy(obs_out + 8 * i, obs, sizeof obs);
+    }
+    return invalid;
+}
+
+// the 200 terrain heights and the hardcore boxes of env i (walker kinds); returns the number of boxes
+int hs_walker_terrain(void *h, int64_t i, float *terrain200, float *boxes /* [40][4] */) {
+    Sim &S = *(Sim *)h;
+    for (int k = 0; k < walker::kTerrain; k++) terrain200[k] = __uint_as_float(S.rec[(int64_t)(walker::W_TERRAIN + k) * S.n + i]);
+    const int np = S.hardcore() ? (int)S.rec[(int64_t)walker::W_NPOLY * S.n + i] : 0;
+    for (int k = 0; k < 4 * np; k++) boxes[k] = __uint_as_float(S.rec[(int64_t)(walker::W_POLY + k) * S.n + i]);
+    return np;
+}
+
+}  // extern "C"

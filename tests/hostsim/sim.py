@@ -1,0 +1,108 @@
+"""ctypes wrapper of tests/hostsim/hostsim.cpp: the device source of the Box2D tasks running on the CPU.
+
+Built on demand with g++ into tests/hostsim/_build/ (git-ignored), with the flags that make float32 arithmetic
+round like the device build does (`-ffp-contract=off`, matching nvcc's `-fmad=false`).
+"""
+import ctypes
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_ROOT = os.path.dirname(os.path.dirname(_HERE))
+_BUILD = os.path.join(_HERE, "_build")
+_LIB = os.path.join(_BUILD, "libhostsim.so")
+_SRCS = [os.path.join(_HERE, "hostsim.cpp"), os.path.join(_HERE, "cuda_shim.h")] + [
+    os.path.join(_ROOT, "gym_b200", "csrc", f) for f in ("rng.cuh", "b2lite.cuh", "lunar.cuh", "walker.cuh", "box2d_consts.h")]
+
+KIND = {"LunarLander": 5, "BipedalWalker": 6, "LunarLanderContinuous": 7, "BipedalWalkerHardcore": 8}
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        if not os.path.exists(_LIB) or os.path.getmtime(_LIB) < max(os.path.getmtime(s) for s in _SRCS):
+            os.makedirs(_BUILD, exist_ok=True)
+            subprocess.check_call(["g++", "-O2", "-std=c++17", "-ffp-contract=off", "-fno-fast-math", "-fPIC", "-shared",
+                                   "-Wno-unknown-pragmas", "-o", _LIB, os.path.join(_HERE, "hostsim.cpp")])
+        L = ctypes.CDLL(_LIB)
+        vp, i64, i32, dbl = ctypes.c_void_p, ctypes.c_int64, ctypes.c_int, ctypes.c_double
+        L.hs_create.restype = vp
+        L.hs_create.argtypes = [i32, i64, i32, i32, dbl, dbl, dbl]
+        L.hs_destroy.argtypes = [vp]
+        L.hs_seed_range.argtypes = [vp, vp, i64]
+        L.hs_set_wind_idx.argtypes = [vp, vp, vp]
+        L.hs_get_wind_idx.argtypes = [vp, vp, vp]
+        L.hs_reset.argtypes = [vp, vp]
+        L.hs_step.restype = i64
+        L.hs_step.argtypes = [vp, vp, vp, vp, vp, vp, vp]
+        L.hs_walker_terrain.restype = i32
+        L.hs_walker_terrain.argtypes = [vp, i64, vp, vp]
+        _lib = L
+    return _lib
+
+
+def _seed_words(seed):
+    s = int(seed)
+    return np.array([(s >> (32 * k)) & 0xFFFFFFFF for k in range(4)], dtype=np.uint32)
+
+
+class HostSim:
+    """One batch of envs stepped by the device source on the CPU; same call shape as oracle.OracleLunar/OracleWalker."""
+
+    def __init__(self, name, num_envs, max_episode_steps, gravity=-10.0, enable_wind=False, wind_power=15.0,
+                 turbulence_power=1.5, wind_idx=None, torque_idx=None):
+        self.kind = KIND[name]
+        self.n = int(num_envs)
+        self.lunar = self.kind in (5, 7)
+        self.obs_dim = 8 if self.lunar else 24
+        self._h = lib().hs_create(self.kind, self.n, int(max_episode_steps or 0), int(bool(enable_wind)), float(gravity),
+                                  float(wind_power), float(turbulence_power))
+        assert self._h
+        if wind_idx is not None:
+            wi = np.ascontiguousarray(np.broadcast_to(wind_idx, (self.n,)), dtype=np.int32)
+            ti = np.ascontiguousarray(np.broadcast_to(torque_idx, (self.n,)), dtype=np.int32)
+            lib().hs_set_wind_idx(self._h, wi.ctypes.data, ti.ctypes.data)
+
+    def close(self):
+        if getattr(self, "_h", None):
+            lib().hs_destroy(self._h)
+            self._h = None
+
+    __del__ = close
+
+    def reset(self, seed=None):
+        if seed is not None:
+            lib().hs_seed_range(self._h, _seed_words(seed).ctypes.data, 0)
+        obs = np.zeros((self.n, self.obs_dim), dtype=np.float32)
+        lib().hs_reset(self._h, obs.ctypes.data)
+        return obs
+
+    def step(self, actions):
+        if self.kind == 5:
+            a = np.ascontiguousarray(actions, dtype=np.int64).reshape(self.n)
+        else:
+            a = np.ascontiguousarray(actions, dtype=np.float32).reshape(self.n, 2 if self.kind == 7 else 4)
+        obs = np.zeros((self.n, self.obs_dim), dtype=np.float32)
+        fo = np.zeros((self.n, self.obs_dim), dtype=np.float32)
+        rew = np.zeros(self.n, dtype=np.float64)
+        te = np.zeros(self.n, dtype=np.uint8)
+        tr = np.zeros(self.n, dtype=np.uint8)
+        bad = lib().hs_step(self._h, a.ctypes.data, obs.ctypes.data, rew.ctypes.data, te.ctypes.data, tr.ctypes.data,
+                            fo.ctypes.data)
+        assert bad == 0
+        return obs, rew, te.astype(bool), tr.astype(bool), fo
+
+    def wind_idx(self):
+        wi = np.zeros(self.n, dtype=np.int32)
+        ti = np.zeros(self.n, dtype=np.int32)
+        lib().hs_get_wind_idx(self._h, wi.ctypes.data, ti.ctypes.data)
+        return wi, ti
+
+    def terrain(self, i=0):
+        t = np.zeros(200, dtype=np.float32)
+        boxes = np.zeros((40, 4), dtype=np.float32)
+        k = lib().hs_walker_terrain(self._h, int(i), t.ctypes.data, boxes.ctypes.data)
+        return t, boxes[:k].copy()

@@ -1,6 +1,6 @@
 // hostsim.cpp -- the device solver source of the Box2D tasks, compiled for the CPU.
 //
-// TEST INFRASTRUCTURE (never shipped, never imported by gym_b200/): includes gym_b200/csrc/{rng,b2lite,lunar,
+// TEST INFRASTRUCTURE (never shipped, never imported by gym_b200/): includes gym_b200/csrc/{rng,envs,b2lite,lunar,
 // walker}.cuh and box2d_consts.h through tests/hostsim/cuda_shim.h and drives them with plain loops that mirror the
 // bodies of lunar_step_kernel / walker_step_kernel / *_reset_kernel in gym_b200/csrc/b200gym.cu (same record layout,
 // same load -> env_step -> TimeLimit -> autoreset -> store sequence).  tests/test_hostsim_cpu.py compares it bit for
@@ -12,6 +12,7 @@
 #include <vector>
 
 #include "../../gym_b200/csrc/rng.cuh"
+#include "../../gym_b200/csrc/envs.cuh"
 #include "../../gym_b200/csrc/box2d_consts.h"
 
 using bgym::Pcg64;
@@ -203,6 +204,145 @@ int hs_walker_terrain(void *h, int64_t i, float *terrain200, float *boxes /* [40
     const int np = S.hardcore() ? (int)S.rec[(int64_t)walker::W_NPOLY * S.n + i] : 0;
     for (int k = 0; k < 4 * np; k++) boxes[k] = __uint_as_float(S.rec[(int64_t)(walker::W_POLY + k) * S.n + i]);
     return np;
+}
+
+}  // extern "C"
+
+// ---------------------------------------------------------------------------------------------------------------
+// classic control: Env<KIND>::step / reset of gym_b200/csrc/envs.cuh driven like advance_env / reset_env of b200gym.cu
+// (autoreset mode: TimeLimit counter, same-step reset with the env's own PCG64 stream, final_obs rows)
+// ---------------------------------------------------------------------------------------------------------------
+namespace {
+
+struct Classic {
+    int kind = 0;
+    int64_t n = 0;
+    int max_steps = 0;
+    double param0 = 0.0;
+    std::vector<double> state;     // [S][n]
+    std::vector<uint64_t> rng;     // [n][4]
+    std::vector<int32_t> elapsed;
+};
+
+template <int KIND>
+void classic_reset(Classic &C, const double *bounds, float *obs) {
+    using E = bgym::Env<KIND>;
+    double lo, hi;
+    E::default_bounds(lo, hi);
+    if (bounds) { lo = bounds[0]; hi = bounds[1]; }
+    for (int64_t i = 0; i < C.n; i++) {
+        double s[E::S];
+        float o[E::D];
+        Pcg64 g = bgym::pcg64_load(&C.rng[4 * i]);
+        E::reset(s, g, lo, hi, o);
+        bgym::pcg64_store(&C.rng[4 * i], g);
+        for (int k = 0; k < E::S; k++) C.state[(int64_t)k * C.n + i] = s[k];
+        C.elapsed[i] = 0;
+        std::memcpy(obs + (int64_t)E::D * i, o, sizeof o);
+    }
+}
+
+template <int KIND>
+int64_t classic_step(Classic &C, const void *actions, float *obs_out, double *reward, uint8_t *term, uint8_t *trunc,
+                     float *final_obs) {
+    using E = bgym::Env<KIND>;
+    int64_t invalid = 0;
+    for (int64_t i = 0; i < C.n; i++) {
+        double s[E::S];
+        for (int k = 0; k < E::S; k++) s[k] = C.state[(int64_t)k * C.n + i];
+        int32_t elapsed = C.elapsed[i];
+        int act = 0;
+        float a0 = 0.0f;
+        if (E::A == 0) {
+            const long long v = ((const int64_t *)actions)[i];
+            if (v < 0 || v >= E::NACT) { invalid++; continue; }
+            act = (int)v;
+        } else {
+            a0 = ((const float *)actions)[i];
+        }
+        float obs[E::D];
+        double r;
+        bool terminated;
+        E::step(s, elapsed == 0, act, a0, C.param0, obs, r, terminated);
+        elapsed += 1;
+        const bool truncated = (C.max_steps > 0) && (elapsed >= C.max_steps);
+        reward[i] = r; term[i] = terminated ? 1 : 0; trunc[i] = truncated ? 1 : 0;
+        if (terminated || truncated) {
+            if (final_obs) std::memcpy(final_obs + (int64_t)E::D * i, obs, sizeof obs);
+            Pcg64 g = bgym::pcg64_load(&C.rng[4 * i]);
+            double lo, hi;
+            E::default_bounds(lo, hi);
+            E::reset(s, g, lo, hi, obs);
+            bgym::pcg64_store(&C.rng[4 * i], g);
+            elapsed = 0;
+        }
+        for (int k = 0; k < E::S; k++) C.state[(int64_t)k * C.n + i] = s[k];
+        C.elapsed[i] = elapsed;
+        std::memcpy(obs_out + (int64_t)E::D * i, obs, sizeof obs);
+    }
+    return invalid;
+}
+
+}  // namespace
+
+extern "C" {
+
+void *hs_classic_create(int kind, int64_t n, int max_steps, double param0) {
+    if (n <= 0 || kind < 0 || kind > 4) return nullptr;
+    Classic *C = new Classic();
+    C->kind = kind; C->n = n; C->max_steps = max_steps; C->param0 = param0;
+    C->state.assign(4 * (size_t)n, 0.0);
+    C->rng.assign(4 * (size_t)n, 0ull);
+    C->elapsed.assign((size_t)n, 0);
+    return C;
+}
+void hs_classic_destroy(void *h) { delete (Classic *)h; }
+
+void hs_classic_seed_range(void *h, const uint32_t base[4], int64_t first) {
+    Classic &C = *(Classic *)h;
+    using bgym::u128;
+    const u128 b = ((u128)base[3] << 96) | ((u128)base[2] << 64) | ((u128)base[1] << 32) | (u128)base[0];
+    for (int64_t i = 0; i < C.n; i++) {
+        const u128 seed = b + (u128)(uint64_t)(first + i);
+        const uint32_t ent[4] = {(uint32_t)seed, (uint32_t)(seed >> 32), (uint32_t)(seed >> 64), (uint32_t)(seed >> 96)};
+        Pcg64 g;
+        bgym::pcg64_from_entropy(g, ent);
+        bgym::pcg64_store_full(&C.rng[4 * i], g);
+    }
+}
+
+void hs_classic_reset(void *h, const double *bounds, float *obs) {
+    Classic &C = *(Classic *)h;
+    switch (C.kind) {
+    case 0: classic_reset<B200GYM_CARTPOLE>(C, bounds, obs); break;
+    case 1: classic_reset<B200GYM_MOUNTAINCAR>(C, bounds, obs); break;
+    case 2: classic_reset<B200GYM_MOUNTAINCAR_CONT>(C, bounds, obs); break;
+    case 3: classic_reset<B200GYM_PENDULUM>(C, bounds, obs); break;
+    default: classic_reset<B200GYM_ACROBOT>(C, bounds, obs); break;
+    }
+}
+
+int64_t hs_classic_step(void *h, const void *actions, float *obs, double *reward, uint8_t *term, uint8_t *trunc,
+                        float *final_obs) {
+    Classic &C = *(Classic *)h;
+    switch (C.kind) {
+    case 0: return classic_step<B200GYM_CARTPOLE>(C, actions, obs, reward, term, trunc, final_obs);
+    case 1: return classic_step<B200GYM_MOUNTAINCAR>(C, actions, obs, reward, term, trunc, final_obs);
+    case 2: return classic_step<B200GYM_MOUNTAINCAR_CONT>(C, actions, obs, reward, term, trunc, final_obs);
+    case 3: return classic_step<B200GYM_PENDULUM>(C, actions, obs, reward, term, trunc, final_obs);
+    default: return classic_step<B200GYM_ACROBOT>(C, actions, obs, reward, term, trunc, final_obs);
+    }
+}
+
+void hs_classic_get_state(void *h, double *state_aos /* [n][S] */, int S) {
+    Classic &C = *(Classic *)h;
+    for (int64_t i = 0; i < C.n; i++)
+        for (int k = 0; k < S; k++) state_aos[i * S + k] = C.state[(int64_t)k * C.n + i];
+}
+
+// CartPole's small-angle sin/cos kernel alone (csrc/envs.cuh: sincos_small)
+void hs_sincos_small(const double *x, int64_t n, double *sn, double *cs) {
+    for (int64_t i = 0; i < n; i++) bgym::sincos_small(x[i], sn[i], cs[i]);
 }
 
 }  // extern "C"

@@ -14,7 +14,8 @@ _ROOT = os.path.dirname(os.path.dirname(_HERE))
 _BUILD = os.path.join(_HERE, "_build")
 _LIB = os.path.join(_BUILD, "libhostsim.so")
 _SRCS = [os.path.join(_HERE, "hostsim.cpp"), os.path.join(_HERE, "cuda_shim.h")] + [
-    os.path.join(_ROOT, "gym_b200", "csrc", f) for f in ("rng.cuh", "b2lite.cuh", "lunar.cuh", "walker.cuh", "box2d_consts.h")]
+    os.path.join(_ROOT, "gym_b200", "csrc", f) for f in ("rng.cuh", "envs.cuh", "b2lite.cuh", "lunar.cuh", "walker.cuh",
+                                                         "box2d_consts.h")]
 
 KIND = {"LunarLander": 5, "BipedalWalker": 6, "LunarLanderContinuous": 7, "BipedalWalkerHardcore": 8}
 _lib = None
@@ -40,6 +41,15 @@ def lib():
         L.hs_step.argtypes = [vp, vp, vp, vp, vp, vp, vp]
         L.hs_walker_terrain.restype = i32
         L.hs_walker_terrain.argtypes = [vp, i64, vp, vp]
+        L.hs_classic_create.restype = vp
+        L.hs_classic_create.argtypes = [i32, i64, i32, dbl]
+        L.hs_classic_destroy.argtypes = [vp]
+        L.hs_classic_seed_range.argtypes = [vp, vp, i64]
+        L.hs_classic_reset.argtypes = [vp, vp, vp]
+        L.hs_classic_step.restype = i64
+        L.hs_classic_step.argtypes = [vp, vp, vp, vp, vp, vp, vp]
+        L.hs_classic_get_state.argtypes = [vp, vp, i32]
+        L.hs_sincos_small.argtypes = [vp, i64, vp, vp]
         _lib = L
     return _lib
 
@@ -106,3 +116,59 @@ class HostSim:
         boxes = np.zeros((40, 4), dtype=np.float32)
         k = lib().hs_walker_terrain(self._h, int(i), t.ctypes.data, boxes.ctypes.data)
         return t, boxes[:k].copy()
+
+
+class HostSimClassic:
+    """Env<KIND>::step / reset of gym_b200/csrc/envs.cuh on the CPU (autoreset mode); call shape of oracle.OracleVec."""
+
+    # kind -> (obs_dim, act_dim, state_dim); enum b200gym_kind
+    DIMS = {0: (4, 0, 4), 1: (2, 0, 2), 2: (2, 1, 2), 3: (3, 1, 2), 4: (6, 0, 4)}
+
+    def __init__(self, kind, num_envs, max_episode_steps, param0=0.0):
+        self.kind, self.n = int(kind), int(num_envs)
+        self.obs_dim, self.act_dim, self.state_dim = self.DIMS[self.kind]
+        self._h = lib().hs_classic_create(self.kind, self.n, int(max_episode_steps or 0), float(param0))
+        assert self._h
+
+    def close(self):
+        if getattr(self, "_h", None):
+            lib().hs_classic_destroy(self._h)
+            self._h = None
+
+    __del__ = close
+
+    def reset(self, seed=None, bounds=None):
+        if seed is not None:
+            lib().hs_classic_seed_range(self._h, _seed_words(seed).ctypes.data, 0)
+        obs = np.zeros((self.n, self.obs_dim), dtype=np.float32)
+        b = None if bounds is None else np.asarray(bounds, dtype=np.float64)
+        lib().hs_classic_reset(self._h, None if b is None else b.ctypes.data, obs.ctypes.data)
+        return obs
+
+    def step(self, actions):
+        if self.act_dim == 0:
+            a = np.ascontiguousarray(actions, dtype=np.int64).reshape(self.n)
+        else:
+            a = np.ascontiguousarray(actions, dtype=np.float32).reshape(self.n)
+        obs = np.zeros((self.n, self.obs_dim), dtype=np.float32)
+        fo = np.zeros((self.n, self.obs_dim), dtype=np.float32)
+        rew = np.zeros(self.n, dtype=np.float64)
+        te = np.zeros(self.n, dtype=np.uint8)
+        tr = np.zeros(self.n, dtype=np.uint8)
+        bad = lib().hs_classic_step(self._h, a.ctypes.data, obs.ctypes.data, rew.ctypes.data, te.ctypes.data,
+                                    tr.ctypes.data, fo.ctypes.data)
+        assert bad == 0
+        return obs, rew, te.astype(bool), tr.astype(bool), fo
+
+    def state(self):
+        s = np.zeros((self.n, self.state_dim), dtype=np.float64)
+        lib().hs_classic_get_state(self._h, s.ctypes.data, self.state_dim)
+        return s
+
+
+def sincos_small(x):
+    """csrc/envs.cuh: sincos_small on an array of float64 angles."""
+    x = np.ascontiguousarray(x, dtype=np.float64)
+    sn, cs = np.zeros_like(x), np.zeros_like(x)
+    lib().hs_sincos_small(x.ctypes.data, x.size, sn.ctypes.data, cs.ctypes.data)
+    return sn, cs

@@ -15,8 +15,11 @@ from hostsim.sim import HostSim
 from oracle import oracle as orc
 
 
-def _compare(t, got, want):
+def _compare(t, got, want, reward_atol=0.0):
     for k, name in enumerate(("obs", "reward", "terminated", "truncated")):
+        if k == 1 and reward_atol:
+            np.testing.assert_allclose(got[1], want[1], rtol=0, atol=reward_atol, err_msg=f"step {t}: reward")
+            continue
         if not np.array_equal(got[k], want[k]):
             bad = np.argwhere(np.asarray(got[k]) != np.asarray(want[k]))
             raise AssertionError(f"step {t}: {name} differs at {bad[0]}: {np.asarray(got[k])[tuple(bad[0])]!r} "
@@ -96,3 +99,61 @@ def test_walker_device_source_on_cpu_equals_oracle(name, hardcore, policy):
                 else:
                     a[i] = gaits[i](want[0][i])
     assert n_done > (N // 2 if policy == "random" or hardcore else 0)
+
+
+# ---------------------------------------------------------------------------------------------------------
+# classic control: gym_b200/csrc/envs.cuh on the CPU
+# ---------------------------------------------------------------------------------------------------------
+CLASSIC = [("CartPole-v1", 0, None), ("MountainCar-v0", 1, None), ("MountainCarContinuous-v0", 2, None),
+           ("Pendulum-v1", 3, 10.0), ("Acrobot-v1", 4, None)]
+
+
+@pytest.mark.parametrize("env_id,kind,param0", CLASSIC)
+def test_classic_device_source_on_cpu_equals_oracle(env_id, kind, param0):
+    """Same libm on both sides (glibc), so the only thing that may differ from the oracle is the transcription of
+    the dynamics in envs.cuh -- and CartPole's own small-angle sin/cos kernel (csrc/envs.cuh: sincos_small), which
+    replaces libm on the device and is within 1 ulp of it (next test)."""
+    from hostsim.sim import HostSimClassic
+    N, T, seed = 512, 600, 17
+    ref = orc.OracleVec(env_id, N, max_episode_steps=150)       # several TimeLimit truncations within T steps
+    sim = HostSimClassic(kind, N, 150, param0 or 0.0)
+    assert np.array_equal(sim.reset(seed=seed), ref.reset(seed=seed))
+    rng = np.random.default_rng(1)
+    n_done = 0
+    for t in range(T):
+        if ref.act_dim == 0:
+            a = rng.integers(0, ref.num_actions, size=N)
+        else:
+            a = rng.uniform(-2.5, 2.5, size=(N, 1)).astype(np.float32)
+        want = ref.step(a)
+        # Pendulum: the device squares the float32 torque as u*u where numpy calls powf(u, 2) (1 float32 ulp apart
+        # for 0.08 % of inputs; DESIGN.md "Numerics"): rewards within 1e-9, everything else identical
+        n_done += int(_compare(t, sim.step(a), want, reward_atol=1e-9 if kind == 3 else 0.0).sum())
+    if kind == 0:   # CartPole: sincos_small is within 1 ulp of glibc, not identical; the float32 outputs above are
+        np.testing.assert_allclose(sim.state(), ref.get_state()[0], rtol=1e-9, atol=1e-12)
+    else:
+        assert np.array_equal(sim.state(), ref.get_state()[0])
+    assert n_done > N // 2
+
+
+def test_cartpole_small_angle_sincos_against_libm():
+    """csrc/envs.cuh: sincos_small (fdlibm's kernels without range reduction) against glibc over the angles CartPole
+    is stepped at (|theta| <= 0.42 rad incl. the terminal step): never more than 1 ulp apart, identical for the
+    overwhelming majority of inputs.  (The 1-ulp cases are why CartPole's float64 STATE is compared with a tolerance
+    while every float32 output -- observations, rewards, flags -- is bit-identical.)"""
+    import math
+    from hostsim.sim import sincos_small
+    rng = np.random.default_rng(0)
+    x = np.concatenate([rng.uniform(-0.42, 0.42, 60000), rng.normal(0, 0.05, 60000).clip(-0.42, 0.42),
+                        np.array([0.0, -0.0, 1e-300, -1e-300, 2.0 ** -27, 0.2094395102393195, 0.42, -0.42])])
+    sn, cs = sincos_small(x)
+    ws = np.array([math.sin(v) for v in x])
+    wc = np.array([math.cos(v) for v in x])
+    ulp_s = np.abs(sn.view(np.int64) - ws.view(np.int64))
+    ulp_c = np.abs(cs.view(np.int64) - wc.view(np.int64))
+    assert ulp_s.max() <= 1 and ulp_c.max() <= 1, (ulp_s.max(), ulp_c.max())
+    assert (ulp_s == 0).mean() > 0.95 and (ulp_c == 0).mean() > 0.95, ((ulp_s == 0).mean(), (ulp_c == 0).mean())
+    nz = x != 0
+    assert np.array_equal(np.signbit(sn[nz]), np.signbit(ws[nz]))
+    # sin(-0.0) comes out as +0.0 (libm: -0.0): only the sign of a zero product / zero sum downstream, never a value
+    assert sn[x == 0].tolist() == [0.0, 0.0]

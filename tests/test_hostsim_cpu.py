@@ -157,3 +157,25 @@ def test_cartpole_small_angle_sincos_against_libm():
     assert np.array_equal(np.signbit(sn[nz]), np.signbit(ws[nz]))
     # sin(-0.0) comes out as +0.0 (libm: -0.0): only the sign of a zero product / zero sum downstream, never a value
     assert sn[x == 0].tolist() == [0.0, 0.0]
+
+
+def test_lunar_random_constructor_arguments_sweep():
+    """Random LunarLander constructor arguments (gravity in (-12, 0), wind and turbulence powers, both action
+    spaces, random wind phases): device source on the CPU == oracle."""
+    rng = np.random.default_rng(123)
+    for case in range(8):
+        cont = bool(rng.integers(0, 2))
+        wind = bool(rng.integers(0, 2))
+        kw = dict(gravity=float(rng.uniform(-11.9, -0.5)))
+        extra = {}
+        if wind:
+            kw.update(enable_wind=True, wind_power=float(rng.uniform(0, 20)), turbulence_power=float(rng.uniform(0, 2)))
+            extra = dict(wind_idx=rng.integers(-9999, 9999, size=32), torque_idx=rng.integers(-9999, 9999, size=32))
+        name = "LunarLanderContinuous" if cont else "LunarLander"
+        sim = HostSim(name, 32, 120, **kw, **extra)
+        ref = orc.OracleLunar(32, max_episode_steps=120, continuous=cont, **kw, **extra)
+        seed = int(rng.integers(0, 2 ** 40))
+        assert np.array_equal(sim.reset(seed=seed), ref.reset(seed=seed)), (case, kw)
+        for t in range(150):
+            a = rng.uniform(-1.2, 1.2, size=(32, 2)).astype(np.float32) if cont else rng.integers(0, 4, size=32)
+            _compare(t, sim.step(a), ref.step(a))

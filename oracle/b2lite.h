@@ -148,6 +148,7 @@ typedef struct {
     float inv_dt0;
     float gravity_y;         /* b2World gravity = (0, gravity_y) */
     int awake;               /* out: 0 when the island went to sleep in this step */
+    int stat_contacts, stat_pos_iters; /* out (workload statistics): touching contacts, position iterations run */
     void (*event)(void *ctx, int body, int begin); /* Begin/EndContact listener */
     void *ctx;
 } b2l_world;
@@ -903,7 +904,9 @@ static void b2l_step(b2l_world *W, float dt, int velIters, int posIters)
     }
     /* position iterations */
     int positionSolved = 0;
+    W->stat_contacts = nvc; W->stat_pos_iters = 0;
     for (int it = 0; it < posIters; it++) {
+        W->stat_pos_iters = it + 1;
         float minSep = 0.0f;
         for (int ci = 0; ci < nvc; ci++) {
             vc_t *k = &vc[ci];

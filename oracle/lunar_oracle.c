@@ -47,6 +47,7 @@ typedef struct {
     double prev_shaping, helipad_y;
     pcg64_t rng;
     int32_t elapsed;
+    int stat_contacts, stat_pos_iters; /* of the last world step (workload statistics for DESIGN.md) */
     int32_t wind_idx, torque_idx; /* lunar_lander.py:234-235: drawn once per env object, never reset */
 } world_t;
 
@@ -84,6 +85,7 @@ static int world_step(world_t *W, float gravity_y, float dt, int velIters, int p
     S.event = lunar_event; S.ctx = W;
     b2l_step(&S, dt, velIters, posIters);
     W->inv_dt0 = S.inv_dt0;
+    W->stat_contacts = S.stat_contacts; W->stat_pos_iters = S.stat_pos_iters;
     return S.awake;
 }
 
@@ -380,6 +382,12 @@ void orc_lunar_step_cont(orc_lunar *v, const float *actions, float *obs, double 
 {
     for (int64_t i = 0; i < v->n; i++)
         lunar_vec_one(v, i, 0, actions + 2 * i, obs, reward, terminated, truncated, final_obs);
+}
+
+/* workload statistics of the last step of every env: {touching contacts, position iterations} */
+void orc_lunar_get_stats(const orc_lunar *v, int32_t *out)
+{
+    for (int64_t i = 0; i < v->n; i++) { out[2 * i] = v->w[i].stat_contacts; out[2 * i + 1] = v->w[i].stat_pos_iters; }
 }
 
 /* debugging / parity: dump the 3 bodies (c.x, c.y, a, v.x, v.y, w) + flags of env i */

@@ -57,6 +57,7 @@ typedef struct {
     double prev_shaping;
     pcg64_t rng;
     int32_t elapsed;
+    int stat_contacts, stat_pos_iters; /* of the last world step (workload statistics for DESIGN.md) */
 } wworld_t;
 
 struct orc_walker {
@@ -95,6 +96,7 @@ static void wworld_step(wworld_t *W)
     S.event = walker_event; S.ctx = W;
     b2l_step(&S, (float)(1.0 / FPS), 6 * 30, 2 * 30);
     W->inv_dt0 = S.inv_dt0;
+    W->stat_contacts = S.stat_contacts; W->stat_pos_iters = S.stat_pos_iters;
     /* step() rewrites every joint's motor each call, which wakes both bodies (b2RevoluteJoint::
      * SetMotorSpeed -> SetAwake(true)): an island that fell asleep is simply awake again next step */
     for (int i = 0; i < NB; i++) W->b[i].awake = 1;
@@ -375,6 +377,11 @@ void orc_walker_step(orc_walker *v, const float *actions, float *obs, double *re
         }
         memcpy(obs + 24 * i, o, sizeof o);
     }
+}
+
+void orc_walker_get_stats(const orc_walker *v, int32_t *out)
+{
+    for (int64_t i = 0; i < v->n; i++) { out[2 * i] = v->w[i].stat_contacts; out[2 * i + 1] = v->w[i].stat_pos_iters; }
 }
 
 void orc_walker_get_terrain(const orc_walker *v, int64_t i, float *y200)

@@ -56,5 +56,34 @@ def main():
               f"one that runs all 60 position iterations with probability {1 - (1 - p_60) ** 32:.2f}")
 
 
+def gait_case(L, n=128, steps=600, warm=50):
+    """BipedalWalker driven by the reference's demo gait instead of random torques."""
+    env = orc.OracleWalker(n)
+    obs = env.reset(seed=3)
+    gaits = [orc.WalkerHeuristic() for _ in range(n)]
+    a = np.zeros((n, 4), np.float32)
+    hc, hp, tot = np.zeros(12, int), np.zeros(61, int), 0
+    for t in range(steps):
+        o, r, te, tr, fo = env.step(a)
+        if t >= warm:
+            st = np.zeros((n, 2), np.int32)
+            L.orc_walker_get_stats(env._h, st.ctypes.data)
+            hc += np.bincount(np.minimum(st[:, 0], 11), minlength=12)
+            hp += np.bincount(st[:, 1], minlength=61)
+            tot += n
+        for i in range(n):
+            if te[i] or tr[i]:
+                gaits[i] = orc.WalkerHeuristic()
+                a[i] = 0
+            else:
+                a[i] = gaits[i](o[i])
+    hc, hp = hc / tot, hp / tot
+    print(f"BipedalWalker-v3 under the reference's demo gait ({n} envs): contacts mean {float((hc * np.arange(12)).sum()):.2f}; "
+          f"position iterations mean {float((hp * np.arange(61)).sum()):.1f};  1: {hp[1]:.3f}  2-5: {hp[2:6].sum():.3f}  "
+          f"6-59: {hp[6:60].sum():.3f}  60: {hp[60]:.3f}   (the 60-iteration regime belongs to random torques: fallen walkers "
+          "with joints pressed against their limits)")
+
+
 if __name__ == "__main__":
     main()
+    gait_case(orc.lib())

@@ -184,3 +184,29 @@ def test_hardcore_random_actions_bit_exact_and_kwarg_selects_the_variant():
         assert int(npoly[i]) == len(want) and np.array_equal(polys[i, :len(want)].cpu().numpy(), want)
     env.close()
     orc.close()
+
+
+# ---------------------------------------------------------------------------------------------------------
+# frozen roll-outs of the oracle (tests/golden_self): LunarLander and BipedalWalker variants through the public API
+# ---------------------------------------------------------------------------------------------------------
+import self_fixtures  # noqa: E402
+
+
+@pytest.mark.parametrize("name", self_fixtures.names())
+def test_kernels_reproduce_the_frozen_rollouts(name):
+    """Regression pins of the re-derived Box2D physics (not reference data: see oracle/gen_self_fixtures.py): the
+    frozen actions replayed on the GPU give the frozen observations, rewards, flags and final observations."""
+    import gym_b200
+    import torch
+    d = self_fixtures.load(name)
+    env_id, kw = self_fixtures.env_id(d)
+    env = gym_b200.vector.make(env_id, d["n"], max_episode_steps=d["max_episode_steps"], **kw)
+    obs, _ = env.reset(seed=d["seed"])
+
+    def step(a):
+        o, r, te, tr, info = env.step(torch.as_tensor(a, device=env.device))
+        return (o.cpu().numpy(), r.cpu().numpy(), te.cpu().numpy(), tr.cpu().numpy(),
+                info["final_observation"].cpu().numpy())
+
+    self_fixtures.check(d, step, obs.cpu().numpy())
+    env.close()

@@ -179,3 +179,19 @@ def test_lunar_random_constructor_arguments_sweep():
         for t in range(150):
             a = rng.uniform(-1.2, 1.2, size=(32, 2)).astype(np.float32) if cont else rng.integers(0, 4, size=32)
             _compare(t, sim.step(a), ref.step(a))
+
+
+import self_fixtures  # noqa: E402
+
+
+@pytest.mark.parametrize("name", self_fixtures.names())
+def test_device_source_on_cpu_reproduces_the_frozen_rollouts(name):
+    d = self_fixtures.load(name)
+    kw = dict(d["kwargs"])
+    if d["family"] == "lunar":
+        sim = HostSim("LunarLanderContinuous" if kw.pop("continuous", False) else "LunarLander", d["n"],
+                      d["max_episode_steps"], **kw)
+    else:
+        sim = HostSim("BipedalWalkerHardcore" if kw.pop("hardcore", False) else "BipedalWalker", d["n"],
+                      d["max_episode_steps"])
+    self_fixtures.check(d, sim.step, sim.reset(seed=d["seed"]))

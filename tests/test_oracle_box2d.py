@@ -449,3 +449,33 @@ def test_landed_lander_comes_to_rest_and_sleeps():
     assert final[6] == 1.0 and final[7] == 1.0                      # both legs on the ground
     assert abs(final[2]) < 0.01 and abs(final[3]) < 0.01 and abs(final[5]) < 0.01
     assert abs(final[0]) < 0.3 and abs(final[4]) < 0.2               # on the pad, upright
+
+
+# ---------------------------------------------------------------------------------------------------------
+# frozen roll-outs (tests/golden_self): the re-derived physics must not move between rounds
+# ---------------------------------------------------------------------------------------------------------
+import self_fixtures  # noqa: E402
+
+
+@pytest.mark.parametrize("name", self_fixtures.names())
+def test_oracle_reproduces_its_frozen_rollouts(name):
+    d = self_fixtures.load(name)
+    kw = dict(d["kwargs"])
+    if d["family"] == "lunar":
+        env = orc.OracleLunar(d["n"], max_episode_steps=d["max_episode_steps"], **kw)
+    else:
+        env = orc.OracleWalker(d["n"], max_episode_steps=d["max_episode_steps"], **kw)
+    self_fixtures.check(d, env.step, env.reset(seed=d["seed"]))
+
+
+def test_frozen_rollouts_cover_the_interesting_events():
+    ds = {n: self_fixtures.load(n) for n in self_fixtures.names()}
+    assert len(ds) >= 7
+    lh = ds["lunarlander_v2_heuristic"]
+    first_done = int(np.argmax(lh["terminated"][:, 0]))
+    assert abs(float(lh["reward"][:first_done + 1, 0].sum()) - 262.03) < 0.01     # the seed-1 landing of DESIGN.md
+    assert (lh["reward"][lh["terminated"]] == 100).all()                          # every episode ends asleep on the pad
+    assert (ds["lunarlander_v2_random"]["reward"][ds["lunarlander_v2_random"]["terminated"]] == -100).any()
+    assert ds["bipedalwalkerhardcore_v3_gait"]["terminated"].any() and ds["bipedalwalker_v3_random"]["terminated"].any()
+    assert not ds["bipedalwalker_v3_gait"]["terminated"].any()                    # the gait keeps walking for 500 steps
+    assert ds["lunarlander_v2_wind_gravity"]["truncated"].any()                   # TimeLimit 300 reached under wind

@@ -161,7 +161,7 @@ def cpu_oracle_throughput(env_id, n, seconds, threads, min_steps=3):
         OracleWalker(n, hardcore="Hardcore" in env_id) if env_id.startswith("BipedalWalker") else OracleVec(env_id, n))
     v.reset(seed=0)
     pool = [random_actions_np(env_id, n, rng) for _ in range(4)]
-    kw = {} if lunar else {"nthreads": threads}
+    kw = {"nthreads": threads}
     v.step(pool[0], **kw)  # warm-up
     steps, t0 = 0, time.perf_counter()
     while True:
@@ -371,13 +371,11 @@ def run_b200(args):
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         threads = host_threads()
-        if args.env.startswith(("LunarLander", "BipedalWalker")):
-            threads = 1  # the Box2D-task oracles are scalar single-thread ports
         v, cpu_steps, cpu_el = cpu_oracle_throughput(args.env, n, args.cpu_seconds, threads)
         cpu = {"value": v, "unit": "env-steps/s", "cores": threads, "kind": "port",
                "sample": f"{cpu_steps} vector steps of 2^{args.log2_envs} envs ({cpu_el:.1f} s) of the same workload, "
-                         + ("the single-threaded C oracle of the Box2D task (oracle/lunar_oracle.c / walker_oracle.c)"
-                            if threads == 1 else "oracle/gym_oracle.c with one pthread per host core")}
+                         + ("oracle/lunar_oracle.c / walker_oracle.c" if args.env.startswith(("LunarLander", "BipedalWalker"))
+                            else "oracle/gym_oracle.c") + " with one pthread per host core"}
 
     if rank == 0:
         peak, peak_src = measured_hbm_peak()

@@ -27,6 +27,7 @@
 #include "lunar_oracle.h"
 
 #include <math.h>
+#include <pthread.h>
 #include <stdlib.h>
 #include <string.h>
 
@@ -364,24 +365,71 @@ static void lunar_vec_one(orc_lunar *v, int64_t i, int action, const float *ca, 
     memcpy(obs + 8 * i, o, sizeof o);
 }
 
-int64_t orc_lunar_step(orc_lunar *v, const int64_t *actions, float *obs, double *reward, uint8_t *terminated,
-                       uint8_t *truncated, float *final_obs)
+/* the envs are independent: a range of them per host thread (bench.py's cpu_baseline / reference arm) */
+typedef struct {
+    orc_lunar *v; const int64_t *ai; const float *af; float *obs; double *reward; uint8_t *terminated, *truncated;
+    float *final_obs; int64_t lo, hi, invalid;
+} lunar_job;
+
+static void *lunar_range(void *arg)
 {
-    int64_t invalid = 0;
+    lunar_job *j = (lunar_job *)arg;
     const float zero[2] = {0.0f, 0.0f};
-    for (int64_t i = 0; i < v->n; i++) {
-        if (actions[i] < 0 || actions[i] > 3) { invalid++; continue; }                     /* :482-484 */
-        lunar_vec_one(v, i, (int)actions[i], zero, obs, reward, terminated, truncated, final_obs);
+    for (int64_t i = j->lo; i < j->hi; i++) {
+        if (j->af) { lunar_vec_one(j->v, i, 0, j->af + 2 * i, j->obs, j->reward, j->terminated, j->truncated, j->final_obs); continue; }
+        if (j->ai[i] < 0 || j->ai[i] > 3) { j->invalid++; continue; }                       /* :482-484 */
+        lunar_vec_one(j->v, i, (int)j->ai[i], zero, j->obs, j->reward, j->terminated, j->truncated, j->final_obs);
     }
+    return NULL;
+}
+
+static int64_t lunar_run(orc_lunar *v, const int64_t *ai, const float *af, float *obs, double *reward, uint8_t *terminated,
+                         uint8_t *truncated, float *final_obs, int nthreads)
+{
+    if (nthreads < 1) nthreads = 1;
+    if (nthreads > 256) nthreads = 256;
+    if ((int64_t)nthreads > v->n) nthreads = (int)v->n;
+    lunar_job jobs[256];
+    pthread_t tid[256];
+    const int64_t chunk = (v->n + nthreads - 1) / nthreads;
+    for (int t = 0; t < nthreads; t++) {
+        lunar_job *j = &jobs[t];
+        j->v = v; j->ai = ai; j->af = af; j->obs = obs; j->reward = reward; j->terminated = terminated;
+        j->truncated = truncated; j->final_obs = final_obs; j->invalid = 0;
+        j->lo = t * chunk;
+        j->hi = (j->lo + chunk < v->n) ? j->lo + chunk : v->n;
+        if (j->lo > j->hi) j->lo = j->hi;
+    }
+    for (int t = 1; t < nthreads; t++) pthread_create(&tid[t], NULL, lunar_range, &jobs[t]);
+    lunar_range(&jobs[0]);
+    int64_t invalid = jobs[0].invalid;
+    for (int t = 1; t < nthreads; t++) { pthread_join(tid[t], NULL); invalid += jobs[t].invalid; }
     return invalid;
 }
 
+int64_t orc_lunar_step_mt(orc_lunar *v, const int64_t *actions, float *obs, double *reward, uint8_t *terminated,
+                          uint8_t *truncated, float *final_obs, int nthreads)
+{
+    return lunar_run(v, actions, NULL, obs, reward, terminated, truncated, final_obs, nthreads);
+}
+
+int64_t orc_lunar_step(orc_lunar *v, const int64_t *actions, float *obs, double *reward, uint8_t *terminated,
+                       uint8_t *truncated, float *final_obs)
+{
+    return lunar_run(v, actions, NULL, obs, reward, terminated, truncated, final_obs, 1);
+}
+
 /* continuous=True: actions [n][2] float32, clipped to [-1, 1] inside the step (:480) */
+void orc_lunar_step_cont_mt(orc_lunar *v, const float *actions, float *obs, double *reward, uint8_t *terminated,
+                            uint8_t *truncated, float *final_obs, int nthreads)
+{
+    (void)lunar_run(v, NULL, actions, obs, reward, terminated, truncated, final_obs, nthreads);
+}
+
 void orc_lunar_step_cont(orc_lunar *v, const float *actions, float *obs, double *reward, uint8_t *terminated,
                          uint8_t *truncated, float *final_obs)
 {
-    for (int64_t i = 0; i < v->n; i++)
-        lunar_vec_one(v, i, 0, actions + 2 * i, obs, reward, terminated, truncated, final_obs);
+    (void)lunar_run(v, NULL, actions, obs, reward, terminated, truncated, final_obs, 1);
 }
 
 /* workload statistics of the last step of every env: {touching contacts, position iterations} */

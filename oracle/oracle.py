@@ -75,6 +75,10 @@ def lib():
         L.orc_lunar_set_wind_idx.argtypes = [vp, vp, vp]
         L.orc_lunar_get_wind_idx.argtypes = [vp, vp, vp]
         L.orc_lunar_step_cont.argtypes = [vp, vp, vp, vp, vp, vp, vp]
+        L.orc_lunar_step_mt.restype = i64
+        L.orc_lunar_step_mt.argtypes = [vp, vp, vp, vp, vp, vp, vp, i32]
+        L.orc_lunar_step_cont_mt.argtypes = [vp, vp, vp, vp, vp, vp, vp, i32]
+        L.orc_walker_step_mt.argtypes = [vp, vp, vp, vp, vp, vp, vp, i32]
         L.orc_lunar_engines.argtypes = [i32, i32, vp, dbl, dbl, dbl, dbl, dbl, vp, vp, vp]
         L.orc_lunar_destroy.argtypes = [vp]
         L.orc_lunar_seed_range.argtypes = [vp, vp, i64]
@@ -255,7 +259,7 @@ class OracleLunar:
         lib().orc_lunar_reset(self._h, obs.ctypes.data)
         return obs
 
-    def step(self, actions):
+    def step(self, actions, nthreads=1):
         obs = np.zeros((self.n, 8), dtype=np.float32)
         fo = np.zeros((self.n, 8), dtype=np.float32)
         rew = np.zeros(self.n, dtype=np.float64)
@@ -263,12 +267,12 @@ class OracleLunar:
         tr = np.zeros(self.n, dtype=np.uint8)
         if self.continuous:
             a = np.ascontiguousarray(actions, dtype=np.float32).reshape(self.n, 2)
-            lib().orc_lunar_step_cont(self._h, a.ctypes.data, obs.ctypes.data, rew.ctypes.data, te.ctypes.data,
-                                      tr.ctypes.data, fo.ctypes.data)
+            lib().orc_lunar_step_cont_mt(self._h, a.ctypes.data, obs.ctypes.data, rew.ctypes.data, te.ctypes.data,
+                                         tr.ctypes.data, fo.ctypes.data, int(nthreads))
             return obs, rew, te.astype(bool), tr.astype(bool), fo
         a = np.ascontiguousarray(actions, dtype=np.int64).reshape(self.n)
-        bad = lib().orc_lunar_step(self._h, a.ctypes.data, obs.ctypes.data, rew.ctypes.data, te.ctypes.data,
-                                   tr.ctypes.data, fo.ctypes.data)
+        bad = lib().orc_lunar_step_mt(self._h, a.ctypes.data, obs.ctypes.data, rew.ctypes.data, te.ctypes.data,
+                                      tr.ctypes.data, fo.ctypes.data, int(nthreads))
         if bad:
             raise AssertionError(f"{bad} invalid discrete action(s)")
         return obs, rew, te.astype(bool), tr.astype(bool), fo
@@ -304,15 +308,15 @@ class OracleWalker:
         lib().orc_walker_reset(self._h, obs.ctypes.data)
         return obs
 
-    def step(self, actions):
+    def step(self, actions, nthreads=1):
         a = np.ascontiguousarray(actions, dtype=np.float32).reshape(self.n, 4)
         obs = np.zeros((self.n, 24), dtype=np.float32)
         fo = np.zeros((self.n, 24), dtype=np.float32)
         rew = np.zeros(self.n, dtype=np.float64)
         te = np.zeros(self.n, dtype=np.uint8)
         tr = np.zeros(self.n, dtype=np.uint8)
-        lib().orc_walker_step(self._h, a.ctypes.data, obs.ctypes.data, rew.ctypes.data, te.ctypes.data,
-                              tr.ctypes.data, fo.ctypes.data)
+        lib().orc_walker_step_mt(self._h, a.ctypes.data, obs.ctypes.data, rew.ctypes.data, te.ctypes.data,
+                                 tr.ctypes.data, fo.ctypes.data, int(nthreads))
         return obs, rew, te.astype(bool), tr.astype(bool), fo
 
     def terrain(self, i=0):

@@ -14,6 +14,7 @@
 #include "walker_oracle.h"
 
 #include <math.h>
+#include <pthread.h>
 #include <stdlib.h>
 #include <string.h>
 
@@ -357,10 +358,20 @@ void orc_walker_reset(orc_walker *v, float *obs)
     for (int64_t i = 0; i < v->n; i++) walker_reset_one(&v->w[i], v->hardcore, obs + 24 * i);
 }
 
-void orc_walker_step(orc_walker *v, const float *actions, float *obs, double *reward, uint8_t *terminated,
-                     uint8_t *truncated, float *final_obs)
+typedef struct {
+    orc_walker *v; const float *actions; float *obs; double *reward; uint8_t *terminated, *truncated; float *final_obs;
+    int64_t lo, hi;
+} walker_job;
+
+static void *walker_range(void *arg)
 {
-    for (int64_t i = 0; i < v->n; i++) {
+    walker_job *j = (walker_job *)arg;
+    orc_walker *v = j->v;
+    const float *actions = j->actions;
+    float *obs = j->obs, *final_obs = j->final_obs;
+    double *reward = j->reward;
+    uint8_t *terminated = j->terminated, *truncated = j->truncated;
+    for (int64_t i = j->lo; i < j->hi; i++) {
         wworld_t *W = &v->w[i];
         float o[24];
         double r;
@@ -377,6 +388,36 @@ void orc_walker_step(orc_walker *v, const float *actions, float *obs, double *re
         }
         memcpy(obs + 24 * i, o, sizeof o);
     }
+    return NULL;
+}
+
+/* the envs are independent: a range of them per host thread (bench.py's cpu_baseline / reference arm) */
+void orc_walker_step_mt(orc_walker *v, const float *actions, float *obs, double *reward, uint8_t *terminated,
+                        uint8_t *truncated, float *final_obs, int nthreads)
+{
+    if (nthreads < 1) nthreads = 1;
+    if (nthreads > 256) nthreads = 256;
+    if ((int64_t)nthreads > v->n) nthreads = (int)v->n;
+    walker_job jobs[256];
+    pthread_t tid[256];
+    const int64_t chunk = (v->n + nthreads - 1) / nthreads;
+    for (int t = 0; t < nthreads; t++) {
+        walker_job *j = &jobs[t];
+        j->v = v; j->actions = actions; j->obs = obs; j->reward = reward; j->terminated = terminated;
+        j->truncated = truncated; j->final_obs = final_obs;
+        j->lo = t * chunk;
+        j->hi = (j->lo + chunk < v->n) ? j->lo + chunk : v->n;
+        if (j->lo > j->hi) j->lo = j->hi;
+    }
+    for (int t = 1; t < nthreads; t++) pthread_create(&tid[t], NULL, walker_range, &jobs[t]);
+    walker_range(&jobs[0]);
+    for (int t = 1; t < nthreads; t++) pthread_join(tid[t], NULL);
+}
+
+void orc_walker_step(orc_walker *v, const float *actions, float *obs, double *reward, uint8_t *terminated,
+                     uint8_t *truncated, float *final_obs)
+{
+    orc_walker_step_mt(v, actions, obs, reward, terminated, truncated, final_obs, 1);
 }
 
 void orc_walker_get_stats(const orc_walker *v, int32_t *out)

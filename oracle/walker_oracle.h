@@ -18,6 +18,8 @@ void orc_walker_step(orc_walker *v, const float *actions, float *obs, double *re
 void orc_walker_get_terrain(const orc_walker *v, int64_t i, float *y200);
 void orc_walker_get_bodies(const orc_walker *v, int64_t i, float out[30], int32_t flags[4]);
 void orc_rng_sequence(const uint32_t ent[4], const int32_t *ops, int64_t n, double *out);
+void orc_walker_step_mt(orc_walker *v, const float *actions, float *obs, double *reward, uint8_t *terminated,
+                        uint8_t *truncated, float *final_obs, int nthreads);
 void orc_walker_get_stats(const orc_walker *v, int32_t *out);
 #ifdef __cplusplus
 }

@@ -479,3 +479,16 @@ def test_frozen_rollouts_cover_the_interesting_events():
     assert ds["bipedalwalkerhardcore_v3_gait"]["terminated"].any() and ds["bipedalwalker_v3_random"]["terminated"].any()
     assert not ds["bipedalwalker_v3_gait"]["terminated"].any()                    # the gait keeps walking for 500 steps
     assert ds["lunarlander_v2_wind_gravity"]["truncated"].any()                   # TimeLimit 300 reached under wind
+
+
+def test_box2d_oracles_give_the_same_results_on_any_number_of_threads():
+    rng = np.random.default_rng(3)
+    for make, act in ((lambda: orc.OracleLunar(37), lambda: rng.integers(0, 4, size=37)),
+                      (lambda: orc.OracleLunar(37, continuous=True), lambda: rng.uniform(-1, 1, (37, 2)).astype(np.float32)),
+                      (lambda: orc.OracleWalker(37, hardcore=True), lambda: rng.uniform(-1, 1, (37, 4)).astype(np.float32))):
+        a, b = make(), make()
+        assert np.array_equal(a.reset(seed=8), b.reset(seed=8))
+        for t in range(120):
+            x = act()
+            ra, rb = a.step(x, nthreads=1), b.step(x, nthreads=5)
+            assert all(np.array_equal(p, q) for p, q in zip(ra, rb)), t

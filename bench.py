@@ -152,13 +152,21 @@ def random_actions_np(env_id, n, rng):
     return rng.uniform(-2.0, 2.0, size=(n, 1)).astype(np.float32)
 
 
+def make_oracle(env_id, n):
+    """The C port of the reference path for `env_id` (oracle/): one object stepping n envs on host threads."""
+    from oracle.oracle import OracleLunar, OracleVec, OracleWalker
+    if env_id.startswith("LunarLander"):
+        return OracleLunar(n, continuous="Continuous" in env_id)
+    if env_id.startswith("BipedalWalker"):
+        hard = "Hardcore" in env_id
+        return OracleWalker(n, hardcore=hard, max_episode_steps=2000 if hard else 1600)
+    return OracleVec(env_id, n)
+
+
 def cpu_oracle_throughput(env_id, n, seconds, threads, min_steps=3):
     """Time the C port of the reference path (oracle/) on the host cores: bounded sample."""
-    from oracle.oracle import OracleLunar, OracleVec, OracleWalker
     rng = np.random.default_rng(0)
-    lunar = env_id.startswith(("LunarLander", "BipedalWalker"))
-    v = OracleLunar(n, continuous="Continuous" in env_id) if env_id.startswith("LunarLander") else (
-        OracleWalker(n, hardcore="Hardcore" in env_id) if env_id.startswith("BipedalWalker") else OracleVec(env_id, n))
+    v = make_oracle(env_id, n)
     v.reset(seed=0)
     pool = [random_actions_np(env_id, n, rng) for _ in range(4)]
     kw = {"nthreads": threads}
@@ -189,9 +197,8 @@ def run_reference(args):
         return
     n = 1 << args.log2_envs
     threads = host_threads()
-    from oracle.oracle import OracleVec
     rng = np.random.default_rng(0)
-    v = OracleVec(args.env, n)
+    v = make_oracle(args.env, n)
     v.reset(seed=0)
     pool = [random_actions_np(args.env, n, rng) for _ in range(8)]
     for w in range(max(args.warmup, 1)):
@@ -208,7 +215,8 @@ def run_reference(args):
     line = {
         "impl": "reference", "metric": "env-steps/sec", "value": value, "unit": "env-steps/s",
         "n_gpus": args.gpus, "steps": steps, "warmup": args.warmup, "ms_per_step": 1e3 * el / steps,
-        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32" if args.env.startswith(("LunarLander", "BipedalWalker")) else "f64", "data": "synthetic",
         "config": {"workload": f"{args.env} num_envs=2^{args.log2_envs}, random actions, "
                                "step+TimeLimit+autoreset on the host cores (C port of the reference path)"},
         "cpu_baseline": {"value": value, "unit": "env-steps/s", "cores": threads, "kind": "port",

@@ -432,6 +432,14 @@ void orc_lunar_step_cont(orc_lunar *v, const float *actions, float *obs, double 
     (void)lunar_run(v, NULL, actions, obs, reward, terminated, truncated, final_obs, 1);
 }
 
+/* the 10 terrain edges of env i as 11 vertex heights (smooth_y, float32 as Box2D stores them) */
+void orc_lunar_get_terrain(const orc_lunar *v, int64_t i, float *y11)
+{
+    const world_t *W = &v->w[i];
+    for (int k = 0; k < 10; k++) y11[k] = W->e[k + 1].v1.y;
+    y11[10] = W->e[10].v2.y;
+}
+
 /* workload statistics of the last step of every env: {touching contacts, position iterations} */
 void orc_lunar_get_stats(const orc_lunar *v, int32_t *out)
 {

@@ -26,6 +26,7 @@ int64_t orc_lunar_step_mt(orc_lunar *v, const int64_t *actions, float *obs, doub
                           uint8_t *truncated, float *final_obs, int nthreads);
 void orc_lunar_step_cont_mt(orc_lunar *v, const float *actions, float *obs, double *reward, uint8_t *terminated,
                             uint8_t *truncated, float *final_obs, int nthreads);
+void orc_lunar_get_terrain(const orc_lunar *v, int64_t i, float *y11);
 void orc_lunar_get_stats(const orc_lunar *v, int32_t *out);
 #ifdef __cplusplus
 }

@@ -86,6 +86,7 @@ def lib():
         L.orc_lunar_step.restype = i64
         L.orc_lunar_step.argtypes = [vp, vp, vp, vp, vp, vp, vp]
         L.orc_lunar_get_bodies.argtypes = [vp, i64, vp, vp]
+        L.orc_lunar_get_terrain.argtypes = [vp, i64, vp]
         L.orc_walker_create.restype = vp
         L.orc_walker_create.argtypes = [i64, i32]
         L.orc_walker_create_ex.restype = vp
@@ -276,6 +277,12 @@ class OracleLunar:
         if bad:
             raise AssertionError(f"{bad} invalid discrete action(s)")
         return obs, rew, te.astype(bool), tr.astype(bool), fo
+
+    def terrain(self, i=0):
+        """the 11 terrain vertex heights (smooth_y) of env i"""
+        y = np.zeros(11, dtype=np.float32)
+        lib().orc_lunar_get_terrain(self._h, int(i), y.ctypes.data)
+        return y
 
     def bodies(self, i=0):
         out = np.zeros(18, dtype=np.float32)

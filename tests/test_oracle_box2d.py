@@ -492,3 +492,42 @@ def test_box2d_oracles_give_the_same_results_on_any_number_of_threads():
             x = act()
             ra, rb = a.step(x, nthreads=1), b.step(x, nthreads=5)
             assert all(np.array_equal(p, q) for p, q in zip(ra, rb)), t
+
+
+def test_lunar_reset_draws_are_pinned_to_numpy():
+    """LunarLander.reset (lunar_lander.py:325-339,371-377): 12 terrain heights from ONE vectorised uniform(0, H/2,
+    size=12), the helipad plateau, the 3-tap smoothing, then the two initial-force draws and the two dispersion draws
+    of the embedded step(0) -- the terrain against a numpy Generator, the stream position through the next episode."""
+    n = 16
+    e = orc.OracleLunar(n)
+    e.reset(seed=50)
+    H = 400 / 30.0
+    for i in range(n):
+        g = np.random.Generator(np.random.PCG64(np.random.SeedSequence(50 + i)))
+        height = g.uniform(0, H / 2, size=(12,))
+        helipad_y = H / 4
+        for k in (-2, -1, 0, 1, 2):
+            height[11 // 2 + k] = helipad_y
+        smooth_y = [0.33 * (height[j - 1] + height[j + 0] + height[j + 1]) for j in range(11)]
+        assert np.array_equal(e.terrain(i), np.asarray(smooth_y, dtype=np.float32)), i
+    # after the 12 + 2 + 2 draws of reset(), every step draws 2 more: the terrain of the NEXT episode pins the count
+    steps = np.zeros(n, dtype=int)
+    done_once = np.zeros(n, dtype=bool)
+    for t in range(400):
+        o, r, te, tr, fo = e.step(np.zeros(n, dtype=np.int64))
+        first = (te | tr) & ~done_once
+        for i in np.flatnonzero(first):
+            g = np.random.Generator(np.random.PCG64(np.random.SeedSequence(50 + i)))
+            g.uniform(0, H / 2, size=(12,))
+            g.uniform(-1000.0, 1000.0, size=2)          # initial force x, y (two scalar draws)
+            g.uniform(-1.0, 1.0, size=2 * (steps[i] + 2))  # dispersion: embedded step(0) + every step so far
+            height = g.uniform(0, H / 2, size=(12,))
+            for k in (-2, -1, 0, 1, 2):
+                height[11 // 2 + k] = H / 4
+            smooth_y = [0.33 * (height[j - 1] + height[j + 0] + height[j + 1]) for j in range(11)]
+            assert np.array_equal(e.terrain(i), np.asarray(smooth_y, dtype=np.float32)), (i, steps[i])
+        done_once |= first
+        steps += 1
+        if done_once.all():
+            break
+    assert done_once.all()

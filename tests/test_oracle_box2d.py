@@ -226,10 +226,11 @@ def test_walker_oracle_invariants():
 # ---------------------------------------------------------------------------------------------------------
 # BipedalWalker / BipedalWalkerHardcore
 # ---------------------------------------------------------------------------------------------------------
-def _numpy_terrain(seed, hardcore):
+def _numpy_terrain(seed, hardcore, g=None):
     """BipedalWalker._generate_terrain (bipedal_walker.py:277-402) driven by a real numpy Generator: returns the
     200 terrain heights and the obstacle boxes (x0, ylo, x1, yhi) as float32, in creation order."""
-    g = np.random.Generator(np.random.PCG64(np.random.SeedSequence(seed)))
+    if g is None:
+        g = np.random.Generator(np.random.PCG64(np.random.SeedSequence(seed)))
     SCALE = 30.0
     STEP, LENGTH, HEIGHT, GRASS_LEN, STARTPAD = 14 / SCALE, 200, 400 / SCALE / 4, 10, 20
     GRASS, STUMP, STAIRS, PIT, STATES = range(5)
@@ -531,3 +532,28 @@ def test_lunar_reset_draws_are_pinned_to_numpy():
         if done_once.all():
             break
     assert done_once.all()
+
+
+@pytest.mark.parametrize("hardcore", [False, True])
+def test_walker_rng_stream_position_is_pinned_across_an_episode(hardcore):
+    """bipedal_walker.py:404-423,450-452: after the terrain, reset() draws 10 clouds x (1 + 5 x 2) uniforms and one
+    hull force; step() draws nothing.  So the terrain of the SECOND episode, generated from the same stream, pins
+    every draw in between -- including numpy's half-consumed 32-bit cache left by Generator.integers."""
+    n = 12
+    e = orc.OracleWalker(n, hardcore=hardcore, max_episode_steps=60)      # the TimeLimit ends the first episode
+    e.reset(seed=900)
+    for t in range(60):
+        o, r, te, tr, fo = e.step(np.zeros((n, 4), dtype=np.float32))
+    assert (te | tr).all()
+    for i in range(n):
+        g = np.random.Generator(np.random.PCG64(np.random.SeedSequence(900 + i)))
+        _numpy_terrain(None, hardcore, g)
+        for _ in range(200 // 20):
+            g.uniform(0, 200)
+            for _ in range(5):
+                g.uniform(0, 5 * 14 / 30.0)
+                g.uniform(0, 5 * 14 / 30.0)
+        g.uniform(-5, 5)
+        ys, boxes = _numpy_terrain(None, hardcore, g)
+        assert np.array_equal(e.terrain(i), ys), i
+        assert np.array_equal(e.polys(i), boxes), i

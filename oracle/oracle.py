@@ -91,6 +91,7 @@ def lib():
         L.orc_walker_create.argtypes = [i64, i32]
         L.orc_walker_create_ex.restype = vp
         L.orc_walker_create_ex.argtypes = [i64, i32, i32]
+        L.orc_walker_action_flow.argtypes = [dbl, vp, vp, vp, vp]
         L.orc_walker_get_polys.restype = i32
         L.orc_walker_get_polys.argtypes = [vp, i64, vp]
         L.orc_walker_destroy.argtypes = [vp]
@@ -342,6 +343,15 @@ class OracleWalker:
         flags = np.zeros(4, dtype=np.int32)
         lib().orc_walker_get_bodies(self._h, int(i), out.ctypes.data, flags.ctypes.data)
         return out.reshape(5, 6), flags
+
+
+def walker_action_flow(shaping_delta, action):
+    """The action-dependent arithmetic of BipedalWalker.step in walker_oracle.c (test hook)."""
+    a = np.ascontiguousarray(action, dtype=np.float32)
+    ms, mt = np.zeros(4, dtype=np.float32), np.zeros(4, dtype=np.float32)
+    r = ctypes.c_double(0.0)
+    lib().orc_walker_action_flow(float(shaping_delta), a.ctypes.data, ms.ctypes.data, mt.ctypes.data, ctypes.byref(r))
+    return ms, mt, r.value
 
 
 class WalkerHeuristic:

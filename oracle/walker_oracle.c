@@ -327,6 +327,21 @@ static void walker_step_one(wworld_t *W, const float *action, int from_reset, fl
     *terminated = term;
 }
 
+/* test hook: the action-dependent arithmetic of step() alone (:528-543,594-596) -- motor speed / torque of the four
+ * joints as Box2D receives them and the reward after the torque costs, given the shaping delta */
+void orc_walker_action_flow(double shaping_delta, const float action[4], float motor_speed[4], float max_torque[4],
+                            double *reward)
+{
+    static const float speed[NJ] = {SPEED_HIP, SPEED_KNEE, SPEED_HIP, SPEED_KNEE};
+    for (int k = 0; k < NJ; k++) {
+        motor_speed[k] = speed[k] * sgnf(action[k]);
+        max_torque[k] = (float)MOTORS_TORQUE * clip01_abs(action[k]);
+    }
+    float r32 = (float)shaping_delta;
+    for (int k = 0; k < NJ; k++) r32 = r32 - (float)(0.00035 * MOTORS_TORQUE) * clip01_abs(action[k]);
+    *reward = (double)r32;
+}
+
 /* ---------------------------------------------------------------- vector API */
 orc_walker *orc_walker_create(int64_t n, int max_episode_steps) { return orc_walker_create_ex(n, max_episode_steps, 0); }
 

@@ -20,6 +20,8 @@ void orc_walker_get_bodies(const orc_walker *v, int64_t i, float out[30], int32_
 void orc_rng_sequence(const uint32_t ent[4], const int32_t *ops, int64_t n, double *out);
 void orc_walker_step_mt(orc_walker *v, const float *actions, float *obs, double *reward, uint8_t *terminated,
                         uint8_t *truncated, float *final_obs, int nthreads);
+void orc_walker_action_flow(double shaping_delta, const float action[4], float motor_speed[4], float max_torque[4],
+                            double *reward);
 void orc_walker_get_stats(const orc_walker *v, int32_t *out);
 #ifdef __cplusplus
 }

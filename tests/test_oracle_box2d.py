@@ -557,3 +557,26 @@ def test_walker_rng_stream_position_is_pinned_across_an_episode(hardcore):
         ys, boxes = _numpy_terrain(None, hardcore, g)
         assert np.array_equal(e.terrain(i), ys), i
         assert np.array_equal(e.polys(i), boxes), i
+
+
+def test_walker_action_arithmetic_follows_numpy_dtype_flow():
+    """bipedal_walker.py:528-543,594-596 with a float32 action (the declared action space): motor speed
+    `float(SPEED * np.sign(a))`, torque `float(MOTORS_TORQUE * np.clip(np.abs(a), 0, 1))` and -- numpy >= 2 --
+    `reward -= 0.00035 * MOTORS_TORQUE * np.clip(np.abs(a), 0, 1)` turning the Python-float reward into a float32
+    that the remaining subtractions then stay in."""
+    rng = np.random.default_rng(9)
+    SPEED = (4, 6, 4, 6)
+    for k in range(3000):
+        action = rng.uniform(-1.6, 1.6, size=4).astype(np.float32)
+        if k % 7 == 0:
+            action[rng.integers(0, 4)] = np.float32(0.0)
+        delta = float(rng.normal(0, 0.3))
+        want_speed = np.array([float(SPEED[j] * np.sign(action[j])) for j in range(4)], dtype=np.float32)
+        want_torque = np.array([float(80 * np.clip(np.abs(action[j]), 0, 1)) for j in range(4)], dtype=np.float32)
+        reward = delta
+        for a in action:
+            reward -= 0.00035 * 80 * np.clip(np.abs(a), 0, 1)
+        assert isinstance(reward, np.float32)
+        ms, mt, r = orc.walker_action_flow(delta, action)
+        assert np.array_equal(ms, want_speed) and np.array_equal(mt, want_torque), (k, action)
+        assert r == float(reward), (k, action, r, float(reward))

@@ -98,13 +98,7 @@ class RecordEpisodeStatistics(VectorWrapper):
         return int(self._counter.item())
 
     def _queue(self, returns):
-        count = self.episode_count
-        k = min(count, self.deque_size)
-        words = self._ring.cpu().numpy().view(np.uint64)
-        vals = (words & np.uint64(0xFFFFFFFF)).astype(np.uint32).view(np.float32) if returns else \
-            (words >> np.uint64(32)).astype(np.int32)
-        order = [(count - k + j) % max(self.deque_size, 1) for j in range(k)]
-        return deque((vals[i].item() for i in order), maxlen=self.deque_size)
+        return unpack_episode_ring(self._ring.cpu().numpy(), self.episode_count, self.deque_size, returns)
 
     @property
     def return_queue(self):
@@ -113,6 +107,17 @@ class RecordEpisodeStatistics(VectorWrapper):
     @property
     def length_queue(self):
         return self._queue(False)
+
+
+def unpack_episode_ring(words, count, deque_size, returns):
+    """The ring written by b200gym_episode_stats -> the reference's deque (record_episode_statistics.py:90-91):
+    slot (episode number mod size) holds length << 32 | float32 bits of the return; oldest kept episode first."""
+    k = min(int(count), int(deque_size))
+    words = np.ascontiguousarray(words).view(np.uint64)
+    vals = (words & np.uint64(0xFFFFFFFF)).astype(np.uint32).view(np.float32) if returns else \
+        (words >> np.uint64(32)).astype(np.int32)
+    order = [(count - k + j) % max(int(deque_size), 1) for j in range(k)]
+    return deque((vals[i].item() for i in order), maxlen=int(deque_size))
 
 
 class _RunningMeanStd:

@@ -52,3 +52,19 @@ def test_step_api_compatibility_roundtrip():
     back = wrappers.step_api_compatibility((obs, rew, dones, infos), output_truncation_bool=True)
     assert back[2].tolist() == term.tolist() and back[3].tolist() == trunc.tolist()
     assert wrappers.step_api_compatibility(five) is five
+
+
+def test_episode_ring_unpacks_to_the_reference_deques():
+    """return_queue / length_queue (record_episode_statistics.py:90-91,123-144): the packed device ring, oldest kept
+    episode first, before and after it wraps."""
+    size = 5
+    ring = np.zeros(size, dtype=np.int64)
+    episodes = [(1.5, 3), (-2.25, 7), (100.0, 1), (0.0, 9), (42.0, 4), (7.0, 8), (-1.0, 2)]
+    for count, (ret, length) in enumerate(episodes, start=1):
+        word = (np.int64(length) << np.int64(32)) | np.int64(np.float32(ret).view(np.uint32))
+        ring[(count - 1) % size] = word
+        kept = episodes[max(0, count - size):count]
+        assert list(wrappers.unpack_episode_ring(ring, count, size, True)) == [r for r, _ in kept]
+        assert list(wrappers.unpack_episode_ring(ring, count, size, False)) == [l for _, l in kept]
+    assert wrappers.unpack_episode_ring(ring, 0, size, True).maxlen == size
+    assert list(wrappers.unpack_episode_ring(ring, 0, size, True)) == []

@@ -87,7 +87,7 @@ SIGNATURES = {
     "b200gym_step": (_i32, [_vp, _vp, _i32, _vp, _vp, _vp, _vp, _vp, _vp]),
     "b200gym_invalid_actions": (_i32, [_vp, _vp, ctypes.POINTER(_i64)]),
     "b200gym_host_buffers": (_i32, [_vp, ctypes.POINTER(HostIO)]),
-    "b200gym_step_host": (_i32, [_vp, _vp, _i32, _vp, _vp, _vp, _vp, _vp]),
+    "b200gym_step_host": (_i32, [_vp, _vp, _i32, _vp, _vp, _vp, _vp, _vp, ctypes.POINTER(_i64)]),
     "b200gym_reset_host": (_i32, [_vp, _vp, _vp, _vp]),
     "b200gym_get_state": (_i32, [_vp, _vp, _vp, _vp, _vp]),
     "b200gym_set_state": (_i32, [_vp, _vp, _vp, _vp, _vp]),
@@ -98,6 +98,7 @@ SIGNATURES = {
     "b200gym_p2p_create": (_i32, [_vp, _i32, _i32, _vp, _vp]),
     "b200gym_p2p_connect": (_i32, [_vp, _vp]),
     "b200gym_step_p2p": (_i32, [_vp, _vp, _i32, _vp, _vp, ctypes.POINTER(_i32)]),
+    "b200gym_p2p_status": (_i32, [_vp, _vp, ctypes.POINTER(_i32)]),
     "b200gym_episode_stats": (_i32, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _i64, _vp]),
     "b200gym_running_norm_obs": (_i32, [_vp, _vp, _i64, _i32, _vp, _vp, _vp, _vp, ctypes.c_double, _i32, _vp]),
     "b200gym_running_norm_reward": (_i32, [_vp, _vp, _vp, _vp, _vp, _i64, _vp, _vp, _vp, _vp, ctypes.c_double,

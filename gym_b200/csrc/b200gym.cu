@@ -53,9 +53,11 @@ struct b200gym {
     lunar::Opts lunar_opts{};
     unsigned long long *invalid = nullptr;  // sticky device counter
     int sm_count = 148;
-    int occ[B200GYM_NUM_KINDS][3] = {};     // cached CTAs/SM of step_kernel_tma per (kind, action width)
-    int kernel_choice = 0;                  // 0: kernel A (default: fastest measured), 1: kernel B (TMA-staged tiles);
-                                            // B200GYM_KERNEL=a|b overrides
+    int occ[B200GYM_NUM_KINDS][3] = {};     // cached CTAs/SM of step_kernel_persistent per (kind, action width)
+    int kernel_choice = 1;                  // 0: kernel A (one tile per CTA), 1: kernel P (resident grid, asynchronous
+                                            // prefetch, deferred resets); B200GYM_KERNEL=a|p overrides
+    int gather_bulk = 1;                    // multi-GPU step: 1 = kernel G (staged tile + bulk pushes), 0 = per-thread
+                                            // peer stores from kernel A; B200GYM_GATHER=bulk|direct overrides
     int block_a = 256;                      // CTA size of kernel A (B200GYM_BLOCK_A=64|128|256, tuning runs)
     int box2d_block = 128;                  // LunarLander step kernel: CTA size (B200GYM_BOX2D_BLOCK=128|256, tuning runs)
     int box2d_defer = 0;                    // Box2D tasks: 1 = the autoresets of a step run in a second, compacted
@@ -70,16 +72,14 @@ struct b200gym {
         unsigned char *peer[B200GYM_MAX_PEERS + 1] = {};  // peer[r]: rank r's allocation mapped here (own = base)
         size_t set_bytes = 0, off_obs = 0, off_reward = 0, off_term = 0, off_trunc = 0, off_flags = 0, bytes = 0;
         unsigned long long step = 0;
+        unsigned long long timeout_ns = 30ull * 1000000000ull;   // B200GYM_P2P_TIMEOUT_S overrides
         bool connected = false;
     } p2p;
     // host-I/O path (lazily created)
     b200gym_host_io hio{};
-    b200gym_host_io dio{};  // device mirrors of the staging buffers
+    b200gym_host_io dio{};  // device side: .actions in HBM; the result pointers are device aliases of hio's mapped buffers
     uint8_t *d_mask = nullptr;
-    // compacted final observations of the host path: only the rows of finishing envs cross PCIe
-    int32_t *d_fin_idx = nullptr, *h_fin_idx = nullptr;
-    float *d_fin_rows = nullptr, *h_fin_rows = nullptr;
-    unsigned long long *d_fin_count = nullptr, *h_fin_count = nullptr;
+    unsigned long long *h_invalid = nullptr;   // page-locked landing word of the invalid-action counter
     cudaEvent_t hevent = nullptr;
     unsigned long long **d_peer_flags = nullptr;
     cudaStream_t hstream[2] = {nullptr, nullptr};
@@ -156,6 +156,8 @@ struct StepArgs {
     int32_t *reset_count;
     // fused all-gather (multi-GPU): every result is ALSO stored into the same rows of the peers'
     // gather buffers over NVLink (peer-mapped pointers, slice offset already applied)
+    int32_t bulk_sink;   // 1: use kernel G's staged bulk stores even without peers (host path: the output arrays are
+                         // mapped host memory, where many small stores are what hurts)
     int32_t npeer;
     float *peer_obs[B200GYM_MAX_PEERS];
     double *peer_reward[B200GYM_MAX_PEERS];
@@ -202,6 +204,31 @@ __device__ __forceinline__ void store_scalars_all(const StepArgs &a, int64_t i, 
     }
 }
 
+// Where the results of env i go.  DirectSink: straight to the caller's arrays (and, when peers are mapped,
+// to theirs) with per-thread stores.  StagedSink: into the CTA's shared-memory tile, which leaves the SM as a few
+// bulk copies per destination (step_kernel_gather).
+struct DirectSink {
+    const StepArgs &a;
+    template <int D>
+    __device__ __forceinline__ void obs(int64_t i, const float (&v)[D]) const { store_obs_all<D>(a, i, v); }
+    __device__ __forceinline__ void scalars(int64_t i, double reward, uint8_t term, uint8_t trunc) const {
+        store_scalars_all(a, i, reward, term, trunc);
+    }
+};
+
+struct StagedSink {
+    float *s_obs;
+    double *s_reward;
+    uint8_t *s_term, *s_trunc;
+    int64_t base;   // env index of row 0 of the tile
+    template <int D>
+    __device__ __forceinline__ void obs(int64_t i, const float (&v)[D]) const { store_row<D>(s_obs, i - base, v); }
+    __device__ __forceinline__ void scalars(int64_t i, double reward, uint8_t term, uint8_t trunc) const {
+        const int r = (int)(i - base);
+        s_reward[r] = reward; s_term[r] = term; s_trunc[r] = trunc;
+    }
+};
+
 // Tuning knobs (overridable at build time for A/B measurements).
 // The per-env work is one long dependent float64 chain, so the SMs are latency-bound and
 // throughput follows the number of resident warps: 8 CTAs x 256 threads = 64 warps/SM (100 %
@@ -221,17 +248,21 @@ struct Tuning {
 // Phase 1, by the thread that owns env i (its inputs are in registers): Env.step, TimeLimit,
 // stores of reward / flags / final_obs, and -- unless the episode ended -- of the new state and
 // observation.  Returns true when the env must be reset by phase 2.
-template <int KIND>
-__device__ __forceinline__ bool advance_env(const StepArgs &a, int64_t i, double (&s)[Env<KIND>::S],
+template <int KIND, typename Sink>
+__device__ __forceinline__ bool advance_env(const StepArgs &a, const Sink &sink, int64_t i, double (&s)[Env<KIND>::S],
                                             int32_t elapsed, long long action_int, float a0) {
     using E = Env<KIND>;
     int act = 0;
     if constexpr (E::A == 0) {
         if (action_int < 0 || action_int >= E::NACT) {
-            // the reference raises (cartpole.py:132 / mountain_car.py:128-130 / acrobot.py:199):
-            // leave the env untouched, flag it, return NaN reward
+            // the reference raises (cartpole.py:132 / mountain_car.py:128-130 / acrobot.py:199): leave the env
+            // untouched, count it (sticky), return a NaN reward and the env's CURRENT observation, so that the
+            // double-buffered output row does not show the observation of two steps ago
             atomicAdd(a.invalid, 1ULL);
-            store_scalars_all(a, i, __longlong_as_double(0x7ff8000000000000LL), 0, 0);
+            float cur[E::D];
+            E::observe(s, cur);
+            sink.scalars(i, __longlong_as_double(0x7ff8000000000000LL), 0, 0);
+            sink.template obs<E::D>(i, cur);
             return false;
         }
         act = (int)action_int;
@@ -257,22 +288,22 @@ __device__ __forceinline__ bool advance_env(const StepArgs &a, int64_t i, double
     const bool truncated = (a.max_steps > 0) && (elapsed >= a.max_steps);  // :53-54
     const bool needs_reset = (terminated || truncated) && a.autoreset;   // sync_vector_env.py:152-156
 
-    store_scalars_all(a, i, reward, terminated ? 1 : 0, truncated ? 1 : 0);
+    sink.scalars(i, reward, terminated ? 1 : 0, truncated ? 1 : 0);
     if (needs_reset) {
         if (a.final_obs) store_row<E::D>(a.final_obs, i, obs);           // info["final_observation"]
     } else {
 #pragma unroll
         for (int k = 0; k < E::S; k++) a.state[k * a.n + i] = s[k];
         a.elapsed[i] = elapsed;
-        store_obs_all<E::D>(a, i, obs);
+        sink.template obs<E::D>(i, obs);
     }
     return needs_reset;
 }
 
 // Phase 2: the unseeded env.reset() of the autoreset (sync_vector_env.py:154) for env i, by
 // whichever thread picked it off the CTA's compacted list.
-template <int KIND>
-__device__ __forceinline__ void reset_env(const StepArgs &a, int64_t i) {
+template <int KIND, typename Sink>
+__device__ __forceinline__ void reset_env(const StepArgs &a, const Sink &sink, int64_t i) {
     using E = Env<KIND>;
     double s[E::S];
     float obs[E::D];
@@ -284,7 +315,7 @@ __device__ __forceinline__ void reset_env(const StepArgs &a, int64_t i) {
 #pragma unroll
     for (int k = 0; k < E::S; k++) a.state[k * a.n + i] = s[k];
     a.elapsed[i] = 0;                                                    // time_limit.py:67
-    store_obs_all<E::D>(a, i, obs);
+    sink.template obs<E::D>(i, obs);
 }
 
 // Why two phases: only ~1 env in 22 finishes per CartPole step, but then 77 % of the warps
@@ -314,225 +345,185 @@ __global__ void __launch_bounds__(kThreads, Tuning<KIND>::kMinCtas) step_kernel(
         const ActT av = __ldg(reinterpret_cast<const ActT *>(a.actions) + i);
         if constexpr (E::A == 0) action_int = (long long)av;
         else a0 = (float)av;
-        if (advance_env<KIND>(a, i, s, elapsed, action_int, a0)) reset_list[atomicAdd(&reset_count, 1)] = threadIdx.x;
+        if (advance_env<KIND>(a, DirectSink{a}, i, s, elapsed, action_int, a0)) reset_list[atomicAdd(&reset_count, 1)] = threadIdx.x;
     }
     __syncthreads();
     const int cnt = reset_count;
     if ((int)threadIdx.x < cnt)
-        reset_env<KIND>(a, a.first + (int64_t)blockIdx.x * blockDim.x + reset_list[threadIdx.x]);
+        reset_env<KIND>(a, DirectSink{a}, a.first + (int64_t)blockIdx.x * blockDim.x + reset_list[threadIdx.x]);
 }
 
-// --- kernel C: two adjacent envs per thread, 16-byte accesses ---------------------------------
-// The step is latency-bound (one dependent float64 chain per env, long-scoreboard stalls on the loads): thread t
-// of a CTA owns envs 2t and 2t+1 of a 512-env tile, so every state row / action / counter arrives as ONE 16-byte
-// (8-byte) load for two envs, the two float64 chains interleave in the pipe (ILP 2), and the results leave as
-// 16-byte stores -- half the memory instructions per env and twice the bytes in flight per warp.  A finishing env
-// is stored like any other (post-step state, terminal observation) and then re-drawn by phase 2, after the CTA
-// barrier: the later store wins.  Needs an even SoA stride, an even range start and 16-byte aligned buffers;
-// anything else (and the odd last env) goes through kernel A.
-template <typename T> struct Pair;
-template <> struct Pair<long long> { using type = longlong2; };
-template <> struct Pair<int> { using type = int2; };
-template <> struct Pair<unsigned char> { using type = uchar2; };
-template <> struct Pair<float> { using type = float2; };
-
-template <int KIND, typename ActT>
-__global__ void __launch_bounds__(kThreads, 4) step_kernel_pair(const StepArgs a) {
-    using E = Env<KIND>;
-    __shared__ int reset_list[2 * kThreads];
-    __shared__ int reset_count;
-    if (threadIdx.x == 0) reset_count = 0;
-    __syncthreads();
-    const int64_t j = 2 * ((int64_t)blockIdx.x * kThreads + threadIdx.x);   // first env of the pair, even
-    if (j < a.count) {                                                      // a.count is even here
-        const int64_t i = a.first + j;
-        double s0[E::S], s1[E::S];
-#pragma unroll
-        for (int k = 0; k < E::S; k++) {
-            const double2 v = *reinterpret_cast<const double2 *>(a.state + k * a.n + i);
-            s0[k] = v.x; s1[k] = v.y;
-        }
-        const int2 el = *reinterpret_cast<const int2 *>(a.elapsed + i);
-        const typename Pair<ActT>::type av = __ldg(reinterpret_cast<const typename Pair<ActT>::type *>(a.actions) + (i >> 1));
-        int act0 = 0, act1 = 0;
-        float f0 = 0.0f, f1 = 0.0f;
-        bool valid = true;
-        if constexpr (E::A == 0) {
-            const long long l0 = (long long)av.x, l1 = (long long)av.y;
-            valid = l0 >= 0 && l0 < E::NACT && l1 >= 0 && l1 < E::NACT;
-            act0 = (int)l0; act1 = (int)l1;
-        } else {
-            f0 = (float)av.x; f1 = (float)av.y;
-        }
-        if (!valid) {
-            // rare error path (the reference raises): per env, exactly as kernel A
-            if (advance_env<KIND>(a, i, s0, el.x, (long long)av.x, 0.0f)) reset_list[atomicAdd(&reset_count, 1)] = 2 * threadIdx.x;
-            if (advance_env<KIND>(a, i + 1, s1, el.y, (long long)av.y, 0.0f)) reset_list[atomicAdd(&reset_count, 1)] = 2 * threadIdx.x + 1;
-        } else {
-            float o0[E::D], o1[E::D];
-            double r0, r1;
-            bool t0, t1;
-            E::step(s0, el.x == 0, act0, f0, a.param0, o0, r0, t0);
-            E::step(s1, el.y == 0, act1, f1, a.param0, o1, r1, t1);
-            const int e0 = el.x + 1, e1 = el.y + 1;                                  // time_limit.py:51
-            const bool u0 = (a.max_steps > 0) && (e0 >= a.max_steps), u1 = (a.max_steps > 0) && (e1 >= a.max_steps);
-#pragma unroll
-            for (int k = 0; k < E::S; k++) *reinterpret_cast<double2 *>(a.state + k * a.n + i) = make_double2(s0[k], s1[k]);
-            *reinterpret_cast<int2 *>(a.elapsed + i) = make_int2(e0, e1);
-            const uchar2 tt = make_uchar2(t0 ? 1 : 0, t1 ? 1 : 0), uu = make_uchar2(u0 ? 1 : 0, u1 ? 1 : 0);
-            *reinterpret_cast<double2 *>(a.reward + i) = make_double2(r0, r1);
-            *reinterpret_cast<uchar2 *>(a.terminated + i) = tt;
-            *reinterpret_cast<uchar2 *>(a.truncated + i) = uu;
-            store_row<E::D>(a.obs, i, o0);
-            store_row<E::D>(a.obs, i + 1, o1);
-            for (int p = 0; p < a.npeer; p++) {
-                *reinterpret_cast<double2 *>(a.peer_reward[p] + i) = make_double2(r0, r1);
-                *reinterpret_cast<uchar2 *>(a.peer_term[p] + i) = tt;
-                *reinterpret_cast<uchar2 *>(a.peer_trunc[p] + i) = uu;
-                store_row<E::D>(a.peer_obs[p], i, o0);
-                store_row<E::D>(a.peer_obs[p], i + 1, o1);
-            }
-            if (t0 || u0) {                                                          // sync_vector_env.py:152-156
-                if (a.final_obs) store_row<E::D>(a.final_obs, i, o0);
-                reset_list[atomicAdd(&reset_count, 1)] = 2 * threadIdx.x;
-            }
-            if (t1 || u1) {
-                if (a.final_obs) store_row<E::D>(a.final_obs, i + 1, o1);
-                reset_list[atomicAdd(&reset_count, 1)] = 2 * threadIdx.x + 1;
-            }
-        }
-    }
-    __syncthreads();
-    const int cnt = reset_count;
-    for (int q = threadIdx.x; q < cnt; q += kThreads)
-        reset_env<KIND>(a, a.first + 2 * (int64_t)blockIdx.x * kThreads + reset_list[q]);
-}
-
-// --- kernel B: persistent CTAs, TMA-staged inputs -------------------------------------
-// Persistent grid (SMs x occupancy CTAs), one thread per env of a 256-env tile, tiles strided
-// by gridDim.x.  Each CTA owns a ring of kStages shared-memory stages; one elected thread keeps
-// the inputs of the next tiles (the S float64 state rows, the TimeLimit counters and the
-// actions of 256 envs, ~11 KB per stage) in flight with cp.async.bulk (TMA, 1-D bulk copies
-// completing on an mbarrier; SASS UBLKCP) while all 256 threads advance the current tile out
-// of shared memory, so the loads of a CTA never wait for its float64 arithmetic and the
-// stores are fire-and-forget.
-namespace tma {
+// --- asynchronous-copy helpers (sm_100a PTX) --------------------------------------------------------
+namespace acp {
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
-__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+// per-thread LDGSTS: global -> shared without a register in between (SASS LDGSTS)
+template <int BYTES>
+__device__ __forceinline__ void ld_async(void *smem_dst, const void *gmem_src) {
+    static_assert(BYTES == 4 || BYTES == 8 || BYTES == 16, "cp.async moves 4, 8 or 16 bytes");
+    if constexpr (BYTES == 16)
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(smem_dst)), "l"(gmem_src) : "memory");
+    else
+        asm volatile("cp.async.ca.shared.global [%0], [%1], %2;" ::"r"(smem_u32(smem_dst)), "l"(gmem_src), "n"(BYTES) : "memory");
 }
-__device__ __forceinline__ void fence_mbar_init() {
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-}
-__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t *bar, uint32_t bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
+__device__ __forceinline__ void ld_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void ld_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+
+// bulk (TMA, SASS UBLKCP) shared -> global store of a contiguous block; works on peer-mapped addresses
+__device__ __forceinline__ void st_bulk(void *gmem_dst, const void *smem_src, uint32_t bytes) {
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gmem_dst), "r"(smem_u32(smem_src)),
+                 "r"(bytes)
                  : "memory");
 }
-__device__ __forceinline__ void load_1d(void *smem_dst, const void *gmem_src, uint32_t bytes, uint64_t *bar) {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
-                     smem_u32(smem_dst)),
-                 "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar))
-                 : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
-    asm volatile(
-        "{\n"
-        ".reg .pred P1;\n"
-        "LAB_WAIT:\n"
-        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
-        "@P1 bra DONE;\n"
-        "bra LAB_WAIT;\n"
-        "DONE:\n"
-        "}" ::"r"(smem_u32(bar)),
-        "r"(parity)
-        : "memory");
-}
+__device__ __forceinline__ void st_bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void st_bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+// generic-proxy writes to shared memory -> visible to the async proxy that executes the bulk copy
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
-}  // namespace tma
+}  // namespace acp
 
-constexpr int kStages = B200_STAGES;
+// --- kernel P: persistent CTAs, per-thread asynchronous prefetch, CTA-deferred resets ---------------
+// Kernel A is latency-bound: every warp issues its six loads, waits a cold HBM round trip, runs a ~330
+// instruction float64 chain, stores and leaves; while it computes it has no load in flight, so the SM never
+// holds the ~70 KB of outstanding reads that 6.5 TB/s x ~1.5 us ask for.  Here a resident grid (SMs x occupancy)
+// walks the tiles; each THREAD copies the inputs of its env in the next tile (S state words, TimeLimit counter,
+// action) into its own shared-memory slots with cp.async (LDGSTS: no registers, no barrier -- a thread only ever
+// reads back what it wrote itself) while it advances the current tile, so loads stay in flight through the whole
+// kernel.  Warps never meet at a barrier inside the loop: finishing envs go onto one CTA-wide list that is
+// drained ONCE, with full lanes, after the loop (a warp where many lanes finish at once -- synchronised
+// TimeLimit truncation -- resets inline instead, which is then equally dense).
+constexpr int kResetCap = 1024;   // entries of the CTA's deferred-reset list; overflow resets inline
 
 template <int KIND, typename ActT>
-struct TileLayout {
+struct PrefetchLayout {
     using E = Env<KIND>;
     static constexpr int kActPerEnv = E::A == 0 ? 1 : E::A;
-    static constexpr int kStateBytes = kThreads * 8;                          // one float64 row
-    static constexpr int kElapsedOff = E::S * kStateBytes;
-    static constexpr int kActOff = kElapsedOff + kThreads * 4;
-    static constexpr int kActBytes = kThreads * kActPerEnv * (int)sizeof(ActT);
-    static constexpr int kTxBytes = kActOff + kActBytes;                      // bytes TMA delivers per tile
-    static constexpr int kStageBytes = (kTxBytes + 127) / 128 * 128;
-    static_assert(kActBytes % 16 == 0, "cp.async.bulk moves multiples of 16 bytes");
+    static constexpr int kActBytes = kActPerEnv * (int)sizeof(ActT);
+    static constexpr bool kActAsync = kActBytes == 4 || kActBytes == 8 || kActBytes == 16;
+    static constexpr int kStateOff = 0;                                   // [S][256] float64
+    static constexpr int kActOff = E::S * kThreads * 8;                   // [256] action (if async)
+    static constexpr int kElapsedOff = kActOff + (kActAsync ? kThreads * kActBytes : 0);   // [256] int32
+    static constexpr int kBytes = kElapsedOff + kThreads * 4;
 };
 
 template <int KIND, typename ActT>
-__global__ void __launch_bounds__(kThreads, Tuning<KIND>::kMinCtas) step_kernel_tma(const StepArgs a, const int num_tiles) {
+__global__ void __launch_bounds__(kThreads, Tuning<KIND>::kMinCtas) step_kernel_persistent(const StepArgs a, const int num_tiles) {
     using E = Env<KIND>;
-    using L = TileLayout<KIND, ActT>;
-    __shared__ __align__(128) unsigned char stage_mem[kStages * L::kStageBytes];
-    __shared__ __align__(8) uint64_t full_bar[kStages];
-    __shared__ int reset_list[kThreads];
-    __shared__ int reset_count[2];  // ping-pong: iteration `it` uses [it & 1]
-
+    using L = PrefetchLayout<KIND, ActT>;
+    __shared__ __align__(16) unsigned char in_mem[L::kBytes];
+    __shared__ int reset_list[kResetCap];
+    __shared__ int reset_count;
     const int tid = threadIdx.x;
-    if (tid == 0) {
-#pragma unroll
-        for (int st = 0; st < kStages; st++) tma::mbar_init(&full_bar[st], 1);
-        tma::fence_mbar_init();
-        reset_count[0] = 0;
-        reset_count[1] = 0;
-    }
+    if (tid == 0) reset_count = 0;
     __syncthreads();
 
-    // producer (thread 0): one expect_tx + (S + 2) bulk copies per tile
-    auto issue = [&](int st, int tile) {
-        const int64_t i0 = a.first + (int64_t)tile * kThreads;
-        unsigned char *dst = stage_mem + st * L::kStageBytes;
-        tma::mbar_arrive_expect_tx(&full_bar[st], (uint32_t)L::kTxBytes);
+    double *s_state = reinterpret_cast<double *>(in_mem + L::kStateOff);
+    int32_t *s_elapsed = reinterpret_cast<int32_t *>(in_mem + L::kElapsedOff);
+    const ActT *actions = reinterpret_cast<const ActT *>(a.actions);
+    const DirectSink sink{a};
+
+    auto prefetch = [&](int tile) {
+        const int64_t j = (int64_t)tile * kThreads + tid;
+        if (j < a.count) {
+            const int64_t i = a.first + j;
 #pragma unroll
-        for (int k = 0; k < E::S; k++)
-            tma::load_1d(dst + k * L::kStateBytes, a.state + k * a.n + i0, L::kStateBytes, &full_bar[st]);
-        tma::load_1d(dst + L::kElapsedOff, a.elapsed + i0, kThreads * 4, &full_bar[st]);
-        tma::load_1d(dst + L::kActOff, reinterpret_cast<const ActT *>(a.actions) + i0 * L::kActPerEnv,
-                     L::kActBytes, &full_bar[st]);
+            for (int k = 0; k < E::S; k++) acp::ld_async<8>(s_state + k * kThreads + tid, a.state + k * a.n + i);
+            acp::ld_async<4>(s_elapsed + tid, a.elapsed + i);
+            if constexpr (L::kActAsync)
+                acp::ld_async<L::kActBytes>(in_mem + L::kActOff + tid * L::kActBytes, actions + i * L::kActPerEnv);
+        }
+        acp::ld_commit();
     };
 
-    if (tid == 0) {
-#pragma unroll
-        for (int st = 0; st < kStages; st++) {
-            const int t = blockIdx.x + st * gridDim.x;
-            if (t < num_tiles) issue(st, t);
-        }
-    }
-
-    int it = 0;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
-        const int st = it % kStages;
-        tma::mbar_wait(&full_bar[st], (uint32_t)((it / kStages) & 1));
-        const unsigned char *src = stage_mem + st * L::kStageBytes;
+    int tile = blockIdx.x;
+    if (tile < num_tiles) prefetch(tile);
+    for (; tile < num_tiles; tile += gridDim.x) {
+        const int64_t j = (int64_t)tile * kThreads + tid;
+        const bool in_range = j < a.count;
+        const int64_t i = a.first + j;
+        ActT av{};
+        if constexpr (!L::kActAsync) { if (in_range) av = __ldg(actions + i * L::kActPerEnv); }
+        acp::ld_wait_all();
         double s[E::S];
 #pragma unroll
-        for (int k = 0; k < E::S; k++) s[k] = reinterpret_cast<const double *>(src + k * L::kStateBytes)[tid];
-        const int32_t elapsed = reinterpret_cast<const int32_t *>(src + L::kElapsedOff)[tid];
-        const ActT av = reinterpret_cast<const ActT *>(src + L::kActOff)[tid * L::kActPerEnv];
-        __syncthreads();  // every thread has drained this stage: it can be refilled
-        if (tid == 0) {
-            const int next = tile + kStages * gridDim.x;
-            if (next < num_tiles) issue(st, next);
-            reset_count[(it + 1) & 1] = 0;  // last read two barriers ago, next written after the next barrier
-        }
+        for (int k = 0; k < E::S; k++) s[k] = s_state[k * kThreads + tid];
+        const int32_t elapsed = s_elapsed[tid];
+        if constexpr (L::kActAsync) av = *reinterpret_cast<const ActT *>(in_mem + L::kActOff + tid * L::kActBytes);
+        // this thread's slots are in registers now: refill them with its env of the next tile
+        if (tile + (int)gridDim.x < num_tiles) prefetch(tile + gridDim.x);
         long long action_int = 0;
         float a0 = 0.0f;
         if constexpr (E::A == 0) action_int = (long long)av;
         else a0 = (float)av;
-        const int64_t i0 = a.first + (int64_t)tile * kThreads;
-        if (advance_env<KIND>(a, i0 + tid, s, elapsed, action_int, a0))
-            reset_list[atomicAdd(&reset_count[it & 1], 1)] = tid;
-        __syncthreads();
-        const int cnt = reset_count[it & 1];
-        if (tid < cnt) reset_env<KIND>(a, i0 + reset_list[tid]);
+        bool need = false;
+        if (in_range) need = advance_env<KIND>(a, sink, i, s, elapsed, action_int, a0);
+        const unsigned m = __ballot_sync(0xffffffffu, need);
+        if (m != 0u) {
+            bool inline_reset = __popc(m) >= 12;          // dense enough: reset right here
+            if (need && !inline_reset) {
+                const int slot = atomicAdd(&reset_count, 1);
+                if (slot < kResetCap) reset_list[slot] = (int)j;
+                else inline_reset = true;                 // list full (whole batch truncating at once)
+            }
+            if (need && inline_reset) reset_env<KIND>(a, sink, i);
+        }
+    }
+    __syncthreads();
+    const int cnt = min(reset_count, kResetCap);
+    for (int q = tid; q < cnt; q += kThreads) reset_env<KIND>(a, sink, a.first + reset_list[q]);
+}
+
+// --- kernel G: one tile per CTA, results staged in shared memory and pushed with bulk stores ---------
+// The multi-GPU step (b200gym_step_p2p): every result must land in this rank's rows of EVERY rank's gather
+// buffers.  Per-thread peer stores put 16-, 8- and 1-byte writes on NVLink; here the 256-env tile of
+// (obs, reward, terminated, truncated) is assembled in shared memory (reset observations included) and warp w
+// pushes it to destination w -- peer w, or this rank's own buffers -- as four bulk copies (cp.async.bulk
+// shared -> global, SASS UBLKCP), so NVLink carries full-size write packets and the LSU carries none of it.
+// Needs 16-byte aligned destination rows; ragged tails and unaligned shards use kernel A's per-thread stores.
+template <int KIND, typename ActT>
+__global__ void __launch_bounds__(kThreads, Tuning<KIND>::kMinCtas) step_kernel_gather(const StepArgs a) {
+    using E = Env<KIND>;
+    __shared__ __align__(128) float s_obs[kThreads * E::D];
+    __shared__ __align__(16) double s_reward[kThreads];
+    __shared__ __align__(16) uint8_t s_term[kThreads];
+    __shared__ __align__(16) uint8_t s_trunc[kThreads];
+    __shared__ int reset_list[kThreads];
+    __shared__ int reset_count;
+    if (threadIdx.x == 0) reset_count = 0;
+    __syncthreads();
+    const int64_t j0 = (int64_t)blockIdx.x * kThreads;      // full tiles only: no bound check
+    const int64_t i0 = a.first + j0;
+    const StagedSink sink{s_obs, s_reward, s_term, s_trunc, i0};
+    {
+        const int64_t i = i0 + threadIdx.x;
+        double s[E::S];
+#pragma unroll
+        for (int k = 0; k < E::S; k++) s[k] = a.state[k * a.n + i];
+        const int32_t elapsed = a.elapsed[i];
+        long long action_int = 0;
+        float a0 = 0.0f;
+        const ActT av = __ldg(reinterpret_cast<const ActT *>(a.actions) + i);
+        if constexpr (E::A == 0) action_int = (long long)av;
+        else a0 = (float)av;
+        if (advance_env<KIND>(a, sink, i, s, elapsed, action_int, a0)) reset_list[atomicAdd(&reset_count, 1)] = threadIdx.x;
+    }
+    __syncthreads();
+    if ((int)threadIdx.x < reset_count) reset_env<KIND>(a, sink, i0 + reset_list[threadIdx.x]);
+    acp::fence_async_smem();
+    __syncthreads();
+    const int warp = threadIdx.x >> 5;
+    if ((threadIdx.x & 31) == 0 && warp <= a.npeer) {
+        float *obs = warp < a.npeer ? a.peer_obs[warp] : a.obs;
+        double *reward = warp < a.npeer ? a.peer_reward[warp] : a.reward;
+        uint8_t *term = warp < a.npeer ? a.peer_term[warp] : a.terminated;
+        uint8_t *trunc = warp < a.npeer ? a.peer_trunc[warp] : a.truncated;
+        acp::st_bulk(obs + i0 * E::D, s_obs, kThreads * E::D * 4);
+        acp::st_bulk(reward + i0, s_reward, kThreads * 8);
+        acp::st_bulk(term + i0, s_term, kThreads);
+        acp::st_bulk(trunc + i0, s_trunc, kThreads);
+        acp::st_bulk_commit();
+        acp::st_bulk_wait_read();    // the tile must stay in shared memory until the copy engine has read it
     }
 }
 
@@ -944,41 +935,34 @@ __global__ void __launch_bounds__(kThreads) normalize_reward_kernel(const double
 }
 
 // ---- cross-GPU step barrier for the fused all-gather ---------------------------------------
-// flags[r] (uint64, in every rank's gather allocation) = number of steps whose results rank r
-// has fully written into THIS rank's buffers.  signal: after my step kernel (stream order) tell
-// every peer; wait: spin until every peer has told me.  Volatile system-scope accesses.
-__global__ void p2p_signal_kernel(unsigned long long *const *peer_flags, int world, int rank, unsigned long long step) {
+// flags[r] (uint64, in every rank's gather allocation) = number of steps whose results rank r has fully written
+// into THIS rank's buffers.  One launch per step, after the step kernel on the same stream: lane p publishes
+// "my rows of step k are in your buffers" to peer p (the kernel boundary has drained the step kernel's stores,
+// bulk ones included; the system-scope fence orders them before the flag) and then waits for peer p's flag.
+// A peer that died does not hang the stream for ever: after `timeout_ns` the lane records the peer in
+// `*timed_out` (sticky, read by b200gym_p2p_status) and gives up.
+__device__ __forceinline__ unsigned long long global_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+
+__global__ void p2p_sync_kernel(unsigned long long *const *peer_flags, const unsigned long long *my_flags, int world,
+                                int rank, unsigned long long step, unsigned long long timeout_ns, int *timed_out) {
     const int p = threadIdx.x;
-    if (p < world) {
+    if (p < world && p != rank) {
         __threadfence_system();
         volatile unsigned long long *f = peer_flags[p] + rank;
         *f = step;
-    }
-}
-
-__global__ void p2p_wait_kernel(const unsigned long long *flags, int world, unsigned long long step) {
-    const int p = threadIdx.x;
-    if (p < world) {
-        const volatile unsigned long long *f = flags + p;
-        while (*f < step) {
+        const volatile unsigned long long *w = my_flags + p;
+        const unsigned long long t0 = global_ns();
+        while (*w < step) {
+            if (global_ns() - t0 > timeout_ns) {
+                atomicExch(timed_out, p + 1);
+                break;
+            }
         }
         __threadfence_system();
-    }
-}
-
-// host path: gather the final observations of the envs that finished in [first, first+count) into a
-// dense list (order irrelevant: every entry carries its env index)
-__global__ void __launch_bounds__(kThreads) compact_final_kernel(const uint8_t *term, const uint8_t *trunc,
-                                                                const float *final_obs, int D, int64_t first,
-                                                                int64_t count, int32_t *idx_out, float *rows_out,
-                                                                unsigned long long *counter) {
-    const int64_t j = (int64_t)blockIdx.x * kThreads + threadIdx.x;
-    if (j >= count) return;
-    const int64_t i = first + j;
-    if (term[i] | trunc[i]) {
-        const unsigned long long slot = atomicAdd(counter, 1ULL);
-        idx_out[slot] = (int32_t)i;
-        for (int k = 0; k < D; k++) rows_out[slot * D + k] = final_obs[i * D + k];
     }
 }
 
@@ -1014,41 +998,39 @@ static inline unsigned blocks_for(int64_t n) { return (unsigned)((n + kThreads -
 // ---------------------------------------------------------------------------
 template <int KIND, typename ActT>
 static int launch_step_typed(b200gym *h, const StepArgs &a, cudaStream_t st) {
-    // kernel B needs 16-byte aligned bulk copies: even SoA stride, 16-aligned range start and
-    // action pointer; and enough tiles to be worth a persistent grid
-    const bool aligned = (a.n % 2 == 0) && (a.first % 16 == 0) && ((uintptr_t)a.actions % 16 == 0) &&
-                         ((uintptr_t)a.state % 16 == 0) && ((uintptr_t)a.elapsed % 16 == 0);
     int64_t done = 0;
     const int64_t tiles = a.count / kThreads;
-    if (aligned && tiles >= h->sm_count && h->kernel_choice == 1) {
-        int &occ = h->occ[KIND][sizeof(ActT) == 8 ? 0 : sizeof(ActT) == 4 ? 1 : 2];
-        if (occ == 0) {
-            CK(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, step_kernel_tma<KIND, ActT>, kThreads, 0));
-            if (occ < 1) occ = 1;
-        }
-        int64_t grid = (int64_t)h->sm_count * occ;
-        if (grid > tiles) grid = tiles;
-        step_kernel_tma<KIND, ActT><<<(unsigned)grid, kThreads, 0, st>>>(a, (int)tiles);
-        CK(h, cudaGetLastError());
-        done = tiles * kThreads;
-    }
-    // kernel C (pairs): autoreset mode only (no per-env `flags` bookkeeping), 16-byte aligned everything
-    if (KIND != B200GYM_ACROBOT /* 2 x RK4 state does not fit 64 registers */ && done == 0 && h->kernel_choice == 2 &&
-        a.autoreset && (a.n % 2 == 0) && (a.first % 2 == 0) && a.count >= 2 &&
-        (uintptr_t)a.state % 16 == 0 && (uintptr_t)a.elapsed % 8 == 0 && (uintptr_t)a.actions % 16 == 0 &&
-        (uintptr_t)a.reward % 16 == 0 && (uintptr_t)a.obs % 16 == 0 && (uintptr_t)a.terminated % 2 == 0 &&
-        (uintptr_t)a.truncated % 2 == 0) {
-        bool peers_ok = true;
-        for (int p = 0; p < a.npeer; p++)
-            peers_ok = peers_ok && (uintptr_t)a.peer_reward[p] % 16 == 0 && (uintptr_t)a.peer_obs[p] % 16 == 0 &&
-                       (uintptr_t)a.peer_term[p] % 2 == 0 && (uintptr_t)a.peer_trunc[p] % 2 == 0;
-        if (peers_ok) {
-            StepArgs t = a;
-            t.count = a.count & ~(int64_t)1;
-            const int64_t pairs = t.count / 2;
-            step_kernel_pair<KIND, ActT><<<(unsigned)((pairs + kThreads - 1) / kThreads), kThreads, 0, st>>>(t);
+    if ((a.npeer > 0 || a.bulk_sink) && h->gather_bulk && tiles > 0) {
+        // kernel G (bulk pushes): every destination row block must be 16-byte aligned
+        auto ok = [&](const float *o, const double *r, const uint8_t *te, const uint8_t *tr) {
+            return (uintptr_t)(o + a.first * Env<KIND>::D) % 16 == 0 && (uintptr_t)(r + a.first) % 16 == 0 &&
+                   (uintptr_t)(te + a.first) % 16 == 0 && (uintptr_t)(tr + a.first) % 16 == 0;
+        };
+        bool aligned = ok(a.obs, a.reward, a.terminated, a.truncated);
+        for (int p = 0; p < a.npeer; p++) aligned = aligned && ok(a.peer_obs[p], a.peer_reward[p], a.peer_term[p], a.peer_trunc[p]);
+        if (aligned) {
+            step_kernel_gather<KIND, ActT><<<(unsigned)tiles, kThreads, 0, st>>>(a);
             CK(h, cudaGetLastError());
-            done = t.count;
+            done = tiles * kThreads;
+        }
+    }
+    if (done == 0 && h->kernel_choice == 1 && a.npeer == 0 && a.count >= (int64_t)h->sm_count * kThreads) {
+        // kernel P: resident grid; needs naturally aligned input words for cp.async (always true for the
+        // handle's own arrays; the caller's action pointer is checked)
+        using L = PrefetchLayout<KIND, ActT>;
+        const bool aligned = !L::kActAsync || ((uintptr_t)a.actions % L::kActBytes == 0);
+        if (aligned) {
+            int &occ = h->occ[KIND][sizeof(ActT) == 8 ? 0 : sizeof(ActT) == 4 ? 1 : 2];
+            if (occ == 0) {
+                CK(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, step_kernel_persistent<KIND, ActT>, kThreads, 0));
+                if (occ < 1) occ = 1;
+            }
+            const int64_t all_tiles = (a.count + kThreads - 1) / kThreads;
+            int64_t grid = (int64_t)h->sm_count * occ;
+            if (grid > all_tiles) grid = all_tiles;
+            step_kernel_persistent<KIND, ActT><<<(unsigned)grid, kThreads, 0, st>>>(a, (int)all_tiles);
+            CK(h, cudaGetLastError());
+            done = a.count;
         }
     }
     if (done < a.count) {
@@ -1219,8 +1201,10 @@ extern "C" int b200gym_create(const b200gym_config *cfg, int64_t num_envs, int d
     {
         const char *fs = getenv("B200GYM_SIMPLE_KERNEL");
         const char *kc = getenv("B200GYM_KERNEL");
-        if (kc && (kc[0] == 'a' || kc[0] == 'b' || kc[0] == 'c')) h->kernel_choice = kc[0] - 'a';
+        if (kc && (kc[0] == 'a' || kc[0] == 'p')) h->kernel_choice = kc[0] == 'p';
         if (fs && fs[0] == '1') h->kernel_choice = 0;
+        const char *gb = getenv("B200GYM_GATHER");
+        if (gb && (gb[0] == 'b' || gb[0] == 'd')) h->gather_bulk = gb[0] == 'b';
         const char *bb = getenv("B200GYM_BOX2D_BLOCK");
         if (bb && (atoi(bb) == 128 || atoi(bb) == 256)) h->box2d_block = atoi(bb);
         const char *bdf = getenv("B200GYM_BOX2D_DEFER");
@@ -1263,12 +1247,12 @@ extern "C" int b200gym_create(const b200gym_config *cfg, int64_t num_envs, int d
             return 1;
         }
     }
-    cudaMemset(h->state, 0, sizeof(double) * n * h->S);
-    cudaMemset(h->elapsed, 0, sizeof(int32_t) * n);
-    cudaMemset(h->flags, 0, n);
-    cudaMemset(h->rng, 0, 32 * n);
-    cudaMemset(h->invalid, 0, sizeof(unsigned long long));
-    if (cudaDeviceSynchronize() != cudaSuccess) {
+    const cudaError_t ms[5] = {cudaMemset(h->state, 0, sizeof(double) * n * (h->S > 0 ? h->S : 1)),
+                               cudaMemset(h->elapsed, 0, sizeof(int32_t) * n), cudaMemset(h->flags, 0, n),
+                               cudaMemset(h->rng, 0, 32 * n), cudaMemset(h->invalid, 0, sizeof(unsigned long long))};
+    bool ms_ok = true;
+    for (cudaError_t mi : ms) ms_ok = ms_ok && mi == cudaSuccess;
+    if (!ms_ok || cudaDeviceSynchronize() != cudaSuccess) {
         fail(nullptr, "b200gym_create: device initialisation failed: %s", cudaGetErrorString(cudaGetLastError()));
         b200gym_destroy(h);
         return 1;
@@ -1281,11 +1265,9 @@ static void free_host_io(b200gym *h) {
     if (!h->host_ready) return;
     cudaFreeHost(h->hio.actions); cudaFreeHost(h->hio.obs); cudaFreeHost(h->hio.reward);
     cudaFreeHost(h->hio.terminated); cudaFreeHost(h->hio.truncated); cudaFreeHost(h->hio.final_obs);
-    cudaFree(h->dio.actions); cudaFree(h->dio.obs); cudaFree(h->dio.reward);
-    cudaFree(h->dio.terminated); cudaFree(h->dio.truncated); cudaFree(h->dio.final_obs);
+    cudaFreeHost(h->h_invalid);
+    cudaFree(h->dio.actions);
     cudaFree(h->d_mask);
-    cudaFree(h->d_fin_idx); cudaFree(h->d_fin_rows); cudaFree(h->d_fin_count);
-    cudaFreeHost(h->h_fin_idx); cudaFreeHost(h->h_fin_rows); cudaFreeHost(h->h_fin_count);
     if (h->hevent) cudaEventDestroy(h->hevent);
     for (cudaStream_t st : h->hstream)
         if (st) cudaStreamDestroy(st);
@@ -1371,6 +1353,7 @@ static StepArgs make_args(b200gym *h, const void *actions, float *obs, double *r
     a.lunar_opts = h->lunar_opts;
     a.reset_list = nullptr; a.reset_count = nullptr;
     a.npeer = 0;
+    a.bulk_sink = 0;
     return a;
 }
 
@@ -1431,8 +1414,12 @@ extern "C" int b200gym_p2p_create(b200gym_t *h, int world, int rank, void *ipc_h
     P.off_term = align_up(P.off_reward + rows * sizeof(double), 256);
     P.off_trunc = align_up(P.off_term + rows, 256);
     P.set_bytes = align_up(P.off_trunc + rows, 256);
-    P.off_flags = 2 * P.set_bytes;
+    P.off_flags = 2 * P.set_bytes;          // [0,64): one uint64 step counter per rank; [128,132): sticky time-out word
     P.bytes = P.off_flags + 256;
+    if (const char *ts = getenv("B200GYM_P2P_TIMEOUT_S")) {
+        const double v = atof(ts);
+        if (v > 0.0) P.timeout_ns = (unsigned long long)(v * 1e9);
+    }
     CK(h, cudaMalloc((void **)&P.base, P.bytes));
     CK(h, cudaMemset(P.base, 0, P.bytes));
     CK(h, cudaDeviceSynchronize());
@@ -1506,15 +1493,27 @@ extern "C" int b200gym_step_p2p(b200gym_t *h, const void *actions_dev, int actio
             CK(h, cudaMalloc((void **)&h->d_peer_flags, sizeof pf));
             CK(h, cudaMemcpy(h->d_peer_flags, pf, sizeof pf, cudaMemcpyHostToDevice));
         }
-        p2p_signal_kernel<<<1, 32, 0, st>>>(h->d_peer_flags, P.world, P.rank, P.step);
-        p2p_wait_kernel<<<1, 32, 0, st>>>((const unsigned long long *)(P.base + P.off_flags), P.world, P.step);
+        p2p_sync_kernel<<<1, 32, 0, st>>>(h->d_peer_flags, (const unsigned long long *)(P.base + P.off_flags), P.world,
+                                          P.rank, P.step, P.timeout_ns, (int *)(P.base + P.off_flags + 128));
         CK(h, cudaGetLastError());
     }
     if (set_out) *set_out = set;
     return 0;
 }
 
-// reset(): fill this rank's rows of set 0 ... (the reset observations are exchanged by the caller)
+extern "C" int b200gym_p2p_status(b200gym_t *h, void *stream, int *timed_out_peer) {
+    if (!h || !timed_out_peer) return fail(h, "b200gym_p2p_status: null argument");
+    auto &P = h->p2p;
+    if (!P.base) return fail(h, "b200gym_p2p_status: no gather allocation");
+    DeviceGuard guard(h->device);
+    int v = 0;
+    CK(h, cudaMemcpyAsync(&v, P.base + P.off_flags + 128, sizeof v, cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+    CK(h, cudaStreamSynchronize((cudaStream_t)stream));
+    *timed_out_peer = v - 1;   // -1: every step barrier completed
+    if (v) return fail(h, "b200gym_step_p2p: rank %d did not deliver its rows within %.0f s (peer lost?)", v - 1,
+                       (double)P.timeout_ns * 1e-9);
+    return 0;
+}
 
 // ---- stateless device utilities for the vector-aware wrappers -----------------------
 extern "C" int b200gym_episode_stats(const double *reward_dev, const uint8_t *terminated_dev, const uint8_t *truncated_dev,
@@ -1568,35 +1567,35 @@ extern "C" int b200gym_running_norm_reward(const double *reward_dev, const uint8
 }
 
 // ---- host-buffer path -------------------------------------------------------
+// The staging buffers are page-locked AND mapped into the device's address space: the step kernel writes its
+// results straight into host memory (for the classic-control kinds as bulk shared->global copies of 256-env
+// tiles, kernel G with the host as its only destination), so the device->host transfer IS the kernel's store
+// stream -- no result mirrors in HBM, no separate D2H copies, no compaction pass for the final observations.
 static int ensure_host_io(b200gym *h) {
     if (h->host_ready) return 0;
     const size_t n = (size_t)h->n;
     const size_t act_bytes = h->A == 0 ? n * sizeof(int64_t) : n * h->A * sizeof(float);
     const size_t obs_bytes = n * h->D * sizeof(float);
+    const unsigned fl = cudaHostAllocMapped;
     for (int k = 0; k < 2; k++) CK(h, cudaStreamCreateWithFlags(&h->hstream[k], cudaStreamNonBlocking));
-    CK(h, cudaHostAlloc(&h->hio.actions, act_bytes, cudaHostAllocDefault));
-    CK(h, cudaHostAlloc((void **)&h->hio.obs, obs_bytes, cudaHostAllocDefault));
-    CK(h, cudaHostAlloc((void **)&h->hio.reward, n * sizeof(double), cudaHostAllocDefault));
-    CK(h, cudaHostAlloc((void **)&h->hio.terminated, n, cudaHostAllocDefault));
-    CK(h, cudaHostAlloc((void **)&h->hio.truncated, n, cudaHostAllocDefault));
-    CK(h, cudaHostAlloc((void **)&h->hio.final_obs, obs_bytes, cudaHostAllocDefault));
+    CK(h, cudaHostAlloc(&h->hio.actions, act_bytes, fl));
+    CK(h, cudaHostAlloc((void **)&h->hio.obs, obs_bytes, fl));
+    CK(h, cudaHostAlloc((void **)&h->hio.reward, n * sizeof(double), fl));
+    CK(h, cudaHostAlloc((void **)&h->hio.terminated, n, fl));
+    CK(h, cudaHostAlloc((void **)&h->hio.truncated, n, fl));
+    CK(h, cudaHostAlloc((void **)&h->hio.final_obs, obs_bytes, fl));
+    CK(h, cudaHostAlloc((void **)&h->h_invalid, sizeof(unsigned long long), fl));
     memset(h->hio.actions, 0, act_bytes);
     memset(h->hio.final_obs, 0, obs_bytes);
-    CK(h, cudaMalloc(&h->dio.actions, act_bytes));
-    CK(h, cudaMalloc((void **)&h->dio.obs, obs_bytes));
-    CK(h, cudaMalloc((void **)&h->dio.reward, n * sizeof(double)));
-    CK(h, cudaMalloc((void **)&h->dio.terminated, n));
-    CK(h, cudaMalloc((void **)&h->dio.truncated, n));
-    CK(h, cudaMalloc((void **)&h->dio.final_obs, obs_bytes));
+    // device aliases of the mapped host buffers (identical to the host pointers under unified addressing)
+    CK(h, cudaHostGetDevicePointer((void **)&h->dio.obs, h->hio.obs, 0));
+    CK(h, cudaHostGetDevicePointer((void **)&h->dio.reward, h->hio.reward, 0));
+    CK(h, cudaHostGetDevicePointer((void **)&h->dio.terminated, h->hio.terminated, 0));
+    CK(h, cudaHostGetDevicePointer((void **)&h->dio.truncated, h->hio.truncated, 0));
+    CK(h, cudaHostGetDevicePointer((void **)&h->dio.final_obs, h->hio.final_obs, 0));
+    CK(h, cudaMalloc(&h->dio.actions, act_bytes));   // the actions do live in HBM: every env reads its own once
     CK(h, cudaMalloc((void **)&h->d_mask, n));
-    CK(h, cudaMalloc((void **)&h->d_fin_idx, n * sizeof(int32_t)));
-    CK(h, cudaMalloc((void **)&h->d_fin_rows, obs_bytes));
-    CK(h, cudaMalloc((void **)&h->d_fin_count, sizeof(unsigned long long)));
-    CK(h, cudaHostAlloc((void **)&h->h_fin_idx, n * sizeof(int32_t), cudaHostAllocDefault));
-    CK(h, cudaHostAlloc((void **)&h->h_fin_rows, obs_bytes, cudaHostAllocDefault));
-    CK(h, cudaHostAlloc((void **)&h->h_fin_count, sizeof(unsigned long long), cudaHostAllocDefault));
     CK(h, cudaEventCreateWithFlags(&h->hevent, cudaEventDisableTiming));
-    CK(h, cudaMemset(h->dio.final_obs, 0, obs_bytes));
     h->host_ready = true;
     return 0;
 }
@@ -1618,41 +1617,20 @@ static size_t action_size(int action_dtype) {
     }
 }
 
-extern "C" int b200gym_step_host(b200gym_t *h, const void *actions_host, int action_dtype, float *obs_host,
-                                 double *reward_host, uint8_t *terminated_host, uint8_t *truncated_host,
-                                 float *final_obs_host) {
-    if (!h) return fail(h, "b200gym_step_host: null handle");
-    DeviceGuard guard(h->device);
-    if (ensure_host_io(h)) return 1;
-    if (h->A == 0 ? (action_dtype == B200GYM_ACT_F32) : (action_dtype != B200GYM_ACT_F32))
-        return fail(h, "b200gym_step_host: action dtype code %d does not fit this env's action space", action_dtype);
-    if (!actions_host) {
-        actions_host = h->hio.actions;
-        action_dtype = h->A == 0 ? B200GYM_ACT_I64 : B200GYM_ACT_F32;
-    }
-    if (!obs_host) obs_host = h->hio.obs;
-    if (!reward_host) reward_host = h->hio.reward;
-    if (!terminated_host) terminated_host = h->hio.terminated;
-    if (!truncated_host) truncated_host = h->hio.truncated;
+// enqueue the chunked pipeline; any failure is reported after both streams have drained
+static int step_host_enqueue(b200gym *h, const void *actions_host, int action_dtype, bool want_final) {
     const size_t asz = action_size(action_dtype) * (h->A == 0 ? 1 : h->A);
-    const size_t osz = sizeof(float) * h->D;
-    // chunked 2-stream pipeline: H2D(actions) -> kernel -> D2H(results) per chunk
     const int64_t n = h->n;
-    int64_t chunks = n >> 17;
-    chunks = chunks < 1 ? 1 : (chunks > 8 ? 8 : chunks);
+    int64_t chunks = n >> 18;                       // 2^20 envs -> 4 chunks: H2D of chunk c+1 under the kernel of c
+    chunks = chunks < 1 ? 1 : (chunks > 4 ? 4 : chunks);
     if (const char *hc = getenv("B200GYM_HOST_CHUNKS")) {  // tuning runs
         const int v = atoi(hc);
         if (v >= 1 && v <= 64) chunks = v;
     }
-    int64_t per = ((n + chunks - 1) / chunks + kThreads - 1) / kThreads * kThreads;
+    const int64_t per = ((n + chunks - 1) / chunks + kThreads - 1) / kThreads * kThreads;
     StepArgs a = make_args(h, h->dio.actions, h->dio.obs, h->dio.reward, h->dio.terminated, h->dio.truncated,
-                           h->dio.final_obs);
-    const bool want_final = final_obs_host != nullptr && h->cfg.autoreset;
-    if (want_final) CK(h, cudaMemsetAsync(h->d_fin_count, 0, sizeof(unsigned long long), h->hstream[0]));
-    if (want_final && chunks > 1) {  // stream 1 must see the cleared counter
-        CK(h, cudaEventRecord(h->hevent, h->hstream[0]));
-        CK(h, cudaStreamWaitEvent(h->hstream[1], h->hevent, 0));
-    }
+                           want_final ? h->dio.final_obs : nullptr);
+    a.bulk_sink = 1;
     int c = 0;
     for (int64_t lo = 0; lo < n; lo += per, c++) {
         const int64_t cnt = (lo + per < n) ? per : n - lo;
@@ -1663,35 +1641,47 @@ extern "C" int b200gym_step_host(b200gym_t *h, const void *actions_host, int act
         a.count = cnt;
         a.reset_count = h->reset_count ? h->reset_count + (c % kResetSlots) : nullptr;
         if (launch_step(h, a, action_dtype, st)) return 1;
-        CK(h, cudaMemcpyAsync((char *)obs_host + lo * osz, (char *)h->dio.obs + lo * osz, cnt * osz,
-                              cudaMemcpyDeviceToHost, st));
-        CK(h, cudaMemcpyAsync(reward_host + lo, h->dio.reward + lo, cnt * sizeof(double), cudaMemcpyDeviceToHost, st));
-        CK(h, cudaMemcpyAsync(terminated_host + lo, h->dio.terminated + lo, cnt, cudaMemcpyDeviceToHost, st));
-        CK(h, cudaMemcpyAsync(truncated_host + lo, h->dio.truncated + lo, cnt, cudaMemcpyDeviceToHost, st));
-        if (want_final) {
-            compact_final_kernel<<<blocks_for(cnt), kThreads, 0, st>>>(h->dio.terminated, h->dio.truncated,
-                                                                      h->dio.final_obs, h->D, lo, cnt, h->d_fin_idx,
-                                                                      h->d_fin_rows, h->d_fin_count);
-            CK(h, cudaGetLastError());
-        }
     }
-    CK(h, cudaStreamSynchronize(h->hstream[1]));
-    if (want_final)
-        CK(h, cudaMemcpyAsync(h->h_fin_count, h->d_fin_count, sizeof(unsigned long long), cudaMemcpyDeviceToHost,
-                              h->hstream[0]));
-    CK(h, cudaStreamSynchronize(h->hstream[0]));
-    if (want_final) {
-        // only the rows of the envs that finished cross PCIe; they are scattered into the dense
-        // [n][obs_dim] host array (rows of the other envs keep their previous content)
-        const size_t m = (size_t)*h->h_fin_count;
-        if (m > 0) {
-            CK(h, cudaMemcpyAsync(h->h_fin_idx, h->d_fin_idx, m * sizeof(int32_t), cudaMemcpyDeviceToHost, h->hstream[0]));
-            CK(h, cudaMemcpyAsync(h->h_fin_rows, h->d_fin_rows, m * osz, cudaMemcpyDeviceToHost, h->hstream[0]));
-            CK(h, cudaStreamSynchronize(h->hstream[0]));
-            for (size_t k = 0; k < m; k++)
-                memcpy((char *)final_obs_host + (size_t)h->h_fin_idx[k] * osz, (const char *)h->h_fin_rows + k * osz, osz);
-        }
+    if (c > 1) {  // stream 0 also waits for the chunks of stream 1
+        CK(h, cudaEventRecord(h->hevent, h->hstream[1]));
+        CK(h, cudaStreamWaitEvent(h->hstream[0], h->hevent, 0));
     }
+    // the sticky invalid-action counter rides along (no separate round trip afterwards)
+    CK(h, cudaMemcpyAsync(h->h_invalid, h->invalid, sizeof(unsigned long long), cudaMemcpyDeviceToHost, h->hstream[0]));
+    CK(h, cudaMemsetAsync(h->invalid, 0, sizeof(unsigned long long), h->hstream[0]));
+    return 0;
+}
+
+extern "C" int b200gym_step_host(b200gym_t *h, const void *actions_host, int action_dtype, float *obs_host,
+                                 double *reward_host, uint8_t *terminated_host, uint8_t *truncated_host,
+                                 float *final_obs_host, int64_t *invalid_out) {
+    if (!h) return fail(h, "b200gym_step_host: null handle");
+    DeviceGuard guard(h->device);
+    if (ensure_host_io(h)) return 1;
+    if (h->A == 0 ? (action_dtype == B200GYM_ACT_F32) : (action_dtype != B200GYM_ACT_F32))
+        return fail(h, "b200gym_step_host: action dtype code %d does not fit this env's action space", action_dtype);
+    if (!actions_host) {
+        actions_host = h->hio.actions;
+        action_dtype = h->A == 0 ? B200GYM_ACT_I64 : B200GYM_ACT_F32;
+    }
+    const bool want_final = final_obs_host != nullptr && h->cfg.autoreset;
+    const int rc = step_host_enqueue(h, actions_host, action_dtype, want_final);
+    // drain both streams whatever happened: nothing may still be writing into host memory when we return
+    const cudaError_t e1 = cudaStreamSynchronize(h->hstream[1]), e0 = cudaStreamSynchronize(h->hstream[0]);
+    if (rc) return 1;
+    if (e0 != cudaSuccess || e1 != cudaSuccess)
+        return fail(h, "b200gym_step_host: %s", cudaGetErrorString(e0 != cudaSuccess ? e0 : e1));
+    if (invalid_out) *invalid_out = (int64_t)*h->h_invalid;
+    // results are in the mapped staging buffers; callers that brought their own arrays get a host copy
+    const size_t n = (size_t)h->n, osz = sizeof(float) * h->D;
+    if (obs_host && obs_host != h->hio.obs) memcpy(obs_host, h->hio.obs, n * osz);
+    if (reward_host && reward_host != h->hio.reward) memcpy(reward_host, h->hio.reward, n * sizeof(double));
+    if (terminated_host && terminated_host != h->hio.terminated) memcpy(terminated_host, h->hio.terminated, n);
+    if (truncated_host && truncated_host != h->hio.truncated) memcpy(truncated_host, h->hio.truncated, n);
+    if (want_final && final_obs_host != h->hio.final_obs)   // rows of the envs that finished in this step only
+        for (size_t i = 0; i < n; i++)
+            if (h->hio.terminated[i] | h->hio.truncated[i])
+                memcpy((char *)final_obs_host + i * osz, (const char *)h->hio.final_obs + i * osz, osz);
     return 0;
 }
 
@@ -1700,17 +1690,17 @@ extern "C" int b200gym_reset_host(b200gym_t *h, const uint8_t *mask_host, const 
     if (!h) return fail(h, "b200gym_reset_host: null handle");
     DeviceGuard guard(h->device);
     if (ensure_host_io(h)) return 1;
-    if (!obs_host) obs_host = h->hio.obs;
     const size_t n = (size_t)h->n;
     cudaStream_t st = h->hstream[0];
-    if (mask_host) {
-        CK(h, cudaMemcpyAsync(h->d_mask, mask_host, n, cudaMemcpyHostToDevice, st));
-        // keep the rows of the envs that are not reset
-        CK(h, cudaMemcpyAsync(h->dio.obs, obs_host, n * h->D * sizeof(float), cudaMemcpyHostToDevice, st));
-    }
-    if (launch_reset(h, mask_host ? h->d_mask : nullptr, bounds_host, h->dio.obs, st)) return 1;
-    CK(h, cudaMemcpyAsync(obs_host, h->dio.obs, n * h->D * sizeof(float), cudaMemcpyDeviceToHost, st));
-    CK(h, cudaStreamSynchronize(st));
+    // the reset kernel writes the rows of the (masked) envs straight into the mapped staging buffer; rows of
+    // envs that are not reset keep their content
+    if (obs_host && obs_host != h->hio.obs && mask_host) memcpy(h->hio.obs, obs_host, n * h->D * sizeof(float));
+    if (mask_host) CK(h, cudaMemcpyAsync(h->d_mask, mask_host, n, cudaMemcpyHostToDevice, st));
+    const int rc = launch_reset(h, mask_host ? h->d_mask : nullptr, bounds_host, h->dio.obs, st);
+    const cudaError_t e = cudaStreamSynchronize(st);
+    if (rc) return 1;
+    if (e != cudaSuccess) return fail(h, "b200gym_reset_host: %s", cudaGetErrorString(e));
+    if (obs_host && obs_host != h->hio.obs) memcpy(obs_host, h->hio.obs, n * h->D * sizeof(float));
     return 0;
 }
 

@@ -119,6 +119,12 @@ struct Env<B200GYM_CARTPOLE> {
         for (int k = 0; k < 4; k++) obs[k] = (float)s[k];             // :207
     }
 
+    // the observation of the current state (cartpole.py:188), without stepping
+    __device__ static void observe(const double (&s)[S], float (&obs)[D]) {
+#pragma unroll
+        for (int k = 0; k < 4; k++) obs[k] = (float)s[k];
+    }
+
     // cartpole.py:130-188, "euler" integrator (:149-153)
     __device__ static void step(double (&s)[S], bool /*fresh*/, int action, float /*a0*/,
                                 double /*param0*/, float (&obs)[D], double &reward, bool &terminated) {
@@ -175,6 +181,8 @@ struct Env<B200GYM_MOUNTAINCAR> {
         obs[1] = 0.0f;
     }
 
+    __device__ static void observe(const double (&s)[S], float (&obs)[D]) { obs[0] = (float)s[0]; obs[1] = (float)s[1]; }
+
     // mountain_car.py:127-148
     __device__ static void step(double (&s)[S], bool /*fresh*/, int action, float /*a0*/,
                                 double goal_velocity, float (&obs)[D], double &reward, bool &terminated) {
@@ -217,6 +225,8 @@ struct Env<B200GYM_MOUNTAINCAR_CONT> {
         obs[0] = (float)s[0];
         obs[1] = 0.0f;
     }
+
+    __device__ static void observe(const double (&s)[S], float (&obs)[D]) { obs[0] = (float)s[0]; obs[1] = (float)s[1]; }
 
     __device__ static void step(double (&s)[S], bool fresh, int /*action*/, float a0,
                                 double goal_velocity, float (&obs)[D], double &reward, bool &terminated) {
@@ -287,6 +297,8 @@ struct Env<B200GYM_PENDULUM> {
         obs[0] = (float)cs; obs[1] = (float)sn; obs[2] = (float)s[1];
     }
 
+    __device__ static void observe(const double (&s)[S], float (&obs)[D]) { get_obs(s, obs); }
+
     // pendulum.py:141-159: uniform(low=-high, high=high) with high = [x_init, y_init]
     __device__ static void reset(double (&s)[S], Pcg64 &g, double x_init, double y_init, float (&obs)[D]) {
         s[0] = pcg64_uniform(g, -x_init, x_init);
@@ -351,6 +363,8 @@ struct Env<B200GYM_ACROBOT> {
         obs[4] = (float)s[2]; obs[5] = (float)s[3];
         cos0 = c0;
     }
+
+    __device__ static void observe(const double (&s)[S], float (&obs)[D]) { double c0; get_obs(s, obs, c0); }
 
     // acrobot.py:181-194: uniform(size=(4,)).astype(np.float32); the reference then
     // evaluates numpy's float32 cos/sin on it -- we return the correctly rounded

@@ -11,7 +11,7 @@ makes lands under ``B200/<id>``.  This module is that plugin:
     B200 = "gym_b200.plugin:register_envs"
 
     import gym
-    env = gym.make("B200/CartPole-v1")            # -> gym_b200.env.B200Env on cuda:0
+    env = gym.make("B200/CartPole-v1")            # -> gym_b200.gym_compat.GymEnv (a gym.Env) on cuda:0
 
 or, without installing the entry point, ``gym_b200.plugin.register_all()`` after ``import gym``.
 
@@ -29,8 +29,8 @@ NAMESPACE = "B200"
 def make_env(env_id, **kwargs):
     """The ``entry_point`` of every registered id: what ``gym.make`` calls as ``env_creator(**kwargs)``
     (registration.py:640)."""
-    from gym_b200.env import B200Env
-    return B200Env(env_id, **kwargs)
+    from gym_b200.gym_compat import GymEnv   # a real gym.Env subclass: this function only runs inside gym
+    return GymEnv(env_id, **kwargs)
 
 
 def register_envs():

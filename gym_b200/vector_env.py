@@ -378,16 +378,16 @@ class B200VectorEnv:
                 a = np.ascontiguousarray(a, dtype=np.float32).reshape(self.num_envs, self.act_dim)
                 code = _lib.ACT_F32
             h = self._hio
-            # actions are read straight from the caller's array; results land in the pinned staging buffers
+            # actions are read straight from the caller's array; the kernel writes the results into the
+            # page-locked, device-mapped staging buffers; the invalid-action count comes back with the call
+            count = ctypes.c_int64(0)
             _lib.check(self._lib.b200gym_step_host(
                 self._handle, a.ctypes.data, code, None, None, None, None,
-                h["final_obs"].ctypes.data if self.autoreset else None), self._handle)
-            if self.discrete and a.size > 4096:
-                count = ctypes.c_int64(0)
-                _lib.check(self._lib.b200gym_invalid_actions(self._handle, None, ctypes.byref(count)), self._handle)
-                if count.value:
-                    raise error.InvalidAction(f"{count.value} out-of-range Discrete action(s) were passed to step(); "
-                                              "the other environments have been stepped")
+                h["final_obs"].ctypes.data if self.autoreset else None, ctypes.byref(count)), self._handle)
+            if count.value:
+                raise error.InvalidAction(f"{count.value} out-of-range Discrete action(s) were passed to step(); "
+                                          "those environments were left untouched (NaN reward), the others have "
+                                          "been stepped")
         self._state = _STATE_WAITING_STEP
 
     def step_wait(self, timeout=None):
@@ -410,9 +410,9 @@ class B200VectorEnv:
             obs, reward, term, trunc = obs.copy(), reward.copy(), term.copy(), trunc.copy()
         infos = {}
         if self.autoreset and self.dense_infos:
-            # dense form for large batches: (N, D) array + mask, always present (no Python loop)
+            # dense form for large batches: (N, D) array + mask (materialised on first access), no Python loop
             fo = h["final_obs"].copy() if self.copy else h["final_obs"]
-            infos = {"final_observation": fo, "_final_observation": term | trunc}
+            infos = FinalInfos(fo, term, trunc)
         elif self.autoreset:
             done = term | trunc
             if done.any():

@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define B200GYM_VERSION 1
+#define B200GYM_VERSION 2
 
 /* Environment kinds: the dynamics classes on the hot path. */
 enum b200gym_kind {
@@ -159,15 +159,19 @@ int b200gym_invalid_actions(b200gym_t *h, void *stream, int64_t *count_out);
 /*
  * Host-buffer step: the same call for a caller that lives on the CPU (what a
  * numpy agent does with SyncVectorEnv.step: numpy actions in, numpy results
- * out).  Copies the actions host->device, runs the step kernel and copies the
- * results device->host, pipelined over chunks of the env range on two streams
- * so that the two PCIe directions and the kernel overlap; returns when all
- * results have landed in host memory.
+ * out).  Copies the actions host->device and runs the step kernel with the
+ * library's page-locked, device-mapped staging buffers as its output arrays:
+ * the kernel's own stores (bulk shared->global copies of 256-env tiles) are the
+ * device->host transfer.  Pipelined over up to 4 chunks of the env range on two
+ * streams so that both PCIe directions overlap; returns when all results have
+ * landed in host memory.
  *   actions_host  [n] integers of `action_dtype` / [n][act_dim] float32, or
  *                 NULL = the library's page-locked staging buffer (see below)
  *   obs_host, reward_host, terminated_host, truncated_host
- *                 destination buffers, or NULL = the staging buffers
- *   final_obs_host destination, or NULL = final observations are not transferred
+ *                 NULL = results stay in the staging buffers (the fast path); otherwise they are
+ *                 additionally copied there on the host
+ *   final_obs_host destination (only the rows of envs that finished are written), or NULL = final
+ *                 observations are not transferred
  * Page-locked (cudaHostAlloc / cudaHostRegister / torch pin_memory) buffers
  * copy at full PCIe speed; pageable memory works but is staged by the driver.
  * b200gym_host_buffers() exposes the library's own page-locked staging buffers
@@ -184,7 +188,8 @@ typedef struct b200gym_host_io {
 int b200gym_host_buffers(b200gym_t *h, b200gym_host_io *out);
 int b200gym_step_host(b200gym_t *h, const void *actions_host, int action_dtype, float *obs_host,
                       double *reward_host, uint8_t *terminated_host, uint8_t *truncated_host,
-                      float *final_obs_host);
+                      float *final_obs_host, int64_t *invalid_out /* out-of-range Discrete actions seen (and
+                      cleared) by this call; may be NULL */);
 /* reset() with the observations delivered to host memory (obs_host NULL = staging). */
 int b200gym_reset_host(b200gym_t *h, const uint8_t *mask_host, const double *bounds_host, float *obs_host);
 
@@ -233,12 +238,17 @@ int b200gym_walker_get_terrain(b200gym_t *h, float *terrain_dev, float *polys_de
  *     obs float32 [world*n][obs_dim], reward float64 [world*n], terminated/truncated uint8 [world*n]
  * plus a flag word per rank, exports it as a CUDA IPC handle (b200gym_p2p_create), maps the
  * peers' allocations (b200gym_p2p_connect, after the caller has all-gathered the 64-byte
- * handles, e.g. with torch.distributed), and from then on b200gym_step_p2p() runs the SAME fused
- * step kernel, whose stores go to this rank's rows in the local set AND, through the mapped
- * peer pointers (NVLink st.global), in every peer's set -- the all-gather is the kernel's own
- * store stream, tile by tile, with no separate collective.  The step ends with a flag exchange:
- * each rank publishes "my rows of step k are complete" to all peers and waits on its own flag
- * words for theirs (two 1-warp kernels on `stream`).
+ * handles, e.g. with torch.distributed), and from then on b200gym_step_p2p() runs the fused step
+ * kernel in its gather form: each 256-env tile of results is assembled in shared memory and pushed
+ * to this rank's rows of the local set AND, through the mapped peer pointers, of every peer's set
+ * with bulk shared->global copies (cp.async.bulk over NVLink 5 / NVSwitch) -- the all-gather is the
+ * kernel's own store stream, tile by tile, overlapped with the arithmetic of the other tiles, with
+ * no separate collective and no extra pass over the data.  (Shards whose rows are not 16-byte
+ * aligned, ragged tails and the Box2D tasks use per-thread peer stores instead.)  The step ends
+ * with ONE 1-warp kernel on `stream`: each rank publishes "my rows of step k are complete" to all
+ * peers (system-scope fence + flag store) and waits on its own flag words for theirs, for at most
+ * B200GYM_P2P_TIMEOUT_S seconds (default 30): a lost peer is recorded, not waited for for ever
+ * (b200gym_p2p_status).
  */
 #define B200GYM_MAX_PEERS 7
 typedef struct b200gym_p2p_layout {
@@ -253,6 +263,9 @@ int b200gym_p2p_connect(b200gym_t *h, const void *all_ipc_handles /* world x 64 
 /* *set_out = which set (0/1) holds this step's global results once `stream` reaches this point */
 int b200gym_step_p2p(b200gym_t *h, const void *actions_dev, int action_dtype, float *final_obs_dev,
                      void *stream, int *set_out);
+/* Synchronises `stream`; *timed_out_peer = -1 when every step barrier so far completed, else the rank
+ * whose rows did not arrive in time (the call then fails). */
+int b200gym_p2p_status(b200gym_t *h, void *stream, int *timed_out_peer);
 
 /*
  * Vector-aware wrappers of the reference, fused on the device.  Stateless utilities:

@@ -33,7 +33,7 @@ def test_library_builds_and_exports_every_declared_symbol():
 
 def test_shape_queries_need_no_device():
     lib = _lib.load()
-    assert lib.b200gym_version() == 1
+    assert lib.b200gym_version() == 2
     assert [lib.b200gym_obs_dim(k) for k in range(9)] == [4, 2, 2, 3, 6, 8, 24, 8, 24]
     assert [lib.b200gym_act_dim(k) for k in range(9)] == [0, 0, 1, 1, 0, 0, 4, 2, 4]
     assert [lib.b200gym_num_actions(k) for k in range(9)] == [2, 3, 0, 0, 3, 4, 0, 0, 0]

@@ -52,6 +52,10 @@ struct b200gym {
     bool is_lunar = false, is_walker = false;
     lunar::Opts lunar_opts{};
     unsigned long long *invalid = nullptr;  // sticky device counter
+    struct {                                // caller-owned buffers of the fused RecordEpisodeStatistics (all null = off)
+        float *acc = nullptr; int32_t *len = nullptr; float *r = nullptr; int32_t *l = nullptr;
+        unsigned long long *ring = nullptr, *counter = nullptr; int ring_size = 0;
+    } ep;
     int sm_count = 148;
     int occ[B200GYM_NUM_KINDS][3] = {};     // cached CTAs/SM of step_kernel_persistent per (kind, action width)
     int kernel_choice = 1;                  // 0: kernel A (one tile per CTA), 1: kernel P (resident grid, asynchronous
@@ -156,6 +160,14 @@ struct StepArgs {
     int32_t *reset_count;
     // fused all-gather (multi-GPU): every result is ALSO stored into the same rows of the peers'
     // gather buffers over NVLink (peer-mapped pointers, slice offset already applied)
+    // RecordEpisodeStatistics fused into the step (b200gym_set_episode_stats; nullptr = off): float32 return and
+    // int32 length accumulators, infos["episode"]["r"/"l"] rows of finishing envs, ring of recent episodes
+    float *ep_acc;
+    int32_t *ep_len;
+    float *ep_r;
+    int32_t *ep_l;
+    unsigned long long *ep_ring, *ep_counter;
+    int32_t ep_ring_size;
     int32_t bulk_sink;   // 1: use kernel G's staged bulk stores even without peers (host path: the output arrays are
                          // mapped host memory, where many small stores are what hurts)
     int32_t npeer;
@@ -201,6 +213,29 @@ __device__ __forceinline__ void store_scalars_all(const StepArgs &a, int64_t i, 
         a.peer_reward[p][i] = reward;
         a.peer_term[p][i] = term;
         a.peer_trunc[p][i] = trunc;
+    }
+}
+
+// RecordEpisodeStatistics.step (gym/wrappers/record_episode_statistics.py:103-151) for env i, fused into the step
+// kernels: `episode_returns += rewards` on a float32 array with float64 rewards (add in float64, round to float32),
+// `episode_lengths += 1`; on terminated | truncated emit both, append to the ring (return_queue / length_queue),
+// start over from zero.
+__device__ __forceinline__ void episode_account(const StepArgs &a, int64_t i, double reward, bool done) {
+    if (!a.ep_acc) return;
+    const float ret = (float)((double)a.ep_acc[i] + reward);
+    const int32_t len = a.ep_len[i] + 1;
+    if (done) {
+        a.ep_r[i] = ret;
+        a.ep_l[i] = len;
+        const unsigned long long slot = atomicAdd(a.ep_counter, 1ULL);
+        if (a.ep_ring_size > 0)   // one 64-bit store per episode {length : return bits}: a slot never mixes two episodes
+            a.ep_ring[slot % (unsigned long long)a.ep_ring_size] =
+                ((unsigned long long)(uint32_t)len << 32) | (unsigned long long)__float_as_uint(ret);
+        a.ep_acc[i] = 0.0f;
+        a.ep_len[i] = 0;
+    } else {
+        a.ep_acc[i] = ret;
+        a.ep_len[i] = len;
     }
 }
 
@@ -289,6 +324,7 @@ __device__ __forceinline__ bool advance_env(const StepArgs &a, const Sink &sink,
     const bool needs_reset = (terminated || truncated) && a.autoreset;   // sync_vector_env.py:152-156
 
     sink.scalars(i, reward, terminated ? 1 : 0, truncated ? 1 : 0);
+    episode_account(a, i, reward, terminated || truncated);
     if (needs_reset) {
         if (a.final_obs) store_row<E::D>(a.final_obs, i, obs);           // info["final_observation"]
     } else {
@@ -619,6 +655,7 @@ __global__ void __launch_bounds__(kLunarMaxThreads, 2) lunar_step_kernel(const S
     elapsed += 1;                                                        // time_limit.py:51
     const bool truncated = (a.max_steps > 0) && (elapsed >= a.max_steps);
     store_scalars_all(a, i, reward, terminated ? 1 : 0, truncated ? 1 : 0);
+    episode_account(a, i, reward, terminated || truncated);
     bool deferred = false;
     if ((terminated || truncated) && a.autoreset) {                      // sync_vector_env.py:152-156
         if (a.final_obs) store_row<8>(a.final_obs, i, obs);
@@ -645,7 +682,7 @@ __global__ void __launch_bounds__(kLunarThreads) lunar_reset_list_kernel(const S
     for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < cnt; idx += gridDim.x * blockDim.x) {
         const int64_t i = a.first + a.reset_list[a.first + idx];
         lunar::World W;
-        W.flags = a.lunar_rec[(int64_t)lunar::W_FLAGS * a.n + i] & 16u;
+        W.flags = a.lunar_rec[(int64_t)lunar::W_FLAGS * a.n + i] & b2l::kFlagsKept;
         W.wind_idx = O.wind ? (int32_t)a.lunar_rec[(int64_t)lunar::W_WIND * a.n + i] : 0;
         W.torque_idx = O.wind ? (int32_t)a.lunar_rec[(int64_t)(lunar::W_WIND + 1) * a.n + i] : 0;
         Pcg64 g = pcg64_load(a.rng + 4 * i);
@@ -665,7 +702,7 @@ __global__ void __launch_bounds__(kLunarThreads) lunar_reset_kernel(uint32_t *re
     if (i >= n) return;
     if (mask && !mask[i]) return;
     lunar::World W;
-    W.flags = rec[(int64_t)lunar::W_FLAGS * n + i] & 16u;  // the b2World object survives reset()
+    W.flags = rec[(int64_t)lunar::W_FLAGS * n + i] & b2l::kFlagsKept;  // the b2World object survives reset()
     W.wind_idx = O.wind ? (int32_t)rec[(int64_t)lunar::W_WIND * n + i] : 0;          // so do wind_idx / torque_idx
     W.torque_idx = O.wind ? (int32_t)rec[(int64_t)(lunar::W_WIND + 1) * n + i] : 0;
     Pcg64 g = pcg64_load(rng + 4 * i);
@@ -698,6 +735,12 @@ __global__ void lunar_bodies_kernel(const uint32_t *rec, const int32_t *elapsed,
     flags[i * 6 + 3] = 1; flags[i * 6 + 4] = elapsed[i]; flags[i * 6 + 5] = touching;
 }
 
+// envs whose manifold table ever overflowed (b2l::kFlagOverflow in the record's flag word)
+__global__ void box2d_overflow_kernel(const uint32_t *flags_row, int64_t n, unsigned long long *count) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n && (flags_row[i] & b2l::kFlagOverflow)) atomicAdd(count, 1ULL);
+}
+
 static int lunar_upload_consts(b200gym *h) {
     lunar::Consts c;
     b2l_host::lunar_consts(c);
@@ -724,6 +767,7 @@ __global__ void __launch_bounds__(kLunarThreads, 4) walker_step_kernel(const Ste
     elapsed += 1;                                                        // time_limit.py:51
     const bool truncated = (a.max_steps > 0) && (elapsed >= a.max_steps);
     store_scalars_all(a, i, reward, terminated ? 1 : 0, truncated ? 1 : 0);
+    episode_account(a, i, reward, terminated || truncated);
     bool deferred = false;
     if ((terminated || truncated) && a.autoreset) {                      // sync_vector_env.py:152-156
         if (a.final_obs) store_row<24>(a.final_obs, i, obs);
@@ -750,7 +794,7 @@ __global__ void __launch_bounds__(kLunarThreads, 4) walker_reset_list_kernel(con
         walker::World W;
         walker::Rng r;
         walker::bind_world(W, a.lunar_rec, a.n, i);
-        W.flags = a.lunar_rec[(int64_t)walker::W_FLAGS * a.n + i] & b2l::kFlagStepped;
+        W.flags = a.lunar_rec[(int64_t)walker::W_FLAGS * a.n + i] & b2l::kFlagsKept;
         r.has32 = a.lunar_rec[(int64_t)walker::W_RNG32 * a.n + i];
         r.val32 = a.lunar_rec[(int64_t)(walker::W_RNG32 + 1) * a.n + i];
         r.g = pcg64_load(a.rng + 4 * i);
@@ -773,7 +817,7 @@ __global__ void __launch_bounds__(kLunarThreads) walker_reset_kernel(uint32_t *r
     walker::World W;
     walker::Rng r;
     walker::bind_world(W, rec, n, i);
-    W.flags = rec[(int64_t)walker::W_FLAGS * n + i] & b2l::kFlagStepped;  // the b2World object survives reset()
+    W.flags = rec[(int64_t)walker::W_FLAGS * n + i] & b2l::kFlagsKept;  // the b2World object survives reset()
     r.has32 = rec[(int64_t)walker::W_RNG32 * n + i];
     r.val32 = rec[(int64_t)(walker::W_RNG32 + 1) * n + i];
     r.g = pcg64_load(rng + 4 * i);
@@ -859,79 +903,101 @@ __global__ void __launch_bounds__(kThreads) episode_stats_kernel(const double *r
     }
 }
 
-// NormalizeObservation / NormalizeReward (gym/wrappers/normalize.py:8-144): RunningMeanStd over the
-// batch axis.  Pass 1 accumulates per-column sum and sum of squared deviations from a pivot (the
-// current running mean: numerically tame) in float64 with one atomic per CTA and column; pass 2
-// (one thread per column) folds the batch moments into the running ones (Chan et al., normalize.py:32-46);
-// pass 3 normalises.  `x` is float32 [n][D] (observations) or float64 [n] (discounted returns, D = 1).
-template <typename T>
-__global__ void __launch_bounds__(kThreads) moments_kernel(const T *x, int64_t n, int D, const double *pivot,
-                                                           double *sum, double *sumsq) {
-    __shared__ double sh[2][kThreads / 32];
-    for (int d = 0; d < D; d++) {
-        double s = 0.0, q = 0.0;
-        const double pv = pivot[d];
-        for (int64_t i = (int64_t)blockIdx.x * kThreads + threadIdx.x; i < n; i += (int64_t)gridDim.x * kThreads) {
-            const double v = (double)x[i * D + d] - pv;
-            s += v;
-            q += v * v;
+// NormalizeObservation / NormalizeReward (gym/wrappers/normalize.py:8-144): RunningMeanStd over the batch axis,
+// two launches per step and ONE pass over the batch for the moments.
+//   launch 1 (moments): the batch is read as a flat [n*D] stream; the CTA size is a multiple of D, so every
+//     thread stays on one column and the loads are perfectly coalesced whatever D is.  Per column: sum and sum of
+//     squares of the deviations from a pivot (the current running mean: numerically tame), float64, reduced through
+//     shared-memory atomics to one global atomic per CTA and column.
+//   (between the launches a sharded env all-reduces the 2*D sums across GPUs: torch.distributed, 8 * 2 * D bytes)
+//   launch 2 (apply): every CTA folds the batch moments into the running ones (Chan et al., normalize.py:32-46) on
+//     its own -- D <= 24 columns, a few dozen flops -- normalises its share of the batch with the NEW statistics
+//     (normalize.py:83-95) and CTA 0 publishes them.  Statistics and scratch are double-buffered by step parity, so
+//     no CTA can read a half-updated value.
+// stats layout (float64, caller-owned): [2][2*D + 1] = {mean[D], var[D], count}; scratch: [2][2*D] = {sum[D], sumsq[D]}.
+constexpr int kMaxNormDim = 24;
+
+__device__ __forceinline__ int norm_block(int D) { return (D == 3 || D == 6 || D == 24) ? 192 : 256; }
+
+template <typename T, bool RETURNS>
+__global__ void rms_moments_kernel(const T *x, double *returns, const double *reward, double gamma, int64_t total, int D,
+                                   const double *stats, double *scratch) {
+    __shared__ double sh[2][kMaxNormDim];
+    const int tid = threadIdx.x;
+    if (tid < D) { sh[0][tid] = 0.0; sh[1][tid] = 0.0; }
+    __syncthreads();
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;      // a multiple of D: the column of a thread is fixed
+    const int64_t start = (int64_t)blockIdx.x * blockDim.x + tid;
+    const int col = (int)(start % D);
+    const double pivot = stats[col];
+    double s = 0.0, q = 0.0;
+    for (int64_t k = start; k < total; k += stride) {
+        double v;
+        if constexpr (RETURNS) {   // NormalizeReward.step (normalize.py:130): returns = returns * gamma + reward
+            v = returns[k] * gamma + reward[k];
+            returns[k] = v;
+        } else {
+            v = (double)x[k];
         }
-        for (int o = 16; o > 0; o >>= 1) { s += __shfl_xor_sync(0xffffffffu, s, o); q += __shfl_xor_sync(0xffffffffu, q, o); }
-        if ((threadIdx.x & 31) == 0) { sh[0][threadIdx.x >> 5] = s; sh[1][threadIdx.x >> 5] = q; }
-        __syncthreads();
-        if (threadIdx.x == 0) {
-            double ts = 0.0, tq = 0.0;
-            for (int w = 0; w < kThreads / 32; w++) { ts += sh[0][w]; tq += sh[1][w]; }
-            atomicAdd(&sum[d], ts);
-            atomicAdd(&sumsq[d], tq);
-        }
-        __syncthreads();
+        v -= pivot;
+        s += v;
+        q += v * v;
+    }
+    atomicAdd(&sh[0][col], s);
+    atomicAdd(&sh[1][col], q);
+    __syncthreads();
+    if (tid < D) {
+        atomicAdd(&scratch[tid], sh[0][tid]);
+        atomicAdd(&scratch[D + tid], sh[1][tid]);
     }
 }
 
-__global__ void rms_update_kernel(double *mean, double *var, double *count, double *sum, double *sumsq, int64_t n, int D) {
-    const int d = blockIdx.x * blockDim.x + threadIdx.x;
-    if (d >= D) return;
-    // batch mean / (population) variance from the pivoted sums
-    const double bn = (double)n;
-    const double dm = sum[d] / bn;                 // batch_mean - pivot (pivot = old mean)
-    const double batch_var = sumsq[d] / bn - dm * dm;
-    const double cnt = count[0];
-    // update_mean_var_count_from_moments (normalize.py:32-46)
-    const double delta = dm;                       // batch_mean - mean
+// update_mean_var_count_from_moments (normalize.py:32-46) for column d, from the pivoted batch sums
+__device__ __forceinline__ void chan_update(const double *stats, const double *scratch, int D, int d, double bn, double &mean,
+                                            double &var, double &count) {
+    const double dm = scratch[d] / bn;                 // batch_mean - pivot (pivot = old mean) = delta
+    const double batch_var = scratch[D + d] / bn - dm * dm;
+    const double cnt = stats[2 * D];
     const double tot = cnt + bn;
-    const double new_mean = mean[d] + delta * bn / tot;
-    const double m2 = var[d] * cnt + batch_var * bn + delta * delta * cnt * bn / tot;
-    mean[d] = new_mean;
-    var[d] = m2 / tot;
-    sum[d] = 0.0;
-    sumsq[d] = 0.0;
+    mean = stats[d] + dm * bn / tot;
+    const double m2 = stats[D + d] * cnt + batch_var * bn + dm * dm * cnt * bn / tot;
+    var = m2 / tot;
+    count = tot;
+}
+
+template <bool REWARD>
+__global__ void rms_apply_kernel(const float *x, float *out, const double *reward, double *out_r, double *returns,
+                                 const uint8_t *term, const uint8_t *trunc, int64_t total, int D, const double *stats,
+                                 double *stats_next, const double *scratch, double *scratch_next, double batch_count,
+                                 double eps, int update) {
+    __shared__ double sh_mean[kMaxNormDim], sh_inv[kMaxNormDim];
+    const int tid = threadIdx.x;
+    if (tid < D) {
+        double mean = stats[tid], var = stats[D + tid], count = stats[2 * D];
+        if (update) chan_update(stats, scratch, D, tid, batch_count, mean, var, count);
+        sh_mean[tid] = mean;
+        sh_inv[tid] = sqrt(var + eps);
+        if (blockIdx.x == 0 && update) {
+            stats_next[tid] = mean;
+            stats_next[D + tid] = var;
+            if (tid == 0) stats_next[2 * D] = count;
+            scratch_next[tid] = 0.0;                   // next step accumulates into the other scratch buffer
+            scratch_next[D + tid] = 0.0;
+        }
+    }
     __syncthreads();
-    if (d == 0) count[0] = tot;
-}
-
-__global__ void __launch_bounds__(kThreads) normalize_obs_kernel(const float *x, float *out, int64_t total, int D,
-                                                                 const double *mean, const double *var, double eps) {
-    const int64_t k = (int64_t)blockIdx.x * kThreads + threadIdx.x;
-    if (k >= total) return;
-    const int d = (int)(k % D);
-    out[k] = (float)(((double)x[k] - mean[d]) / sqrt(var[d] + eps));   // normalize.py:95
-}
-
-// NormalizeReward.step (normalize.py:130-138): returns = returns * gamma + reward ... returns[dones] = 0
-__global__ void __launch_bounds__(kThreads) discounted_return_kernel(double *returns, const double *reward, double gamma,
-                                                                     int64_t n) {
-    const int64_t i = (int64_t)blockIdx.x * kThreads + threadIdx.x;
-    if (i >= n) return;
-    returns[i] = returns[i] * gamma + reward[i];
-}
-__global__ void __launch_bounds__(kThreads) normalize_reward_kernel(const double *reward, double *out, double *returns,
-                                                                    const uint8_t *term, const uint8_t *trunc, int64_t n,
-                                                                    const double *var, double eps) {
-    const int64_t i = (int64_t)blockIdx.x * kThreads + threadIdx.x;
-    if (i >= n) return;
-    out[i] = reward[i] / sqrt(var[0] + eps);                           // normalize.py:143
-    if (term[i] | trunc[i]) returns[i] = 0.0;                          // :135-136
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    const int64_t start = (int64_t)blockIdx.x * blockDim.x + tid;
+    const int col = (int)(start % D);
+    const double mean = sh_mean[col], sd = sh_inv[col];
+    for (int64_t k = start; k < total; k += stride) {
+        if constexpr (REWARD) {
+            out_r[k] = reward[k] / sd;                                 // normalize.py:143 (no mean subtraction)
+            if (term[k] | trunc[k]) returns[k] = 0.0;                  // :135-136
+        } else {
+            out[k] = (float)(((double)x[k] - mean) / sd);              // normalize.py:95
+        }
+    }
 }
 
 // ---- cross-GPU step barrier for the fused all-gather ---------------------------------------
@@ -1170,6 +1236,16 @@ struct DeviceGuard {
     }
 };
 
+// the device a caller-owned buffer lives on (these utilities take no handle)
+static int device_of(const void *ptr) {
+    cudaPointerAttributes at;
+    if (cudaPointerGetAttributes(&at, ptr) != cudaSuccess || at.type != cudaMemoryTypeDevice) {
+        cudaGetLastError();
+        return -1;
+    }
+    return at.device;
+}
+
 extern "C" int b200gym_create(const b200gym_config *cfg, int64_t num_envs, int device, b200gym_t **out) {
     if (!cfg || !out) return fail(nullptr, "b200gym_create: null argument");
     *out = nullptr;
@@ -1354,6 +1430,8 @@ static StepArgs make_args(b200gym *h, const void *actions, float *obs, double *r
     a.reset_list = nullptr; a.reset_count = nullptr;
     a.npeer = 0;
     a.bulk_sink = 0;
+    a.ep_acc = h->ep.acc; a.ep_len = h->ep.len; a.ep_r = h->ep.r; a.ep_l = h->ep.l;
+    a.ep_ring = h->ep.ring; a.ep_counter = h->ep.counter; a.ep_ring_size = h->ep.ring_size;
     return a;
 }
 
@@ -1376,6 +1454,27 @@ extern "C" int b200gym_invalid_actions(b200gym_t *h, void *stream, int64_t *coun
     CK(h, cudaMemcpyAsync(&v, h->invalid, sizeof v, cudaMemcpyDeviceToHost, st));
     CK(h, cudaMemsetAsync(h->invalid, 0, sizeof v, st));
     CK(h, cudaStreamSynchronize(st));
+    *count_out = (int64_t)v;
+    return 0;
+}
+
+extern "C" int b200gym_box2d_overflows(b200gym_t *h, void *stream, int64_t *count_out) {
+    if (!h || !count_out) return fail(h, "b200gym_box2d_overflows: null argument");
+    if (!h->is_lunar && !h->is_walker) return fail(h, "b200gym_box2d_overflows: not a Box2D-task handle");
+    DeviceGuard guard(h->device);
+    cudaStream_t st = (cudaStream_t)stream;
+    unsigned long long *d = nullptr, v = 0;
+    CK(h, cudaMalloc((void **)&d, sizeof *d));
+    cudaError_t e = cudaMemsetAsync(d, 0, sizeof *d, st);
+    if (e == cudaSuccess) {
+        const int64_t row = h->is_lunar ? lunar::W_FLAGS : walker::W_FLAGS;
+        box2d_overflow_kernel<<<blocks_for(h->n), kThreads, 0, st>>>(h->lunar_rec + row * h->n, h->n, d);
+        e = cudaGetLastError();
+    }
+    if (e == cudaSuccess) e = cudaMemcpyAsync(&v, d, sizeof v, cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+    cudaFree(d);
+    if (e != cudaSuccess) return fail(h, "b200gym_box2d_overflows: %s", cudaGetErrorString(e));
     *count_out = (int64_t)v;
     return 0;
 }
@@ -1516,6 +1615,20 @@ extern "C" int b200gym_p2p_status(b200gym_t *h, void *stream, int *timed_out_pee
 }
 
 // ---- stateless device utilities for the vector-aware wrappers -----------------------
+extern "C" int b200gym_set_episode_stats(b200gym_t *h, float *return_acc_dev, int32_t *length_acc_dev, float *episode_r_dev,
+                                         int32_t *episode_l_dev, uint64_t *ring_dev, uint64_t *counter_dev, int ring_size) {
+    if (!h) return fail(h, "b200gym_set_episode_stats: null handle");
+    if (!return_acc_dev) {   // off
+        h->ep = {};
+        return 0;
+    }
+    if (!length_acc_dev || !episode_r_dev || !episode_l_dev || !counter_dev || ring_size < 0 || (ring_size > 0 && !ring_dev))
+        return fail(h, "b200gym_set_episode_stats: bad argument");
+    h->ep.acc = return_acc_dev; h->ep.len = length_acc_dev; h->ep.r = episode_r_dev; h->ep.l = episode_l_dev;
+    h->ep.ring = (unsigned long long *)ring_dev; h->ep.counter = (unsigned long long *)counter_dev; h->ep.ring_size = ring_size;
+    return 0;
+}
+
 extern "C" int b200gym_episode_stats(const double *reward_dev, const uint8_t *terminated_dev, const uint8_t *truncated_dev,
                                      float *return_acc_dev, int32_t *length_acc_dev, float *episode_r_dev,
                                      int32_t *episode_l_dev, uint8_t *episode_mask_dev, uint64_t *ring_dev,
@@ -1523,6 +1636,9 @@ extern "C" int b200gym_episode_stats(const double *reward_dev, const uint8_t *te
     if (!reward_dev || !terminated_dev || !truncated_dev || !return_acc_dev || !length_acc_dev || !episode_r_dev ||
         !episode_l_dev || !episode_mask_dev || !counter_dev || n <= 0 || (ring_size > 0 && !ring_dev))
         return fail(nullptr, "b200gym_episode_stats: bad argument");
+    const int dev = device_of(reward_dev);
+    if (dev < 0) return fail(nullptr, "b200gym_episode_stats: reward is not a device pointer");
+    DeviceGuard guard(dev);
     episode_stats_kernel<<<blocks_for(n), kThreads, 0, (cudaStream_t)stream>>>(
         reward_dev, terminated_dev, truncated_dev, return_acc_dev, length_acc_dev, episode_r_dev, episode_l_dev,
         episode_mask_dev, (unsigned long long *)ring_dev, (unsigned long long *)counter_dev, ring_size, n);
@@ -1530,38 +1646,77 @@ extern "C" int b200gym_episode_stats(const double *reward_dev, const uint8_t *te
     return 0;
 }
 
-extern "C" int b200gym_running_norm_obs(const float *obs_dev, float *out_dev, int64_t n, int dim, double *mean_dev,
-                                        double *var_dev, double *count_dev, double *scratch_dev /* 2*dim doubles, zeroed */,
-                                        double epsilon, int update, void *stream) {
-    if (!obs_dev || !out_dev || !mean_dev || !var_dev || !count_dev || !scratch_dev || n <= 0 || dim <= 0)
-        return fail(nullptr, "b200gym_running_norm_obs: bad argument");
+static int norm_dims_ok(int dim) { return dim == 1 || dim == 2 || dim == 3 || dim == 4 || dim == 6 || dim == 8 || dim == 24; }
+
+static unsigned norm_grid(int64_t total, int block) {
+    int64_t g = (total + block - 1) / block;
+    if (g > 1184) g = 1184;       // 148 SMs x 8: one resident wave, grid-stride beyond
+    return (unsigned)(g < 1 ? 1 : g);
+}
+
+extern "C" int b200gym_rms_moments(const void *x_dev, int is_f64, int64_t n, int dim, const double *stats_dev,
+                                   double *scratch_dev, void *stream) {
+    if (!x_dev || !stats_dev || !scratch_dev || n <= 0 || !norm_dims_ok(dim))
+        return fail(nullptr, "b200gym_rms_moments: bad argument (dim must be one of 1, 2, 3, 4, 6, 8, 24)");
+    const int dev = device_of(x_dev);
+    if (dev < 0) return fail(nullptr, "b200gym_rms_moments: x is not a device pointer");
+    DeviceGuard guard(dev);
+    const int block = (dim == 3 || dim == 6 || dim == 24) ? 192 : 256;
+    const int64_t total = n * dim;
     cudaStream_t st = (cudaStream_t)stream;
-    if (update) {
-        int64_t g = (n + kThreads - 1) / kThreads;
-        if (g > 592) g = 592;
-        moments_kernel<float><<<(unsigned)g, kThreads, 0, st>>>(obs_dev, n, dim, mean_dev, scratch_dev, scratch_dev + dim);
-        rms_update_kernel<<<1, 32 * ((dim + 31) / 32), 0, st>>>(mean_dev, var_dev, count_dev, scratch_dev, scratch_dev + dim, n, dim);
-    }
-    normalize_obs_kernel<<<blocks_for(n * dim), kThreads, 0, st>>>(obs_dev, out_dev, n * dim, dim, mean_dev, var_dev, epsilon);
+    if (is_f64)
+        rms_moments_kernel<double, false><<<norm_grid(total, block), block, 0, st>>>((const double *)x_dev, nullptr, nullptr,
+                                                                                   0.0, total, dim, stats_dev, scratch_dev);
+    else
+        rms_moments_kernel<float, false><<<norm_grid(total, block), block, 0, st>>>((const float *)x_dev, nullptr, nullptr,
+                                                                                  0.0, total, dim, stats_dev, scratch_dev);
     CK(nullptr, cudaGetLastError());
     return 0;
 }
 
-extern "C" int b200gym_running_norm_reward(const double *reward_dev, const uint8_t *terminated_dev,
-                                           const uint8_t *truncated_dev, double *returns_dev, double *out_dev, int64_t n,
-                                           double *mean_dev, double *var_dev, double *count_dev,
-                                           double *scratch_dev /* 2 doubles, zeroed */, double gamma, double epsilon,
-                                           void *stream) {
-    if (!reward_dev || !terminated_dev || !truncated_dev || !returns_dev || !out_dev || !mean_dev || !var_dev || !count_dev || !scratch_dev || n <= 0)
-        return fail(nullptr, "b200gym_running_norm_reward: bad argument");
-    cudaStream_t st = (cudaStream_t)stream;
-    discounted_return_kernel<<<blocks_for(n), kThreads, 0, st>>>(returns_dev, reward_dev, gamma, n);
-    int64_t g = (n + kThreads - 1) / kThreads;
-    if (g > 592) g = 592;
-    moments_kernel<double><<<(unsigned)g, kThreads, 0, st>>>(returns_dev, n, 1, mean_dev, scratch_dev, scratch_dev + 1);
-    rms_update_kernel<<<1, 32, 0, st>>>(mean_dev, var_dev, count_dev, scratch_dev, scratch_dev + 1, n, 1);
-    normalize_reward_kernel<<<blocks_for(n), kThreads, 0, st>>>(reward_dev, out_dev, returns_dev, terminated_dev, truncated_dev, n,
-                                                                var_dev, epsilon);
+extern "C" int b200gym_return_moments(double *returns_dev, const double *reward_dev, double gamma, int64_t n,
+                                      const double *stats_dev, double *scratch_dev, void *stream) {
+    if (!returns_dev || !reward_dev || !stats_dev || !scratch_dev || n <= 0)
+        return fail(nullptr, "b200gym_return_moments: bad argument");
+    const int dev = device_of(returns_dev);
+    if (dev < 0) return fail(nullptr, "b200gym_return_moments: returns is not a device pointer");
+    DeviceGuard guard(dev);
+    rms_moments_kernel<double, true><<<norm_grid(n, 256), 256, 0, (cudaStream_t)stream>>>(nullptr, returns_dev, reward_dev, gamma,
+                                                                                         n, 1, stats_dev, scratch_dev);
+    CK(nullptr, cudaGetLastError());
+    return 0;
+}
+
+extern "C" int b200gym_rms_apply_obs(const float *obs_dev, float *out_dev, int64_t n, int dim, const double *stats_dev,
+                                     double *stats_next_dev, const double *scratch_dev, double *scratch_next_dev,
+                                     double batch_count, double epsilon, int update, void *stream) {
+    if (!obs_dev || !out_dev || !stats_dev || !stats_next_dev || !scratch_dev || !scratch_next_dev || n <= 0 ||
+        !norm_dims_ok(dim))
+        return fail(nullptr, "b200gym_rms_apply_obs: bad argument");
+    const int dev = device_of(obs_dev);
+    if (dev < 0) return fail(nullptr, "b200gym_rms_apply_obs: obs is not a device pointer");
+    DeviceGuard guard(dev);
+    const int block = (dim == 3 || dim == 6 || dim == 24) ? 192 : 256;
+    rms_apply_kernel<false><<<norm_grid(n * dim, block), block, 0, (cudaStream_t)stream>>>(
+        obs_dev, out_dev, nullptr, nullptr, nullptr, nullptr, nullptr, n * dim, dim, stats_dev, stats_next_dev, scratch_dev,
+        scratch_next_dev, batch_count, epsilon, update);
+    CK(nullptr, cudaGetLastError());
+    return 0;
+}
+
+extern "C" int b200gym_rms_apply_reward(const double *reward_dev, double *out_dev, double *returns_dev,
+                                        const uint8_t *terminated_dev, const uint8_t *truncated_dev, int64_t n,
+                                        const double *stats_dev, double *stats_next_dev, const double *scratch_dev,
+                                        double *scratch_next_dev, double batch_count, double epsilon, void *stream) {
+    if (!reward_dev || !out_dev || !returns_dev || !terminated_dev || !truncated_dev || !stats_dev || !stats_next_dev ||
+        !scratch_dev || !scratch_next_dev || n <= 0)
+        return fail(nullptr, "b200gym_rms_apply_reward: bad argument");
+    const int dev = device_of(reward_dev);
+    if (dev < 0) return fail(nullptr, "b200gym_rms_apply_reward: reward is not a device pointer");
+    DeviceGuard guard(dev);
+    rms_apply_kernel<true><<<norm_grid(n, 256), 256, 0, (cudaStream_t)stream>>>(
+        nullptr, nullptr, reward_dev, out_dev, returns_dev, terminated_dev, truncated_dev, n, 1, stats_dev, stats_next_dev,
+        scratch_dev, scratch_next_dev, batch_count, epsilon, 1);
     CK(nullptr, cudaGetLastError());
     return 0;
 }

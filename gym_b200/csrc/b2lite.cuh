@@ -101,6 +101,9 @@ constexpr float kFltMax = 3.402823466e+38f;
 
 constexpr int MAXV = 6;
 constexpr uint32_t kFlagStepped = 16u;  // World::flags bit: the b2World has stepped before (inv_dt0 != 0)
+constexpr uint32_t kFlagOverflow = 32u; // World::flags bit (sticky, survives reset): a touching pair was dropped because
+                                        // the scene's manifold table (kMaxVC) was full -- see world_step
+constexpr uint32_t kFlagsKept = kFlagStepped | kFlagOverflow;   // what reset() keeps of World::flags
 
 // Shape / mass constants of a polygon fixture + its body, computed once on the host with the same
 // float32 operations Box2D uses (b2PolygonShape::Set / ComputeMass, b2Body::ResetMassData).
@@ -607,10 +610,18 @@ __device__ __noinline__ void world_step(typename Scene::World &W, v2 force0, flo
             const int e = f;
             f--;
             if (f > e_hi && f < NE + p_lo) f = e_hi;   // from the lowest candidate polygon down to the highest candidate edge
-            const bool touching = m.pointCount > 0;
+            bool touching = m.pointCount > 0;
+            if (touching && nvc >= kMaxVC) {
+                // manifold table full: the pair is treated as NOT touching (no constraint, no warm-start slot, no
+                // BeginContact; EndContact if it was touching) -- the oracle applies the same rule with the same
+                // capacity (oracle/b2lite.h: max_contacts), so the two stay bit-identical even here; the env is
+                // marked so that tests / b200gym_box2d_overflows can assert it never happens in practice
+                touching = false;
+                W.flags |= kFlagOverflow;
+            }
             if (touching != was) Scene::on_event(W, b, touching);  // Begin/EndContact listener
             if (!touching) continue;
-            if (nvc < kMaxVC) {
+            {
                 VC &k = vc[nvc++];
                 k.body = b; k.edge = e; k.mType = m.type; k.mPointCount = m.pointCount; k.pointCount = m.pointCount;
                 k.localNormal = m.localNormal; k.localPoint = m.localPoint;

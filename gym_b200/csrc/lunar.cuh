@@ -10,18 +10,23 @@
 #include <cstdint>
 
 #include "b2lite.cuh"
+#include "glibc_trig.cuh"
 #include "rng.cuh"
 
 namespace lunar {
 
 using namespace b2l;
 using bgym::Pcg64;
+namespace gt = bgym::gt;   // math.sin / math.cos as glibc evaluates them
 
 #define LD __device__ __forceinline__
 
 constexpr int NB = 3;    // dynamic bodies: 0 lander, 1 leg (i=-1), 2 leg (i=+1)
 constexpr int NJ = 2;
 constexpr int NE = 11;   // ground edges: 0 base, 1..10 terrain
+#ifndef B2L_LUNAR_MAX_VC
+#define B2L_LUNAR_MAX_VC 8   // manifold-table capacity (the oracle's g_lunar_max_contacts); tests build a smaller one
+#endif
 constexpr int kSlots = 8;
 
 struct Consts {
@@ -59,7 +64,7 @@ struct World : WorldBase<NB, NJ, kSlots> {
 };
 
 struct Scene {
-    static constexpr int NB = lunar::NB, NJ = lunar::NJ, NE = lunar::NE, kSlots = lunar::kSlots, kMaxVC = 8;
+    static constexpr int NB = lunar::NB, NJ = lunar::NJ, NE = lunar::NE, kSlots = lunar::kSlots, kMaxVC = B2L_LUNAR_MAX_VC;
     static constexpr int NP = 0;   // no static polygons in this scene
     using World = lunar::World;
     LD static const ShapeConst &shape(int b) { return kC.shape[b == 0 ? 0 : 1]; }
@@ -95,16 +100,15 @@ LD void env_step(World &W, Pcg64 &rng, const Opts &O, int action, float ca0, flo
     float torque = 0.0f;
     if (O.wind && !(W.flags & 6u)) {                                             // :449-477
         const double kPi = 3.141592653589793;
-        const double wind_mag = tanh(sin(0.02 * W.wind_idx) + sin(kPi * 0.01 * W.wind_idx)) * O.wind_power;
+        const double wind_mag = tanh(gt::sin(0.02 * W.wind_idx) + gt::sin(kPi * 0.01 * W.wind_idx)) * O.wind_power;
         W.wind_idx += 1;
         lander_force = add(lander_force, V((float)wind_mag, 0.0f));              // ApplyForceToCenter
-        const double torque_mag = tanh(sin(0.02 * W.torque_idx) + sin(kPi * 0.01 * W.torque_idx)) * O.turbulence_power;
+        const double torque_mag = tanh(gt::sin(0.02 * W.torque_idx) + gt::sin(kPi * 0.01 * W.torque_idx)) * O.turbulence_power;
         W.torque_idx += 1;
         torque += (float)torque_mag;                                             // ApplyTorque
     }
     const double ang = (double)L.a;
-    double tip0, tip1;
-    sincos(ang, &tip0, &tip1);                                                   // :487
+    const double tip0 = gt::sin(ang), tip1 = gt::cos(ang);                       // :487 math.sin / math.cos
     const double side0 = -tip1, side1 = tip0;
     const double disp0 = bgym::pcg64_uniform(rng, -1.0, +1.0) / SCALE;          // :489
     const double disp1 = bgym::pcg64_uniform(rng, -1.0, +1.0) / SCALE;
@@ -188,7 +192,7 @@ LD void env_step(World &W, Pcg64 &rng, const Opts &O, int action, float ca0, flo
 LD void env_reset(World &W, Pcg64 &rng, const Opts &O, float (&obs)[8]) {
     const double SCALE = 30.0;
     const double Wd = 600 / SCALE, Hd = 400 / SCALE;
-    const uint32_t stepped = W.flags & 16u;
+    const uint32_t stepped = W.flags & kFlagsKept;
     double height[12];
     for (int i = 0; i < 12; i++) height[i] = bgym::pcg64_uniform(rng, 0, Hd / 2);   // :326
     const double helipad_y = Hd / 4;

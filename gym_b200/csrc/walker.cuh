@@ -23,6 +23,9 @@ using bgym::Pcg64;
 constexpr int NB = 5;     // 0 hull, 1 leg(-1), 2 lower(-1), 3 leg(+1), 4 lower(+1)
 constexpr int NJ = 4;     // 0 hip(-1), 1 knee(-1), 2 hip(+1), 3 knee(+1)   (self.joints order)
 constexpr int NE = 199;   // terrain edges i -> i+1
+#ifndef B2L_WALKER_MAX_VC
+#define B2L_WALKER_MAX_VC 10   // manifold-table capacity (the oracle's g_walker_max_contacts)
+#endif
 constexpr int kSlots = 10;
 constexpr int kTerrain = 200;
 
@@ -73,7 +76,7 @@ LD void poly_window(const World &W, float lo_x, float hi_x, int &lo, int &hi) {
 
 template <bool HC>
 struct SceneT {
-    static constexpr int NB = walker::NB, NJ = walker::NJ, NE = walker::NE, kSlots = walker::kSlots, kMaxVC = 10;
+    static constexpr int NB = walker::NB, NJ = walker::NJ, NE = walker::NE, kSlots = walker::kSlots, kMaxVC = B2L_WALKER_MAX_VC;
     static constexpr int NP = HC ? walker::NP : 0;
     using World = walker::World;
     // fd_polygon: friction 2.5 (bipedal_walker.py:180-184)
@@ -262,7 +265,7 @@ __device__ __noinline__ void env_reset(World &W, Rng &rng, float (&obs)[24]) {
     uint32_t *terrain_out = W.terrain;
     const double SCALE = 30.0;
     const double TERRAIN_HEIGHT = 400 / SCALE / 4, TERRAIN_STEP = 14 / SCALE;
-    const uint32_t stepped = W.flags & kFlagStepped;
+    const uint32_t stepped = W.flags & kFlagsKept;
     {   // _generate_terrain(hardcore) :277-402
         enum { GRASS = 0, STUMP, STAIRS, PIT, STATES };
         int state = GRASS;

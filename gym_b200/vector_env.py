@@ -465,6 +465,15 @@ class B200VectorEnv:
                                                       ctypes.c_void_p(flags.data_ptr()), self._stream()), self._handle)
         return bodies.view(self.num_envs, 3, 6), flags
 
+    def box2d_overflows(self):
+        """Box2D tasks: number of envs in which a touching pair was ever dropped because the scene's manifold table
+        (8 pairs for LunarLander*, 10 for BipedalWalker*) was full -- i.e. where the physics knowingly departs from
+        Box2D (include/b200gym.h: b200gym_box2d_overflows).  Synchronises."""
+        self._assert_open("box2d_overflows")
+        count = ctypes.c_int64(0)
+        _lib.check(self._lib.b200gym_box2d_overflows(self._handle, self._stream(), ctypes.byref(count)), self._handle)
+        return int(count.value)
+
     def lunar_wind_idx(self):
         """LunarLander(enable_wind=True) only: the per-env (wind_idx, torque_idx) int32 arrays
         (lunar_lander.py:234-235,461,472), read back from the device."""

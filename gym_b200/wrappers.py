@@ -5,9 +5,11 @@
 * ``VectorListInfo``  gym/wrappers/vector_list_info.py:56-111
 * ``step_api_compatibility``  gym/utils/step_api_compatibility.py:24-161
 
-The first three run as fused CUDA kernels through the C ABI (one or a few launches per step,
-no Python loop over the batch, no host synchronisation); the last two are host-side adapters.
-They wrap a ``B200VectorEnv`` with ``backend="torch"``.
+The first three run on the device through the C ABI -- ``RecordEpisodeStatistics`` inside the step
+kernel itself (no extra launch), the normalisers as two launches per step with one pass over the batch
+for the moments and, for sharded envs, an all-reduce of the 2 x dim batch sums in between -- with no
+Python loop over the batch and no host synchronisation; the last two are host-side adapters.  They wrap
+a ``B200VectorEnv`` with ``backend="torch"`` (or a ``ShardedVectorEnv``).
 """
 import ctypes
 import time
@@ -80,17 +82,38 @@ class RecordEpisodeStatistics(VectorWrapper):
         self.episode_lengths.zero_()
         return out
 
+    def _fused_target(self):
+        """The engine handle whose step kernel can do the bookkeeping itself: the wrapped env must be the
+        B200VectorEnv proper (torch backend) -- not a sharded env returning gathered global tensors, not another
+        wrapper that changes rewards."""
+        from gym_b200.vector_env import B200VectorEnv
+        e = self.env
+        return e if (isinstance(e, B200VectorEnv) and e.backend == "torch" and e.num_envs == self.num_envs) else None
+
     def step(self, actions):
-        obs, rew, term, trunc, infos = self.env.step(actions)
         self._flip ^= 1
         k = self._flip
-        env = self.env.unwrapped
-        _lib.check(env._lib.b200gym_episode_stats(
-            _p(rew), _p(term), _p(trunc), _p(self.episode_returns), _p(self.episode_lengths), _p(self._ep_r[k]),
-            _p(self._ep_l[k]), _p(self._ep_m[k]), _p(self._ring), _p(self._counter),
-            self.deque_size, self.num_envs, env._stream()))
+        fused = self._fused_target()
+        if fused is not None:
+            # one call that only stores pointers; the step kernel launched next does the accounting
+            _lib.check(fused._lib.b200gym_set_episode_stats(
+                fused._handle, _p(self.episode_returns), _p(self.episode_lengths), _p(self._ep_r[k]), _p(self._ep_l[k]),
+                _p(self._ring), _p(self._counter), self.deque_size), fused._handle)
+            try:
+                obs, rew, term, trunc, infos = self.env.step(actions)
+            finally:
+                fused._lib.b200gym_set_episode_stats(fused._handle, None, None, None, None, None, None, 0)
+            mask = term | trunc
+        else:
+            obs, rew, term, trunc, infos = self.env.step(actions)
+            env = self.env.unwrapped
+            _lib.check(env._lib.b200gym_episode_stats(
+                _p(rew), _p(term), _p(trunc), _p(self.episode_returns), _p(self.episode_lengths), _p(self._ep_r[k]),
+                _p(self._ep_l[k]), _p(self._ep_m[k]), _p(self._ring), _p(self._counter),
+                self.deque_size, self.num_envs, env._stream()))
+            mask = self._ep_m[k]
         infos["episode"] = {"r": self._ep_r[k], "l": self._ep_l[k], "t": round(time.perf_counter() - self.t0, 6)}
-        infos["_episode"] = self._ep_m[k]
+        infos["_episode"] = mask
         return obs, rew, term, trunc, infos
 
     @property
@@ -121,36 +144,87 @@ def unpack_episode_ring(words, count, deque_size, returns):
 
 
 class _RunningMeanStd:
-    """Device copy of RunningMeanStd's state (normalize.py:8-29): mean 0, var 1, count epsilon."""
+    """Device copy of RunningMeanStd's state (normalize.py:8-29): mean 0, var 1, count epsilon.
 
-    def __init__(self, torch, shape, device, epsilon=1e-4):
-        self.mean = torch.zeros(shape, dtype=torch.float64, device=device)
-        self.var = torch.ones(shape, dtype=torch.float64, device=device)
-        self.count = torch.full((1,), epsilon, dtype=torch.float64, device=device)
-        self.scratch = torch.zeros(2 * max(int(np.prod(shape)), 1), dtype=torch.float64, device=device)
+    ``stats[2][2*d + 1]`` = {mean, var, count} and ``scratch[2][2*d]`` = this step's batch sums, both
+    double-buffered by step parity (include/b200gym.h); ``cur`` is the set holding the current statistics."""
+
+    def __init__(self, torch, d, device, epsilon=1e-4):
+        self.d = int(d)
+        self.stats = torch.zeros((2, 2 * self.d + 1), dtype=torch.float64, device=device)
+        self.stats[:, self.d:2 * self.d] = 1.0
+        self.stats[:, 2 * self.d] = epsilon
+        self.scratch = torch.zeros((2, 2 * self.d), dtype=torch.float64, device=device)
+        self.cur = 0
+
+    @property
+    def mean(self):
+        return self.stats[self.cur, :self.d]
+
+    @property
+    def var(self):
+        return self.stats[self.cur, self.d:2 * self.d]
+
+    @property
+    def count(self):
+        return self.stats[self.cur, 2 * self.d:]
+
+
+def _shard_group(env, group):
+    """(process group, world size) when the batch statistics must be combined across GPUs: the wrapped env is this
+    rank's shard of a global batch (``first_index``/``ShardedVectorEnv(gather=None)``) and torch.distributed is up."""
+    if group is False:
+        return None, 1
+    try:
+        import torch.distributed as dist
+    except Exception:
+        return None, 1
+    if not (dist.is_available() and dist.is_initialized()):
+        return None, 1
+    if group is None and not getattr(env, "shards_global_batch", False):
+        return None, 1
+    g = None if group in (None, True) else group
+    return (g if g is not None else dist.group.WORLD), dist.get_world_size(g)
 
 
 class NormalizeObservation(VectorWrapper):
-    """obs -> (obs - running_mean) / sqrt(running_var + epsilon), statistics over the whole batch."""
+    """obs -> (obs - running_mean) / sqrt(running_var + epsilon), statistics over the whole batch.
 
-    def __init__(self, env, epsilon=1e-8):
+    ``group``: a torch.distributed process group (or True for the default one) when ``env`` is ONE RANK'S SHARD of
+    a global batch: the per-column batch sums are all-reduced over the group before the running statistics are
+    updated (normalize.py:32-46 applied to the global batch), so every rank normalises with the same numbers."""
+
+    def __init__(self, env, epsilon=1e-8, group=None):
         super().__init__(env)
         import torch
         self._torch = torch
         self.num_envs, self.is_vector_env = env.num_envs, True
         self.epsilon = float(epsilon)
         d = env.single_observation_space.shape[0]
-        self.obs_rms = _RunningMeanStd(torch, (d,), env.device)
-        self._out = [torch.zeros((env.num_envs, d), dtype=torch.float32, device=env.device) for _ in range(2)]
+        self.obs_rms = _RunningMeanStd(torch, d, env.unwrapped.device)
+        self._out = [None, None]
         self._flip = 0
+        self._group, self._world = _shard_group(env, group)
 
     def _normalize(self, obs):
+        torch = self._torch
         self._flip ^= 1
+        if self._out[self._flip] is None or self._out[self._flip].shape != obs.shape:
+            self._out[self._flip] = torch.empty_like(obs)
         out = self._out[self._flip]
         env = self.env.unwrapped
-        r = self.obs_rms
-        _lib.check(env._lib.b200gym_running_norm_obs(_p(obs), _p(out), obs.shape[0], obs.shape[1], _p(r.mean), _p(r.var),
-                                                     _p(r.count), _p(r.scratch), self.epsilon, 1, env._stream()))
+        r, lib = self.obs_rms, env._lib
+        n, d = obs.shape
+        st, sc = r.stats[r.cur], r.scratch[r.cur]
+        with torch.cuda.device(obs.device):
+            _lib.check(lib.b200gym_rms_moments(_p(obs), 0, n, d, _p(st), _p(sc), env._stream()))
+            if self._group is not None:
+                import torch.distributed as dist
+                dist.all_reduce(sc, group=self._group)
+            _lib.check(lib.b200gym_rms_apply_obs(_p(obs), _p(out), n, d, _p(st), _p(r.stats[r.cur ^ 1]), _p(sc),
+                                                 _p(r.scratch[r.cur ^ 1]), float(n * self._world), self.epsilon, 1,
+                                                 env._stream()))
+        r.cur ^= 1
         return out
 
     def reset(self, **kwargs):
@@ -165,25 +239,41 @@ class NormalizeObservation(VectorWrapper):
 class NormalizeReward(VectorWrapper):
     """Scale rewards so that the discounted return has unit running variance (normalize.py:98-144)."""
 
-    def __init__(self, env, gamma=0.99, epsilon=1e-8):
+    def __init__(self, env, gamma=0.99, epsilon=1e-8, group=None):
         super().__init__(env)
         import torch
+        self._torch = torch
         self.num_envs, self.is_vector_env = env.num_envs, True
         self.gamma, self.epsilon = float(gamma), float(epsilon)
-        self.return_rms = _RunningMeanStd(torch, (1,), env.device)
-        self.returns = torch.zeros(env.num_envs, dtype=torch.float64, device=env.device)
-        self._out = [torch.zeros(env.num_envs, dtype=torch.float64, device=env.device) for _ in range(2)]
+        dev = env.unwrapped.device
+        self.return_rms = _RunningMeanStd(torch, 1, dev)
+        self.returns = None
+        self._out = [None, None]
         self._flip = 0
+        self._group, self._world = _shard_group(env, group)
 
     def step(self, actions):
+        torch = self._torch
         obs, rew, term, trunc, infos = self.env.step(actions)
+        if self.returns is None or self.returns.shape != rew.shape:
+            self.returns = torch.zeros_like(rew)
         self._flip ^= 1
+        if self._out[self._flip] is None or self._out[self._flip].shape != rew.shape:
+            self._out[self._flip] = torch.empty_like(rew)
         out = self._out[self._flip]
         env = self.env.unwrapped
-        r = self.return_rms
-        _lib.check(env._lib.b200gym_running_norm_reward(_p(rew), _p(term), _p(trunc), _p(self.returns), _p(out),
-                                                        self.num_envs, _p(r.mean), _p(r.var), _p(r.count), _p(r.scratch),
-                                                        self.gamma, self.epsilon, env._stream()))
+        r, lib = self.return_rms, env._lib
+        n = rew.shape[0]
+        st, sc = r.stats[r.cur], r.scratch[r.cur]
+        with torch.cuda.device(rew.device):
+            _lib.check(lib.b200gym_return_moments(_p(self.returns), _p(rew), self.gamma, n, _p(st), _p(sc), env._stream()))
+            if self._group is not None:
+                import torch.distributed as dist
+                dist.all_reduce(sc, group=self._group)
+            _lib.check(lib.b200gym_rms_apply_reward(_p(rew), _p(out), _p(self.returns), _p(term), _p(trunc), n, _p(st),
+                                                    _p(r.stats[r.cur ^ 1]), _p(sc), _p(r.scratch[r.cur ^ 1]),
+                                                    float(n * self._world), self.epsilon, env._stream()))
+        r.cur ^= 1
         return obs, out, term, trunc, infos
 
 

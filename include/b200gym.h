@@ -268,36 +268,67 @@ int b200gym_step_p2p(b200gym_t *h, const void *actions_dev, int action_dtype, fl
 int b200gym_p2p_status(b200gym_t *h, void *stream, int *timed_out_peer);
 
 /*
- * Vector-aware wrappers of the reference, fused on the device.  Stateless utilities:
- * all state lives in caller-owned device buffers; errors are reported through b200gym_last_error(NULL).
+ * Vector-aware wrappers of the reference, on the device.  All state lives in caller-owned
+ * device buffers; the stateless utilities report errors through b200gym_last_error(NULL) and run on the
+ * device their buffers live on.
  *
- * b200gym_episode_stats replaces RecordEpisodeStatistics.step's Python loop over the batch
- * (gym/wrappers/record_episode_statistics.py:103-151): float32 return / int32 length accumulators,
- * infos["episode"]["r"/"l"] rows + `_episode` mask for finishing envs, and a ring of `ring_size`
- * recently finished episodes (return_queue / length_queue); *counter_dev counts finished episodes.
- * ring_dev[k] = (uint64)length << 32 | float32 bits of the return, written with one store per episode
- * into slot (episode number mod ring_size); episodes that finish in the same step are numbered in no
- * particular order (the reference appends them in env order), and when more than ring_size finish at once
- * the ring keeps an arbitrary ring_size of them.
+ * RecordEpisodeStatistics (gym/wrappers/record_episode_statistics.py:79-151), fused INTO the step kernels:
+ * after b200gym_set_episode_stats() every step launch also keeps the float32 return / int32 length
+ * accumulators (`episode_returns += rewards` on a float32 array: add in float64, round to float32),
+ * writes infos["episode"]["r"/"l"] for the envs whose episode ended in that step (the `_episode` mask is
+ * terminated | truncated) and appends them to a ring of `ring_size` recent episodes (return_queue /
+ * length_queue); *counter_dev counts finished episodes.  ring_dev[k] = (uint64)length << 32 | float32 bits
+ * of the return, one store per episode into slot (episode number mod ring_size); episodes that finish in
+ * the same step are numbered in no particular order (the reference appends them in env order), and when
+ * more than ring_size finish at once the ring keeps an arbitrary ring_size of them.  The pointers may be
+ * changed between steps (double buffering of the r / l rows); return_acc_dev == NULL switches it off.
+ * No extra launch, no extra pass over reward / flags.
  */
+int b200gym_set_episode_stats(b200gym_t *h, float *return_acc_dev, int32_t *length_acc_dev, float *episode_r_dev,
+                              int32_t *episode_l_dev, uint64_t *ring_dev, uint64_t *counter_dev, int ring_size);
+/* The same bookkeeping as ONE stand-alone launch over arbitrary (reward, terminated, truncated) device arrays --
+ * e.g. the gathered global tensors of a sharded env; also writes the `_episode` mask. */
 int b200gym_episode_stats(const double *reward_dev, const uint8_t *terminated_dev, const uint8_t *truncated_dev,
                           float *return_acc_dev, int32_t *length_acc_dev, float *episode_r_dev, int32_t *episode_l_dev,
                           uint8_t *episode_mask_dev, uint64_t *ring_dev, uint64_t *counter_dev,
                           int ring_size, int64_t n, void *stream);
 /*
- * NormalizeObservation (gym/wrappers/normalize.py:50-95): fold this batch into the running mean /
- * variance / count (RunningMeanStd, :8-46; float64 [dim], [dim], [1]) when `update`, then write
- * (obs - mean) / sqrt(var + epsilon) as float32.  scratch_dev: 2*dim float64, zero on first use.
+ * NormalizeObservation / NormalizeReward (gym/wrappers/normalize.py:8-144): RunningMeanStd over the batch axis in
+ * two launches per step and ONE pass over the batch for the moments.
+ *   stats   float64 [2][2*dim + 1] = {mean[dim], var[dim], count}, double-buffered: a step reads set `cur` and
+ *           writes set `cur ^ 1` (initialise set 0 to mean 0, var 1, count 1e-4: normalize.py:11-15)
+ *   scratch float64 [2][2*dim]     = per-column sums of (x - mean) and (x - mean)^2 of THIS step's batch,
+ *           accumulated into set `cur` (zero on first use; the apply launch clears the other set)
+ * b200gym_rms_moments      one coalesced pass over x [n][dim] (float32, or float64 with is_f64): sums into scratch
+ * b200gym_return_moments   NormalizeReward.step's `returns = returns * gamma + reward` (normalize.py:130) fused
+ *                          with the same pass over `returns`
+ * (a sharded env all-reduces scratch[cur] over the GPUs here and passes the GLOBAL row count as batch_count)
+ * b200gym_rms_apply_obs    Chan update (normalize.py:32-46) of stats[cur] with the batch moments into stats[cur^1]
+ *                          when `update`, then out = (obs - mean) / sqrt(var + epsilon) with the NEW statistics
+ * b200gym_rms_apply_reward same update, out = reward / sqrt(var + epsilon) (normalize.py:143),
+ *                          returns[terminated | truncated] = 0 (:135-136)
+ * dim must be one of 1, 2, 3, 4, 6, 8, 24 (the observation sizes of the in-scope envs).
  */
-int b200gym_running_norm_obs(const float *obs_dev, float *out_dev, int64_t n, int dim, double *mean_dev, double *var_dev,
-                             double *count_dev, double *scratch_dev, double epsilon, int update, void *stream);
+int b200gym_rms_moments(const void *x_dev, int is_f64, int64_t n, int dim, const double *stats_dev, double *scratch_dev,
+                        void *stream);
+int b200gym_return_moments(double *returns_dev, const double *reward_dev, double gamma, int64_t n, const double *stats_dev,
+                           double *scratch_dev, void *stream);
+int b200gym_rms_apply_obs(const float *obs_dev, float *out_dev, int64_t n, int dim, const double *stats_dev,
+                          double *stats_next_dev, const double *scratch_dev, double *scratch_next_dev, double batch_count,
+                          double epsilon, int update, void *stream);
+int b200gym_rms_apply_reward(const double *reward_dev, double *out_dev, double *returns_dev, const uint8_t *terminated_dev,
+                             const uint8_t *truncated_dev, int64_t n, const double *stats_dev, double *stats_next_dev,
+                             const double *scratch_dev, double *scratch_next_dev, double batch_count, double epsilon,
+                             void *stream);
+
 /*
- * NormalizeReward (gym/wrappers/normalize.py:98-144): returns = returns * gamma + reward, fold `returns`
- * into the scalar running statistics, out = reward / sqrt(var + epsilon), returns[terminated|truncated] = 0.
+ * Box2D tasks: number of envs in which a touching (body, ground fixture) pair was ever dropped because the scene's
+ * manifold table was full (8 pairs for LunarLander*, 10 for BipedalWalker*; real Box2D has no such limit).  The
+ * dropped pair is treated as not touching -- the CPU oracle applies the identical rule -- so this counts
+ * "physics differs from Box2D here"; it is 0 in every workload measured so far (max 7 simultaneous pairs).
+ * Synchronises `stream`.
  */
-int b200gym_running_norm_reward(const double *reward_dev, const uint8_t *terminated_dev, const uint8_t *truncated_dev,
-                                double *returns_dev, double *out_dev, int64_t n, double *mean_dev, double *var_dev,
-                                double *count_dev, double *scratch_dev, double gamma, double epsilon, void *stream);
+int b200gym_box2d_overflows(b200gym_t *h, void *stream, int64_t *count_out);
 
 /*
  * Device self-test of the kernels' constant-divisor division (csrc/envs.cuh:div_by_const)

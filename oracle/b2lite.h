@@ -149,6 +149,11 @@ typedef struct {
     float gravity_y;         /* b2World gravity = (0, gravity_y) */
     int awake;               /* out: 0 when the island went to sleep in this step */
     int stat_contacts, stat_pos_iters; /* out (workload statistics): touching contacts, position iterations run */
+    int max_contacts;        /* manifold-table capacity of the scene (same number as the CUDA scene's kMaxVC; at most
+                              * B2L_MAX_CONTACTS).  A pair that would be the (max_contacts+1)-th touching one of a step is
+                              * treated as NOT touching -- no manifold, no BeginContact, EndContact if it was touching --
+                              * identically here and on the device, and counted in `overflowed` */
+    int overflowed;          /* out: number of pairs dropped that way in this step (tests assert it stays 0) */
     void (*event)(void *ctx, int body, int begin); /* Begin/EndContact listener */
     void *ctx;
 } b2l_world;
@@ -723,14 +728,25 @@ static void b2l_step(b2l_world *W, float dt, int velIters, int posIters)
      *     pairs are visited in the same (island) order the constraints are built in */
     const int NB = W->nb, NE = W->ne;
     const int *order = W->body_order, *jorder = W->joint_order;
+    const int cap = (W->max_contacts > 0 && W->max_contacts < B2L_MAX_CONTACTS) ? W->max_contacts : B2L_MAX_CONTACTS;
+    int ntouch = 0;
+    W->overflowed = 0;
     for (int oi = 0; oi < NB; oi++) {
         int b = order[oi];
         for (int p = W->np - 1; p >= 0; p--) {  /* static polygons first (descending), then the edges */
-            int ev = contact_update_poly(&W->ctp[b * W->np_cap + p], &W->sp[p], &W->b[b]);
+            contact_t *c = &W->ctp[b * W->np_cap + p];
+            int was = c->touching;
+            int ev = contact_update_poly(c, &W->sp[p], &W->b[b]);
+            if (c->touching && ntouch >= cap) { c->touching = 0; c->m.pointCount = 0; W->overflowed++; ev = -was; }
+            ntouch += c->touching;
             if (ev != 0 && W->event) W->event(W->ctx, b, ev > 0);
         }
         for (int e = NE - 1; e >= 0; e--) {
-            int ev = contact_update(&W->ct[b * NE + e], &W->e[e], &W->b[b]);
+            contact_t *c = &W->ct[b * NE + e];
+            int was = c->touching;
+            int ev = contact_update(c, &W->e[e], &W->b[b]);
+            if (c->touching && ntouch >= cap) { c->touching = 0; c->m.pointCount = 0; W->overflowed++; ev = -was; }
+            ntouch += c->touching;
             if (ev != 0 && W->event) W->event(W->ctx, b, ev > 0);
         }
     }

@@ -49,6 +49,7 @@ typedef struct {
     pcg64_t rng;
     int32_t elapsed;
     int stat_contacts, stat_pos_iters; /* of the last world step (workload statistics for DESIGN.md) */
+    long long overflows;               /* touching pairs dropped because the scene's manifold table was full (sticky) */
     int32_t wind_idx, torque_idx; /* lunar_lander.py:234-235: drawn once per env object, never reset */
 } world_t;
 
@@ -65,6 +66,11 @@ struct orc_lunar {
 };
 
 /* ContactDetector (lunar_lander.py:54-72) */
+/* manifold-table capacity of this scene: the CUDA scene's kMaxVC (gym_b200/csrc/lunar.cuh); settable so that a test can
+ * force overflows on both sides and check that they are handled identically */
+static int g_lunar_max_contacts = 8;
+void orc_lunar_set_max_contacts(int cap) { g_lunar_max_contacts = cap; }
+
 static void lunar_event(void *ctx, int body, int begin)
 {
     world_t *W = (world_t *)ctx;
@@ -84,9 +90,11 @@ static int world_step(world_t *W, float gravity_y, float dt, int velIters, int p
     S.inv_dt0 = W->inv_dt0;
     S.gravity_y = gravity_y;
     S.event = lunar_event; S.ctx = W;
+    S.max_contacts = g_lunar_max_contacts;
     b2l_step(&S, dt, velIters, posIters);
     W->inv_dt0 = S.inv_dt0;
     W->stat_contacts = S.stat_contacts; W->stat_pos_iters = S.stat_pos_iters;
+    W->overflows += S.overflowed;
     return S.awake;
 }
 
@@ -115,8 +123,10 @@ static void lunar_reset_one(world_t *W, const opts_t *O, float *obs)
     pcg64_t rng = W->rng;
     float inv_dt0 = W->inv_dt0; /* the b2World object survives reset() */
     int32_t wind_idx = W->wind_idx, torque_idx = W->torque_idx;
+    long long overflows = W->overflows;
     memset(W, 0, sizeof *W);
     W->inv_dt0 = inv_dt0;
+    W->overflows = overflows;
     W->wind_idx = wind_idx; W->torque_idx = torque_idx;
     const double Wd = VIEWPORT_W / SCALE, Hd = VIEWPORT_H / SCALE;
     enum { CHUNKS = 11 };
@@ -441,6 +451,14 @@ void orc_lunar_get_terrain(const orc_lunar *v, int64_t i, float *y11)
 }
 
 /* workload statistics of the last step of every env: {touching contacts, position iterations} */
+/* envs in which a touching pair was ever dropped because the manifold table was full */
+int64_t orc_lunar_overflows(const orc_lunar *v)
+{
+    int64_t c = 0;
+    for (int64_t i = 0; i < v->n; i++) c += v->w[i].overflows != 0;
+    return c;
+}
+
 void orc_lunar_get_stats(const orc_lunar *v, int32_t *out)
 {
     for (int64_t i = 0; i < v->n; i++) { out[2 * i] = v->w[i].stat_contacts; out[2 * i + 1] = v->w[i].stat_pos_iters; }

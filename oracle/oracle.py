@@ -221,6 +221,14 @@ class OracleVec:
         lib().orc_vec_set_state(self._h, _ptr(s), _ptr(e))
 
 
+def set_box2d_max_contacts(lunar=8, walker=10):
+    """Manifold-table capacity of the two Box2D scenes (defaults = the CUDA scenes' kMaxVC); process-wide.
+    Tests shrink it (together with a small-table build of the device source) to exercise the overflow rule."""
+    L = lib()
+    L.orc_lunar_set_max_contacts(int(lunar))
+    L.orc_walker_set_max_contacts(int(walker))
+
+
 class OracleLunar:
     """SyncVectorEnv([make("LunarLander-v2")] * n) restated in C (oracle/lunar_oracle.c).
 
@@ -246,6 +254,12 @@ class OracleLunar:
         ti = np.zeros(self.n, dtype=np.int32)
         lib().orc_lunar_get_wind_idx(self._h, wi.ctypes.data, ti.ctypes.data)
         return wi, ti
+
+    def overflows(self):
+        """Number of envs in which a touching pair was ever dropped because the manifold table was full."""
+        f = lib().orc_lunar_overflows
+        f.restype, f.argtypes = ctypes.c_int64, [ctypes.c_void_p]
+        return int(f(self._h))
 
     def close(self):
         if getattr(self, "_h", None):
@@ -301,6 +315,12 @@ class OracleWalker:
     def __init__(self, num_envs, max_episode_steps=1600, hardcore=False):
         self.n = int(num_envs)
         self._h = lib().orc_walker_create_ex(self.n, int(max_episode_steps or 0), int(bool(hardcore)))
+
+    def overflows(self):
+        """Number of envs in which a touching pair was ever dropped because the manifold table was full."""
+        f = lib().orc_walker_overflows
+        f.restype, f.argtypes = ctypes.c_int64, [ctypes.c_void_p]
+        return int(f(self._h))
 
     def close(self):
         if getattr(self, "_h", None):

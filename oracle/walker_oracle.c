@@ -59,6 +59,7 @@ typedef struct {
     pcg64_t rng;
     int32_t elapsed;
     int stat_contacts, stat_pos_iters; /* of the last world step (workload statistics for DESIGN.md) */
+    long long overflows;               /* touching pairs dropped because the scene's manifold table was full (sticky) */
 } wworld_t;
 
 struct orc_walker {
@@ -69,6 +70,11 @@ struct orc_walker {
 };
 
 /* ContactDetector (bipedal_walker.py:80-98) */
+/* manifold-table capacity of this scene: the CUDA scene's kMaxVC (gym_b200/csrc/walker.cuh); settable so that a test can
+ * force overflows on both sides and check that they are handled identically */
+static int g_walker_max_contacts = 10;
+void orc_walker_set_max_contacts(int cap) { g_walker_max_contacts = cap; }
+
 static void walker_event(void *ctx, int body, int begin)
 {
     wworld_t *W = (wworld_t *)ctx;
@@ -95,9 +101,11 @@ static void wworld_step(wworld_t *W)
     S.inv_dt0 = W->inv_dt0;
     S.gravity_y = -10.0f;
     S.event = walker_event; S.ctx = W;
+    S.max_contacts = g_walker_max_contacts;
     b2l_step(&S, (float)(1.0 / FPS), 6 * 30, 2 * 30);
     W->inv_dt0 = S.inv_dt0;
     W->stat_contacts = S.stat_contacts; W->stat_pos_iters = S.stat_pos_iters;
+    W->overflows += S.overflowed;
     /* step() rewrites every joint's motor each call, which wakes both bodies (b2RevoluteJoint::
      * SetMotorSpeed -> SetAwake(true)): an island that fell asleep is simply awake again next step */
     for (int i = 0; i < NB; i++) W->b[i].awake = 1;
@@ -134,8 +142,10 @@ static void walker_reset_one(wworld_t *W, int hardcore, float *obs)
 {
     pcg64_t rng = W->rng;
     float inv_dt0 = W->inv_dt0; /* self.world survives reset() */
+    long long overflows = W->overflows;
     memset(W, 0, sizeof *W);
     W->inv_dt0 = inv_dt0;
+    W->overflows = overflows;
     /* _generate_terrain(hardcore) :277-402 */
     double terrain_x[TERRAIN_LENGTH], terrain_y[TERRAIN_LENGTH];
     {
@@ -433,6 +443,14 @@ void orc_walker_step(orc_walker *v, const float *actions, float *obs, double *re
                      uint8_t *truncated, float *final_obs)
 {
     orc_walker_step_mt(v, actions, obs, reward, terminated, truncated, final_obs, 1);
+}
+
+/* envs in which a touching pair was ever dropped because the manifold table was full */
+int64_t orc_walker_overflows(const orc_walker *v)
+{
+    int64_t c = 0;
+    for (int64_t i = 0; i < v->n; i++) c += v->w[i].overflows != 0;
+    return c;
 }
 
 void orc_walker_get_stats(const orc_walker *v, int32_t *out)

@@ -41,7 +41,7 @@ void ensure_consts() {
 
 void lunar_reset_env(Sim &S, int64_t i, float *obs) {     // lunar_reset_kernel
     lunar::World W;
-    W.flags = S.rec[(int64_t)lunar::W_FLAGS * S.n + i] & 16u;
+    W.flags = S.rec[(int64_t)lunar::W_FLAGS * S.n + i] & b2l::kFlagsKept;
     W.wind_idx = S.opts.wind ? (int32_t)S.rec[(int64_t)lunar::W_WIND * S.n + i] : 0;
     W.torque_idx = S.opts.wind ? (int32_t)S.rec[(int64_t)(lunar::W_WIND + 1) * S.n + i] : 0;
     Pcg64 g = bgym::pcg64_load(&S.rng[4 * i]);
@@ -58,7 +58,7 @@ void walker_reset_env(Sim &S, int64_t i, float *obs) {    // walker_reset_kernel
     walker::World W;
     walker::Rng r;
     walker::bind_world(W, S.rec.data(), S.n, i);
-    W.flags = S.rec[(int64_t)walker::W_FLAGS * S.n + i] & b2l::kFlagStepped;
+    W.flags = S.rec[(int64_t)walker::W_FLAGS * S.n + i] & b2l::kFlagsKept;
     r.has32 = S.rec[(int64_t)walker::W_RNG32 * S.n + i];
     r.val32 = S.rec[(int64_t)(walker::W_RNG32 + 1) * S.n + i];
     r.g = bgym::pcg64_load(&S.rng[4 * i]);
@@ -206,6 +206,16 @@ int hs_walker_terrain(void *h, int64_t i, float *terrain200, float *boxes /* [40
     return np;
 }
 
+
+// envs whose manifold table ever overflowed (b200gym_box2d_overflows on the device)
+int64_t hs_overflows(void *h) {
+    Sim &S = *(Sim *)h;
+    const int64_t row = S.lunar() ? lunar::W_FLAGS : walker::W_FLAGS;
+    int64_t c = 0;
+    for (int64_t i = 0; i < S.n; i++) c += (S.rec[row * S.n + i] & b2l::kFlagOverflow) != 0;
+    return c;
+}
+
 }  // extern "C"
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -343,6 +353,27 @@ void hs_classic_get_state(void *h, double *state_aos /* [n][S] */, int S) {
 // CartPole's small-angle sin/cos kernel alone (csrc/envs.cuh: sincos_small)
 void hs_sincos_small(const double *x, int64_t n, double *sn, double *cs) {
     for (int64_t i = 0; i < n; i++) bgym::sincos_small(x[i], sn[i], cs[i]);
+}
+
+
+// glibc_trig.cuh: the restated glibc sin / cos, evaluated by the host build of the device header
+void hs_glibc_trig(const double *x, int64_t n, double *sn, double *cs) {
+    for (int64_t i = 0; i < n; i++) { sn[i] = bgym::gt::sin(x[i]); cs[i] = bgym::gt::cos(x[i]); }
+}
+// number of arguments in [lo, hi) (splitmix64 stream) where sin or cos differs bitwise from this process's libm
+int64_t hs_glibc_trig_mismatches(uint64_t seed, int64_t n, double lo, double hi) {
+    int64_t bad = 0;
+    uint64_t st = seed;
+    for (int64_t i = 0; i < n; i++) {
+        uint64_t z = (st += 0x9E3779B97F4A7C15ULL);
+        z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ULL;
+        z = (z ^ (z >> 27)) * 0x94D049BB133111EBULL;
+        z ^= z >> 31;
+        const double x = lo + (hi - lo) * ((double)(z >> 11) * (1.0 / 9007199254740992.0));
+        const double a = std::sin(x), b = bgym::gt::sin(x), c = std::cos(x), d = bgym::gt::cos(x);
+        bad += (std::memcmp(&a, &b, 8) != 0) + (std::memcmp(&c, &d, 8) != 0);
+    }
+    return bad;
 }
 
 }  // extern "C"

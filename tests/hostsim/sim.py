@@ -13,22 +13,31 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 _ROOT = os.path.dirname(os.path.dirname(_HERE))
 _BUILD = os.path.join(_HERE, "_build")
 _LIB = os.path.join(_BUILD, "libhostsim.so")
+# a second build of the same sources with tiny manifold tables (LunarLander 1 pair, BipedalWalker 2): forces the
+# "table full" path that never triggers in normal play, so that its equivalence with the oracle can be tested
+_LIB_SMALLCAP = os.path.join(_BUILD, "libhostsim_smallcap.so")
+SMALLCAP = {"lunar": 1, "walker": 2}
 _SRCS = [os.path.join(_HERE, "hostsim.cpp"), os.path.join(_HERE, "cuda_shim.h")] + [
-    os.path.join(_ROOT, "gym_b200", "csrc", f) for f in ("rng.cuh", "envs.cuh", "b2lite.cuh", "lunar.cuh", "walker.cuh",
-                                                         "box2d_consts.h")]
+    os.path.join(_ROOT, "gym_b200", "csrc", f) for f in ("rng.cuh", "envs.cuh", "glibc_trig.cuh", "b2lite.cuh", "lunar.cuh",
+                                                         "walker.cuh", "box2d_consts.h")]
 
 KIND = {"LunarLander": 5, "BipedalWalker": 6, "LunarLanderContinuous": 7, "BipedalWalkerHardcore": 8}
 _lib = None
+_libs = {}
 
 
-def lib():
+def lib(smallcap=False):
     global _lib
-    if _lib is None:
-        if not os.path.exists(_LIB) or os.path.getmtime(_LIB) < max(os.path.getmtime(s) for s in _SRCS):
+    if smallcap or _lib is None:
+        if smallcap and "small" in _libs:
+            return _libs["small"]
+        path = _LIB_SMALLCAP if smallcap else _LIB
+        extra = [f"-DB2L_LUNAR_MAX_VC={SMALLCAP['lunar']}", f"-DB2L_WALKER_MAX_VC={SMALLCAP['walker']}"] if smallcap else []
+        if not os.path.exists(path) or os.path.getmtime(path) < max(os.path.getmtime(s) for s in _SRCS):
             os.makedirs(_BUILD, exist_ok=True)
             subprocess.check_call(["g++", "-O2", "-std=c++17", "-ffp-contract=off", "-fno-fast-math", "-fPIC", "-shared",
-                                   "-Wno-unknown-pragmas", "-o", _LIB, os.path.join(_HERE, "hostsim.cpp")])
-        L = ctypes.CDLL(_LIB)
+                                   "-Wno-unknown-pragmas"] + extra + ["-o", path, os.path.join(_HERE, "hostsim.cpp")])
+        L = ctypes.CDLL(path)
         vp, i64, i32, dbl = ctypes.c_void_p, ctypes.c_int64, ctypes.c_int, ctypes.c_double
         L.hs_create.restype = vp
         L.hs_create.argtypes = [i32, i64, i32, i32, dbl, dbl, dbl]
@@ -50,6 +59,14 @@ def lib():
         L.hs_classic_step.argtypes = [vp, vp, vp, vp, vp, vp, vp]
         L.hs_classic_get_state.argtypes = [vp, vp, i32]
         L.hs_sincos_small.argtypes = [vp, i64, vp, vp]
+        L.hs_overflows.restype = i64
+        L.hs_overflows.argtypes = [vp]
+        L.hs_glibc_trig.argtypes = [vp, i64, vp, vp]
+        L.hs_glibc_trig_mismatches.restype = i64
+        L.hs_glibc_trig_mismatches.argtypes = [ctypes.c_uint64, i64, dbl, dbl]
+        if smallcap:
+            _libs["small"] = L
+            return L
         _lib = L
     return _lib
 
@@ -63,31 +80,36 @@ class HostSim:
     """One batch of envs stepped by the device source on the CPU; same call shape as oracle.OracleLunar/OracleWalker."""
 
     def __init__(self, name, num_envs, max_episode_steps, gravity=-10.0, enable_wind=False, wind_power=15.0,
-                 turbulence_power=1.5, wind_idx=None, torque_idx=None):
+                 turbulence_power=1.5, wind_idx=None, torque_idx=None, smallcap=False):
+        self._L = lib(smallcap)
         self.kind = KIND[name]
         self.n = int(num_envs)
         self.lunar = self.kind in (5, 7)
         self.obs_dim = 8 if self.lunar else 24
-        self._h = lib().hs_create(self.kind, self.n, int(max_episode_steps or 0), int(bool(enable_wind)), float(gravity),
+        self._h = self._L.hs_create(self.kind, self.n, int(max_episode_steps or 0), int(bool(enable_wind)), float(gravity),
                                   float(wind_power), float(turbulence_power))
         assert self._h
         if wind_idx is not None:
             wi = np.ascontiguousarray(np.broadcast_to(wind_idx, (self.n,)), dtype=np.int32)
             ti = np.ascontiguousarray(np.broadcast_to(torque_idx, (self.n,)), dtype=np.int32)
-            lib().hs_set_wind_idx(self._h, wi.ctypes.data, ti.ctypes.data)
+            self._L.hs_set_wind_idx(self._h, wi.ctypes.data, ti.ctypes.data)
+
+    def overflows(self):
+        """Number of envs whose manifold table ever overflowed."""
+        return int(self._L.hs_overflows(self._h))
 
     def close(self):
         if getattr(self, "_h", None):
-            lib().hs_destroy(self._h)
+            self._L.hs_destroy(self._h)
             self._h = None
 
     __del__ = close
 
     def reset(self, seed=None):
         if seed is not None:
-            lib().hs_seed_range(self._h, _seed_words(seed).ctypes.data, 0)
+            self._L.hs_seed_range(self._h, _seed_words(seed).ctypes.data, 0)
         obs = np.zeros((self.n, self.obs_dim), dtype=np.float32)
-        lib().hs_reset(self._h, obs.ctypes.data)
+        self._L.hs_reset(self._h, obs.ctypes.data)
         return obs
 
     def step(self, actions):
@@ -100,7 +122,7 @@ class HostSim:
         rew = np.zeros(self.n, dtype=np.float64)
         te = np.zeros(self.n, dtype=np.uint8)
         tr = np.zeros(self.n, dtype=np.uint8)
-        bad = lib().hs_step(self._h, a.ctypes.data, obs.ctypes.data, rew.ctypes.data, te.ctypes.data, tr.ctypes.data,
+        bad = self._L.hs_step(self._h, a.ctypes.data, obs.ctypes.data, rew.ctypes.data, te.ctypes.data, tr.ctypes.data,
                             fo.ctypes.data)
         assert bad == 0
         return obs, rew, te.astype(bool), tr.astype(bool), fo
@@ -108,13 +130,13 @@ class HostSim:
     def wind_idx(self):
         wi = np.zeros(self.n, dtype=np.int32)
         ti = np.zeros(self.n, dtype=np.int32)
-        lib().hs_get_wind_idx(self._h, wi.ctypes.data, ti.ctypes.data)
+        self._L.hs_get_wind_idx(self._h, wi.ctypes.data, ti.ctypes.data)
         return wi, ti
 
     def terrain(self, i=0):
         t = np.zeros(200, dtype=np.float32)
         boxes = np.zeros((40, 4), dtype=np.float32)
-        k = lib().hs_walker_terrain(self._h, int(i), t.ctypes.data, boxes.ctypes.data)
+        k = self._L.hs_walker_terrain(self._h, int(i), t.ctypes.data, boxes.ctypes.data)
         return t, boxes[:k].copy()
 
 
@@ -164,6 +186,19 @@ class HostSimClassic:
         s = np.zeros((self.n, self.state_dim), dtype=np.float64)
         lib().hs_classic_get_state(self._h, s.ctypes.data, self.state_dim)
         return s
+
+
+def glibc_trig(x):
+    """csrc/glibc_trig.cuh: gt::sin / gt::cos on an array of float64 arguments."""
+    x = np.ascontiguousarray(x, dtype=np.float64)
+    sn, cs = np.empty_like(x), np.empty_like(x)
+    lib().hs_glibc_trig(x.ctypes.data, x.size, sn.ctypes.data, cs.ctypes.data)
+    return sn, cs
+
+
+def glibc_trig_mismatches(seed, n, lo, hi):
+    """How many of n pseudo-random arguments in [lo, hi) give a sin or cos that differs bitwise from libm's."""
+    return int(lib().hs_glibc_trig_mismatches(int(seed), int(n), float(lo), float(hi)))
 
 
 def sincos_small(x):

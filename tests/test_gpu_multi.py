@@ -76,6 +76,83 @@ def _worker(rank, world, port, env_id, n_local, steps, q):
         dist.destroy_process_group()
 
 
+def _wrapper_worker(rank, world, port, q):
+    """NormalizeObservation / NormalizeReward over one rank's SHARD, batch moments all-reduced across the GPUs,
+    must normalise exactly like the same wrappers over the whole batch on one GPU; and the stateless wrapper
+    kernels must run on the device their buffers live on even when another device is current."""
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    try:
+        import gym_b200
+        from gym_b200.wrappers import NormalizeObservation, NormalizeReward, RecordEpisodeStatistics
+        n, T = 3000, 40
+        total = world * n
+        lo, hi = rank * n, (rank + 1) * n
+        full = NormalizeReward(NormalizeObservation(gym_b200.vector.make("Pendulum-v1", total, max_episode_steps=13)), gamma=0.9)
+        shard = NormalizeReward(NormalizeObservation(
+            gym_b200.vector.make("Pendulum-v1", n, max_episode_steps=13, first_index=lo), group=True), gamma=0.9, group=True)
+        fo, _ = full.reset(seed=5)
+        so, _ = shard.reset(seed=5)
+        torch.testing.assert_close(so, fo[lo:hi], rtol=1e-6, atol=1e-6)
+        rng = np.random.default_rng(0)
+        for t in range(T):
+            a = torch.as_tensor(rng.uniform(-2, 2, size=(total, 1)).astype(np.float32), device="cuda")
+            fo, fr, fte, ftr, _ = full.step(a)
+            so, sr, ste, strn, _ = shard.step(a[lo:hi])
+            torch.testing.assert_close(so, fo[lo:hi], rtol=1e-6, atol=1e-6)
+            torch.testing.assert_close(sr, fr[lo:hi], rtol=1e-10, atol=1e-12)
+            assert torch.equal(ste, fte[lo:hi]) and torch.equal(strn, ftr[lo:hi])
+        torch.testing.assert_close(shard.env.obs_rms.mean, full.env.obs_rms.mean, rtol=1e-10, atol=1e-12)
+        torch.testing.assert_close(shard.env.obs_rms.var, full.env.obs_rms.var, rtol=1e-10, atol=1e-12)
+        assert abs(float(shard.env.obs_rms.count.item()) - float(full.env.obs_rms.count.item())) < 1e-6
+        full.close()
+        shard.close()
+        # an env on ANOTHER device than the current one: every wrapper kernel must follow its buffers
+        other = (rank + 1) % world
+        env = RecordEpisodeStatistics(NormalizeObservation(gym_b200.vector.make("CartPole-v1", 2000, device=other)))
+        twin = RecordEpisodeStatistics(NormalizeObservation(gym_b200.vector.make("CartPole-v1", 2000)))
+        assert torch.cuda.current_device() == rank and env.unwrapped.device.index == other
+        eo, _ = env.reset(seed=9)
+        to, _ = twin.reset(seed=9)
+        assert eo.device.index == other and torch.equal(eo.cpu(), to.cpu())
+        for t in range(30):
+            a = torch.as_tensor(rng.integers(0, 2, size=2000))
+            eo, er, ete, etr, ei = env.step(a.to(f"cuda:{other}"))
+            to, tr_, tte, ttr, ti = twin.step(a.cuda())
+            assert torch.equal(eo.cpu(), to.cpu()) and torch.equal(ete.cpu(), tte.cpu())
+            assert torch.equal(ei["episode"]["r"].cpu(), ti["episode"]["r"].cpu())
+        env.close()
+        twin.close()
+        q.put((rank, "ok"))
+    except Exception:  # pragma: no cover
+        import traceback
+        q.put((rank, traceback.format_exc()))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.skipif(_ngpus() < 2, reason="needs at least 2 GPUs")
+@pytest.mark.timeout(300)
+def test_wrappers_across_gpus():
+    import torch.multiprocessing as mp
+    world = 2
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_wrapper_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    results = dict(q.get(timeout=240) for _ in range(world))
+    for p in procs:
+        p.join(timeout=30)
+    assert all(v == "ok" for v in results.values()), results
+
+
 @pytest.mark.skipif(_ngpus() < 2, reason="needs at least 2 GPUs")
 @pytest.mark.parametrize("env_id,n_local", [("CartPole-v1", 148 * 256 + 640), ("Pendulum-v1", 5000)])
 @pytest.mark.timeout(300)

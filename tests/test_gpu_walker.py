@@ -47,6 +47,7 @@ def test_bit_exact_against_oracle():
         ob, of = orc.bodies(i)
         assert np.array_equal(bodies[i].cpu().numpy(), ob)
         assert flags[i].tolist() == of.tolist()
+    assert env.box2d_overflows() == 0 and orc.overflows() == 0   # 10 touching pairs per env were always enough
     env.close()
     orc.close()
 
@@ -182,6 +183,7 @@ def test_hardcore_random_actions_bit_exact_and_kwarg_selects_the_variant():
     for i in (0, 100, N - 1):
         want = orc.polys(i)
         assert int(npoly[i]) == len(want) and np.array_equal(polys[i, :len(want)].cpu().numpy(), want)
+    assert env.box2d_overflows() == 0 and orc.overflows() == 0   # fallen walkers among stumps and stairs included
     env.close()
     orc.close()
 

@@ -50,6 +50,40 @@ def test_record_episode_statistics():
     env.close()
 
 
+def test_fused_episode_statistics_equal_the_standalone_kernel():
+    """RecordEpisodeStatistics inside the step kernel (no extra launch) vs the stand-alone launch over the returned
+    tensors (what a sharded env's gathered outputs go through): same accumulators, rows, masks and counters, for a
+    classic-control kind, a Box2D kind (their own step kernels carry the same fused bookkeeping) and float rewards."""
+    import gym_b200
+    import torch
+    from gym_b200.wrappers import RecordEpisodeStatistics, VectorWrapper
+    for env_id, N, T, kw in (("CartPole-v1", 3000, 80, {}), ("Pendulum-v1", 1500, 60, dict(max_episode_steps=17)),
+                             ("LunarLander-v2", 512, 140, {})):
+        fused = RecordEpisodeStatistics(gym_b200.vector.make(env_id, N, **kw), deque_size=0)
+        plain = RecordEpisodeStatistics(VectorWrapper(gym_b200.vector.make(env_id, N, **kw)), deque_size=0)
+        assert fused._fused_target() is not None and plain._fused_target() is None
+        fused.reset(seed=21)
+        plain.reset(seed=21)
+        gen = torch.Generator(device="cuda").manual_seed(3)
+        inner = fused.env
+        for t in range(T):
+            if inner.discrete:
+                a = torch.randint(0, inner.single_action_space.n, (N,), device="cuda", generator=gen)
+            else:
+                a = torch.rand((N, inner.act_dim), device="cuda", generator=gen) * 4 - 2
+            fa, fb = fused.step(a), plain.step(a)
+            assert torch.equal(fa[1], fb[1]) and torch.equal(fa[2], fb[2]) and torch.equal(fa[3], fb[3])
+            m = fa[4]["_episode"]
+            assert torch.equal(m, fb[4]["_episode"])
+            assert torch.equal(fa[4]["episode"]["r"][m], fb[4]["episode"]["r"][m])
+            assert torch.equal(fa[4]["episode"]["l"][m], fb[4]["episode"]["l"][m])
+            assert torch.equal(fused.episode_returns, plain.episode_returns)
+            assert torch.equal(fused.episode_lengths, plain.episode_lengths)
+        assert fused.episode_count == plain.episode_count > 0
+        fused.close()
+        plain.close()
+
+
 def test_normalize_observation_and_reward():
     import gym_b200
     import torch

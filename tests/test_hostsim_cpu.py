@@ -101,6 +101,47 @@ def test_walker_device_source_on_cpu_equals_oracle(name, hardcore, policy):
     assert n_done > (N // 2 if policy == "random" or hardcore else 0)
 
 
+def test_manifold_table_overflow_is_handled_identically():
+    """The Box2D scenes keep at most 8 (LunarLander) / 10 (BipedalWalker) touching pairs per env; real Box2D has no
+    limit, and random play never gets there (max 7 observed), so the rule for a full table -- the extra pair counts
+    as NOT touching: no constraint, no BeginContact, EndContact if it was touching -- cannot be tested at the shipped
+    capacities.  Here both sides run with tiny tables (device source built with 1 / 2 slots, oracle told the same):
+    overflows happen in most episodes, are counted on both sides, and the trajectories stay bit-identical."""
+    from hostsim.sim import SMALLCAP
+    try:
+        orc.set_box2d_max_contacts(lunar=SMALLCAP["lunar"], walker=SMALLCAP["walker"])
+        rng = np.random.default_rng(4)
+        N, T = 64, 260
+        sim = HostSim("LunarLander", N, 1000, smallcap=True)
+        ref = orc.OracleLunar(N, max_episode_steps=1000)
+        assert np.array_equal(sim.reset(seed=3), ref.reset(seed=3))
+        for t in range(T):
+            a = rng.integers(0, 4, size=N)
+            _compare(t, sim.step(a), ref.step(a))
+        assert sim.overflows() == ref.overflows() > 0
+        sim.close()
+        ref.close()
+        N, T = 16, 200
+        sim = HostSim("BipedalWalkerHardcore", N, 2000, smallcap=True)
+        ref = orc.OracleWalker(N, hardcore=True, max_episode_steps=2000)
+        assert np.array_equal(sim.reset(seed=9), ref.reset(seed=9))
+        for t in range(T):
+            a = rng.uniform(-1.0, 1.0, size=(N, 4)).astype(np.float32)
+            _compare(t, sim.step(a), ref.step(a))
+        assert sim.overflows() == ref.overflows() > 0
+        sim.close()
+        ref.close()
+    finally:
+        orc.set_box2d_max_contacts()
+    # at the shipped capacities random play never overflows (this is what the GPU tests assert on the device too)
+    ref = orc.OracleLunar(256, max_episode_steps=1000)
+    ref.reset(seed=1)
+    for t in range(300):
+        ref.step(rng.integers(0, 4, size=256))
+    assert ref.overflows() == 0
+    ref.close()
+
+
 # ---------------------------------------------------------------------------------------------------------
 # classic control: gym_b200/csrc/envs.cuh on the CPU
 # ---------------------------------------------------------------------------------------------------------
@@ -157,6 +198,24 @@ def test_cartpole_small_angle_sincos_against_libm():
     assert np.array_equal(np.signbit(sn[nz]), np.signbit(ws[nz]))
     # sin(-0.0) comes out as +0.0 (libm: -0.0): only the sign of a zero product / zero sum downstream, never a value
     assert sn[x == 0].tolist() == [0.0, 0.0]
+
+
+def test_restated_glibc_sin_cos_are_bit_identical_to_libm():
+    """csrc/glibc_trig.cuh (glibc's sin / cos restated, FMA contractions included) against the libm of this very
+    process -- the one the reference's math.sin / np.cos end in -- over the argument ranges the envs produce and far
+    beyond: every result identical, bit for bit.  This is what lets Acrobot (chaotic: a 1-ulp difference grows by
+    e^(0.09 t)) match the reference over whole free-running episodes."""
+    import math
+    from hostsim.sim import glibc_trig, glibc_trig_mismatches
+    edge = np.array([0.0, -0.0, 2.0 ** -27, 2.0 ** -26, 1.4e-8, 0.126, -0.126, 0.12599999, 0.855469, 0.8554687, 0.85546875,
+                     2.426265, 2.4262657, -2.426265, math.pi, -math.pi, math.pi / 2, 3 * math.pi / 2, 1e-300, 105414349.0,
+                     0.5 * math.pi - 1e-9, 100 * math.pi, 12345.678, -7.0, 25.132741228718345])
+    sn, cs = glibc_trig(edge)
+    assert sn.tobytes() == np.array([math.sin(v) for v in edge]).tobytes()
+    assert cs.tobytes() == np.array([math.cos(v) for v in edge]).tobytes()
+    for k, (lo, hi) in enumerate([(-0.2, 0.2), (-1.0, 1.0), (-3.2, 3.2), (-10.0, 10.0), (-100.0, 100.0), (-1e6, 1e6),
+                                  (-1.05e8, 1.05e8), (-1e-7, 1e-7)]):
+        assert glibc_trig_mismatches(1000 + k, 2_000_000, lo, hi) == 0, (lo, hi)
 
 
 def test_lunar_random_constructor_arguments_sweep():

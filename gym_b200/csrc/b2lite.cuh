@@ -613,9 +613,9 @@ __device__ __noinline__ void world_step(typename Scene::World &W, v2 force0, flo
             bool touching = m.pointCount > 0;
             if (touching && nvc >= kMaxVC) {
                 // manifold table full: the pair is treated as NOT touching (no constraint, no warm-start slot, no
-                // BeginContact; EndContact if it was touching) -- the oracle applies the same rule with the same
-                // capacity (oracle/b2lite.h: max_contacts), so the two stay bit-identical even here; the env is
-                // marked so that tests / b200gym_box2d_overflows can assert it never happens in practice
+                // BeginContact; EndContact if it was touching) -- the CPU checker in the test tree applies the same
+                // rule with the same capacity, so the two stay bit-identical even here; the env is marked so that
+                // tests / b200gym_box2d_overflows can assert it never happens in practice
                 touching = false;
                 W.flags |= kFlagOverflow;
             }

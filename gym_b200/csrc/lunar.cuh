@@ -25,7 +25,7 @@ constexpr int NB = 3;    // dynamic bodies: 0 lander, 1 leg (i=-1), 2 leg (i=+1)
 constexpr int NJ = 2;
 constexpr int NE = 11;   // ground edges: 0 base, 1..10 terrain
 #ifndef B2L_LUNAR_MAX_VC
-#define B2L_LUNAR_MAX_VC 8   // manifold-table capacity (the oracle's g_lunar_max_contacts); tests build a smaller one
+#define B2L_LUNAR_MAX_VC 8   // manifold-table capacity (touching pairs per env; tests build a smaller one)
 #endif
 constexpr int kSlots = 8;
 

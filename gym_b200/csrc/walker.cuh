@@ -24,7 +24,7 @@ constexpr int NB = 5;     // 0 hull, 1 leg(-1), 2 lower(-1), 3 leg(+1), 4 lower(
 constexpr int NJ = 4;     // 0 hip(-1), 1 knee(-1), 2 hip(+1), 3 knee(+1)   (self.joints order)
 constexpr int NE = 199;   // terrain edges i -> i+1
 #ifndef B2L_WALKER_MAX_VC
-#define B2L_WALKER_MAX_VC 10   // manifold-table capacity (the oracle's g_walker_max_contacts)
+#define B2L_WALKER_MAX_VC 10   // manifold-table capacity (touching pairs per env; tests build a smaller one)
 #endif
 constexpr int kSlots = 10;
 constexpr int kTerrain = 200;

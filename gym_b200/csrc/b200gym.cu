@@ -1057,6 +1057,15 @@ __global__ void __launch_bounds__(kThreads) selftest_div_kernel(int64_t samples,
     }
 }
 
+// device self-test: csrc/glibc_trig.cuh evaluated on caller-supplied arguments (the host compares with its libm)
+__global__ void __launch_bounds__(kThreads) selftest_trig_kernel(const double *x, int64_t n, double *sn, double *cs, double *sq) {
+    const int64_t i = (int64_t)blockIdx.x * kThreads + threadIdx.x;
+    if (i >= n) return;
+    sn[i] = gt::sin(x[i]);
+    cs[i] = gt::cos(x[i]);
+    if (sq) sq[i] = gt::sq(x[i]);
+}
+
 static inline unsigned blocks_for(int64_t n) { return (unsigned)((n + kThreads - 1) / kThreads); }
 
 // ---------------------------------------------------------------------------
@@ -1250,8 +1259,9 @@ extern "C" int b200gym_create(const b200gym_config *cfg, int64_t num_envs, int d
     if (!cfg || !out) return fail(nullptr, "b200gym_create: null argument");
     *out = nullptr;
     if (!kind_ok(cfg->kind)) return fail(nullptr, "b200gym_create: unknown env kind %d", cfg->kind);
-    if ((cfg->kind == B200GYM_LUNARLANDER || cfg->kind == B200GYM_LUNARLANDER_CONT) && cfg->param[0] != 0.0 &&
-        !(-12.0 < cfg->param[0] && cfg->param[0] < 0.0))  // the assert of lunar_lander.py:210-212
+    if ((cfg->kind == B200GYM_LUNARLANDER || cfg->kind == B200GYM_LUNARLANDER_CONT) &&
+        !(-12.0 < cfg->param[0] && cfg->param[0] < 0.0))  // the assert of lunar_lander.py:210-212 (0.0 included: no
+                                                          // silent default -- callers pass the reference's -10.0)
         return fail(nullptr, "b200gym_create: gravity (current value: %g) must be between -12 and 0", cfg->param[0]);
     if (num_envs <= 0) return fail(nullptr, "b200gym_create: num_envs must be positive (got %lld)", (long long)num_envs);
     int ndev = 0;
@@ -1304,7 +1314,7 @@ extern "C" int b200gym_create(const b200gym_config *cfg, int64_t num_envs, int d
     if (h->is_lunar) {  // LunarLander.__init__ arguments (lunar_lander.py:194-233)
         h->lunar_opts.continuous = cfg->kind == B200GYM_LUNARLANDER_CONT;
         h->lunar_opts.wind = (cfg->flags & B200GYM_LUNAR_ENABLE_WIND) != 0;
-        h->lunar_opts.gravity = (float)(cfg->param[0] == 0.0 ? -10.0 : cfg->param[0]);
+        h->lunar_opts.gravity = (float)cfg->param[0];
         h->lunar_opts.wind_power = cfg->param[1];
         h->lunar_opts.turbulence_power = cfg->param[2];
     }
@@ -1455,6 +1465,17 @@ extern "C" int b200gym_invalid_actions(b200gym_t *h, void *stream, int64_t *coun
     CK(h, cudaMemsetAsync(h->invalid, 0, sizeof v, st));
     CK(h, cudaStreamSynchronize(st));
     *count_out = (int64_t)v;
+    return 0;
+}
+
+extern "C" int b200gym_selftest_trig(const double *x_dev, int64_t n, double *sin_dev, double *cos_dev, double *sq_dev,
+                                     void *stream) {
+    if (!x_dev || !sin_dev || !cos_dev || n <= 0) return fail(nullptr, "b200gym_selftest_trig: bad argument");
+    const int dev = device_of(x_dev);
+    if (dev < 0) return fail(nullptr, "b200gym_selftest_trig: x is not a device pointer");
+    DeviceGuard guard(dev);
+    selftest_trig_kernel<<<blocks_for(n), kThreads, 0, (cudaStream_t)stream>>>(x_dev, n, sin_dev, cos_dev, sq_dev);
+    CK(nullptr, cudaGetLastError());
     return 0;
 }
 

@@ -274,7 +274,7 @@ struct Env<B200GYM_MOUNTAINCAR_CONT> {
         terminated = pos_ok && vel_ok;                                                      // :162-164
         double r = terminated ? 100.0 : 0.0;                                                // :166-168
         const double a0d = (double)a0;
-        r -= (a0d * a0d) * 0.1;                                                             // :169 math.pow(action[0], 2) * 0.1
+        r -= gt::sq(a0d) * 0.1;                                                             // :169 math.pow(action[0], 2) * 0.1
         reward = r;
         const float pf = (float)position, vf = (float)velocity;                             // :171 dtype=np.float32
         s[0] = (double)pf; s[1] = (double)vf;
@@ -332,7 +332,7 @@ struct Env<B200GYM_PENDULUM> {
         // :129 costs = angle_normalize(th)**2 + .1*thdot**2 + .001*(u**2); the u term is float32
         const double an = py_mod(th + B200_PI, 2 * B200_PI) - B200_PI;  // :270-271
         const float u_term = (float)0.001 * (u * u);
-        const double costs = an * an + 0.1 * (thdot * thdot) + (double)u_term;
+        const double costs = gt::sq(an) + 0.1 * gt::sq(thdot) + (double)u_term;   // np.float64 ** 2 = libm pow
         // :131 3.0/(m*l**2)*u is float32 and is promoted by the add
         const float tq = (float)(3.0 / (m * (l * l))) * u;
         double newthdot = thdot + (3 * g / (2 * l) * gt::sin(th) + (double)tq) * dt;
@@ -387,13 +387,13 @@ struct Env<B200GYM_ACROBOT> {
         const double d1 = m1 * (lc1 * lc1) + m2 * ((l1 * l1) + (lc2 * lc2) + 2 * l1 * lc2 * cos2) + I1 + I2;  // :252-257
         const double d2 = m2 * ((lc2 * lc2) + l1 * lc2 * cos2) + I2;                          // :258
         const double phi2 = m2 * lc2 * g * gt::cos(theta1 + theta2 - B200_PI / 2.0);             // :259
-        const double phi1 = -m2 * l1 * lc2 * (dtheta2 * dtheta2) * sin2
+        const double phi1 = -m2 * l1 * lc2 * gt::sq(dtheta2) * sin2
                             - 2 * m2 * l1 * lc2 * dtheta2 * dtheta1 * sin2
                             + (m1 * lc1 + m2 * l1) * g * gt::cos(theta1 - B200_PI / 2)
                             + phi2;                                                          // :260-265
         const double ddtheta2 =
-            (a + d2 / d1 * phi1 - m2 * l1 * lc2 * (dtheta1 * dtheta1) * sin2 - phi2) /
-            (m2 * (lc2 * lc2) + I2 - (d2 * d2) / d1);                                         // :273-275
+            (a + d2 / d1 * phi1 - m2 * l1 * lc2 * gt::sq(dtheta1) * sin2 - phi2) /
+            (m2 * (lc2 * lc2) + I2 - gt::sq(d2) / d1);      // x**2 = libm pow(x, 2.0)                                         // :273-275
         const double ddtheta1 = -(d2 * ddtheta2 + phi1) / d1;                                // :276
         k[0] = dtheta1; k[1] = dtheta2; k[2] = ddtheta1; k[3] = ddtheta2;                    // :277
     }

@@ -326,6 +326,9 @@ def step_api_compatibility(step_returns, output_truncation_bool=True, is_vector_
     if len(step_returns) == 4:
         return step_returns
     obs, rew, terminated, truncated, infos = step_returns
-    if isinstance(infos, dict):
+    done = terminated | truncated
+    # like the reference (:114-118) the key only appears in steps where some env finished (for device tensors this
+    # `any` is the one host synchronisation of the adapter)
+    if isinstance(infos, dict) and bool(done.any()):
         infos["TimeLimit.truncated"] = truncated & ~terminated
-    return obs, rew, terminated | truncated, infos
+    return obs, rew, done, infos

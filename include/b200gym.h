@@ -72,7 +72,8 @@ typedef struct b200gym_config {
     int32_t flags;             /* B200GYM_LUNAR_ENABLE_WIND, else 0 */
     double param[4];           /* param[0]: Pendulum `g` (pendulum.py:95), MountainCar* `goal_velocity`
                                   (mountain_car.py:103, continuous_mountain_car.py:108), LunarLander* `gravity`
-                                  (lunar_lander.py:195,210-213; 0 = the default -10.0; must lie in (-12, 0));
+                                  (lunar_lander.py:195,210-213; must lie in (-12, 0) like the reference asserts -- the
+                                  reference's default is -10.0; 0.0 is rejected, not defaulted);
                                   param[1], param[2]: LunarLander* `wind_power`, `turbulence_power`
                                   (lunar_lander.py:197-198), read only with B200GYM_LUNAR_ENABLE_WIND */
 } b200gym_config;
@@ -336,6 +337,12 @@ int b200gym_box2d_overflows(b200gym_t *h, void *stream, int64_t *count_out);
  * Synchronous; *mismatches_out must come back 0.
  */
 int b200gym_selftest(int device, int64_t samples, uint64_t seed, int64_t *mismatches_out);
+/*
+ * Device self-test of the float64 sin / cos / x**2 the dynamics use (csrc/glibc_trig.cuh: glibc's results, bit for
+ * bit): evaluates them on x_dev[n]; the caller compares with its own libm (math.sin, math.cos, math.pow(x, 2.0)).
+ * sq_dev may be NULL.  Asynchronous.
+ */
+int b200gym_selftest_trig(const double *x_dev, int64_t n, double *sin_dev, double *cos_dev, double *sq_dev, void *stream);
 
 #ifdef __cplusplus
 }

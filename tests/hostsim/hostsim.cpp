@@ -360,6 +360,26 @@ void hs_sincos_small(const double *x, int64_t n, double *sn, double *cs) {
 void hs_glibc_trig(const double *x, int64_t n, double *sn, double *cs) {
     for (int64_t i = 0; i < n; i++) { sn[i] = bgym::gt::sin(x[i]); cs[i] = bgym::gt::cos(x[i]); }
 }
+// arguments in [lo, hi) (splitmix64 stream) where gt::sq(x) differs bitwise from libm pow(x, 2.0); *neq_out counts
+// those where pow(x, 2.0) itself differs from x * x (why the restatement exists)
+int64_t hs_glibc_sq_mismatches(uint64_t seed, int64_t n, double lo, double hi, int64_t *neq_out) {
+    int64_t bad = 0, neq = 0;
+    uint64_t st = seed;
+    volatile double two = 2.0;   // keep the compiler from folding pow(x, 2.0) into x * x
+    for (int64_t i = 0; i < n; i++) {
+        uint64_t z = (st += 0x9E3779B97F4A7C15ULL);
+        z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ULL;
+        z = (z ^ (z >> 27)) * 0x94D049BB133111EBULL;
+        z ^= z >> 31;
+        const double x = lo + (hi - lo) * ((double)(z >> 11) * (1.0 / 9007199254740992.0));
+        const double a = std::pow(x, two), b = bgym::gt::sq(x), c = x * x;
+        bad += std::memcmp(&a, &b, 8) != 0;
+        neq += std::memcmp(&a, &c, 8) != 0;
+    }
+    if (neq_out) *neq_out = neq;
+    return bad;
+}
+
 // number of arguments in [lo, hi) (splitmix64 stream) where sin or cos differs bitwise from this process's libm
 int64_t hs_glibc_trig_mismatches(uint64_t seed, int64_t n, double lo, double hi) {
     int64_t bad = 0;

@@ -62,6 +62,8 @@ def lib(smallcap=False):
         L.hs_overflows.restype = i64
         L.hs_overflows.argtypes = [vp]
         L.hs_glibc_trig.argtypes = [vp, i64, vp, vp]
+        L.hs_glibc_sq_mismatches.restype = i64
+        L.hs_glibc_sq_mismatches.argtypes = [ctypes.c_uint64, i64, dbl, dbl, ctypes.POINTER(i64)]
         L.hs_glibc_trig_mismatches.restype = i64
         L.hs_glibc_trig_mismatches.argtypes = [ctypes.c_uint64, i64, dbl, dbl]
         if smallcap:
@@ -199,6 +201,13 @@ def glibc_trig(x):
 def glibc_trig_mismatches(seed, n, lo, hi):
     """How many of n pseudo-random arguments in [lo, hi) give a sin or cos that differs bitwise from libm's."""
     return int(lib().hs_glibc_trig_mismatches(int(seed), int(n), float(lo), float(hi)))
+
+
+def glibc_sq_mismatches(seed, n, lo, hi):
+    """(#arguments where gt::sq(x) != libm pow(x, 2.0), #arguments where pow(x, 2.0) != x * x) of n in [lo, hi)."""
+    neq = ctypes.c_int64(0)
+    bad = lib().hs_glibc_sq_mismatches(int(seed), int(n), float(lo), float(hi), ctypes.byref(neq))
+    return int(bad), int(neq.value)
 
 
 def sincos_small(x):

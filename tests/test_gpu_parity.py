@@ -348,6 +348,34 @@ def test_persistent_kernel_equals_simple_kernel(env_id, monkeypatch):
         e.close()
 
 
+def test_device_sin_cos_are_bit_identical_to_the_hosts_libm():
+    """csrc/glibc_trig.cuh compiled by nvcc, on the device, against math.sin / math.cos of this process (the libm the
+    reference's results come from): every bit, over the ranges the envs produce and beyond."""
+    import ctypes
+    import math
+    from gym_b200 import _lib
+    torch = _torch()
+    lib = _lib.load()
+    rng = np.random.default_rng(3)
+    parts = [rng.uniform(-s, s, 200000) for s in (0.2, 1.0, 3.2, 10.0, 100.0, 1e6, 1.05e8, 1e-7)]
+    parts.append(np.array([0.0, -0.0, 0.126, -0.126, 0.855469, 2.426265, math.pi, math.pi / 2, 105414349.0, 1e-300]))
+    x = np.concatenate(parts)
+    xd = torch.as_tensor(x, device="cuda")
+    sn, cs, sq = torch.empty_like(xd), torch.empty_like(xd), torch.empty_like(xd)
+    _lib.check(lib.b200gym_selftest_trig(ctypes.c_void_p(xd.data_ptr()), x.size, ctypes.c_void_p(sn.data_ptr()),
+                                         ctypes.c_void_p(cs.data_ptr()), ctypes.c_void_p(sq.data_ptr()), None))
+    torch.cuda.synchronize()
+    ws = np.array([math.sin(v) for v in x])
+    wc = np.array([math.cos(v) for v in x])
+    wq = np.array([math.pow(v, 2.0) for v in x])      # what `x**2` is in the reference; differs from x*x in ~0.09 %
+    bad_s = np.flatnonzero(sn.cpu().numpy().view(np.int64) != ws.view(np.int64))
+    bad_c = np.flatnonzero(cs.cpu().numpy().view(np.int64) != wc.view(np.int64))
+    bad_q = np.flatnonzero(sq.cpu().numpy().view(np.int64) != wq.view(np.int64))
+    assert bad_s.size == 0 and bad_c.size == 0, (bad_s[:5], x[bad_s[:5]], bad_c[:5], x[bad_c[:5]])
+    assert bad_q.size == 0, (bad_q[:5], x[bad_q[:5]])
+    assert np.count_nonzero(wq != x * x) > 100
+
+
 def test_constant_division_fast_path_is_ieee_exact():
     """csrc/envs.cuh:div_by_const (Markstein residual correction with a folded reciprocal) must be
     bit-identical to IEEE division: 2^28 pseudo-random doubles x 4 divisors on the device."""

@@ -64,7 +64,8 @@ def test_engine_equals_the_references_sync_vector_env(gym, env_id):
             n_done += int(rinfo["_final_observation"].sum())
         exact += int((o == ro).sum())
         total += o.size
-    assert n_done > 0 or env_id.startswith(("Pendulum", "MountainCarContinuous"))   # these two only truncate (200 / 999)
+    # Pendulum / MountainCarContinuous only truncate (200 / 999); a random Acrobot rarely swings up within 320 steps
+    assert n_done > 0 or env_id.startswith(("Pendulum", "MountainCarContinuous", "Acrobot"))
     if not env_id.startswith("Acrobot"):
         assert exact / total > 0.999
     ref.close()
@@ -168,7 +169,10 @@ def test_reference_info_wrappers_on_engine_infos(gym):
         x = ref_compat(five, output_truncation_bool=False, is_vector_env=True)
         y = ref_compat(r.step(acts[t]), output_truncation_bool=False, is_vector_env=True)
         assert len(x) == 4 and len(z) == 4 and np.array_equal(x[2], y[2]) and np.array_equal(z[2], y[2])
-        assert np.array_equal(x[3]["TimeLimit.truncated"], y[3]["TimeLimit.truncated"])
-        assert np.array_equal(z[3]["TimeLimit.truncated"], y[3]["TimeLimit.truncated"])
+        # the key only exists in steps where some env finished (step_api_compatibility.py:114-118)
+        assert ("TimeLimit.truncated" in x[3]) == ("TimeLimit.truncated" in y[3]) == ("TimeLimit.truncated" in z[3])
+        if "TimeLimit.truncated" in y[3]:
+            assert np.array_equal(x[3]["TimeLimit.truncated"], y[3]["TimeLimit.truncated"])
+            assert np.array_equal(z[3]["TimeLimit.truncated"], y[3]["TimeLimit.truncated"])
     for w in (a, b, c, e, r):
         w.close()

@@ -218,6 +218,19 @@ def test_restated_glibc_sin_cos_are_bit_identical_to_libm():
         assert glibc_trig_mismatches(1000 + k, 2_000_000, lo, hi) == 0, (lo, hi)
 
 
+def test_restated_glibc_square_is_bit_identical_to_libm_pow():
+    """`x**2` in the reference is libm pow(x, 2.0), which is NOT x * x (1 ulp apart in ~0.09 % of arguments: enough to
+    lose a chaotic Acrobot trajectory); csrc/glibc_trig.cuh: gt::sq restates glibc's pow for that exponent.  Against
+    the libm of this process: identical everywhere."""
+    from hostsim.sim import glibc_sq_mismatches
+    total_neq = 0
+    for k, (lo, hi) in enumerate([(-4.0, 4.0), (-30.0, 30.0), (0.9, 1.1), (-1e-3, 1e-3), (-1e6, 1e6), (1.0, 2.5)]):
+        bad, neq = glibc_sq_mismatches(50 + k, 2_000_000, lo, hi)
+        assert bad == 0, (lo, hi, bad)
+        total_neq += neq
+    assert total_neq > 1000     # the premise: pow(x, 2.0) really differs from x * x
+
+
 def test_lunar_random_constructor_arguments_sweep():
     """Random LunarLander constructor arguments (gravity in (-12, 0), wind and turbulence powers, both action
     spaces, random wind phases): device source on the CPU == oracle."""

@@ -19,6 +19,8 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <cmath>
+#include <type_traits>
 
 #include <cstdarg>
 #include <cstdio>
@@ -57,7 +59,9 @@ struct b200gym {
         unsigned long long *ring = nullptr, *counter = nullptr; int ring_size = 0;
     } ep;
     int sm_count = 148;
-    int occ[B200GYM_NUM_KINDS][3] = {};     // cached CTAs/SM of step_kernel_persistent per (kind, action width)
+    int occ[B200GYM_NUM_KINDS][3][2] = {};  // cached CTAs/SM of step_kernel_persistent per (kind, action width, lean)
+    int p_ctas = -1;                        // kernel P/L: resident CTAs per SM; -1 = occupancy limit, 0 = balance the tile
+                                            // rounds (see launch_step_typed), k > 0 = exactly k (B200GYM_P_CTAS, tuning runs)
     int kernel_choice = 1;                  // 0: kernel A (one tile per CTA), 1: kernel P (resident grid, asynchronous
                                             // prefetch, deferred resets); B200GYM_KERNEL=a|p overrides
     int gather_bulk = 1;                    // multi-GPU step: 1 = kernel G (staged tile + bulk pushes), 0 = per-thread
@@ -177,8 +181,8 @@ struct StepArgs {
     uint8_t *peer_trunc[B200GYM_MAX_PEERS];
 };
 
-template <int D>
-__device__ __forceinline__ void store_row(float *base, int64_t i, const float (&v)[D]) {
+template <int D, typename I>
+__device__ __forceinline__ void store_row(float *base, I i, const float (&v)[D]) {
     if constexpr (D == 4) {
         reinterpret_cast<float4 *>(base)[i] = make_float4(v[0], v[1], v[2], v[3]);
     } else if constexpr (D == 2) {
@@ -198,13 +202,14 @@ __device__ __forceinline__ void store_row(float *base, int64_t i, const float (&
     }
 }
 
-template <int D>
-__device__ __forceinline__ void store_obs_all(const StepArgs &a, int64_t i, const float (&v)[D]) {
+template <int D, typename I>
+__device__ __forceinline__ void store_obs_all(const StepArgs &a, I i, const float (&v)[D]) {
     store_row<D>(a.obs, i, v);
     for (int p = 0; p < a.npeer; p++) store_row<D>(a.peer_obs[p], i, v);
 }
 
-__device__ __forceinline__ void store_scalars_all(const StepArgs &a, int64_t i, double reward, uint8_t term,
+template <typename I>
+__device__ __forceinline__ void store_scalars_all(const StepArgs &a, I i, double reward, uint8_t term,
                                                   uint8_t trunc) {
     a.reward[i] = reward;
     a.terminated[i] = term;
@@ -220,7 +225,8 @@ __device__ __forceinline__ void store_scalars_all(const StepArgs &a, int64_t i, 
 // kernels: `episode_returns += rewards` on a float32 array with float64 rewards (add in float64, round to float32),
 // `episode_lengths += 1`; on terminated | truncated emit both, append to the ring (return_queue / length_queue),
 // start over from zero.
-__device__ __forceinline__ void episode_account(const StepArgs &a, int64_t i, double reward, bool done) {
+template <typename I>
+__device__ __forceinline__ void episode_account(const StepArgs &a, I i, double reward, bool done) {
     if (!a.ep_acc) return;
     const float ret = (float)((double)a.ep_acc[i] + reward);
     const int32_t len = a.ep_len[i] + 1;
@@ -242,23 +248,33 @@ __device__ __forceinline__ void episode_account(const StepArgs &a, int64_t i, do
 // Where the results of env i go.  DirectSink: straight to the caller's arrays (and, when peers are mapped,
 // to theirs) with per-thread stores.  StagedSink: into the CTA's shared-memory tile, which leaves the SM as a few
 // bulk copies per destination (step_kernel_gather).
-struct DirectSink {
+// PEERS = false: the caller knows there are no peer-mapped destinations (single-GPU step), so the per-destination
+// loops and their constant-bank traffic disappear from the hot loop.
+template <bool PEERS>
+struct DirectSinkT {
     const StepArgs &a;
-    template <int D>
-    __device__ __forceinline__ void obs(int64_t i, const float (&v)[D]) const { store_obs_all<D>(a, i, v); }
-    __device__ __forceinline__ void scalars(int64_t i, double reward, uint8_t term, uint8_t trunc) const {
-        store_scalars_all(a, i, reward, term, trunc);
+    template <int D, typename I>
+    __device__ __forceinline__ void obs(I i, const float (&v)[D]) const {
+        if constexpr (PEERS) store_obs_all<D>(a, i, v);
+        else store_row<D>(a.obs, i, v);
+    }
+    template <typename I>
+    __device__ __forceinline__ void scalars(I i, double reward, uint8_t term, uint8_t trunc) const {
+        if constexpr (PEERS) store_scalars_all(a, i, reward, term, trunc);
+        else { a.reward[i] = reward; a.terminated[i] = term; a.truncated[i] = trunc; }
     }
 };
+using DirectSink = DirectSinkT<true>;
 
 struct StagedSink {
     float *s_obs;
     double *s_reward;
     uint8_t *s_term, *s_trunc;
     int64_t base;   // env index of row 0 of the tile
-    template <int D>
-    __device__ __forceinline__ void obs(int64_t i, const float (&v)[D]) const { store_row<D>(s_obs, i - base, v); }
-    __device__ __forceinline__ void scalars(int64_t i, double reward, uint8_t term, uint8_t trunc) const {
+    template <int D, typename I>
+    __device__ __forceinline__ void obs(I i, const float (&v)[D]) const { store_row<D>(s_obs, (int)(i - base), v); }
+    template <typename I>
+    __device__ __forceinline__ void scalars(I i, double reward, uint8_t term, uint8_t trunc) const {
         const int r = (int)(i - base);
         s_reward[r] = reward; s_term[r] = term; s_trunc[r] = trunc;
     }
@@ -283,8 +299,8 @@ struct Tuning {
 // Phase 1, by the thread that owns env i (its inputs are in registers): Env.step, TimeLimit,
 // stores of reward / flags / final_obs, and -- unless the episode ended -- of the new state and
 // observation.  Returns true when the env must be reset by phase 2.
-template <int KIND, typename Sink>
-__device__ __forceinline__ bool advance_env(const StepArgs &a, const Sink &sink, int64_t i, double (&s)[Env<KIND>::S],
+template <int KIND, bool EP = true, typename Sink, typename I>
+__device__ __forceinline__ bool advance_env(const StepArgs &a, const Sink &sink, I i, double (&s)[Env<KIND>::S],
                                             int32_t elapsed, long long action_int, float a0) {
     using E = Env<KIND>;
     int act = 0;
@@ -324,7 +340,7 @@ __device__ __forceinline__ bool advance_env(const StepArgs &a, const Sink &sink,
     const bool needs_reset = (terminated || truncated) && a.autoreset;   // sync_vector_env.py:152-156
 
     sink.scalars(i, reward, terminated ? 1 : 0, truncated ? 1 : 0);
-    episode_account(a, i, reward, terminated || truncated);
+    if constexpr (EP) episode_account(a, i, reward, terminated || truncated);
     if (needs_reset) {
         if (a.final_obs) store_row<E::D>(a.final_obs, i, obs);           // info["final_observation"]
     } else {
@@ -338,16 +354,16 @@ __device__ __forceinline__ bool advance_env(const StepArgs &a, const Sink &sink,
 
 // Phase 2: the unseeded env.reset() of the autoreset (sync_vector_env.py:154) for env i, by
 // whichever thread picked it off the CTA's compacted list.
-template <int KIND, typename Sink>
-__device__ __forceinline__ void reset_env(const StepArgs &a, const Sink &sink, int64_t i) {
+template <int KIND, typename Sink, typename I>
+__device__ __forceinline__ void reset_env(const StepArgs &a, const Sink &sink, I i) {
     using E = Env<KIND>;
     double s[E::S];
     float obs[E::D];
-    Pcg64 g = pcg64_load(a.rng + 4 * i);
+    Pcg64 g = pcg64_load(a.rng + 4 * (size_t)i);
     double lo, hi;
     E::default_bounds(lo, hi);
     E::reset(s, g, lo, hi, obs);
-    pcg64_store(a.rng + 4 * i, g);
+    pcg64_store(a.rng + 4 * (size_t)i, g);
 #pragma unroll
     for (int k = 0; k < E::S; k++) a.state[k * a.n + i] = s[k];
     a.elapsed[i] = 0;                                                    // time_limit.py:67
@@ -443,10 +459,14 @@ struct PrefetchLayout {
     static constexpr int kBytes = kElapsedOff + kThreads * 4;
 };
 
-template <int KIND, typename ActT>
+// LEAN (the single-GPU step without the fused RecordEpisodeStatistics, fewer than 2^31 envs): 32-bit env indices
+// (one IMAD.WIDE per address instead of a 64-bit add chain), no per-peer store loops, no episode accounting --
+// same arithmetic, same stores, fewer issue slots.
+template <int KIND, typename ActT, bool LEAN>
 __global__ void __launch_bounds__(kThreads, Tuning<KIND>::kMinCtas) step_kernel_persistent(const StepArgs a, const int num_tiles) {
     using E = Env<KIND>;
     using L = PrefetchLayout<KIND, ActT>;
+    using Idx = typename std::conditional<LEAN, uint32_t, int64_t>::type;
     __shared__ __align__(16) unsigned char in_mem[L::kBytes];
     __shared__ int reset_list[kResetCap];
     __shared__ int reset_count;
@@ -457,17 +477,18 @@ __global__ void __launch_bounds__(kThreads, Tuning<KIND>::kMinCtas) step_kernel_
     double *s_state = reinterpret_cast<double *>(in_mem + L::kStateOff);
     int32_t *s_elapsed = reinterpret_cast<int32_t *>(in_mem + L::kElapsedOff);
     const ActT *actions = reinterpret_cast<const ActT *>(a.actions);
-    const DirectSink sink{a};
+    const DirectSinkT<!LEAN> sink{a};
+    const Idx first = (Idx)a.first, count = (Idx)a.count;
 
     auto prefetch = [&](int tile) {
-        const int64_t j = (int64_t)tile * kThreads + tid;
-        if (j < a.count) {
-            const int64_t i = a.first + j;
+        const Idx j = (Idx)tile * kThreads + tid;
+        if (j < count) {
+            const Idx i = first + j;
 #pragma unroll
             for (int k = 0; k < E::S; k++) acp::ld_async<8>(s_state + k * kThreads + tid, a.state + k * a.n + i);
             acp::ld_async<4>(s_elapsed + tid, a.elapsed + i);
             if constexpr (L::kActAsync)
-                acp::ld_async<L::kActBytes>(in_mem + L::kActOff + tid * L::kActBytes, actions + i * L::kActPerEnv);
+                acp::ld_async<L::kActBytes>(in_mem + L::kActOff + tid * L::kActBytes, actions + (size_t)i * L::kActPerEnv);
         }
         acp::ld_commit();
     };
@@ -475,11 +496,11 @@ __global__ void __launch_bounds__(kThreads, Tuning<KIND>::kMinCtas) step_kernel_
     int tile = blockIdx.x;
     if (tile < num_tiles) prefetch(tile);
     for (; tile < num_tiles; tile += gridDim.x) {
-        const int64_t j = (int64_t)tile * kThreads + tid;
-        const bool in_range = j < a.count;
-        const int64_t i = a.first + j;
+        const Idx j = (Idx)tile * kThreads + tid;
+        const bool in_range = j < count;
+        const Idx i = first + j;
         ActT av{};
-        if constexpr (!L::kActAsync) { if (in_range) av = __ldg(actions + i * L::kActPerEnv); }
+        if constexpr (!L::kActAsync) { if (in_range) av = __ldg(actions + (size_t)i * L::kActPerEnv); }
         acp::ld_wait_all();
         double s[E::S];
 #pragma unroll
@@ -493,7 +514,7 @@ __global__ void __launch_bounds__(kThreads, Tuning<KIND>::kMinCtas) step_kernel_
         if constexpr (E::A == 0) action_int = (long long)av;
         else a0 = (float)av;
         bool need = false;
-        if (in_range) need = advance_env<KIND>(a, sink, i, s, elapsed, action_int, a0);
+        if (in_range) need = advance_env<KIND, !LEAN>(a, sink, i, s, elapsed, action_int, a0);
         const unsigned m = __ballot_sync(0xffffffffu, need);
         if (m != 0u) {
             bool inline_reset = __popc(m) >= 12;          // dense enough: reset right here
@@ -507,7 +528,7 @@ __global__ void __launch_bounds__(kThreads, Tuning<KIND>::kMinCtas) step_kernel_
     }
     __syncthreads();
     const int cnt = min(reset_count, kResetCap);
-    for (int q = tid; q < cnt; q += kThreads) reset_env<KIND>(a, sink, a.first + reset_list[q]);
+    for (int q = tid; q < cnt; q += kThreads) reset_env<KIND>(a, sink, (Idx)(first + (Idx)reset_list[q]));
 }
 
 // --- kernel G: one tile per CTA, results staged in shared memory and pushed with bulk stores ---------
@@ -1089,21 +1110,40 @@ static int launch_step_typed(b200gym *h, const StepArgs &a, cudaStream_t st) {
             done = tiles * kThreads;
         }
     }
-    if (done == 0 && h->kernel_choice == 1 && a.npeer == 0 && a.count >= (int64_t)h->sm_count * kThreads) {
+    if (done == 0 && h->kernel_choice >= 1 && a.npeer == 0 && a.count >= (int64_t)h->sm_count * kThreads) {
         // kernel P: resident grid; needs naturally aligned input words for cp.async (always true for the
         // handle's own arrays; the caller's action pointer is checked)
         using L = PrefetchLayout<KIND, ActT>;
         const bool aligned = !L::kActAsync || ((uintptr_t)a.actions % L::kActBytes == 0);
         if (aligned) {
-            int &occ = h->occ[KIND][sizeof(ActT) == 8 ? 0 : sizeof(ActT) == 4 ? 1 : 2];
+            // the lean instantiation: no fused episode statistics, every index fits 32 bits
+            const bool lean = h->kernel_choice == 2 && !a.ep_acc && h->n < (int64_t)1 << 30;
+            int &occ = h->occ[KIND][sizeof(ActT) == 8 ? 0 : sizeof(ActT) == 4 ? 1 : 2][lean ? 1 : 0];
             if (occ == 0) {
-                CK(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, step_kernel_persistent<KIND, ActT>, kThreads, 0));
+                if (lean) CK(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, step_kernel_persistent<KIND, ActT, true>, kThreads, 0));
+                else CK(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, step_kernel_persistent<KIND, ActT, false>, kThreads, 0));
                 if (occ < 1) occ = 1;
             }
             const int64_t all_tiles = (a.count + kThreads - 1) / kThreads;
-            int64_t grid = (int64_t)h->sm_count * occ;
+            // resident CTAs per SM: the occupancy limit, or -- when that leaves the last round of tiles mostly
+            // empty -- the smaller count that makes every CTA walk (nearly) the same number of tiles
+            int per_sm = occ;
+            if (h->p_ctas > 0 && h->p_ctas < occ) per_sm = h->p_ctas;
+            else if (h->p_ctas == 0) {
+                double best = 0.0;
+                for (int c = occ; c >= (occ > 2 ? occ - 2 : 1); c--) {
+                    const int64_t g = (int64_t)h->sm_count * c;
+                    const int64_t rounds = (all_tiles + g - 1) / g;
+                    // throughput model: tiles per round-time; a round's time grows with the resident warps only
+                    // weakly (latency-bound), so weigh occupancy by its square root
+                    const double score = (double)all_tiles / (double)(rounds * g) * sqrt((double)c / occ);
+                    if (score > best + 1e-9) { best = score; per_sm = c; }
+                }
+            }
+            int64_t grid = (int64_t)h->sm_count * per_sm;
             if (grid > all_tiles) grid = all_tiles;
-            step_kernel_persistent<KIND, ActT><<<(unsigned)grid, kThreads, 0, st>>>(a, (int)all_tiles);
+            if (lean) step_kernel_persistent<KIND, ActT, true><<<(unsigned)grid, kThreads, 0, st>>>(a, (int)all_tiles);
+            else step_kernel_persistent<KIND, ActT, false><<<(unsigned)grid, kThreads, 0, st>>>(a, (int)all_tiles);
             CK(h, cudaGetLastError());
             done = a.count;
         }
@@ -1287,7 +1327,9 @@ extern "C" int b200gym_create(const b200gym_config *cfg, int64_t num_envs, int d
     {
         const char *fs = getenv("B200GYM_SIMPLE_KERNEL");
         const char *kc = getenv("B200GYM_KERNEL");
-        if (kc && (kc[0] == 'a' || kc[0] == 'p')) h->kernel_choice = kc[0] == 'p';
+        if (kc && (kc[0] == 'a' || kc[0] == 'p' || kc[0] == 'l')) h->kernel_choice = kc[0] == 'a' ? 0 : kc[0] == 'p' ? 1 : 2;
+        const char *pc = getenv("B200GYM_P_CTAS");
+        if (pc && atoi(pc) >= -1 && atoi(pc) <= 8) h->p_ctas = atoi(pc);
         if (fs && fs[0] == '1') h->kernel_choice = 0;
         const char *gb = getenv("B200GYM_GATHER");
         if (gb && (gb[0] == 'b' || gb[0] == 'd')) h->gather_bulk = gb[0] == 'b';

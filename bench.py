@@ -589,7 +589,7 @@ def run_b200(args):
         bpe = BYTES_PER_ENV_STEP.get(args.env, 0)
         achieved = bpe * n / (kernel_ms * 1e-3) / 1e9
         kernel_name = {"a": "step_kernel", "p": "step_kernel_persistent", "l": "step_kernel_persistent<LEAN>"}[
-            os.environ.get("B200GYM_KERNEL", "p")[:1]]
+            os.environ.get("B200GYM_KERNEL", "l")[:1]]
         if is_box2d(args.env):
             kernel_name = "lunar_step_kernel" if args.env.startswith("Lunar") else "walker_step_kernel"
         line = {

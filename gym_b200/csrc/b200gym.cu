@@ -62,8 +62,9 @@ struct b200gym {
     int occ[B200GYM_NUM_KINDS][3][2] = {};  // cached CTAs/SM of step_kernel_persistent per (kind, action width, lean)
     int p_ctas = -1;                        // kernel P/L: resident CTAs per SM; -1 = occupancy limit, 0 = balance the tile
                                             // rounds (see launch_step_typed), k > 0 = exactly k (B200GYM_P_CTAS, tuning runs)
-    int kernel_choice = 1;                  // 0: kernel A (one tile per CTA), 1: kernel P (resident grid, asynchronous
-                                            // prefetch, deferred resets); B200GYM_KERNEL=a|p overrides
+    int kernel_choice = 2;                  // 0: kernel A (one tile per CTA), 1: kernel P (resident grid, asynchronous
+                                            // prefetch, deferred resets), 2: P's lean instantiation where it applies
+                                            // (else P); B200GYM_KERNEL=a|p|l overrides
     int gather_bulk = 1;                    // multi-GPU step: 1 = kernel G (staged tile + bulk pushes), 0 = per-thread
                                             // peer stores from kernel A; B200GYM_GATHER=bulk|direct overrides
     int block_a = 256;                      // CTA size of kernel A (B200GYM_BLOCK_A=64|128|256, tuning runs)
@@ -281,11 +282,14 @@ struct StagedSink {
 };
 
 // Tuning knobs (overridable at build time for A/B measurements).
-// The per-env work is one long dependent float64 chain, so the SMs are latency-bound and
-// throughput follows the number of resident warps: 8 CTAs x 256 threads = 64 warps/SM (100 %
-// occupancy) needs <= 32 registers per thread.
+// The per-env work is one long dependent float64 chain and the SMs are latency-bound, but occupancy is not the
+// lever: at 32 registers (8 CTAs x 256 threads = 64 warps/SM) the hot loop spills the state across the division
+// slow-path calls, and those local-memory round trips cost more than the extra warps hide.  Measured on B200
+// (CartPole, 2^20 envs, cold L2, median of 400 launches, profiles/r2b_register_budget_ab.txt):
+//   32 registers / 8 CTAs: kernel A 26.7 us, P 28.7, lean P 30.7;  40 / 6: A 26.7, P 26.5, lean P 24.6;
+//   48 / 5: A 26.7, P 24.6, lean P 24.6.   -> 6 CTAs/SM (40 registers, no spills in the lean loop).
 #ifndef B200_MIN_CTAS
-#define B200_MIN_CTAS 8
+#define B200_MIN_CTAS 6
 #endif
 #ifndef B200_STAGES
 #define B200_STAGES 2

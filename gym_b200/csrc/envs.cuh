@@ -71,6 +71,17 @@ __constant__ double kCosCoef[6] = {4.16666666666666019037e-02, -1.38888888888741
                                    2.48015872894767294178e-05, -2.75573143513906633035e-07,
                                    2.08757232129817482790e-09, -1.13596475577881948265e-11};
 
+// the library path of sincos_small, out of line: it only runs in plain-Env mode after termination, and inlined it
+// costs the 32-register hot loop of the step kernels spill slots
+__device__ __noinline__ void sincos_library(double x, double *sn, double *cs) {
+#ifdef B200_DIAG_CUDA_SINCOS   // diagnosis builds only (scripts/r2b_variants.sh): CUDA's own sincos on the cold path
+    sincos(x, sn, cs);
+#else
+    *sn = gt::sin(x);
+    *cs = gt::cos(x);
+#endif
+}
+
 __device__ __forceinline__ void sincos_small(double x, double &sn, double &cs) {
     if (fabs(x) < 0.7) {
         const double z = x * x;
@@ -93,8 +104,7 @@ __device__ __forceinline__ void sincos_small(double x, double &sn, double &cs) {
         const double hz = fma(0.5, z, -qx);
         cs = (1.0 - qx) - (hz - z * zr);
     } else {
-        sn = gt::sin(x);
-        cs = gt::cos(x);
+        sincos_library(x, &sn, &cs);
     }
 }
 

@@ -9,9 +9,9 @@
  *   warm-start impulse matching by feature id) -> island solve (integrate velocities, joints, 2-point
  *   block contact solver with friction, position integration with translation clamps, Baumgarte
  *   position iterations with early exit) -> sleeping.
- * PARITY UNPINNED.  Deliberate deviations from Box2D: continuous collision (TOI sub-stepping) is
- * not modelled; the broad phase is replaced by testing every (body, edge) pair behind the same fat
- * AABB reject; constraints are ordered by the scene's island order x descending edge index; sin/cos
+ *   -> SolveTOI (b2lite_toi.h: b2TimeOfImpact + TOI sub-steps of dynamic bodies against static fixtures).
+ * PARITY UNPINNED.  Deliberate deviations from Box2D: the broad phase is replaced by testing every
+ * (body, edge) pair behind the same fat AABB reject; constraints are ordered by the scene's island order x descending edge index; sin/cos
  * of body angles use the polynomial below instead of the platform libm.
  * All arithmetic is IEEE float32 with separate rounding of every operation (-ffp-contract=off).
  */
@@ -96,6 +96,7 @@ typedef struct {
     xform xf;
     v2 localCenter, c0, c, v, force;
     float a0, a, w, torque, mass, invMass, I, invI, sleepTime;
+    float alpha0;            /* b2Sweep::alpha0 (continuous collision, b2lite_toi.h) */
     int awake;
 } body_t;
 
@@ -156,6 +157,10 @@ typedef struct {
     int overflowed;          /* out: number of pairs dropped that way in this step (tests assert it stays 0) */
     void (*event)(void *ctx, int body, int begin); /* Begin/EndContact listener */
     void *ctx;
+    int toi;                 /* 1: b2World::SolveTOI after the discrete solve (m_continuousPhysics, Box2D's default) */
+    int one_static_body;     /* 1: every static fixture belongs to ONE static body (LunarLander's moon); 0: one static
+                              * body per fixture (BipedalWalker's terrain).  Matters for the static sweeps' alpha0 */
+    int stat_toi_calls, stat_toi_events; /* out: b2TimeOfImpact evaluations / TOI sub-steps of this step */
 } b2l_world;
 
 /* ---------------------------------------------------------------- shapes & mass (b2PolygonShape) */
@@ -718,6 +723,8 @@ static int joint_solve_position(joint_t *j, bstate_t *sA, bstate_t *sB)
     return positionError <= LINEAR_SLOP && angularError <= ANGULAR_SLOP;
 }
 
+#include "b2lite_toi.h"
+
 /* ---------------------------------------------------------------- b2World::Step */
 static void b2l_step(b2l_world *W, float dt, int velIters, int posIters)
 {
@@ -992,6 +999,9 @@ static void b2l_step(b2l_world *W, float dt, int velIters, int posIters)
             b->awake = 0; b->sleepTime = 0.0f; b->v = V(0.0f, 0.0f); b->w = 0.0f;
         }
     }
+    /* --- SolveTOI: continuous collision against the static fixtures (sleeping islands are skipped) */
+    W->stat_toi_calls = 0; W->stat_toi_events = 0;
+    if (W->toi && W->awake) b2l_solve_toi(W, dt, velIters);
     for (int i = 0; i < NB; i++) { W->b[i].force = V(0.0f, 0.0f); W->b[i].torque = 0.0f; }
     W->inv_dt0 = inv_dt;
 }

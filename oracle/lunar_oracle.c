@@ -49,6 +49,7 @@ typedef struct {
     pcg64_t rng;
     int32_t elapsed;
     int stat_contacts, stat_pos_iters; /* of the last world step (workload statistics for DESIGN.md) */
+    long long toi_calls, toi_events;   /* b2TimeOfImpact evaluations / TOI sub-steps since the env was created (sticky) */
     long long overflows;               /* touching pairs dropped because the scene's manifold table was full (sticky) */
     int32_t wind_idx, torque_idx; /* lunar_lander.py:234-235: drawn once per env object, never reset */
 } world_t;
@@ -70,6 +71,10 @@ struct orc_lunar {
  * force overflows on both sides and check that they are handled identically */
 static int g_lunar_max_contacts = 8;
 void orc_lunar_set_max_contacts(int cap) { g_lunar_max_contacts = cap; }
+/* continuous collision (b2World::SolveTOI, b2lite_toi.h); on like Box2D's m_continuousPhysics, switchable so that a test
+ * can show what it prevents */
+static int g_lunar_toi = 1;
+void orc_lunar_set_toi(int on) { g_lunar_toi = on; }
 
 static void lunar_event(void *ctx, int body, int begin)
 {
@@ -91,9 +96,11 @@ static int world_step(world_t *W, float gravity_y, float dt, int velIters, int p
     S.gravity_y = gravity_y;
     S.event = lunar_event; S.ctx = W;
     S.max_contacts = g_lunar_max_contacts;
+    S.toi = g_lunar_toi; S.one_static_body = 1;
     b2l_step(&S, dt, velIters, posIters);
     W->inv_dt0 = S.inv_dt0;
     W->stat_contacts = S.stat_contacts; W->stat_pos_iters = S.stat_pos_iters;
+    W->toi_calls += S.stat_toi_calls; W->toi_events += S.stat_toi_events;
     W->overflows += S.overflowed;
     return S.awake;
 }
@@ -123,10 +130,10 @@ static void lunar_reset_one(world_t *W, const opts_t *O, float *obs)
     pcg64_t rng = W->rng;
     float inv_dt0 = W->inv_dt0; /* the b2World object survives reset() */
     int32_t wind_idx = W->wind_idx, torque_idx = W->torque_idx;
-    long long overflows = W->overflows;
+    long long overflows = W->overflows, toi_calls = W->toi_calls, toi_events = W->toi_events;
     memset(W, 0, sizeof *W);
     W->inv_dt0 = inv_dt0;
-    W->overflows = overflows;
+    W->overflows = overflows; W->toi_calls = toi_calls; W->toi_events = toi_events;
     W->wind_idx = wind_idx; W->torque_idx = torque_idx;
     const double Wd = VIEWPORT_W / SCALE, Hd = VIEWPORT_H / SCALE;
     enum { CHUNKS = 11 };
@@ -459,9 +466,24 @@ int64_t orc_lunar_overflows(const orc_lunar *v)
     return c;
 }
 
+/* {b2TimeOfImpact evaluations, TOI sub-steps} summed over all envs since creation */
+void orc_lunar_toi_stats(const orc_lunar *v, int64_t out[2])
+{
+    out[0] = 0; out[1] = 0;
+    for (int64_t i = 0; i < v->n; i++) { out[0] += v->w[i].toi_calls; out[1] += v->w[i].toi_events; }
+}
+
 void orc_lunar_get_stats(const orc_lunar *v, int32_t *out)
 {
     for (int64_t i = 0; i < v->n; i++) { out[2 * i] = v->w[i].stat_contacts; out[2 * i + 1] = v->w[i].stat_pos_iters; }
+}
+
+/* test hook: overwrite the velocity of one body of env i (tunnelling tests) */
+void orc_lunar_set_body_velocity(orc_lunar *v, int64_t i, int body, float vx, float vy, float w)
+{
+    world_t *W = &v->w[i];
+    W->b[body].v = V(vx, vy);
+    W->b[body].w = w;
 }
 
 /* debugging / parity: dump the 3 bodies (c.x, c.y, a, v.x, v.y, w) + flags of env i */

@@ -28,6 +28,9 @@ void orc_lunar_step_cont_mt(orc_lunar *v, const float *actions, float *obs, doub
                             uint8_t *truncated, float *final_obs, int nthreads);
 void orc_lunar_get_terrain(const orc_lunar *v, int64_t i, float *y11);
 void orc_lunar_get_stats(const orc_lunar *v, int32_t *out);
+void orc_lunar_toi_stats(const orc_lunar *v, int64_t out[2]);
+void orc_lunar_set_toi(int on);
+void orc_lunar_set_body_velocity(orc_lunar *v, int64_t i, int body, float vx, float vy, float w);
 #ifdef __cplusplus
 }
 #endif

@@ -229,6 +229,14 @@ def set_box2d_max_contacts(lunar=8, walker=10):
     L.orc_walker_set_max_contacts(int(walker))
 
 
+def set_box2d_toi(on=True):
+    """Continuous collision (b2World::SolveTOI, oracle/b2lite_toi.h) of the two Box2D scenes; process-wide, on by
+    default like Box2D's m_continuousPhysics.  Tests switch it off to show what it prevents."""
+    L = lib()
+    L.orc_lunar_set_toi(int(bool(on)))
+    L.orc_walker_set_toi(int(bool(on)))
+
+
 class OracleLunar:
     """SyncVectorEnv([make("LunarLander-v2")] * n) restated in C (oracle/lunar_oracle.c).
 
@@ -260,6 +268,18 @@ class OracleLunar:
         f = lib().orc_lunar_overflows
         f.restype, f.argtypes = ctypes.c_int64, [ctypes.c_void_p]
         return int(f(self._h))
+
+    def toi_stats(self):
+        """(b2TimeOfImpact evaluations, TOI sub-steps) summed over all envs since creation."""
+        out = np.zeros(2, dtype=np.int64)
+        lib().orc_lunar_toi_stats(ctypes.c_void_p(self._h), ctypes.c_void_p(out.ctypes.data))
+        return int(out[0]), int(out[1])
+
+    def set_body_velocity(self, i, body, vx, vy, w=0.0):
+        """test hook: overwrite the velocity of one body (0 lander, 1 / 2 legs) of env i"""
+        f = lib().orc_lunar_set_body_velocity
+        f.restype, f.argtypes = None, [ctypes.c_void_p, ctypes.c_int64, ctypes.c_int, ctypes.c_float, ctypes.c_float, ctypes.c_float]
+        f(self._h, int(i), int(body), float(vx), float(vy), float(w))
 
     def close(self):
         if getattr(self, "_h", None):
@@ -321,6 +341,12 @@ class OracleWalker:
         f = lib().orc_walker_overflows
         f.restype, f.argtypes = ctypes.c_int64, [ctypes.c_void_p]
         return int(f(self._h))
+
+    def toi_stats(self):
+        """(b2TimeOfImpact evaluations, TOI sub-steps) summed over all envs since creation."""
+        out = np.zeros(2, dtype=np.int64)
+        lib().orc_walker_toi_stats(ctypes.c_void_p(self._h), ctypes.c_void_p(out.ctypes.data))
+        return int(out[0]), int(out[1])
 
     def close(self):
         if getattr(self, "_h", None):

@@ -59,6 +59,7 @@ typedef struct {
     pcg64_t rng;
     int32_t elapsed;
     int stat_contacts, stat_pos_iters; /* of the last world step (workload statistics for DESIGN.md) */
+    long long toi_calls, toi_events;   /* b2TimeOfImpact evaluations / TOI sub-steps since the env was created (sticky) */
     long long overflows;               /* touching pairs dropped because the scene's manifold table was full (sticky) */
 } wworld_t;
 
@@ -74,6 +75,10 @@ struct orc_walker {
  * force overflows on both sides and check that they are handled identically */
 static int g_walker_max_contacts = 10;
 void orc_walker_set_max_contacts(int cap) { g_walker_max_contacts = cap; }
+/* continuous collision (b2World::SolveTOI, b2lite_toi.h); on like Box2D's m_continuousPhysics, switchable so that a test
+ * can show what it prevents */
+static int g_walker_toi = 1;
+void orc_walker_set_toi(int on) { g_walker_toi = on; }
 
 static void walker_event(void *ctx, int body, int begin)
 {
@@ -102,9 +107,11 @@ static void wworld_step(wworld_t *W)
     S.gravity_y = -10.0f;
     S.event = walker_event; S.ctx = W;
     S.max_contacts = g_walker_max_contacts;
+    S.toi = g_walker_toi; S.one_static_body = 0;
     b2l_step(&S, (float)(1.0 / FPS), 6 * 30, 2 * 30);
     W->inv_dt0 = S.inv_dt0;
     W->stat_contacts = S.stat_contacts; W->stat_pos_iters = S.stat_pos_iters;
+    W->toi_calls += S.stat_toi_calls; W->toi_events += S.stat_toi_events;
     W->overflows += S.overflowed;
     /* step() rewrites every joint's motor each call, which wakes both bodies (b2RevoluteJoint::
      * SetMotorSpeed -> SetAwake(true)): an island that fell asleep is simply awake again next step */
@@ -142,10 +149,10 @@ static void walker_reset_one(wworld_t *W, int hardcore, float *obs)
 {
     pcg64_t rng = W->rng;
     float inv_dt0 = W->inv_dt0; /* self.world survives reset() */
-    long long overflows = W->overflows;
+    long long overflows = W->overflows, toi_calls = W->toi_calls, toi_events = W->toi_events;
     memset(W, 0, sizeof *W);
     W->inv_dt0 = inv_dt0;
-    W->overflows = overflows;
+    W->overflows = overflows; W->toi_calls = toi_calls; W->toi_events = toi_events;
     /* _generate_terrain(hardcore) :277-402 */
     double terrain_x[TERRAIN_LENGTH], terrain_y[TERRAIN_LENGTH];
     {
@@ -451,6 +458,13 @@ int64_t orc_walker_overflows(const orc_walker *v)
     int64_t c = 0;
     for (int64_t i = 0; i < v->n; i++) c += v->w[i].overflows != 0;
     return c;
+}
+
+/* {b2TimeOfImpact evaluations, TOI sub-steps} summed over all envs since creation */
+void orc_walker_toi_stats(const orc_walker *v, int64_t out[2])
+{
+    out[0] = 0; out[1] = 0;
+    for (int64_t i = 0; i < v->n; i++) { out[0] += v->w[i].toi_calls; out[1] += v->w[i].toi_events; }
 }
 
 void orc_walker_get_stats(const orc_walker *v, int32_t *out)

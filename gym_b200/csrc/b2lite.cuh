@@ -15,7 +15,8 @@
 // One THREAD per environment: sequential impulses are a Gauss-Seidel sweep, inherently serial
 // per env, while 2^16 envs give 2^16-way parallelism; every lane runs the same 180-iteration
 // loop so a warp stays converged except for contact-dependent work.
-// Deviations from Box2D (also listed in DESIGN.md): no TOI sub-stepping, exhaustive pair tests
+//   TOI:     b2World::SolveTOI for dynamic-vs-static pairs (b2lite_toi.cuh).
+// Deviations from Box2D (also listed in DESIGN.md): exhaustive pair tests
 // behind the fat-AABB reject instead of the dynamic-tree broad phase, fixed in-island constraint
 // order (scene's island order x descending edge index), polynomial sin/cos for body angles.
 // float32 throughout, one rounding per operation (-fmad=false), so an independent CPU
@@ -121,6 +122,9 @@ struct Body {
     v2 c, v;
     float a, w, sleepTime;
     xform xf;
+    // b2Sweep of the current step (continuous collision, b2lite_toi.cuh); not part of the persistent record
+    v2 c0;
+    float a0, alpha0;
 };
 struct MPoint { v2 localPoint; float nI, tI; uint32_t id; };
 struct Manifold { int type, pointCount; v2 localNormal, localPoint; MPoint pts[2]; };
@@ -539,6 +543,8 @@ LD bool joint_solve_position(const Joint &j, const JointDef &d, const ShapeConst
     return positionError <= kLinearSlop && angularError <= kAngularSlop;
 }
 
+#include "b2lite_toi.cuh"
+
 // ---- b2World::Step(1/50, 180, 60) for one env ------------------------------------------------------
 // Scene supplies: NB, NJ, kSlots, kMaxVC, World (with b[], j[], flags, slot_*), shape(b), jdef(k),
 // body_order(k), joint_order(k), joint_body_a(k), joint_body_b(k) (all constexpr), edge(W, e, v1, v2, friction), edge_range(W, lox, hix, lo, hi), NP (+ poly(W, p,
@@ -911,6 +917,7 @@ __device__ __noinline__ void world_step(typename Scene::World &W, v2 force0, flo
     static_for<0, NB>([&](auto I) {
         constexpr int i = decltype(I)::value;
         Body &b = W.b[i];
+        b.c0 = b.c; b.a0 = b.a;   // b2Island::Solve: "store positions for continuous collision"
         b.c = st[i].c; b.a = st[i].a; b.v = st[i].v; b.w = st[i].w;
         sync_xf(b, Scene::shape(i));
         if (b.w * b.w > angTol || dot(b.v, b.v) > linTol) { b.sleepTime = 0.0f; minSleep = 0.0f; }
@@ -921,6 +928,8 @@ __device__ __noinline__ void world_step(typename Scene::World &W, v2 force0, flo
         island_awake = false;
         for (int i = 0; i < NB; i++) { W.b[i].sleepTime = 0.0f; W.b[i].v = V(0.0f, 0.0f); W.b[i].w = 0.0f; }
     }
+    // --- SolveTOI: continuous collision against the static fixtures (a sleeping island is skipped)
+    if (island_awake) solve_toi<Scene>(W, dt);
     W.flags |= kFlagStepped;
 }
 

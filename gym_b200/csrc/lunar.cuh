@@ -66,6 +66,7 @@ struct World : WorldBase<NB, NJ, kSlots> {
 struct Scene {
     static constexpr int NB = lunar::NB, NJ = lunar::NJ, NE = lunar::NE, kSlots = lunar::kSlots, kMaxVC = B2L_LUNAR_MAX_VC;
     static constexpr int NP = 0;   // no static polygons in this scene
+    static constexpr bool kOneStaticBody = true;   // every edge is a fixture of the one static body `moon`
     using World = lunar::World;
     LD static const ShapeConst &shape(int b) { return kC.shape[b == 0 ? 0 : 1]; }
     LD static const JointDef &jdef(int k) { return kC.jd[k]; }

@@ -78,6 +78,7 @@ template <bool HC>
 struct SceneT {
     static constexpr int NB = walker::NB, NJ = walker::NJ, NE = walker::NE, kSlots = walker::kSlots, kMaxVC = B2L_WALKER_MAX_VC;
     static constexpr int NP = HC ? walker::NP : 0;
+    static constexpr bool kOneStaticBody = false;  // one static body per terrain edge / box (bipedal_walker.py:375-396)
     using World = walker::World;
     // fd_polygon: friction 2.5 (bipedal_walker.py:180-184)
     LD static void poly(const World &W, int p, float &x0, float &ylo, float &x1, float &yhi, float &friction) {

@@ -21,7 +21,7 @@
 #define B2_PI 3.14159265359f
 #define MAX_SUB_STEPS 8
 #define TOI_BAUMGARTE 0.75f
-#define B2L_MAX_TOI_CAND 24
+#define B2L_MAX_TOI_CAND 48
 
 /* ---------------------------------------------------------------- b2Sweep */
 typedef struct { v2 localCenter, c0, c; float a0, a, alpha0; } sweep_t;

@@ -28,7 +28,7 @@ CASES = [
     ("lunarlander_v2_wind_gravity", "lunar", dict(enable_wind=True, wind_power=12.0, turbulence_power=1.0, gravity=-8.0,
                                                   wind_idx=[5, -40, 999, 1234], torque_idx=[-7, 80, -999, 4321]), 300,
      "heuristic", 4, 320, 11),
-    ("bipedalwalker_v3_gait", "walker", dict(), 1600, "gait", 3, 500, 2),
+    ("bipedalwalker_v3_gait", "walker", dict(), 1600, "gait", 3, 500, 4),
     ("bipedalwalker_v3_random", "walker", dict(), 1600, "random", 4, 220, 5),
     ("bipedalwalkerhardcore_v3_gait", "walker", dict(hardcore=True), 2000, "gait", 3, 420, 0),
 ]

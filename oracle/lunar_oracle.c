@@ -478,6 +478,22 @@ void orc_lunar_get_stats(const orc_lunar *v, int32_t *out)
     for (int64_t i = 0; i < v->n; i++) { out[2 * i] = v->w[i].stat_contacts; out[2 * i + 1] = v->w[i].stat_pos_iters; }
 }
 
+/* test hook: b2TimeOfImpact (b2lite_toi.h) of a convex polygon (local vertices, body origin = centre of mass) sweeping
+ * from (c0, a0) to (c1, a1) against the static edge v1-v2; returns the b2TOIOutput state (3 = e_touching,
+ * 4 = e_separated, 2 = e_overlapped, 1 = e_failed) and writes t */
+int orc_b2l_toi_probe(const float *poly_xy, int n, const float c0[2], float a0, const float c1[2], float a1,
+                      const float v1[2], const float v2_[2], float *t_out)
+{
+    dproxy_t pA, pB;
+    pA.count = 2; pA.v[0] = V(v1[0], v1[1]); pA.v[1] = V(v2_[0], v2_[1]);
+    pB.count = n;
+    for (int i = 0; i < n && i < MAXV; i++) pB.v[i] = V(poly_xy[2 * i], poly_xy[2 * i + 1]);
+    sweep_t sA, sB;
+    sA.localCenter = V(0.0f, 0.0f); sA.c0 = V(0.0f, 0.0f); sA.c = V(0.0f, 0.0f); sA.a0 = 0.0f; sA.a = 0.0f; sA.alpha0 = 0.0f;
+    sB.localCenter = V(0.0f, 0.0f); sB.c0 = V(c0[0], c0[1]); sB.c = V(c1[0], c1[1]); sB.a0 = a0; sB.a = a1; sB.alpha0 = 0.0f;
+    return time_of_impact(t_out, &pA, &sA, &pB, &sB, 1.0f);
+}
+
 /* test hook: overwrite the velocity of one body of env i (tunnelling tests) */
 void orc_lunar_set_body_velocity(orc_lunar *v, int64_t i, int body, float vx, float vy, float w)
 {

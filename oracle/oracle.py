@@ -237,6 +237,21 @@ def set_box2d_toi(on=True):
     L.orc_walker_set_toi(int(bool(on)))
 
 
+def toi_probe(poly, c0, a0, c1, a1, v1, v2):
+    """b2TimeOfImpact of a convex polygon (local vertices) sweeping from (c0, a0) to (c1, a1) against the static edge
+    v1-v2 -> (state, t); state 3 = touching, 4 = separated, 2 = overlapped, 1 = failed."""
+    f = lib().orc_b2l_toi_probe
+    f.restype = ctypes.c_int
+    fp = ctypes.POINTER(ctypes.c_float)
+    f.argtypes = [fp, ctypes.c_int, fp, ctypes.c_float, fp, ctypes.c_float, fp, fp, fp]
+    arr = lambda x: np.ascontiguousarray(x, dtype=np.float32).ravel()
+    P, C0, C1, V1, V2 = arr(poly), arr(c0), arr(c1), arr(v1), arr(v2)
+    t = ctypes.c_float(0.0)
+    as_p = lambda a: a.ctypes.data_as(fp)
+    st = f(as_p(P), len(P) // 2, as_p(C0), float(a0), as_p(C1), float(a1), as_p(V1), as_p(V2), ctypes.byref(t))
+    return int(st), float(t.value)
+
+
 class OracleLunar:
     """SyncVectorEnv([make("LunarLander-v2")] * n) restated in C (oracle/lunar_oracle.c).
 

@@ -18,7 +18,7 @@ _LIB = os.path.join(_BUILD, "libhostsim.so")
 _LIB_SMALLCAP = os.path.join(_BUILD, "libhostsim_smallcap.so")
 SMALLCAP = {"lunar": 1, "walker": 2}
 _SRCS = [os.path.join(_HERE, "hostsim.cpp"), os.path.join(_HERE, "cuda_shim.h")] + [
-    os.path.join(_ROOT, "gym_b200", "csrc", f) for f in ("rng.cuh", "envs.cuh", "glibc_trig.cuh", "b2lite.cuh", "lunar.cuh",
+    os.path.join(_ROOT, "gym_b200", "csrc", f) for f in ("rng.cuh", "envs.cuh", "glibc_trig.cuh", "b2lite.cuh", "b2lite_toi.cuh", "lunar.cuh",
                                                          "walker.cuh", "box2d_consts.h")]
 
 KIND = {"LunarLander": 5, "BipedalWalker": 6, "LunarLanderContinuous": 7, "BipedalWalkerHardcore": 8}

@@ -653,20 +653,27 @@ constexpr int kLunarMaxThreads = 256;
 template <typename ActT, bool CONT>
 __global__ void __launch_bounds__(kLunarMaxThreads, 2) lunar_step_kernel(const StepArgs a) {
     const int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (j >= a.count) return;
+    const bool in_range = j < a.count;
     const int64_t i = a.first + j;
     long long act = 0;
     float ca0 = 0.0f, ca1 = 0.0f;
-    if constexpr (CONT) {
-        const float2 c = __ldg(reinterpret_cast<const float2 *>(a.actions) + i);   // Box(2) float32, lunar_lander.py:285-287
-        ca0 = c.x; ca1 = c.y;
-    } else {
-        act = (long long)__ldg(reinterpret_cast<const ActT *>(a.actions) + i);
-        if (act < 0 || act > 3) {  // lunar_lander.py:482-484
-            atomicAdd(a.invalid, 1ULL);
-            store_scalars_all(a, i, __longlong_as_double(0x7ff8000000000000LL), 0, 0);
-            return;
+    bool valid = in_range;
+    if (in_range) {
+        if constexpr (CONT) {
+            const float2 c = __ldg(reinterpret_cast<const float2 *>(a.actions) + i);   // Box(2) float32, lunar_lander.py:285-287
+            ca0 = c.x; ca1 = c.y;
+        } else {
+            act = (long long)__ldg(reinterpret_cast<const ActT *>(a.actions) + i);
+            valid = !(act < 0 || act > 3);   // lunar_lander.py:482-484
         }
+    }
+    // the lanes that step an env: they stay together through the solver's warp-synchronous TOI rounds
+    const unsigned live = __ballot_sync(0xffffffffu, valid);
+    if (!in_range) return;
+    if (!valid) {
+        atomicAdd(a.invalid, 1ULL);
+        store_scalars_all(a, i, __longlong_as_double(0x7ff8000000000000LL), 0, 0);
+        return;
     }
     const lunar::Opts &O = a.lunar_opts;
     lunar::World W;
@@ -676,7 +683,7 @@ __global__ void __launch_bounds__(kLunarMaxThreads, 2) lunar_step_kernel(const S
     float obs[8];
     double reward;
     bool terminated;
-    lunar::env_step(W, g, O, (int)act, ca0, ca1, lunar::V(0.0f, 0.0f), obs, reward, terminated);
+    lunar::env_step(W, g, O, (int)act, ca0, ca1, lunar::V(0.0f, 0.0f), obs, reward, terminated, live);
     elapsed += 1;                                                        // time_limit.py:51
     const bool truncated = (a.max_steps > 0) && (elapsed >= a.max_steps);
     store_scalars_all(a, i, reward, terminated ? 1 : 0, truncated ? 1 : 0);
@@ -777,7 +784,9 @@ static int lunar_upload_consts(b200gym *h) {
 template <bool HC>
 __global__ void __launch_bounds__(kLunarThreads, 4) walker_step_kernel(const StepArgs a) {
     const int64_t j = (int64_t)blockIdx.x * kLunarThreads + threadIdx.x;
-    if (j >= a.count) return;
+    const bool in_range = j < a.count;
+    const unsigned live = __ballot_sync(0xffffffffu, in_range);   // the lanes that step an env (see solve_toi)
+    if (!in_range) return;
     const int64_t i = a.first + j;
     const float4 av = __ldg(reinterpret_cast<const float4 *>(a.actions) + i);
     const float action[4] = {av.x, av.y, av.z, av.w};
@@ -788,7 +797,7 @@ __global__ void __launch_bounds__(kLunarThreads, 4) walker_step_kernel(const Ste
     float obs[24];
     double reward;
     bool terminated;
-    walker::env_step<HC>(W, action, false, walker::V(0.0f, 0.0f), obs, reward, terminated);
+    walker::env_step<HC>(W, action, false, walker::V(0.0f, 0.0f), obs, reward, terminated, live);
     elapsed += 1;                                                        // time_limit.py:51
     const bool truncated = (a.max_steps > 0) && (elapsed >= a.max_steps);
     store_scalars_all(a, i, reward, terminated ? 1 : 0, truncated ? 1 : 0);

@@ -549,10 +549,11 @@ LD bool joint_solve_position(const Joint &j, const JointDef &d, const ShapeConst
 // Scene supplies: NB, NJ, kSlots, kMaxVC, World (with b[], j[], flags, slot_*), shape(b), jdef(k),
 // body_order(k), joint_order(k), joint_body_a(k), joint_body_b(k) (all constexpr), edge(W, e, v1, v2, friction), edge_range(W, lox, hix, lo, hi), NP (+ poly(W, p,
 // x0, ylo, x1, yhi, friction), poly_range(W, lox, hix, lo, hi) when NP > 0), on_event(W, body, begin).  `force0` / `torque0` are the force and torque accumulated on body 0 before the
-// step (b2Body::ApplyForceToCenter / ApplyTorque), `gravity_y` the world's gravity (0, gravity_y).
+// step (b2Body::ApplyForceToCenter / ApplyTorque), `gravity_y` the world's gravity (0, gravity_y).  `live`: mask of
+// the warp's lanes that call world_step together (they synchronise inside solve_toi), or 0.
 template <typename Scene>
 __device__ __noinline__ void world_step(typename Scene::World &W, v2 force0, float torque0, float gravity_y,
-                                        bool &island_awake) {
+                                        bool &island_awake, unsigned live = 0u) {
     constexpr int NB = Scene::NB, NJ = Scene::NJ, kSlots = Scene::kSlots, kMaxVC = Scene::kMaxVC;
     constexpr int NE = Scene::NE, NP = Scene::NP, NF = NE + NP;
     const float dt = (float)(1.0 / 50);
@@ -929,7 +930,8 @@ __device__ __noinline__ void world_step(typename Scene::World &W, v2 force0, flo
         for (int i = 0; i < NB; i++) { W.b[i].sleepTime = 0.0f; W.b[i].v = V(0.0f, 0.0f); W.b[i].w = 0.0f; }
     }
     // --- SolveTOI: continuous collision against the static fixtures (a sleeping island is skipped)
-    if (island_awake) solve_toi<Scene>(W, dt);
+    // (`live`: the warp's lanes that are in this call together, see solve_toi; 0 on divergent callers)
+    if (live != 0u || island_awake) solve_toi<Scene>(W, dt, island_awake, live);
     W.flags |= kFlagStepped;
 }
 

@@ -603,16 +603,24 @@ __device__ __noinline__ void island_solve_toi(typename Scene::World &W, int body
     sync_xf(B, sh);
 }
 
+// `live`: the lanes of this warp that run solve_toi together (0: the caller is on a divergent path, e.g. the step
+// embedded in reset(): no warp-level synchronisation).  TOI events are rare per env but a warp of 32 envs has one
+// in most steps, and an event costs a 180-iteration solve: the loop below runs in warp-synchronous ROUNDS -- every
+// lane looks for its earliest event, then all lanes that found one advance / update / solve at the same time -- so
+// a warp pays for the lane with the most events, not for the sum over its lanes.  Per env the sequence of
+// operations is exactly the serial b2World::SolveTOI loop.
 template <typename Scene>
-__device__ __noinline__ void solve_toi(typename Scene::World &W, float dt) {
+__device__ __noinline__ void solve_toi(typename Scene::World &W, float dt, bool active, unsigned live) {
     constexpr int NB = Scene::NB, NE = Scene::NE, kMaxVC = Scene::kMaxVC;
+    const bool sync = live != 0u;
     ToiCand cand[kMaxToiCand];
     float alphaS[kMaxToiCand];
     int statId[kMaxToiCand];
     int ncand = 0, nstat = 0;
-    for (int i = 0; i < NB; i++) W.b[i].alpha0 = 0.0f;
-    for (int oi = 0; oi < NB; oi++) toi_add_candidates<Scene>(W, cand, ncand, alphaS, statId, nstat, Scene::body_order(oi));
-    if (ncand == 0) return;
+    if (active) {
+        for (int i = 0; i < NB; i++) W.b[i].alpha0 = 0.0f;
+        for (int oi = 0; oi < NB; oi++) toi_add_candidates<Scene>(W, cand, ncand, alphaS, statId, nstat, Scene::body_order(oi));
+    }
     for (;;) {
         int minIdx = -1;
         float minAlpha = 1.0f;
@@ -633,7 +641,7 @@ __device__ __noinline__ void solve_toi(typename Scene::World &W, float dt) {
                     sweep_advance(s, alpha0);
                     B.c0 = s.c0; B.a0 = s.a0; B.alpha0 = s.alpha0;
                 }
-                DProxy pA, pB;
+                DProxy pA;
                 if (Scene::NP > 0 && c.f >= NE) {
                     if constexpr (Scene::NP > 0) {
                         float x0, ylo, x1, yhi, fr;
@@ -646,67 +654,110 @@ __device__ __noinline__ void solve_toi(typename Scene::World &W, float dt) {
                     pA.count = 2;
                     Scene::edge(W, c.f, pA.v[0], pA.v[1], fr);
                 }
-                pB.count = sh.count;
-                for (int i = 0; i < sh.count; i++) pB.v[i] = sh.verts[i];
-                Sweep sA;
-                sA.localCenter = V(0.0f, 0.0f); sA.c0 = V(0.0f, 0.0f); sA.c = V(0.0f, 0.0f); sA.a0 = 0.0f; sA.a = 0.0f; sA.alpha0 = alpha0;
                 const Sweep sB = body_sweep(B, sh);
-                float beta;
-                const int state = time_of_impact(beta, pA, sA, pB, sB, 1.0f);
-                if (state == TOI_TOUCHING) alpha = fmin_(alpha0 + (1.0f - alpha0) * beta, 1.0f);
-                else alpha = 1.0f;
+                // Shortcut (results unchanged): b2TimeOfImpact can only report e_touching if some transform of the
+                // sweep brings the core shapes within target + tolerance = 1.25 linearSlop.  Every vertex moves from
+                // its start to its end position within R * (1 - cos(d/2)) <= R * d^2 / 8 of the straight segment
+                // between the two (R: its distance from the centre of mass, d: the rotation over the sweep), so the
+                // polygon never leaves the box around its start and end poses widened by that amount.  If that box,
+                // widened once more by 1.25 linearSlop and a safety margin far above float32 rounding, misses the
+                // fixture's box, every outcome is "separated" (or "failed"), i.e. alpha = 1.
+                bool far_apart = false;
+                {
+                    const xform xf0 = sweep_xf(sB, 0.0f);
+                    float lox = kFltMax, loy = kFltMax, hix = -kFltMax, hiy = -kFltMax, r2 = 0.0f;
+                    for (int i = 0; i < sh.count; i++) {
+                        const v2 p = xmul(xf0, sh.verts[i]), q = xmul(B.xf, sh.verts[i]);
+                        lox = fmin_(lox, fmin_(p.x, q.x)); loy = fmin_(loy, fmin_(p.y, q.y));
+                        hix = fmax_(hix, fmax_(p.x, q.x)); hiy = fmax_(hiy, fmax_(p.y, q.y));
+                        const v2 r = sub(sh.verts[i], sh.localCenter);
+                        r2 = fmax_(r2, dot(r, r));
+                    }
+                    const float d = fabsf(sB.a - sB.a0);
+                    if (d < 0.5f) {
+                        const float m = 1.25f * kLinearSlop + 0.002f + sqrtf(r2) * d * d * 0.125f;
+                        float flox = kFltMax, floy = kFltMax, fhix = -kFltMax, fhiy = -kFltMax;
+                        for (int i = 0; i < pA.count; i++) {
+                            flox = fmin_(flox, pA.v[i].x); floy = fmin_(floy, pA.v[i].y);
+                            fhix = fmax_(fhix, pA.v[i].x); fhiy = fmax_(fhiy, pA.v[i].y);
+                        }
+                        far_apart = lox - m > fhix || flox > hix + m || loy - m > fhiy || floy > hiy + m;
+                    }
+                }
+                if (far_apart) alpha = 1.0f;
+                else {
+                    DProxy pB;
+                    pB.count = sh.count;
+                    for (int i = 0; i < sh.count; i++) pB.v[i] = sh.verts[i];
+                    Sweep sA;
+                    sA.localCenter = V(0.0f, 0.0f); sA.c0 = V(0.0f, 0.0f); sA.c = V(0.0f, 0.0f); sA.a0 = 0.0f; sA.a = 0.0f; sA.alpha0 = alpha0;
+                    float beta;
+                    const int state = time_of_impact(beta, pA, sA, pB, sB, 1.0f);
+                    if (state == TOI_TOUCHING) alpha = fmin_(alpha0 + (1.0f - alpha0) * beta, 1.0f);
+                    else alpha = 1.0f;
+                }
                 c.toi = alpha; c.toiValid = true;
             }
             if (alpha < minAlpha) { minIdx = ci; minAlpha = alpha; }
         }
-        if (minIdx < 0 || 1.0f - 10.0f * kEpsilon < minAlpha) break;
-        ToiCand &mc = cand[minIdx];
-        Body &B = W.b[mc.body];
-        const ShapeConst &sh = Scene::shape(mc.body);
-        // advance the bodies to the TOI
-        const float backupS = alphaS[mc.sidx];
-        const v2 bc0 = B.c0, bc = B.c;
-        const float ba0 = B.a0, ba = B.a, balpha0 = B.alpha0;
-        alphaS[mc.sidx] = minAlpha;
-        {   // b2Body::Advance
-            Sweep s = body_sweep(B, sh);
-            sweep_advance(s, minAlpha);
-            B.c0 = s.c0; B.a0 = s.a0; B.alpha0 = s.alpha0;
-            B.c = B.c0; B.a = B.a0;
-            sync_xf(B, sh);
-        }
+        const bool have = minIdx >= 0 && !(1.0f - 10.0f * kEpsilon < minAlpha);
+        if (!(sync ? (__any_sync(live, have) != 0) : have)) break;
         Manifold mf[kMaxVC];
         float fric[kMaxVC];
-        int nic = 0;
-        const bool touching = toi_pair_update<Scene>(W, mc.body, mc.f, mf[0], fric[0]);
-        mc.toiValid = false;
-        ++mc.toiCount;
-        if (!touching) {
-            mc.enabled = false;
-            alphaS[mc.sidx] = backupS;
-            B.c0 = bc0; B.c = bc; B.a0 = ba0; B.a = ba; B.alpha0 = balpha0;
-            sync_xf(B, sh);
-            continue;
+        int nic = 0, moved = -1;
+        float h = 0.0f;
+        bool solve = false;
+        if (have) {
+            ToiCand &mc = cand[minIdx];
+            Body &B = W.b[mc.body];
+            const ShapeConst &sh = Scene::shape(mc.body);
+            // advance the bodies to the TOI
+            const float backupS = alphaS[mc.sidx];
+            const v2 bc0 = B.c0, bc = B.c;
+            const float ba0 = B.a0, ba = B.a, balpha0 = B.alpha0;
+            alphaS[mc.sidx] = minAlpha;
+            {   // b2Body::Advance
+                Sweep s = body_sweep(B, sh);
+                sweep_advance(s, minAlpha);
+                B.c0 = s.c0; B.a0 = s.a0; B.alpha0 = s.alpha0;
+                B.c = B.c0; B.a = B.a0;
+                sync_xf(B, sh);
+            }
+            const bool touching = toi_pair_update<Scene>(W, mc.body, mc.f, mf[0], fric[0]);
+            mc.toiValid = false;
+            ++mc.toiCount;
+            if (!touching) {
+                mc.enabled = false;
+                alphaS[mc.sidx] = backupS;
+                B.c0 = bc0; B.c = bc; B.a0 = ba0; B.a = ba; B.alpha0 = balpha0;
+                sync_xf(B, sh);
+            } else {
+                // the island: the TOI contact, then the body's other touching contacts against static bodies
+                nic = 1;
+                uint64_t inIsland = 1ull << mc.sidx;   // static bodies (by sidx) already in the island
+                for (int ci = 0; ci < ncand; ci++) {
+                    ToiCand &oc = cand[ci];
+                    if (ci == minIdx || oc.body != mc.body) continue;
+                    if (nic == kMaxVC) break;
+                    const float backup = alphaS[oc.sidx];
+                    if (!((inIsland >> oc.sidx) & 1ull)) alphaS[oc.sidx] = minAlpha;
+                    const bool t2 = toi_pair_update<Scene>(W, oc.body, oc.f, mf[nic], fric[nic]);
+                    oc.enabled = true;   // b2Contact::Update re-enables the contact
+                    if (!t2) { alphaS[oc.sidx] = backup; continue; }
+                    nic++;
+                    inIsland |= 1ull << oc.sidx;
+                }
+                solve = true;
+                moved = mc.body;
+                h = (1.0f - minAlpha) * dt;
+            }
         }
-        // the island: the TOI contact, then the body's other touching contacts against static bodies
-        nic = 1;
-        uint64_t inIsland = 1ull << mc.sidx;   // static bodies (by sidx) already in the island
-        for (int ci = 0; ci < ncand; ci++) {
-            ToiCand &oc = cand[ci];
-            if (ci == minIdx || oc.body != mc.body) continue;
-            if (nic == kMaxVC) break;
-            const float backup = alphaS[oc.sidx];
-            if (!((inIsland >> oc.sidx) & 1ull)) alphaS[oc.sidx] = minAlpha;
-            const bool t2 = toi_pair_update<Scene>(W, oc.body, oc.f, mf[nic], fric[nic]);
-            oc.enabled = true;   // b2Contact::Update re-enables the contact
-            if (!t2) { alphaS[oc.sidx] = backup; continue; }
-            nic++;
-            inIsland |= 1ull << oc.sidx;
+        if (sync) __syncwarp(live);
+        if (solve) island_solve_toi<Scene>(W, moved, mf, fric, nic, h);
+        if (solve) {
+            // invalidate all contact TOIs on the displaced body; its moved proxy may create new contacts
+            for (int ci = 0; ci < ncand; ci++) if (cand[ci].body == moved) cand[ci].toiValid = false;
+            toi_add_candidates<Scene>(W, cand, ncand, alphaS, statId, nstat, moved);
         }
-        island_solve_toi<Scene>(W, mc.body, mf, fric, nic, (1.0f - minAlpha) * dt);
-        // invalidate all contact TOIs on the displaced body; its moved proxy may create new contacts
-        const int moved = mc.body;
-        for (int ci = 0; ci < ncand; ci++) if (cand[ci].body == moved) cand[ci].toiValid = false;
-        toi_add_candidates<Scene>(W, cand, ncand, alphaS, statId, nstat, moved);
     }
 }

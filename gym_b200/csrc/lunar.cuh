@@ -93,7 +93,7 @@ struct Scene {
 // continuous variant.  In the continuous branch m_power / s_power / direction are numpy float32 scalars:
 // under NEP 50 every Python float they meet is rounded to float32 first, which is what the casts restate.
 LD void env_step(World &W, Pcg64 &rng, const Opts &O, int action, float ca0, float ca1, v2 lander_force,
-                 float (&obs)[8], double &reward, bool &terminated) {
+                 float (&obs)[8], double &reward, bool &terminated, unsigned live = 0u) {
     const double SCALE = 30.0, FPS = 50;
     const double VW = 600 / SCALE, VH = 400 / SCALE;
     Body &L = W.b[0];
@@ -161,7 +161,7 @@ LD void env_step(World &W, Pcg64 &rng, const Opts &O, int action, float ca0, flo
         L.w += sh.invI * crs(sub(pt, L.c), imp);
     }
     bool awake;
-    world_step<Scene>(W, lander_force, torque, O.gravity, awake);                                          // :556
+    world_step<Scene>(W, lander_force, torque, O.gravity, awake, live);                                    // :556
     double st[8];
     const double helipad_y = VH / 4;
     st[0] = ((double)L.xf.p.x - VW / 2) / (VW / 2);                              // :560-569

@@ -173,7 +173,7 @@ LD float clip01_abs(float a) { float x = fabsf(a); x = x < 0.0f ? 0.0f : x; retu
 // bipedal_walker.py:517-606
 template <bool HC>
 __device__ __noinline__ void env_step(World &W, const float (&action)[4], bool from_reset, v2 hull_force, float (&obs)[24],
-                                      double &reward, bool &terminated) {
+                                      double &reward, bool &terminated, unsigned live = 0u) {
     const double SCALE = 30.0, FPS = 50;
     const float speed[NJ] = {4.0f, 6.0f, 4.0f, 6.0f};                            // SPEED_HIP, SPEED_KNEE
     for (int k = 0; k < NJ; k++) {                                               // :528-543
@@ -185,7 +185,7 @@ __device__ __noinline__ void env_step(World &W, const float (&action)[4], bool f
         // every body stays within two leg lengths (2 x 34/30 m) of the hull: one window of boxes for all of them
         poly_window(W, W.b[0].c.x - 4.0f, W.b[0].c.x + 4.0f, W.p_lo, W.p_hi);
     }
-    world_step<SceneT<HC>>(W, hull_force, 0.0f, -10.0f, awake);                  // :545
+    world_step<SceneT<HC>>(W, hull_force, 0.0f, -10.0f, awake, live);            // :545
     const Body &H = W.b[0];
     const double posx = (double)H.xf.p.x, posy = (double)H.xf.p.y;
     double st[24];

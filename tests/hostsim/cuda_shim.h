@@ -20,3 +20,8 @@ static inline long long __double_as_longlong(double d) { long long v; std::memcp
 
 struct ulonglong2 { unsigned long long x, y; };
 static inline ulonglong2 make_ulonglong2(unsigned long long x, unsigned long long y) { ulonglong2 r = {x, y}; return r; }
+
+// warp votes of a one-lane "warp"
+static inline int __any_sync(unsigned, int p) { return p; }
+static inline unsigned __ballot_sync(unsigned, int p) { return p ? 1u : 0u; }
+static inline void __syncwarp(unsigned = 0xffffffffu) {}

@@ -86,6 +86,7 @@ SIGNATURES = {
     "b200gym_reset": (_i32, [_vp, _vp, _vp, _vp, _vp]),
     "b200gym_step": (_i32, [_vp, _vp, _i32, _vp, _vp, _vp, _vp, _vp, _vp]),
     "b200gym_invalid_actions": (_i32, [_vp, _vp, ctypes.POINTER(_i64)]),
+    "b200gym_invalid_seen": (_i32, [_vp]),
     "b200gym_host_buffers": (_i32, [_vp, ctypes.POINTER(HostIO)]),
     "b200gym_step_host": (_i32, [_vp, _vp, _i32, _vp, _vp, _vp, _vp, _vp, ctypes.POINTER(_i64)]),
     "b200gym_reset_host": (_i32, [_vp, _vp, _vp, _vp]),

@@ -54,6 +54,8 @@ struct b200gym {
     bool is_lunar = false, is_walker = false;
     lunar::Opts lunar_opts{};
     unsigned long long *invalid = nullptr;  // sticky device counter
+    unsigned long long *invalid_seen = nullptr;      // page-locked, device-mapped word: set to 1 by any kernel that meets an
+    unsigned long long *invalid_seen_dev = nullptr;  // invalid action (host-visible WITHOUT a synchronisation); device alias
     struct {                                // caller-owned buffers of the fused RecordEpisodeStatistics (all null = off)
         float *acc = nullptr; int32_t *len = nullptr; float *r = nullptr; int32_t *l = nullptr;
         unsigned long long *ring = nullptr, *counter = nullptr; int ring_size = 0;
@@ -145,6 +147,7 @@ struct StepArgs {
     uint8_t *flags;
     uint64_t *rng;
     unsigned long long *invalid;
+    unsigned long long *invalid_seen;   // device-mapped host word, see b200gym_invalid_seen
     uint32_t *lunar_rec;
     const void *actions;
     float *obs;
@@ -314,6 +317,7 @@ __device__ __forceinline__ bool advance_env(const StepArgs &a, const Sink &sink,
             // untouched, count it (sticky), return a NaN reward and the env's CURRENT observation, so that the
             // double-buffered output row does not show the observation of two steps ago
             atomicAdd(a.invalid, 1ULL);
+            *reinterpret_cast<volatile unsigned long long *>(a.invalid_seen) = 1ULL;
             float cur[E::D];
             E::observe(s, cur);
             sink.scalars(i, __longlong_as_double(0x7ff8000000000000LL), 0, 0);
@@ -672,6 +676,7 @@ __global__ void __launch_bounds__(kLunarMaxThreads, 2) lunar_step_kernel(const S
     if (!in_range) return;
     if (!valid) {
         atomicAdd(a.invalid, 1ULL);
+        *reinterpret_cast<volatile unsigned long long *>(a.invalid_seen) = 1ULL;
         store_scalars_all(a, i, __longlong_as_double(0x7ff8000000000000LL), 0, 0);
         return;
     }
@@ -1364,6 +1369,13 @@ extern "C" int b200gym_create(const b200gym_config *cfg, int64_t num_envs, int d
             b200gym_destroy(h);
             return 1;
         }
+    if (cudaHostAlloc((void **)&h->invalid_seen, sizeof(unsigned long long), cudaHostAllocMapped) != cudaSuccess ||
+        cudaHostGetDevicePointer((void **)&h->invalid_seen_dev, h->invalid_seen, 0) != cudaSuccess) {
+        fail(nullptr, "b200gym_create: cannot allocate the mapped invalid-action flag: %s", cudaGetErrorString(cudaGetLastError()));
+        b200gym_destroy(h);
+        return 1;
+    }
+    *h->invalid_seen = 0ULL;
     h->is_lunar = cfg->kind == B200GYM_LUNARLANDER || cfg->kind == B200GYM_LUNARLANDER_CONT;
     h->is_walker = cfg->kind == B200GYM_BIPEDALWALKER || cfg->kind == B200GYM_BIPEDALWALKER_HARDCORE;
     if (h->is_lunar) {  // LunarLander.__init__ arguments (lunar_lander.py:194-233)
@@ -1424,6 +1436,7 @@ extern "C" void b200gym_destroy(b200gym_t *h) {
     cudaFree(h->flags);
     cudaFree(h->rng);
     cudaFree(h->invalid);
+    if (h->invalid_seen) cudaFreeHost(h->invalid_seen);
     cudaFree(h->lunar_rec);
     cudaFree(h->reset_list);
     cudaFree(h->reset_count);
@@ -1486,6 +1499,7 @@ static StepArgs make_args(b200gym *h, const void *actions, float *obs, double *r
                           uint8_t *trunc, float *final_obs) {
     StepArgs a;
     a.state = h->state; a.elapsed = h->elapsed; a.flags = h->flags; a.rng = h->rng; a.invalid = h->invalid;
+    a.invalid_seen = h->invalid_seen_dev;
     a.lunar_rec = h->lunar_rec;
     a.actions = actions; a.obs = obs; a.reward = reward; a.terminated = term; a.truncated = trunc;
     a.final_obs = final_obs;
@@ -1519,8 +1533,14 @@ extern "C" int b200gym_invalid_actions(b200gym_t *h, void *stream, int64_t *coun
     CK(h, cudaMemcpyAsync(&v, h->invalid, sizeof v, cudaMemcpyDeviceToHost, st));
     CK(h, cudaMemsetAsync(h->invalid, 0, sizeof v, st));
     CK(h, cudaStreamSynchronize(st));
+    *h->invalid_seen = 0ULL;
     *count_out = (int64_t)v;
     return 0;
+}
+
+extern "C" int b200gym_invalid_seen(const b200gym_t *h) {
+    if (!h || !h->invalid_seen) return -1;
+    return *reinterpret_cast<volatile unsigned long long *>(h->invalid_seen) != 0ULL ? 1 : 0;
 }
 
 extern "C" int b200gym_selftest_trig(const double *x_dev, int64_t n, double *sin_dev, double *cos_dev, double *sq_dev,
@@ -1903,6 +1923,7 @@ extern "C" int b200gym_step_host(b200gym_t *h, const void *actions_host, int act
     if (e0 != cudaSuccess || e1 != cudaSuccess)
         return fail(h, "b200gym_step_host: %s", cudaGetErrorString(e0 != cudaSuccess ? e0 : e1));
     if (invalid_out) *invalid_out = (int64_t)*h->h_invalid;
+    *h->invalid_seen = 0ULL;   // reported (and the device counter cleared) with this call
     // results are in the mapped staging buffers; callers that brought their own arrays get a host copy
     const size_t n = (size_t)h->n, osz = sizeof(float) * h->D;
     if (obs_host && obs_host != h->hio.obs) memcpy(obs_host, h->hio.obs, n * osz);

@@ -348,6 +348,11 @@ class B200VectorEnv:
         if not self._has_reset:
             raise error.ResetNeeded("Cannot call env.step() before calling env.reset()")
         if self.backend == "torch":
+            # the reference asserts on an out-of-range Discrete action (cartpole.py:132); the device cannot raise and
+            # this backend never waits for it, so the kernels flag it in host-visible memory and the error surfaces
+            # at the next call (no synchronisation unless the flag is up)
+            if self.discrete and self._lib.b200gym_invalid_seen(self._handle) == 1:
+                self.check_actions()
             act, code = self._device_actions(actions)
             self._flip ^= 1
             out = self._out[self._flip]

@@ -157,6 +157,14 @@ int b200gym_step(b200gym_t *h, const void *actions_dev, int action_dtype, float 
 /* Number of invalid Discrete actions seen since the last call (synchronises `stream`). */
 int b200gym_invalid_actions(b200gym_t *h, void *stream, int64_t *count_out);
 
+/* 1 when some kernel launched on this handle has met an invalid Discrete action since the last
+ * b200gym_invalid_actions() / b200gym_step_host(), 0 otherwise, -1 on a null handle.  Never synchronises: the
+ * kernels raise a flag in page-locked host memory, so a caller that must not stall its stream (the torch backend)
+ * can poll this before every step and raise the reference's error (cartpole.py:132, mountain_car.py:128-130,
+ * acrobot.py:199, lunar_lander.py:482-484: `assert self.action_space.contains(action)`) one call late instead of
+ * never. */
+int b200gym_invalid_seen(const b200gym_t *h);
+
 /*
  * Host-buffer step: the same call for a caller that lives on the CPU (what a
  * numpy agent does with SyncVectorEnv.step: numpy actions in, numpy results

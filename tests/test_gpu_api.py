@@ -93,6 +93,13 @@ def test_invalid_actions_raise():
     with pytest.raises(error.InvalidAction):
         envs.check_actions()
     assert envs.check_actions() == 0
+    # ... and without asking: the kernels raise a host-visible flag, so the NEXT step() raises the reference's error
+    # (one call late, no synchronisation on the clean path) and the flag is consumed by it
+    envs.step(torch.tensor([0, 1, 7, 2], device="cuda"))
+    torch.cuda.synchronize()
+    with pytest.raises(error.InvalidAction):
+        envs.step(torch.tensor([0, 1, 2, 2], device="cuda"))
+    envs.step(torch.tensor([0, 1, 2, 2], device="cuda"))
     with pytest.raises(error.InvalidAction):
         envs.step(torch.zeros(4, device="cuda"))     # float actions for a Discrete space
     with pytest.raises(error.InvalidAction):

@@ -56,13 +56,13 @@ BYTES_PER_ENV_STEP["BipedalWalkerHardcore-v3"] = BYTES_PER_ENV_STEP["BipedalWalk
 # what bounds each kernel (ncu summaries in profiles/): the HBM fraction is only meaningful for the first group
 BOUND = {"CartPole-v1": "hbm", "CartPole-v0": "hbm", "Pendulum-v1": "hbm (latency: 1 wave at 2^18)",
          "MountainCar-v0": "hbm (latency: 1 wave at 2^18)", "MountainCarContinuous-v0": "hbm (latency: 1 wave at 2^18)",
-         "Acrobot-v1": "fp64 pipe / issue slots (4 x RK4 stage, ~17 sin/cos per env-step)",
+         "Acrobot-v1": "fp64 pipe / issue slots (4 x RK4 stage, 21 glibc-exact sin/cos + 12 glibc-exact pow(x, 2) per env-step)",
          "LunarLander-v2": "instruction issue under divergence (serial Gauss-Seidel solve per env)",
          "LunarLanderContinuous-v2": "instruction issue under divergence (serial Gauss-Seidel solve per env)",
          "BipedalWalker-v3": "instruction issue (serial Gauss-Seidel solve per env)",
          "BipedalWalkerHardcore-v3": "instruction issue (serial Gauss-Seidel solve per env)"}
 # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed ncu --set full capture (2^20 envs)
-NCU_DRAM = {"file": "profiles/r1_cartpole_step_kernel_A_ncu_full.txt", "read": 56.20e6, "write": 25.84e6}
+NCU_DRAM = {"file": "profiles/r2b_cartpole_step_kernel_L_40reg_ncu_full.txt", "read": 52.76e6, "write": 22.86e6}
 FALLBACK_HBM_GBS = 6650.0  # /opt/skills/guides/B200_PROFILING.md fallback
 EXTRA_CONFIGS = [("Pendulum-v1", 18, 300), ("Acrobot-v1", 18, 300), ("MountainCar-v0", 18, 300),
                  ("LunarLander-v2", 16, 150), ("BipedalWalker-v3", 16, 60)]

@@ -74,6 +74,11 @@ struct b200gym {
     int box2d_defer = 0;                    // Box2D tasks: 1 = the autoresets of a step run in a second, compacted
                                             // kernel (B200GYM_BOX2D_DEFER=1).  Measured neutral at 2^16 envs (the step
                                             // is bound by its slowest warps, not by reset work), so inline is the default
+    int box2d_toi_defer = 1;                // Box2D tasks: 1 = envs with a possible TOI event finish in the compacted TOI kernel
+                                            // (B200GYM_BOX2D_TOI_DEFER=0: SolveTOI inline in the step kernel)
+    int32_t *toi_list = nullptr;            // [n] env offsets parked for the TOI kernel, per launch range
+    int32_t *toi_count = nullptr;           // [kResetSlots]
+    uint32_t *toi_mid = nullptr;            // [kToiMidWords][n] SoA side buffer of the parked envs
     int32_t *reset_list = nullptr;          // [n] env offsets to reset, filled per launch range
     int32_t *reset_count = nullptr;         // [kResetSlots] one counter per concurrently running launch range
     // fused all-gather over peer memory (b200gym_p2p_*)
@@ -166,6 +171,12 @@ struct StepArgs {
     // the *_reset_list_kernel that follows on the stream; nullptr: reset inline
     int32_t *reset_list;
     int32_t *reset_count;
+    // Box2D tasks: envs whose step may contain a continuous-collision event (b2l::toi_needed) are parked after the
+    // discrete solve -- world record + the sweep starts / env intermediates in toi_mid -- and finished by the
+    // *_toi_kernel that follows on the stream, in warps full of such envs; nullptr: everything inline
+    int32_t *toi_list;
+    int32_t *toi_count;
+    uint32_t *toi_mid;
     // fused all-gather (multi-GPU): every result is ALSO stored into the same rows of the peers'
     // gather buffers over NVLink (peer-mapped pointers, slice offset already applied)
     // RecordEpisodeStatistics fused into the step (b200gym_set_episode_stats; nullptr = off): float32 return and
@@ -654,6 +665,63 @@ constexpr int kResetSlots = 64;   // launch ranges of one handle that may be in 
 
 constexpr int kLunarMaxThreads = 256;
 
+// side buffer of a parked env ([kToiMidWords][n] SoA): the sweep starts of the 3 bodies + env_pre's intermediates
+constexpr int kToiMidWords = 20;   // LunarLander uses 13, BipedalWalker 15
+
+__device__ __forceinline__ void lunar_store_mid(const StepArgs &a, int64_t i, const lunar::World &W, const lunar::Mid &mid) {
+    uint32_t *m = a.toi_mid + i;
+    for (int b = 0; b < lunar::NB; b++) {
+        m[(int64_t)(3 * b + 0) * a.n] = __float_as_uint(W.b[b].c0.x);
+        m[(int64_t)(3 * b + 1) * a.n] = __float_as_uint(W.b[b].c0.y);
+        m[(int64_t)(3 * b + 2) * a.n] = __float_as_uint(W.b[b].a0);
+    }
+    const unsigned long long mc = (unsigned long long)__double_as_longlong(mid.main_cost);
+    const unsigned long long sc = (unsigned long long)__double_as_longlong(mid.side_cost);
+    m[(int64_t)9 * a.n] = (uint32_t)mc; m[(int64_t)10 * a.n] = (uint32_t)(mc >> 32);
+    m[(int64_t)11 * a.n] = (uint32_t)sc; m[(int64_t)12 * a.n] = (uint32_t)(sc >> 32);
+}
+
+__device__ __forceinline__ void lunar_load_mid(const StepArgs &a, int64_t i, lunar::World &W, lunar::Mid &mid) {
+    const uint32_t *m = a.toi_mid + i;
+    for (int b = 0; b < lunar::NB; b++) {
+        W.b[b].c0.x = __uint_as_float(m[(int64_t)(3 * b + 0) * a.n]);
+        W.b[b].c0.y = __uint_as_float(m[(int64_t)(3 * b + 1) * a.n]);
+        W.b[b].a0 = __uint_as_float(m[(int64_t)(3 * b + 2) * a.n]);
+    }
+    mid.main_cost = __longlong_as_double((long long)(((unsigned long long)m[(int64_t)10 * a.n] << 32) | m[(int64_t)9 * a.n]));
+    mid.side_cost = __longlong_as_double((long long)(((unsigned long long)m[(int64_t)12 * a.n] << 32) | m[(int64_t)11 * a.n]));
+    mid.awake = true;   // only awake islands are parked
+}
+
+// everything after world.Step of LunarLander.step, then TimeLimit, outputs and the same-step autoreset
+__device__ __noinline__ void lunar_finish(const StepArgs &a, int64_t i, int64_t j, lunar::World &W, Pcg64 &g, int32_t elapsed,
+                                          const lunar::Mid &mid) {
+    const lunar::Opts &O = a.lunar_opts;
+    float obs[8];
+    double reward;
+    bool terminated;
+    lunar::env_post(W, mid, obs, reward, terminated);
+    elapsed += 1;                                                        // time_limit.py:51
+    const bool truncated = (a.max_steps > 0) && (elapsed >= a.max_steps);
+    store_scalars_all(a, i, reward, terminated ? 1 : 0, truncated ? 1 : 0);
+    episode_account(a, i, reward, terminated || truncated);
+    bool deferred = false;
+    if ((terminated || truncated) && a.autoreset) {                      // sync_vector_env.py:152-156
+        if (a.final_obs) store_row<8>(a.final_obs, i, obs);
+        if (a.reset_list) {  // the new episode is drawn by lunar_reset_list_kernel, in warps full of resetting envs
+            a.reset_list[a.first + atomicAdd(a.reset_count, 1)] = (int32_t)j;
+            deferred = true;
+        } else {
+            lunar::env_reset(W, g, O, obs);
+            elapsed = 0;
+        }
+    }
+    lunar::store_world(W, a.lunar_rec, a.n, i, O.wind != 0);
+    pcg64_store(a.rng + 4 * i, g);
+    a.elapsed[i] = elapsed;
+    if (!deferred) store_obs_all<8>(a, i, obs);
+}
+
 template <typename ActT, bool CONT>
 __global__ void __launch_bounds__(kLunarMaxThreads, 2) lunar_step_kernel(const StepArgs a) {
     const int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -680,34 +748,51 @@ __global__ void __launch_bounds__(kLunarMaxThreads, 2) lunar_step_kernel(const S
         store_scalars_all(a, i, __longlong_as_double(0x7ff8000000000000LL), 0, 0);
         return;
     }
+    (void)live;
     const lunar::Opts &O = a.lunar_opts;
     lunar::World W;
     lunar::load_world(W, a.lunar_rec, a.n, i, O.wind != 0);
     Pcg64 g = pcg64_load(a.rng + 4 * i);
-    int32_t elapsed = a.elapsed[i];
-    float obs[8];
-    double reward;
-    bool terminated;
-    lunar::env_step(W, g, O, (int)act, ca0, ca1, lunar::V(0.0f, 0.0f), obs, reward, terminated, live);
-    elapsed += 1;                                                        // time_limit.py:51
-    const bool truncated = (a.max_steps > 0) && (elapsed >= a.max_steps);
-    store_scalars_all(a, i, reward, terminated ? 1 : 0, truncated ? 1 : 0);
-    episode_account(a, i, reward, terminated || truncated);
-    bool deferred = false;
-    if ((terminated || truncated) && a.autoreset) {                      // sync_vector_env.py:152-156
-        if (a.final_obs) store_row<8>(a.final_obs, i, obs);
-        if (a.reset_list) {  // the new episode is drawn by lunar_reset_list_kernel, in warps full of resetting envs
-            a.reset_list[a.first + atomicAdd(a.reset_count, 1)] = (int32_t)j;
-            deferred = true;
-        } else {
-            lunar::env_reset(W, g, O, obs);
-            elapsed = 0;
+    const int32_t elapsed = a.elapsed[i];
+    lunar::Mid mid;
+    lunar::env_pre(W, g, O, (int)act, ca0, ca1, lunar::V(0.0f, 0.0f), mid, 0u, /*run_toi=*/false);
+    if (mid.awake && b2l::toi_needed<lunar::Scene>(W)) {
+        if (a.toi_list) {   // park the env for lunar_toi_kernel
+            lunar::store_world(W, a.lunar_rec, a.n, i, O.wind != 0);
+            pcg64_store(a.rng + 4 * i, g);
+            lunar_store_mid(a, i, W, mid);
+            a.toi_list[a.first + atomicAdd(a.toi_count, 1)] = (int32_t)j;
+            return;
+        }
+        b2l::solve_toi<lunar::Scene>(W, (float)(1.0 / 50), true, 0u);
+    }
+    lunar_finish(a, i, j, W, g, elapsed, mid);
+}
+
+// The continuous-collision phase of the envs that lunar_step_kernel parked, one warp of parked envs per CTA: the
+// TOI code (GJK, root finder, the sub-step solver) is large and runs for a few percent of the envs, so it gets
+// its own launch -- dense warps and a warm instruction cache instead of one or two lanes per warp walking it at the
+// end of every warp's critical path -- and the warp-synchronous event rounds of b2l::solve_toi.
+__global__ void __launch_bounds__(32) lunar_toi_kernel(const StepArgs a) {
+    const int cnt = *a.toi_count;
+    const lunar::Opts &O = a.lunar_opts;
+    for (int base = blockIdx.x * 32; base < cnt; base += gridDim.x * 32) {
+        const int idx = base + (int)threadIdx.x;
+        const bool on = idx < cnt;
+        const unsigned live = __ballot_sync(0xffffffffu, on);
+        if (on) {
+            const int64_t j = a.toi_list[a.first + idx];
+            const int64_t i = a.first + j;
+            lunar::World W;
+            lunar::load_world(W, a.lunar_rec, a.n, i, O.wind != 0);
+            lunar::Mid mid;
+            lunar_load_mid(a, i, W, mid);
+            Pcg64 g = pcg64_load(a.rng + 4 * i);
+            const int32_t elapsed = a.elapsed[i];
+            b2l::solve_toi<lunar::Scene>(W, (float)(1.0 / 50), true, live);
+            lunar_finish(a, i, j, W, g, elapsed, mid);
         }
     }
-    lunar::store_world(W, a.lunar_rec, a.n, i, O.wind != 0);
-    pcg64_store(a.rng + 4 * i, g);
-    a.elapsed[i] = elapsed;
-    if (!deferred) store_obs_all<8>(a, i, obs);
 }
 
 // The autoresets of one step, compacted: a lone finishing env would otherwise keep its whole warp waiting through
@@ -1214,6 +1299,18 @@ static int launch_step(b200gym *h, const StepArgs &a, int action_dtype, cudaStre
         } else {
             b.reset_list = nullptr; b.reset_count = nullptr;
         }
+        // continuous collision of the parked envs in its own launch (LunarLander; see lunar_toi_kernel)
+        const bool toi_defer = h->is_lunar && h->box2d_toi_defer && h->toi_list;
+        if (toi_defer) {
+            b.toi_list = h->toi_list;
+            b.toi_mid = h->toi_mid;
+            if (!b.toi_count) b.toi_count = h->toi_count;
+            CK(h, cudaMemsetAsync(b.toi_count, 0, sizeof(int32_t), st));
+        } else {
+            b.toi_list = nullptr; b.toi_count = nullptr; b.toi_mid = nullptr;
+        }
+        // one warp per CTA, at most 8 per SM in flight; the kernel strides over the list
+        const unsigned tgrid = (unsigned)std::min<int64_t>((b.count + 31) / 32, 8 * h->sm_count);
         // at most this many CTAs of the compacted reset kernel (it strides over the list)
         const unsigned rgrid = (unsigned)std::min<int64_t>((b.count + kLunarThreads - 1) / kLunarThreads, 2 * h->sm_count);
         if (h->is_lunar) {
@@ -1232,6 +1329,10 @@ static int launch_step(b200gym *h, const StepArgs &a, int action_dtype, cudaStre
                 }
             }
             CK(h, cudaGetLastError());
+            if (toi_defer) {
+                lunar_toi_kernel<<<tgrid, 32, 0, st>>>(b);
+                CK(h, cudaGetLastError());
+            }
             if (defer) lunar_reset_list_kernel<<<rgrid, kLunarThreads, 0, st>>>(b);
         } else {
             if (action_dtype != B200GYM_ACT_F32) return fail(h, "Box env needs float32 actions (got dtype code %d)", action_dtype);
@@ -1353,6 +1454,8 @@ extern "C" int b200gym_create(const b200gym_config *cfg, int64_t num_envs, int d
         if (gb && (gb[0] == 'b' || gb[0] == 'd')) h->gather_bulk = gb[0] == 'b';
         const char *bb = getenv("B200GYM_BOX2D_BLOCK");
         if (bb && (atoi(bb) == 128 || atoi(bb) == 256)) h->box2d_block = atoi(bb);
+        const char *btd = getenv("B200GYM_BOX2D_TOI_DEFER");
+        if (btd && (btd[0] == '0' || btd[0] == '1')) h->box2d_toi_defer = btd[0] - '0';
         const char *bdf = getenv("B200GYM_BOX2D_DEFER");
         if (bdf && (bdf[0] == '0' || bdf[0] == '1')) h->box2d_defer = bdf[0] - '0';
         const char *ba = getenv("B200GYM_BLOCK_A");
@@ -1392,6 +1495,10 @@ extern "C" int b200gym_create(const b200gym_config *cfg, int64_t num_envs, int d
         if (cudaMalloc(&h->lunar_rec, sizeof(uint32_t) * words * n) != cudaSuccess ||
             cudaMemset(h->lunar_rec, 0, sizeof(uint32_t) * words * n) != cudaSuccess ||
             cudaMalloc((void **)&h->reset_list, sizeof(int32_t) * n) != cudaSuccess ||
+            cudaMalloc((void **)&h->toi_list, sizeof(int32_t) * n) != cudaSuccess ||
+            cudaMalloc((void **)&h->toi_count, sizeof(int32_t) * kResetSlots) != cudaSuccess ||
+            cudaMemset(h->toi_count, 0, sizeof(int32_t) * kResetSlots) != cudaSuccess ||
+            cudaMalloc((void **)&h->toi_mid, sizeof(uint32_t) * kToiMidWords * n) != cudaSuccess ||
             cudaMalloc((void **)&h->reset_count, sizeof(int32_t) * kResetSlots) != cudaSuccess ||
             cudaMemset(h->reset_count, 0, sizeof(int32_t) * kResetSlots) != cudaSuccess ||
             (lun ? lunar_upload_consts(h) : walker_upload_consts(h))) {
@@ -1440,6 +1547,9 @@ extern "C" void b200gym_destroy(b200gym_t *h) {
     cudaFree(h->lunar_rec);
     cudaFree(h->reset_list);
     cudaFree(h->reset_count);
+    cudaFree(h->toi_list);
+    cudaFree(h->toi_count);
+    cudaFree(h->toi_mid);
     if (h->p2p.base) {
         for (int r = 0; r < h->p2p.world; r++)
             if (r != h->p2p.rank && h->p2p.peer[r]) cudaIpcCloseMemHandle(h->p2p.peer[r]);
@@ -1507,6 +1617,7 @@ static StepArgs make_args(b200gym *h, const void *actions, float *obs, double *r
     a.max_steps = h->cfg.max_episode_steps; a.autoreset = h->cfg.autoreset; a.param0 = h->cfg.param[0];
     a.lunar_opts = h->lunar_opts;
     a.reset_list = nullptr; a.reset_count = nullptr;
+    a.toi_list = nullptr; a.toi_count = nullptr; a.toi_mid = nullptr;
     a.npeer = 0;
     a.bulk_sink = 0;
     a.ep_acc = h->ep.acc; a.ep_len = h->ep.len; a.ep_r = h->ep.r; a.ep_l = h->ep.l;
@@ -1891,6 +2002,7 @@ static int step_host_enqueue(b200gym *h, const void *actions_host, int action_dt
         a.first = lo;
         a.count = cnt;
         a.reset_count = h->reset_count ? h->reset_count + (c % kResetSlots) : nullptr;
+        a.toi_count = h->toi_count ? h->toi_count + (c % kResetSlots) : nullptr;
         if (launch_step(h, a, action_dtype, st)) return 1;
     }
     if (c > 1) {  // stream 0 also waits for the chunks of stream 1

@@ -553,7 +553,7 @@ LD bool joint_solve_position(const Joint &j, const JointDef &d, const ShapeConst
 // the warp's lanes that call world_step together (they synchronise inside solve_toi), or 0.
 template <typename Scene>
 __device__ __noinline__ void world_step(typename Scene::World &W, v2 force0, float torque0, float gravity_y,
-                                        bool &island_awake, unsigned live = 0u) {
+                                        bool &island_awake, unsigned live = 0u, bool run_toi = true) {
     constexpr int NB = Scene::NB, NJ = Scene::NJ, kSlots = Scene::kSlots, kMaxVC = Scene::kMaxVC;
     constexpr int NE = Scene::NE, NP = Scene::NP, NF = NE + NP;
     const float dt = (float)(1.0 / 50);
@@ -931,7 +931,8 @@ __device__ __noinline__ void world_step(typename Scene::World &W, v2 force0, flo
     }
     // --- SolveTOI: continuous collision against the static fixtures (a sleeping island is skipped)
     // (`live`: the warp's lanes that are in this call together, see solve_toi; 0 on divergent callers)
-    if (live != 0u || island_awake) solve_toi<Scene>(W, dt, island_awake, live);
+    // run_toi = false: the caller runs SolveTOI itself (deferred to the TOI kernel, see toi_needed)
+    if (run_toi && (live != 0u || island_awake)) solve_toi<Scene>(W, dt, island_awake, live);
     W.flags |= kFlagStepped;
 }
 

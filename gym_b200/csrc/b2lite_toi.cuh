@@ -20,6 +20,15 @@
 // float32, one rounding per operation, the same operation order as the CPU checker in the test tree.
 #pragma once
 
+// workload counters of the host build (tests/hostsim with -DB2L_TOI_STATS): {pairs examined, skipped by the AABB
+// shortcut, skipped by the resting-contact shortcut, b2TimeOfImpact evaluations, TOI sub-steps, velocity iterations run}
+#if defined(B2L_TOI_STATS) && !defined(__CUDA_ARCH__)
+extern long long b2l_toi_stats[6];
+#define B2L_STAT(i, n) (b2l_toi_stats[i] += (n))
+#else
+#define B2L_STAT(i, n) ((void)0)
+#endif
+
 constexpr float kEpsilon = 1.1920929e-07f;
 constexpr float kPi = 3.14159265359f;
 constexpr int kMaxSubSteps = 8;
@@ -303,6 +312,89 @@ LD Sweep body_sweep(const Body &B, const ShapeConst &sh) {
     Sweep s;
     s.localCenter = sh.localCenter; s.c0 = B.c0; s.c = B.c; s.a0 = B.a0; s.a = B.a; s.alpha0 = B.alpha0;
     return s;
+}
+
+// the distance proxy of static fixture f: an edge's two vertices, or a box's four corners in b2PolygonShape::Set order
+template <typename Scene>
+LD void fixture_proxy(const typename Scene::World &W, int f, DProxy &pA) {
+    constexpr int NE = Scene::NE;
+    if (Scene::NP > 0 && f >= NE) {
+        if constexpr (Scene::NP > 0) {
+            float x0, ylo, x1, yhi, fr;
+            Scene::poly(W, f - NE, x0, ylo, x1, yhi, fr);
+            pA.count = 4;
+            pA.v[0] = V(x1, ylo); pA.v[1] = V(x1, yhi); pA.v[2] = V(x0, yhi); pA.v[3] = V(x0, ylo);
+        }
+    } else {
+        float fr;
+        pA.count = 2;
+        Scene::edge(W, f, pA.v[0], pA.v[1], fr);
+    }
+}
+
+// true when b2TimeOfImpact of the polygon `sh` sweeping along sB (current transform xf1 = the sweep's end) against
+// the static fixture pA provably cannot report e_touching, i.e. the pair's alpha is 1 without running it.
+__device__ __noinline__ bool toi_cannot_touch(const ShapeConst &sh, const xform &xf1, const Sweep &sB, const DProxy &pA) {
+    // Shortcut (results unchanged): b2TimeOfImpact can only report e_touching if some transform of the
+    // sweep brings the core shapes within target + tolerance = 1.25 linearSlop.  Every vertex moves from
+    // its start to its end position within R * (1 - cos(d/2)) <= R * d^2 / 8 of the straight segment
+    // between the two (R: its distance from the centre of mass, d: the rotation over the sweep), so the
+    // polygon never leaves the box around its start and end poses widened by that amount.  If that box,
+    // widened once more by 1.25 linearSlop and a safety margin far above float32 rounding, misses the
+    // fixture's box, every outcome is "separated" (or "failed"), i.e. alpha = 1.
+    bool far_apart = false;
+    {
+        const xform xf0 = sweep_xf(sB, 0.0f);
+        float lox = kFltMax, loy = kFltMax, hix = -kFltMax, hiy = -kFltMax, r2 = 0.0f;
+        v2 p0[MAXV];
+        for (int i = 0; i < sh.count; i++) {
+            const v2 p = xmul(xf0, sh.verts[i]), q = xmul(xf1, sh.verts[i]);
+            p0[i] = p;
+            lox = fmin_(lox, fmin_(p.x, q.x)); loy = fmin_(loy, fmin_(p.y, q.y));
+            hix = fmax_(hix, fmax_(p.x, q.x)); hiy = fmax_(hiy, fmax_(p.y, q.y));
+            const v2 r = sub(sh.verts[i], sh.localCenter);
+            r2 = fmax_(r2, dot(r, r));
+        }
+        const float d = fabsf(sB.a - sB.a0);
+        const float touch = 1.25f * kLinearSlop + 0.002f;   // target + tolerance + safety
+        if (d < 0.5f) {
+            const float m = touch + sqrtf(r2) * d * d * 0.125f;
+            float flox = kFltMax, floy = kFltMax, fhix = -kFltMax, fhiy = -kFltMax;
+            for (int i = 0; i < pA.count; i++) {
+                flox = fmin_(flox, pA.v[i].x); floy = fmin_(floy, pA.v[i].y);
+                fhix = fmax_(fhix, pA.v[i].x); fhiy = fmax_(fhiy, pA.v[i].y);
+            }
+            far_apart = lox - m > fhix || flox > hix + m || loy - m > fhiy || floy > hiy + m;
+            if (far_apart) B2L_STAT(1, 1);
+        }
+        // Second shortcut, for RESTING and sliding contacts (the bulk of the list: feet on the ground):
+        // over the sweep no vertex moves farther than D = |c - c0| + R * |a - a0| from where it starts.
+        // If at the start the whole polygon lies on one side of a face line of the fixture by more than
+        // D + 1.25 linearSlop (+ safety), it stays beyond the touching distance of that line -- hence of
+        // the fixture, which lies on the line's other side -- for the whole step: alpha = 1.  (Resting
+        // contacts sit at 3 linearSlop: the position solver leaves one slop of the 2 x polygonRadius.)
+        if (!far_apart) {
+            const v2 dc = sub(sB.c, sB.c0);
+            const float D = sqrtf(dot(dc, dc)) + sqrtf(r2) * d + touch;
+            const int nf = pA.count == 2 ? 1 : pA.count;   // an edge has one line, a box four
+            for (int e = 0; e < nf && !far_apart; e++) {
+                const v2 a0 = pA.v[e], a1 = pA.v[e + 1 < pA.count ? e + 1 : 0];
+                v2 n = V(a1.y - a0.y, a0.x - a1.x);          // normal of the line a0-a1 (either sign)
+                const float len = sqrtf(dot(n, n));
+                if (len < 1e-6f) continue;
+                n = scl(1.0f / len, n);
+                float smin = kFltMax, smax = -kFltMax;
+                for (int i = 0; i < sh.count; i++) {
+                    const float sd = dot(n, sub(p0[i], a0));
+                    smin = fmin_(smin, sd); smax = fmax_(smax, sd);
+                }
+                if (pA.count == 2) far_apart = smin > D || smax < -D;   // an edge is two-sided
+                else far_apart = smin > D;                               // outside this face of the box
+            }
+            if (far_apart) B2L_STAT(2, 1);
+        }
+    }
+    return far_apart;
 }
 
 // b2Contact::Update of one (body, static fixture) pair during SolveTOI: the manifold at the body's current
@@ -595,6 +687,7 @@ __device__ __noinline__ void island_solve_toi(typename Scene::World &W, int body
                 }
             }
         }
+        B2L_STAT(5, 1);
         {   // periodicity check
             uint32_t cur[3 + 4 * kMaxVC];
             cur[0] = __float_as_uint(vB.x); cur[1] = __float_as_uint(vB.y); cur[2] = __float_as_uint(wB);
@@ -623,6 +716,29 @@ __device__ __noinline__ void island_solve_toi(typename Scene::World &W, int body
     }
     B.c = cB; B.a = aB; B.v = vB; B.w = wB;
     sync_xf(B, sh);
+}
+
+// Is there any pair on the step's contact list for which b2TimeOfImpact has to be evaluated at all?  (Same list,
+// same sweeps and the same shortcut as the first round of solve_toi; when this returns false solve_toi would find
+// every alpha = 1 and change nothing.)  The step kernels use it to finish the common case -- free flight, resting
+// contacts -- right away and to hand only the envs with a possible event to the TOI kernel.
+template <typename Scene>
+__device__ __noinline__ bool toi_needed(typename Scene::World &W) {
+    constexpr int NB = Scene::NB;
+    ToiCand cand[kMaxToiCand];
+    float alphaS[kMaxToiCand];
+    int statId[kMaxToiCand];
+    int ncand = 0, nstat = 0;
+    for (int i = 0; i < NB; i++) W.b[i].alpha0 = 0.0f;
+    for (int oi = 0; oi < NB; oi++) toi_add_candidates<Scene>(W, cand, ncand, alphaS, statId, nstat, Scene::body_order(oi));
+    for (int ci = 0; ci < ncand; ci++) {
+        const ShapeConst &sh = Scene::shape(cand[ci].body);
+        const Body &B = W.b[cand[ci].body];
+        DProxy pA;
+        fixture_proxy<Scene>(W, cand[ci].f, pA);
+        if (!toi_cannot_touch(sh, B.xf, body_sweep(B, sh), pA)) return true;
+    }
+    return false;
 }
 
 // `live`: the lanes of this warp that run solve_toi together (0: the caller is on a divergent path, e.g. the step
@@ -664,48 +780,10 @@ __device__ __noinline__ void solve_toi(typename Scene::World &W, float dt, bool 
                     B.c0 = s.c0; B.a0 = s.a0; B.alpha0 = s.alpha0;
                 }
                 DProxy pA;
-                if (Scene::NP > 0 && c.f >= NE) {
-                    if constexpr (Scene::NP > 0) {
-                        float x0, ylo, x1, yhi, fr;
-                        Scene::poly(W, c.f - NE, x0, ylo, x1, yhi, fr);
-                        pA.count = 4;
-                        pA.v[0] = V(x1, ylo); pA.v[1] = V(x1, yhi); pA.v[2] = V(x0, yhi); pA.v[3] = V(x0, ylo);
-                    }
-                } else {
-                    float fr;
-                    pA.count = 2;
-                    Scene::edge(W, c.f, pA.v[0], pA.v[1], fr);
-                }
+                fixture_proxy<Scene>(W, c.f, pA);
                 const Sweep sB = body_sweep(B, sh);
-                // Shortcut (results unchanged): b2TimeOfImpact can only report e_touching if some transform of the
-                // sweep brings the core shapes within target + tolerance = 1.25 linearSlop.  Every vertex moves from
-                // its start to its end position within R * (1 - cos(d/2)) <= R * d^2 / 8 of the straight segment
-                // between the two (R: its distance from the centre of mass, d: the rotation over the sweep), so the
-                // polygon never leaves the box around its start and end poses widened by that amount.  If that box,
-                // widened once more by 1.25 linearSlop and a safety margin far above float32 rounding, misses the
-                // fixture's box, every outcome is "separated" (or "failed"), i.e. alpha = 1.
-                bool far_apart = false;
-                {
-                    const xform xf0 = sweep_xf(sB, 0.0f);
-                    float lox = kFltMax, loy = kFltMax, hix = -kFltMax, hiy = -kFltMax, r2 = 0.0f;
-                    for (int i = 0; i < sh.count; i++) {
-                        const v2 p = xmul(xf0, sh.verts[i]), q = xmul(B.xf, sh.verts[i]);
-                        lox = fmin_(lox, fmin_(p.x, q.x)); loy = fmin_(loy, fmin_(p.y, q.y));
-                        hix = fmax_(hix, fmax_(p.x, q.x)); hiy = fmax_(hiy, fmax_(p.y, q.y));
-                        const v2 r = sub(sh.verts[i], sh.localCenter);
-                        r2 = fmax_(r2, dot(r, r));
-                    }
-                    const float d = fabsf(sB.a - sB.a0);
-                    if (d < 0.5f) {
-                        const float m = 1.25f * kLinearSlop + 0.002f + sqrtf(r2) * d * d * 0.125f;
-                        float flox = kFltMax, floy = kFltMax, fhix = -kFltMax, fhiy = -kFltMax;
-                        for (int i = 0; i < pA.count; i++) {
-                            flox = fmin_(flox, pA.v[i].x); floy = fmin_(floy, pA.v[i].y);
-                            fhix = fmax_(fhix, pA.v[i].x); fhiy = fmax_(fhiy, pA.v[i].y);
-                        }
-                        far_apart = lox - m > fhix || flox > hix + m || loy - m > fhiy || floy > hiy + m;
-                    }
-                }
+                B2L_STAT(0, 1);
+                const bool far_apart = toi_cannot_touch(sh, B.xf, sB, pA);
                 if (far_apart) alpha = 1.0f;
                 else {
                     DProxy pB;
@@ -714,6 +792,7 @@ __device__ __noinline__ void solve_toi(typename Scene::World &W, float dt, bool 
                     Sweep sA;
                     sA.localCenter = V(0.0f, 0.0f); sA.c0 = V(0.0f, 0.0f); sA.c = V(0.0f, 0.0f); sA.a0 = 0.0f; sA.a = 0.0f; sA.alpha0 = alpha0;
                     float beta;
+                    B2L_STAT(3, 1);
                     const int state = time_of_impact(beta, pA, sA, pB, sB, 1.0f);
                     if (state == TOI_TOUCHING) alpha = fmin_(alpha0 + (1.0f - alpha0) * beta, 1.0f);
                     else alpha = 1.0f;
@@ -775,7 +854,7 @@ __device__ __noinline__ void solve_toi(typename Scene::World &W, float dt, bool 
             }
         }
         if (sync) __syncwarp(live);
-        if (solve) island_solve_toi<Scene>(W, moved, mf, fric, nic, h);
+        if (solve) { B2L_STAT(4, 1); island_solve_toi<Scene>(W, moved, mf, fric, nic, h); }
         if (solve) {
             // invalidate all contact TOIs on the displaced body; its moved proxy may create new contacts
             for (int ci = 0; ci < ncand; ci++) if (cand[ci].body == moved) cand[ci].toiValid = false;

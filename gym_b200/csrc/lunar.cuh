@@ -92,10 +92,14 @@ struct Scene {
 // lunar_lander.py:444-600.  `action` is the Discrete(4) action, `ca` the Box(2) float32 action of the
 // continuous variant.  In the continuous branch m_power / s_power / direction are numpy float32 scalars:
 // under NEP 50 every Python float they meet is rounded to float32 first, which is what the casts restate.
-LD void env_step(World &W, Pcg64 &rng, const Opts &O, int action, float ca0, float ca1, v2 lander_force,
-                 float (&obs)[8], double &reward, bool &terminated, unsigned live = 0u) {
-    const double SCALE = 30.0, FPS = 50;
-    const double VW = 600 / SCALE, VH = 400 / SCALE;
+// what env_pre hands to env_post across world.Step (and, for envs whose continuous-collision phase is deferred to
+// the TOI kernel, across kernels: b200gym.cu keeps it in a side buffer)
+struct Mid { double main_cost, side_cost; bool awake; };
+
+// lunar_lander.py:444-556: wind, engines, world.Step.  run_toi = false leaves b2World::SolveTOI to the caller.
+LD void env_pre(World &W, Pcg64 &rng, const Opts &O, int action, float ca0, float ca1, v2 lander_force, Mid &mid,
+                unsigned live, bool run_toi) {
+    const double SCALE = 30.0;
     Body &L = W.b[0];
     const ShapeConst &sh = kC.shape[0];
     float torque = 0.0f;
@@ -161,7 +165,17 @@ LD void env_step(World &W, Pcg64 &rng, const Opts &O, int action, float ca0, flo
         L.w += sh.invI * crs(sub(pt, L.c), imp);
     }
     bool awake;
-    world_step<Scene>(W, lander_force, torque, O.gravity, awake, live);                                    // :556
+    world_step<Scene>(W, lander_force, torque, O.gravity, awake, live, run_toi);                           // :556
+    mid.main_cost = main_cost; mid.side_cost = side_cost; mid.awake = awake;
+}
+
+// lunar_lander.py:558-600: observation, shaping reward, termination
+LD void env_post(World &W, const Mid &mid, float (&obs)[8], double &reward, bool &terminated) {
+    const double SCALE = 30.0, FPS = 50;
+    const double VW = 600 / SCALE, VH = 400 / SCALE;
+    const Body &L = W.b[0];
+    const double main_cost = mid.main_cost, side_cost = mid.side_cost;
+    const bool awake = mid.awake;
     double st[8];
     const double helipad_y = VH / 4;
     st[0] = ((double)L.xf.p.x - VW / 2) / (VW / 2);                              // :560-569
@@ -187,6 +201,13 @@ LD void env_step(World &W, Pcg64 &rng, const Opts &O, int action, float ca0, flo
     for (int k = 0; k < 8; k++) obs[k] = (float)st[k];                           // :600
     reward = r;
     terminated = term;
+}
+
+LD void env_step(World &W, Pcg64 &rng, const Opts &O, int action, float ca0, float ca1, v2 lander_force,
+                 float (&obs)[8], double &reward, bool &terminated, unsigned live = 0u) {
+    Mid mid;
+    env_pre(W, rng, O, action, ca0, ca1, lander_force, mid, live, true);
+    env_post(W, mid, obs, reward, terminated);
 }
 
 // lunar_lander.py:308-420 (the b2World object survives reset(): bit4 of flags is kept)

@@ -665,6 +665,16 @@ constexpr int kResetSlots = 64;   // launch ranges of one handle that may be in 
 
 constexpr int kLunarMaxThreads = 256;
 
+// The TOI kernels run one warp per CTA and give each warp as FEW parked envs as the resident grid allows: the lanes
+// of a warp diverge completely in this code (different contact lists, GJK / root-finder trip counts, event counts),
+// so a warp takes the SUM of its lanes' paths, and with a few thousand parked envs on 148 SMs there are more warp
+// slots than envs.  Measured (LunarLander, 2^16 envs, ~3 300 parked per step): 32 envs per warp 1.19 ms for the
+// launch, the step kernel before it 0.71 ms.
+__device__ __forceinline__ int toi_lanes_per_warp(int cnt, int nwarps) {
+    const int L = (cnt + nwarps - 1) / nwarps;
+    return L < 1 ? 1 : (L > 32 ? 32 : L);
+}
+
 // side buffer of a parked env ([kToiMidWords][n] SoA): the sweep starts of the 3 bodies + env_pre's intermediates
 constexpr int kToiMidWords = 20;   // LunarLander uses 13, BipedalWalker 15
 
@@ -776,9 +786,10 @@ __global__ void __launch_bounds__(kLunarMaxThreads, 2) lunar_step_kernel(const S
 __global__ void __launch_bounds__(32) lunar_toi_kernel(const StepArgs a) {
     const int cnt = *a.toi_count;
     const lunar::Opts &O = a.lunar_opts;
-    for (int base = blockIdx.x * 32; base < cnt; base += gridDim.x * 32) {
+    const int L = toi_lanes_per_warp(cnt, (int)gridDim.x);
+    for (int base = blockIdx.x * L; base < cnt; base += gridDim.x * L) {
         const int idx = base + (int)threadIdx.x;
-        const bool on = idx < cnt;
+        const bool on = (int)threadIdx.x < L && idx < cnt;
         const unsigned live = __ballot_sync(0xffffffffu, on);
         if (on) {
             const int64_t j = a.toi_list[a.first + idx];
@@ -871,23 +882,14 @@ static int lunar_upload_consts(b200gym *h) {
 }
 
 // ---- BipedalWalker-v3 (walker.cuh): one thread per env --------------------------------------------
+// everything after world.Step of BipedalWalker.step, then TimeLimit, outputs and the same-step autoreset
 template <bool HC>
-__global__ void __launch_bounds__(kLunarThreads, 4) walker_step_kernel(const StepArgs a) {
-    const int64_t j = (int64_t)blockIdx.x * kLunarThreads + threadIdx.x;
-    const bool in_range = j < a.count;
-    const unsigned live = __ballot_sync(0xffffffffu, in_range);   // the lanes that step an env (see solve_toi)
-    if (!in_range) return;
-    const int64_t i = a.first + j;
-    const float4 av = __ldg(reinterpret_cast<const float4 *>(a.actions) + i);
-    const float action[4] = {av.x, av.y, av.z, av.w};
-    walker::World W;
-    walker::Rng rng;
-    walker::load_world(W, a.lunar_rec, a.n, i, rng, HC);
-    int32_t elapsed = a.elapsed[i];
+__device__ __noinline__ void walker_finish(const StepArgs &a, int64_t i, int64_t j, walker::World &W, walker::Rng &rng,
+                                           int32_t elapsed, const float (&action)[4]) {
     float obs[24];
     double reward;
     bool terminated;
-    walker::env_step<HC>(W, action, false, walker::V(0.0f, 0.0f), obs, reward, terminated, live);
+    walker::env_post<HC>(W, action, false, obs, reward, terminated);
     elapsed += 1;                                                        // time_limit.py:51
     const bool truncated = (a.max_steps > 0) && (elapsed >= a.max_steps);
     store_scalars_all(a, i, reward, terminated ? 1 : 0, truncated ? 1 : 0);
@@ -908,6 +910,68 @@ __global__ void __launch_bounds__(kLunarThreads, 4) walker_step_kernel(const Ste
     walker::store_world(W, a.lunar_rec, a.n, i, rng, HC);
     a.elapsed[i] = elapsed;
     if (!deferred) store_obs_all<24>(a, i, obs);
+}
+
+template <bool HC>
+__global__ void __launch_bounds__(kLunarThreads, 4) walker_step_kernel(const StepArgs a) {
+    const int64_t j = (int64_t)blockIdx.x * kLunarThreads + threadIdx.x;
+    if (j >= a.count) return;
+    const int64_t i = a.first + j;
+    const float4 av = __ldg(reinterpret_cast<const float4 *>(a.actions) + i);
+    const float action[4] = {av.x, av.y, av.z, av.w};
+    walker::World W;
+    walker::Rng rng;
+    walker::load_world(W, a.lunar_rec, a.n, i, rng, HC);
+    const int32_t elapsed = a.elapsed[i];
+    bool awake;
+    walker::env_pre<HC>(W, action, walker::V(0.0f, 0.0f), awake, 0u, /*run_toi=*/false);
+    if (awake && b2l::toi_needed<walker::SceneT<HC>>(W)) {
+        if (a.toi_list) {   // park the env for walker_toi_kernel: the record after the discrete solve + the sweep starts
+            walker::store_world(W, a.lunar_rec, a.n, i, rng, HC);
+            uint32_t *m = a.toi_mid + i;
+            for (int b = 0; b < walker::NB; b++) {
+                m[(int64_t)(3 * b + 0) * a.n] = __float_as_uint(W.b[b].c0.x);
+                m[(int64_t)(3 * b + 1) * a.n] = __float_as_uint(W.b[b].c0.y);
+                m[(int64_t)(3 * b + 2) * a.n] = __float_as_uint(W.b[b].a0);
+            }
+            a.toi_list[a.first + atomicAdd(a.toi_count, 1)] = (int32_t)j;
+            return;
+        }
+        b2l::solve_toi<walker::SceneT<HC>>(W, (float)(1.0 / 50), true, 0u);
+    }
+    walker_finish<HC>(a, i, j, W, rng, elapsed, action);
+}
+
+// the continuous-collision phase of the parked envs (see lunar_toi_kernel)
+template <bool HC>
+__global__ void __launch_bounds__(32) walker_toi_kernel(const StepArgs a) {
+    const int cnt = *a.toi_count;
+    const int L = toi_lanes_per_warp(cnt, (int)gridDim.x);
+    for (int base = blockIdx.x * L; base < cnt; base += gridDim.x * L) {
+        const int idx = base + (int)threadIdx.x;
+        const bool on = (int)threadIdx.x < L && idx < cnt;
+        const unsigned live = __ballot_sync(0xffffffffu, on);
+        if (on) {
+            const int64_t j = a.toi_list[a.first + idx];
+            const int64_t i = a.first + j;
+            const float4 av = __ldg(reinterpret_cast<const float4 *>(a.actions) + i);
+            const float action[4] = {av.x, av.y, av.z, av.w};
+            walker::World W;
+            walker::Rng rng;
+            walker::load_world(W, a.lunar_rec, a.n, i, rng, HC);
+            const uint32_t *m = a.toi_mid + i;
+            for (int b = 0; b < walker::NB; b++) {
+                W.b[b].c0.x = __uint_as_float(m[(int64_t)(3 * b + 0) * a.n]);
+                W.b[b].c0.y = __uint_as_float(m[(int64_t)(3 * b + 1) * a.n]);
+                W.b[b].a0 = __uint_as_float(m[(int64_t)(3 * b + 2) * a.n]);
+            }
+            // the window of obstacle boxes env_pre computed around the hull's position before the step
+            if constexpr (HC) walker::poly_window(W, W.b[0].c0.x - 4.0f, W.b[0].c0.x + 4.0f, W.p_lo, W.p_hi);
+            const int32_t elapsed = a.elapsed[i];
+            b2l::solve_toi<walker::SceneT<HC>>(W, (float)(1.0 / 50), true, live);
+            walker_finish<HC>(a, i, j, W, rng, elapsed, action);
+        }
+    }
 }
 
 template <bool HC>
@@ -1299,8 +1363,8 @@ static int launch_step(b200gym *h, const StepArgs &a, int action_dtype, cudaStre
         } else {
             b.reset_list = nullptr; b.reset_count = nullptr;
         }
-        // continuous collision of the parked envs in its own launch (LunarLander; see lunar_toi_kernel)
-        const bool toi_defer = h->is_lunar && h->box2d_toi_defer && h->toi_list;
+        // continuous collision of the parked envs in its own launch (see lunar_toi_kernel)
+        const bool toi_defer = h->box2d_toi_defer && h->toi_list;
         if (toi_defer) {
             b.toi_list = h->toi_list;
             b.toi_mid = h->toi_mid;
@@ -1309,8 +1373,8 @@ static int launch_step(b200gym *h, const StepArgs &a, int action_dtype, cudaStre
         } else {
             b.toi_list = nullptr; b.toi_count = nullptr; b.toi_mid = nullptr;
         }
-        // one warp per CTA, at most 8 per SM in flight; the kernel strides over the list
-        const unsigned tgrid = (unsigned)std::min<int64_t>((b.count + 31) / 32, 8 * h->sm_count);
+        // one warp per CTA, 12 per SM (the 156-register kernel's residency); the kernel strides over the list
+        const unsigned tgrid = (unsigned)std::min<int64_t>(b.count, 12 * h->sm_count);
         // at most this many CTAs of the compacted reset kernel (it strides over the list)
         const unsigned rgrid = (unsigned)std::min<int64_t>((b.count + kLunarThreads - 1) / kLunarThreads, 2 * h->sm_count);
         if (h->is_lunar) {
@@ -1342,6 +1406,11 @@ static int launch_step(b200gym *h, const StepArgs &a, int action_dtype, cudaStre
             if (hc) walker_step_kernel<true><<<grid, kLunarThreads, 0, st>>>(b);
             else walker_step_kernel<false><<<grid, kLunarThreads, 0, st>>>(b);
             CK(h, cudaGetLastError());
+            if (toi_defer) {
+                if (hc) walker_toi_kernel<true><<<tgrid, 32, 0, st>>>(b);
+                else walker_toi_kernel<false><<<tgrid, 32, 0, st>>>(b);
+                CK(h, cudaGetLastError());
+            }
             if (defer) {
                 if (hc) walker_reset_list_kernel<true><<<rgrid, kLunarThreads, 0, st>>>(b);
                 else walker_reset_list_kernel<false><<<rgrid, kLunarThreads, 0, st>>>(b);

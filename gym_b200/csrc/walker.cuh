@@ -171,21 +171,26 @@ LD float sgnf(float a) { return a > 0.0f ? 1.0f : (a < 0.0f ? -1.0f : 0.0f); }
 LD float clip01_abs(float a) { float x = fabsf(a); x = x < 0.0f ? 0.0f : x; return x > 1.0f ? 1.0f : x; }
 
 // bipedal_walker.py:517-606
+// bipedal_walker.py:517-545: motor commands, world.Step.  run_toi = false leaves b2World::SolveTOI to the caller.
 template <bool HC>
-__device__ __noinline__ void env_step(World &W, const float (&action)[4], bool from_reset, v2 hull_force, float (&obs)[24],
-                                      double &reward, bool &terminated, unsigned live = 0u) {
-    const double SCALE = 30.0, FPS = 50;
+LD void env_pre(World &W, const float (&action)[4], v2 hull_force, bool &awake, unsigned live, bool run_toi) {
     const float speed[NJ] = {4.0f, 6.0f, 4.0f, 6.0f};                            // SPEED_HIP, SPEED_KNEE
     for (int k = 0; k < NJ; k++) {                                               // :528-543
         W.j[k].motorSpeed = speed[k] * sgnf(action[k]);
         W.j[k].maxMotorTorque = 80.0f * clip01_abs(action[k]);
     }
-    bool awake;
     if constexpr (HC) {
         // every body stays within two leg lengths (2 x 34/30 m) of the hull: one window of boxes for all of them
         poly_window(W, W.b[0].c.x - 4.0f, W.b[0].c.x + 4.0f, W.p_lo, W.p_hi);
     }
-    world_step<SceneT<HC>>(W, hull_force, 0.0f, -10.0f, awake, live);            // :545
+    world_step<SceneT<HC>>(W, hull_force, 0.0f, -10.0f, awake, live, run_toi);   // :545
+}
+
+// bipedal_walker.py:547-606: lidar, observation, shaping reward, termination
+template <bool HC>
+__device__ __noinline__ void env_post(World &W, const float (&action)[4], bool from_reset, float (&obs)[24], double &reward,
+                                      bool &terminated) {
+    const double SCALE = 30.0, FPS = 50;
     const Body &H = W.b[0];
     const double posx = (double)H.xf.p.x, posy = (double)H.xf.p.y;
     double st[24];
@@ -258,6 +263,14 @@ __device__ __noinline__ void env_step(World &W, const float (&action)[4], bool f
     for (int k = 0; k < 24; k++) obs[k] = (float)st[k];                          // :606
     reward = rew;
     terminated = term;
+}
+
+template <bool HC>
+__device__ __noinline__ void env_step(World &W, const float (&action)[4], bool from_reset, v2 hull_force, float (&obs)[24],
+                                      double &reward, bool &terminated, unsigned live = 0u) {
+    bool awake;
+    env_pre<HC>(W, action, hull_force, awake, live, true);
+    env_post<HC>(W, action, from_reset, obs, reward, terminated);
 }
 
 // bipedal_walker.py:425-515 (W.terrain / W.n must be bound to this env's record)

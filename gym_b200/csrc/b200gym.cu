@@ -71,9 +71,11 @@ struct b200gym {
                                             // peer stores from kernel A; B200GYM_GATHER=bulk|direct overrides
     int block_a = 256;                      // CTA size of kernel A (B200GYM_BLOCK_A=64|128|256, tuning runs)
     int box2d_block = 128;                  // LunarLander step kernel: CTA size (B200GYM_BOX2D_BLOCK=128|256, tuning runs)
-    int box2d_defer = 0;                    // Box2D tasks: 1 = the autoresets of a step run in a second, compacted
-                                            // kernel (B200GYM_BOX2D_DEFER=1).  Measured neutral at 2^16 envs (the step
-                                            // is bound by its slowest warps, not by reset work), so inline is the default
+    int box2d_defer = 1;                    // Box2D tasks: 1 = the autoresets of a step run in a last, compacted kernel
+                                            // (B200GYM_BOX2D_DEFER=0: inline).  Neutral in round 1; with the TOI kernel
+                                            // it takes reset() + its embedded world step off the critical path of the
+                                            // envs that crash in a TOI sub-step (LunarLander 1.83 -> 1.74 ms, BipedalWalker
+                                            // 7.9 -> 7.4 ms per 2^16-env step)
     int box2d_toi_defer = 1;                // Box2D tasks: 1 = envs with a possible TOI event finish in the compacted TOI kernel
                                             // (B200GYM_BOX2D_TOI_DEFER=0: SolveTOI inline in the step kernel)
     int32_t *toi_list = nullptr;            // [n] env offsets parked for the TOI kernel, per launch range
@@ -668,8 +670,9 @@ constexpr int kLunarMaxThreads = 256;
 // The TOI kernels run one warp per CTA and give each warp as FEW parked envs as the resident grid allows: the lanes
 // of a warp diverge completely in this code (different contact lists, GJK / root-finder trip counts, event counts),
 // so a warp takes the SUM of its lanes' paths, and with a few thousand parked envs on 148 SMs there are more warp
-// slots than envs.  Measured (LunarLander, 2^16 envs, ~3 300 parked per step): 32 envs per warp 1.19 ms for the
-// launch, the step kernel before it 0.71 ms.
+// slots than envs.  Measured (LunarLander, 2^16 envs, ~3 300 parked per step, ncu): 32 envs per warp 1.19 ms for
+// the launch, 2 per warp 1.06 ms, 1 per warp 0.87 ms -- the floor is ONE env's serial chain (up to 5 sub-steps and
+// ~30 b2TimeOfImpact evaluations of dependent, local-memory-heavy code at ~13 cycles per instruction).
 __device__ __forceinline__ int toi_lanes_per_warp(int cnt, int nwarps) {
     const int L = (cnt + nwarps - 1) / nwarps;
     return L < 1 ? 1 : (L > 32 ? 32 : L);
@@ -1373,8 +1376,12 @@ static int launch_step(b200gym *h, const StepArgs &a, int action_dtype, cudaStre
         } else {
             b.toi_list = nullptr; b.toi_count = nullptr; b.toi_mid = nullptr;
         }
-        // one warp per CTA, 12 per SM (the 156-register kernel's residency); the kernel strides over the list
-        const unsigned tgrid = (unsigned)std::min<int64_t>(b.count, 12 * h->sm_count);
+        // one warp per CTA, 12 CTAs per SM (what is resident with the 156-register kernel); the kernel strides over
+        // the list.  Larger grids (fewer envs per warp) were measured: LunarLander 1.74 / 1.82 / 1.85 ms at 12 / 64 / 256
+        // CTAs per SM, BipedalWalker (nearly every env parked) 7.4 / 12.2 / 17.1 ms
+        int tg = 12;
+        if (const char *tge = getenv("B200GYM_TOI_GRID")) { const int v = atoi(tge); if (v >= 1 && v <= 1024) tg = v; }
+        const unsigned tgrid = (unsigned)std::min<int64_t>(b.count, (int64_t)tg * h->sm_count);
         // at most this many CTAs of the compacted reset kernel (it strides over the list)
         const unsigned rgrid = (unsigned)std::min<int64_t>((b.count + kLunarThreads - 1) / kLunarThreads, 2 * h->sm_count);
         if (h->is_lunar) {

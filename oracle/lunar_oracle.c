@@ -50,6 +50,7 @@ typedef struct {
     int32_t elapsed;
     int stat_contacts, stat_pos_iters; /* of the last world step (workload statistics for DESIGN.md) */
     long long toi_calls, toi_events;   /* b2TimeOfImpact evaluations / TOI sub-steps since the env was created (sticky) */
+    int toi_events_max;                /* most TOI sub-steps this env ever ran in ONE world step (sticky) */
     long long overflows;               /* touching pairs dropped because the scene's manifold table was full (sticky) */
     int32_t wind_idx, torque_idx; /* lunar_lander.py:234-235: drawn once per env object, never reset */
 } world_t;
@@ -101,6 +102,7 @@ static int world_step(world_t *W, float gravity_y, float dt, int velIters, int p
     W->inv_dt0 = S.inv_dt0;
     W->stat_contacts = S.stat_contacts; W->stat_pos_iters = S.stat_pos_iters;
     W->toi_calls += S.stat_toi_calls; W->toi_events += S.stat_toi_events;
+    if (S.stat_toi_events > W->toi_events_max) W->toi_events_max = S.stat_toi_events;
     W->overflows += S.overflowed;
     return S.awake;
 }
@@ -131,9 +133,10 @@ static void lunar_reset_one(world_t *W, const opts_t *O, float *obs)
     float inv_dt0 = W->inv_dt0; /* the b2World object survives reset() */
     int32_t wind_idx = W->wind_idx, torque_idx = W->torque_idx;
     long long overflows = W->overflows, toi_calls = W->toi_calls, toi_events = W->toi_events;
+    int toi_events_max = W->toi_events_max;
     memset(W, 0, sizeof *W);
     W->inv_dt0 = inv_dt0;
-    W->overflows = overflows; W->toi_calls = toi_calls; W->toi_events = toi_events;
+    W->overflows = overflows; W->toi_calls = toi_calls; W->toi_events = toi_events; W->toi_events_max = toi_events_max;
     W->wind_idx = wind_idx; W->torque_idx = torque_idx;
     const double Wd = VIEWPORT_W / SCALE, Hd = VIEWPORT_H / SCALE;
     enum { CHUNKS = 11 };
@@ -466,11 +469,14 @@ int64_t orc_lunar_overflows(const orc_lunar *v)
     return c;
 }
 
-/* {b2TimeOfImpact evaluations, TOI sub-steps} summed over all envs since creation */
-void orc_lunar_toi_stats(const orc_lunar *v, int64_t out[2])
+/* {b2TimeOfImpact evaluations, TOI sub-steps} summed over all envs since creation, {most sub-steps in one world step} */
+void orc_lunar_toi_stats(const orc_lunar *v, int64_t out[3])
 {
-    out[0] = 0; out[1] = 0;
-    for (int64_t i = 0; i < v->n; i++) { out[0] += v->w[i].toi_calls; out[1] += v->w[i].toi_events; }
+    out[0] = 0; out[1] = 0; out[2] = 0;
+    for (int64_t i = 0; i < v->n; i++) {
+        out[0] += v->w[i].toi_calls; out[1] += v->w[i].toi_events;
+        if (v->w[i].toi_events_max > out[2]) out[2] = v->w[i].toi_events_max;
+    }
 }
 
 void orc_lunar_get_stats(const orc_lunar *v, int32_t *out)

@@ -28,7 +28,7 @@ void orc_lunar_step_cont_mt(orc_lunar *v, const float *actions, float *obs, doub
                             uint8_t *truncated, float *final_obs, int nthreads);
 void orc_lunar_get_terrain(const orc_lunar *v, int64_t i, float *y11);
 void orc_lunar_get_stats(const orc_lunar *v, int32_t *out);
-void orc_lunar_toi_stats(const orc_lunar *v, int64_t out[2]);
+void orc_lunar_toi_stats(const orc_lunar *v, int64_t out[3]);
 void orc_lunar_set_toi(int on);
 int orc_b2l_toi_probe(const float *poly_xy, int n, const float c0[2], float a0, const float c1[2], float a1,
                       const float v1[2], const float v2_[2], float *t_out);

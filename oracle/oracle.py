@@ -286,8 +286,9 @@ class OracleLunar:
 
     def toi_stats(self):
         """(b2TimeOfImpact evaluations, TOI sub-steps) summed over all envs since creation."""
-        out = np.zeros(2, dtype=np.int64)
+        out = np.zeros(3, dtype=np.int64)
         lib().orc_lunar_toi_stats(ctypes.c_void_p(self._h), ctypes.c_void_p(out.ctypes.data))
+        self.toi_events_max = int(out[2])     # most TOI sub-steps any env ran in one world step
         return int(out[0]), int(out[1])
 
     def set_body_velocity(self, i, body, vx, vy, w=0.0):
@@ -359,8 +360,9 @@ class OracleWalker:
 
     def toi_stats(self):
         """(b2TimeOfImpact evaluations, TOI sub-steps) summed over all envs since creation."""
-        out = np.zeros(2, dtype=np.int64)
+        out = np.zeros(3, dtype=np.int64)
         lib().orc_walker_toi_stats(ctypes.c_void_p(self._h), ctypes.c_void_p(out.ctypes.data))
+        self.toi_events_max = int(out[2])     # most TOI sub-steps any env ran in one world step
         return int(out[0]), int(out[1])
 
     def close(self):

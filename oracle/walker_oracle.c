@@ -60,6 +60,7 @@ typedef struct {
     int32_t elapsed;
     int stat_contacts, stat_pos_iters; /* of the last world step (workload statistics for DESIGN.md) */
     long long toi_calls, toi_events;   /* b2TimeOfImpact evaluations / TOI sub-steps since the env was created (sticky) */
+    int toi_events_max;                /* most TOI sub-steps this env ever ran in ONE world step (sticky) */
     long long overflows;               /* touching pairs dropped because the scene's manifold table was full (sticky) */
 } wworld_t;
 
@@ -112,6 +113,7 @@ static void wworld_step(wworld_t *W)
     W->inv_dt0 = S.inv_dt0;
     W->stat_contacts = S.stat_contacts; W->stat_pos_iters = S.stat_pos_iters;
     W->toi_calls += S.stat_toi_calls; W->toi_events += S.stat_toi_events;
+    if (S.stat_toi_events > W->toi_events_max) W->toi_events_max = S.stat_toi_events;
     W->overflows += S.overflowed;
     /* step() rewrites every joint's motor each call, which wakes both bodies (b2RevoluteJoint::
      * SetMotorSpeed -> SetAwake(true)): an island that fell asleep is simply awake again next step */
@@ -150,9 +152,10 @@ static void walker_reset_one(wworld_t *W, int hardcore, float *obs)
     pcg64_t rng = W->rng;
     float inv_dt0 = W->inv_dt0; /* self.world survives reset() */
     long long overflows = W->overflows, toi_calls = W->toi_calls, toi_events = W->toi_events;
+    int toi_events_max = W->toi_events_max;
     memset(W, 0, sizeof *W);
     W->inv_dt0 = inv_dt0;
-    W->overflows = overflows; W->toi_calls = toi_calls; W->toi_events = toi_events;
+    W->overflows = overflows; W->toi_calls = toi_calls; W->toi_events = toi_events; W->toi_events_max = toi_events_max;
     /* _generate_terrain(hardcore) :277-402 */
     double terrain_x[TERRAIN_LENGTH], terrain_y[TERRAIN_LENGTH];
     {
@@ -460,11 +463,14 @@ int64_t orc_walker_overflows(const orc_walker *v)
     return c;
 }
 
-/* {b2TimeOfImpact evaluations, TOI sub-steps} summed over all envs since creation */
-void orc_walker_toi_stats(const orc_walker *v, int64_t out[2])
+/* {b2TimeOfImpact evaluations, TOI sub-steps} summed over all envs since creation, {most sub-steps in one world step} */
+void orc_walker_toi_stats(const orc_walker *v, int64_t out[3])
 {
-    out[0] = 0; out[1] = 0;
-    for (int64_t i = 0; i < v->n; i++) { out[0] += v->w[i].toi_calls; out[1] += v->w[i].toi_events; }
+    out[0] = 0; out[1] = 0; out[2] = 0;
+    for (int64_t i = 0; i < v->n; i++) {
+        out[0] += v->w[i].toi_calls; out[1] += v->w[i].toi_events;
+        if (v->w[i].toi_events_max > out[2]) out[2] = v->w[i].toi_events_max;
+    }
 }
 
 void orc_walker_get_stats(const orc_walker *v, int32_t *out)

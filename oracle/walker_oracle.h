@@ -23,7 +23,7 @@ void orc_walker_step_mt(orc_walker *v, const float *actions, float *obs, double 
 void orc_walker_action_flow(double shaping_delta, const float action[4], float motor_speed[4], float max_torque[4],
                             double *reward);
 void orc_walker_get_stats(const orc_walker *v, int32_t *out);
-void orc_walker_toi_stats(const orc_walker *v, int64_t out[2]);
+void orc_walker_toi_stats(const orc_walker *v, int64_t out[3]);
 void orc_walker_set_toi(int on);
 #ifdef __cplusplus
 }

@@ -61,7 +61,8 @@ struct b200gym {
         unsigned long long *ring = nullptr, *counter = nullptr; int ring_size = 0;
     } ep;
     int sm_count = 148;
-    int occ[B200GYM_NUM_KINDS][3][2] = {};  // cached CTAs/SM of step_kernel_persistent per (kind, action width, lean)
+    int occ[B200GYM_NUM_KINDS][3][4] = {};  // cached CTAs/SM of step_kernel_persistent per (kind, action width, lean + 2 * deep)
+    int p_depth = 1;                        // kernel P/L: tiles in flight per thread (B200GYM_P_DEPTH=1|2)
     int p_ctas = -1;                        // kernel P/L: resident CTAs per SM; -1 = occupancy limit, 0 = balance the tile
                                             // rounds (see launch_step_typed), k > 0 = exactly k (B200GYM_P_CTAS, tuning runs)
     int kernel_choice = 2;                  // 0: kernel A (one tile per CTA), 1: kernel P (resident grid, asynchronous
@@ -442,6 +443,7 @@ __device__ __forceinline__ void ld_async(void *smem_dst, const void *gmem_src) {
 }
 __device__ __forceinline__ void ld_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void ld_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void ld_wait_all_but_one() { asm volatile("cp.async.wait_group 1;" ::: "memory"); }
 
 // bulk (TMA, SASS UBLKCP) shared -> global store of a contiguous block; works on peer-mapped addresses
 __device__ __forceinline__ void st_bulk(void *gmem_dst, const void *smem_src, uint32_t bytes) {
@@ -483,53 +485,63 @@ struct PrefetchLayout {
 // LEAN (the single-GPU step without the fused RecordEpisodeStatistics, fewer than 2^31 envs): 32-bit env indices
 // (one IMAD.WIDE per address instead of a 64-bit add chain), no per-peer store loops, no episode accounting --
 // same arithmetic, same stores, fewer issue slots.
-template <int KIND, typename ActT, bool LEAN>
+template <int KIND, typename ActT, bool LEAN, int DEPTH>
 __global__ void __launch_bounds__(kThreads, Tuning<KIND>::kMinCtas) step_kernel_persistent(const StepArgs a, const int num_tiles) {
     using E = Env<KIND>;
     using L = PrefetchLayout<KIND, ActT>;
     using Idx = typename std::conditional<LEAN, uint32_t, int64_t>::type;
-    __shared__ __align__(16) unsigned char in_mem[L::kBytes];
+    static_assert(DEPTH == 1 || DEPTH == 2, "one or two tiles in flight per thread");
+    // DEPTH stages of per-thread input slots: the tile being advanced + DEPTH tiles in flight behind it would need
+    // DEPTH + 1 stages if a slot were still in use while its refill is issued; it is not -- a thread moves its slot
+    // into registers before it refills it -- so DEPTH stages hold DEPTH tiles in flight
+    __shared__ __align__(16) unsigned char in_mem[DEPTH * L::kBytes];
     __shared__ int reset_list[kResetCap];
     __shared__ int reset_count;
     const int tid = threadIdx.x;
     if (tid == 0) reset_count = 0;
     __syncthreads();
 
-    double *s_state = reinterpret_cast<double *>(in_mem + L::kStateOff);
-    int32_t *s_elapsed = reinterpret_cast<int32_t *>(in_mem + L::kElapsedOff);
     const ActT *actions = reinterpret_cast<const ActT *>(a.actions);
     const DirectSinkT<!LEAN> sink{a};
     const Idx first = (Idx)a.first, count = (Idx)a.count;
 
-    auto prefetch = [&](int tile) {
+    auto prefetch = [&](int tile, int stage) {
+        unsigned char *base = in_mem + stage * L::kBytes;
+        double *s_state = reinterpret_cast<double *>(base + L::kStateOff);
+        int32_t *s_elapsed = reinterpret_cast<int32_t *>(base + L::kElapsedOff);
         const Idx j = (Idx)tile * kThreads + tid;
-        if (j < count) {
+        if (tile < num_tiles && j < count) {
             const Idx i = first + j;
 #pragma unroll
             for (int k = 0; k < E::S; k++) acp::ld_async<8>(s_state + k * kThreads + tid, a.state + k * a.n + i);
             acp::ld_async<4>(s_elapsed + tid, a.elapsed + i);
             if constexpr (L::kActAsync)
-                acp::ld_async<L::kActBytes>(in_mem + L::kActOff + tid * L::kActBytes, actions + (size_t)i * L::kActPerEnv);
+                acp::ld_async<L::kActBytes>(base + L::kActOff + tid * L::kActBytes, actions + (size_t)i * L::kActPerEnv);
         }
-        acp::ld_commit();
+        acp::ld_commit();   // always one group per call: the wait below counts groups
     };
 
     int tile = blockIdx.x;
-    if (tile < num_tiles) prefetch(tile);
+    prefetch(tile, 0);
+    if constexpr (DEPTH == 2) prefetch(tile + (int)gridDim.x, 1);
+    int stage = 0;
     for (; tile < num_tiles; tile += gridDim.x) {
         const Idx j = (Idx)tile * kThreads + tid;
         const bool in_range = j < count;
         const Idx i = first + j;
         ActT av{};
         if constexpr (!L::kActAsync) { if (in_range) av = __ldg(actions + (size_t)i * L::kActPerEnv); }
-        acp::ld_wait_all();
+        if constexpr (DEPTH == 2) acp::ld_wait_all_but_one(); else acp::ld_wait_all();
+        unsigned char *base = in_mem + stage * L::kBytes;
+        const double *s_state = reinterpret_cast<const double *>(base + L::kStateOff);
         double s[E::S];
 #pragma unroll
         for (int k = 0; k < E::S; k++) s[k] = s_state[k * kThreads + tid];
-        const int32_t elapsed = s_elapsed[tid];
-        if constexpr (L::kActAsync) av = *reinterpret_cast<const ActT *>(in_mem + L::kActOff + tid * L::kActBytes);
-        // this thread's slots are in registers now: refill them with its env of the next tile
-        if (tile + (int)gridDim.x < num_tiles) prefetch(tile + gridDim.x);
+        const int32_t elapsed = reinterpret_cast<const int32_t *>(base + L::kElapsedOff)[tid];
+        if constexpr (L::kActAsync) av = *reinterpret_cast<const ActT *>(base + L::kActOff + tid * L::kActBytes);
+        // this thread's slots are in registers now: refill them with its env DEPTH tiles ahead
+        prefetch(tile + DEPTH * (int)gridDim.x, stage);
+        if constexpr (DEPTH == 2) stage ^= 1;
         long long action_int = 0;
         float a0 = 0.0f;
         if constexpr (E::A == 0) action_int = (long long)av;
@@ -1288,10 +1300,13 @@ static int launch_step_typed(b200gym *h, const StepArgs &a, cudaStream_t st) {
         if (aligned) {
             // the lean instantiation: no fused episode statistics, every index fits 32 bits
             const bool lean = h->kernel_choice == 2 && !a.ep_acc && h->n < (int64_t)1 << 30;
-            int &occ = h->occ[KIND][sizeof(ActT) == 8 ? 0 : sizeof(ActT) == 4 ? 1 : 2][lean ? 1 : 0];
+            const bool deep = h->p_depth == 2;
+            int &occ = h->occ[KIND][sizeof(ActT) == 8 ? 0 : sizeof(ActT) == 4 ? 1 : 2][(lean ? 1 : 0) + (deep ? 2 : 0)];
             if (occ == 0) {
-                if (lean) CK(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, step_kernel_persistent<KIND, ActT, true>, kThreads, 0));
-                else CK(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, step_kernel_persistent<KIND, ActT, false>, kThreads, 0));
+                if (lean && deep) CK(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, step_kernel_persistent<KIND, ActT, true, 2>, kThreads, 0));
+                else if (lean) CK(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, step_kernel_persistent<KIND, ActT, true, 1>, kThreads, 0));
+                else if (deep) CK(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, step_kernel_persistent<KIND, ActT, false, 2>, kThreads, 0));
+                else CK(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, step_kernel_persistent<KIND, ActT, false, 1>, kThreads, 0));
                 if (occ < 1) occ = 1;
             }
             const int64_t all_tiles = (a.count + kThreads - 1) / kThreads;
@@ -1312,8 +1327,10 @@ static int launch_step_typed(b200gym *h, const StepArgs &a, cudaStream_t st) {
             }
             int64_t grid = (int64_t)h->sm_count * per_sm;
             if (grid > all_tiles) grid = all_tiles;
-            if (lean) step_kernel_persistent<KIND, ActT, true><<<(unsigned)grid, kThreads, 0, st>>>(a, (int)all_tiles);
-            else step_kernel_persistent<KIND, ActT, false><<<(unsigned)grid, kThreads, 0, st>>>(a, (int)all_tiles);
+            if (lean && deep) step_kernel_persistent<KIND, ActT, true, 2><<<(unsigned)grid, kThreads, 0, st>>>(a, (int)all_tiles);
+            else if (lean) step_kernel_persistent<KIND, ActT, true, 1><<<(unsigned)grid, kThreads, 0, st>>>(a, (int)all_tiles);
+            else if (deep) step_kernel_persistent<KIND, ActT, false, 2><<<(unsigned)grid, kThreads, 0, st>>>(a, (int)all_tiles);
+            else step_kernel_persistent<KIND, ActT, false, 1><<<(unsigned)grid, kThreads, 0, st>>>(a, (int)all_tiles);
             CK(h, cudaGetLastError());
             done = a.count;
         }
@@ -1523,6 +1540,8 @@ extern "C" int b200gym_create(const b200gym_config *cfg, int64_t num_envs, int d
         const char *fs = getenv("B200GYM_SIMPLE_KERNEL");
         const char *kc = getenv("B200GYM_KERNEL");
         if (kc && (kc[0] == 'a' || kc[0] == 'p' || kc[0] == 'l')) h->kernel_choice = kc[0] == 'a' ? 0 : kc[0] == 'p' ? 1 : 2;
+        const char *pd = getenv("B200GYM_P_DEPTH");
+        if (pd && (pd[0] == '1' || pd[0] == '2')) h->p_depth = pd[0] - '0';
         const char *pc = getenv("B200GYM_P_CTAS");
         if (pc && atoi(pc) >= -1 && atoi(pc) <= 8) h->p_ctas = atoi(pc);
         if (fs && fs[0] == '1') h->kernel_choice = 0;

@@ -235,6 +235,12 @@ def collect_python_reference(proc, timeout=180):
 
 
 # --------------------------------------------------------------------------- reference arm
+def workload_name(env_id, log2_envs, world):
+    """The workload both arms (this engine, --impl reference) name in config.workload: same string, same batch."""
+    return (f"{env_id} num_envs=2^{log2_envs} per GPU x {world} GPU(s) = {(1 << log2_envs) * world} envs, random actions, "
+            "step + TimeLimit + same-step autoreset, one vector step per timed step")
+
+
 def run_reference(args):
     """--impl reference: the reference's CPU implementation of the path on the host cores.
 
@@ -275,8 +281,10 @@ def run_reference(args):
         "n_gpus": args.gpus, "steps": done, "warmup": args.warmup, "ms_per_step": 1e3 * el / done,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32" if is_box2d(args.env) else "f64", "data": "synthetic",
-        "config": {"workload": f"{args.env} num_envs=2^{args.log2_envs} x {world}, random actions, "
-                               "step+TimeLimit+autoreset on the host cores (C port of the reference path)"},
+        "config": {"workload": workload_name(args.env, args.log2_envs, world),
+                   "arm": "the reference path on the host cores: C port of step / reset / TimeLimit / autoreset "
+                          f"(oracle/, bit-exact against openai/gym 0.26.2), {threads} threads; the unmodified Python "
+                          "reference is timed beside it in cpu_baseline_python"},
         "cpu_baseline": {"value": value, "unit": "env-steps/s", "cores": threads, "kind": "port",
                          "sample": f"{done} vector steps of {n} envs"},
         "cpu_baseline_python": py_ref,
@@ -596,14 +604,14 @@ def run_b200(args):
             "metric": "env-steps/sec", "value": value, "unit": "env-steps/s", "n_gpus": world, "steps": K,
             "warmup": W, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32" if is_box2d(args.env) else "f64", "data": "synthetic",
-            "config": {"workload": f"{args.env} num_envs=2^{args.log2_envs} per GPU x {world} GPU(s), random "
-                                   f"{'int64' if inner.discrete else 'float32'} "
-                                   "actions resident in HBM, fused step+TimeLimit+autoreset"
-                                   + ((", all-gather of (obs,reward,terminated,truncated) per step fused into the "
-                                       "step kernel (bulk pushes over NVLink peer memory + one flag exchange)"
-                                       if gather == "p2p" else
-                                       ", NCCL all-gather of (obs,reward,terminated,truncated) per step")
-                                      if world > 1 else ""),
+            "config": {"workload": workload_name(args.env, args.log2_envs, world),
+                       "arm": f"{'int64' if inner.discrete else 'float32'} actions resident in HBM, fused "
+                              "step+TimeLimit+autoreset kernel"
+                              + ((", all-gather of (obs,reward,terminated,truncated) per step fused into the "
+                                  "step kernel (bulk pushes over NVLink peer memory + one flag exchange)"
+                                  if gather == "p2p" else
+                                  ", NCCL all-gather of (obs,reward,terminated,truncated) per step")
+                                 if world > 1 else ""),
                        "state": "float64 (reference-faithful)", "l2": l2_note,
                        "parallelism": f"env-batch data parallel x{world}"},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",

@@ -553,8 +553,11 @@ __global__ void __launch_bounds__(kThreads, Tuning<KIND>::kMinCtas) step_kernel_
             bool inline_reset = __popc(m) >= 12;          // dense enough: reset right here
             if (need && !inline_reset) {
                 const int slot = atomicAdd(&reset_count, 1);
-                if (slot < kResetCap) reset_list[slot] = (int)j;
-                else inline_reset = true;                 // list full (whole batch truncating at once)
+                if (slot < kResetCap) {
+                    reset_list[slot] = (int)j;
+                    // the drain after the loop starts with this env's 32-byte PCG64 record: have it in L2 by then
+                    asm volatile("prefetch.global.L2 [%0];" ::"l"(a.rng + 4 * (size_t)i));
+                } else inline_reset = true;               // list full (whole batch truncating at once)
             }
             if (need && inline_reset) reset_env<KIND>(a, sink, i);
         }

@@ -396,4 +396,33 @@ int64_t hs_glibc_trig_mismatches(uint64_t seed, int64_t n, double lo, double hi)
     return bad;
 }
 
+
+// The device's b2TimeOfImpact and the conservative shortcut in front of it (b2lite_toi.cuh), for one sweep of a
+// task polygon (shape 0 = lander, 1 = lander leg, 2 = walker hull, 3 = walker upper leg, 4 = walker lower leg)
+// against the static edge v1-v2 or, with `box` set, the axis-aligned box {x0, ylo, x1, yhi}.
+// Returns the b2TOIOutput state (3 = touching), *t_out, and *cannot_touch = what toi_cannot_touch says.
+int hs_toi_probe(int shape, const float *c0, float a0, const float *c1, float a1, const float *v1, const float *v2,
+                 const float *box, float *t_out, int *cannot_touch) {
+    ensure_consts();
+    const b2l::ShapeConst &sh = shape < 2 ? lunar::kC.shape[shape] : walker::kC.shape[shape - 2];
+    b2l::DProxy pA, pB;
+    if (box) {
+        pA.count = 4;
+        pA.v[0] = b2l::V(box[2], box[1]); pA.v[1] = b2l::V(box[2], box[3]); pA.v[2] = b2l::V(box[0], box[3]); pA.v[3] = b2l::V(box[0], box[1]);
+    } else {
+        pA.count = 2;
+        pA.v[0] = b2l::V(v1[0], v1[1]); pA.v[1] = b2l::V(v2[0], v2[1]);
+    }
+    pB.count = sh.count;
+    for (int i = 0; i < sh.count; i++) pB.v[i] = sh.verts[i];
+    b2l::Sweep sA, sB;
+    sA.localCenter = b2l::V(0.0f, 0.0f); sA.c0 = b2l::V(0.0f, 0.0f); sA.c = b2l::V(0.0f, 0.0f); sA.a0 = 0.0f; sA.a = 0.0f; sA.alpha0 = 0.0f;
+    sB.localCenter = sh.localCenter; sB.c0 = b2l::V(c0[0], c0[1]); sB.c = b2l::V(c1[0], c1[1]); sB.a0 = a0; sB.a = a1; sB.alpha0 = 0.0f;
+    b2l::xform xf1;
+    xf1.q = b2l::rot_of(a1);
+    xf1.p = b2l::sub(sB.c, b2l::rmul(xf1.q, sh.localCenter));
+    *cannot_touch = b2l::toi_cannot_touch(sh, xf1, sB, pA) ? 1 : 0;
+    return b2l::time_of_impact(*t_out, pA, sA, pB, sB, 1.0f);
+}
+
 }  // extern "C"

@@ -66,6 +66,9 @@ def lib(smallcap=False):
         L.hs_glibc_sq_mismatches.argtypes = [ctypes.c_uint64, i64, dbl, dbl, ctypes.POINTER(i64)]
         L.hs_glibc_trig_mismatches.restype = i64
         L.hs_glibc_trig_mismatches.argtypes = [ctypes.c_uint64, i64, dbl, dbl]
+        fp, f32 = ctypes.POINTER(ctypes.c_float), ctypes.c_float
+        L.hs_toi_probe.restype = i32
+        L.hs_toi_probe.argtypes = [i32, fp, f32, fp, f32, fp, fp, fp, fp, ctypes.POINTER(i32)]
         if smallcap:
             _libs["small"] = L
             return L
@@ -216,3 +219,21 @@ def sincos_small(x):
     sn, cs = np.zeros_like(x), np.zeros_like(x)
     lib().hs_sincos_small(x.ctypes.data, x.size, sn.ctypes.data, cs.ctypes.data)
     return sn, cs
+
+
+def toi_probe(shape, c0, a0, c1, a1, edge=None, box=None):
+    """The device source's b2TimeOfImpact + its conservative shortcut for one sweep of a task polygon (0 lander, 1 its
+    leg, 2 walker hull, 3 / 4 walker upper / lower leg) against a static edge ((x1, y1), (x2, y2)) or an axis-aligned
+    box (x0, ylo, x1, yhi) -> (state, t, cannot_touch); state 3 = touching."""
+    fp = ctypes.POINTER(ctypes.c_float)
+    arr = lambda x: np.ascontiguousarray(x, dtype=np.float32).ravel()
+    C0, C1 = arr(c0), arr(c1)
+    V1, V2 = (arr(edge[0]), arr(edge[1])) if edge is not None else (arr([0, 0]), arr([0, 0]))
+    B = arr(box) if box is not None else None
+    t = ctypes.c_float(0.0)
+    ct = ctypes.c_int(0)
+    p = lambda a: a.ctypes.data_as(fp)
+    st = lib().hs_toi_probe(int(shape), p(C0), float(a0), p(C1), float(a1), p(V1), p(V2), p(B) if B is not None else None,
+                            ctypes.byref(t), ctypes.byref(ct))
+    return int(st), float(t.value), bool(ct.value)
+

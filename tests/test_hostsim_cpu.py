@@ -11,6 +11,7 @@ generation -- that is what the `-m gpu` tests are for.)
 import numpy as np
 import pytest
 
+from hostsim import sim
 from hostsim.sim import HostSim
 from oracle import oracle as orc
 
@@ -267,3 +268,39 @@ def test_device_source_on_cpu_reproduces_the_frozen_rollouts(name):
         sim = HostSim("BipedalWalkerHardcore" if kw.pop("hardcore", False) else "BipedalWalker", d["n"],
                       d["max_episode_steps"])
     self_fixtures.check(d, sim.step, sim.reset(seed=d["seed"]))
+
+
+def test_toi_shortcuts_never_dismiss_a_pair_that_touches():
+    """b2lite_toi.cuh skips b2TimeOfImpact when `toi_cannot_touch` proves that the pair's alpha is 1 (the polygon's
+    box over its sweep stays beyond the touching distance of the fixture's box, or the whole polygon starts beyond a
+    face line of the fixture by more than it can move).  The oracle applies no shortcut, so the bit-for-bit roll-outs
+    above already check this; here the claim itself is fuzzed: 60 000 random sweeps of the task polygons near an
+    edge / a box -- resting, sliding, rotating, approaching, tunnelling -- and whenever the shortcut fires the full
+    b2TimeOfImpact of the same sweep must not report e_touching.  Both outcomes must occur often."""
+    rng = np.random.default_rng(42)
+    fired = touching = both = 0
+    for k in range(60000):
+        shape = int(rng.integers(0, 5))
+        slope = rng.uniform(-0.6, 0.6)
+        edge = ((-1.0, -slope), (1.0, slope))
+        box = None
+        if k % 4 == 3:
+            edge, box = None, (-0.5, -1.0, 0.5, 0.0)
+        mode = k % 3
+        x0 = rng.uniform(-1.2, 1.2)
+        h0 = abs(rng.normal(0.0, 0.6)) if mode else rng.uniform(0.0, 0.05)     # height of the body's centre region
+        c0 = (x0, (slope * x0 if box is None else 0.0) + 0.6 * rng.uniform(0.2, 1.6) + h0)
+        a0 = rng.uniform(-3.2, 3.2)
+        if mode == 0:      # nearly at rest
+            dc, da = rng.normal(0, 0.002, 2), rng.normal(0, 0.002)
+        elif mode == 1:    # moderate motion
+            dc, da = rng.normal(0, 0.08, 2), rng.normal(0, 0.08)
+        else:              # fast, mostly downwards
+            dc, da = np.array([rng.normal(0, 0.3), -abs(rng.normal(0, 1.0))]), rng.normal(0, 0.4)
+        st, t, skip = sim.toi_probe(shape, c0, a0, (c0[0] + dc[0], c0[1] + dc[1]), a0 + da, edge=edge, box=box)
+        fired += skip
+        touching += st == 3
+        both += skip and st == 3
+    assert both == 0, f"{both} sweeps were dismissed although b2TimeOfImpact reports e_touching"
+    assert fired > 5000 and touching > 5000, (fired, touching)
+

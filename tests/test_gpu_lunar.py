@@ -275,14 +275,18 @@ def test_wind_indices_default_to_numpy_global_generator():
 
 @pytest.mark.parametrize("env_id", ["LunarLander-v2", "BipedalWalkerHardcore-v3"])
 def test_compacted_autoreset_kernel_equals_inline_reset(env_id, monkeypatch):
-    """B200GYM_BOX2D_DEFER=1: the episodes that end in a step are restarted by a second, compacted kernel
-    (*_reset_list_kernel).  Same results as the inline reset, on the device path and on the chunked host path."""
+    """The three-launch step of the Box2D tasks (step kernel -> TOI kernel over the parked envs -> compacted reset
+    kernel; the default) against the single-launch step with continuous collision and resets inline
+    (B200GYM_BOX2D_TOI_DEFER=0, B200GYM_BOX2D_DEFER=0): same results, on the device path and on the chunked host path
+    (every chunk has its own parked-env / reset counters)."""
     import gym_b200
     import torch
     N, T = 3000, 220
     monkeypatch.setenv("B200GYM_BOX2D_DEFER", "0")
+    monkeypatch.setenv("B200GYM_BOX2D_TOI_DEFER", "0")
     inline = gym_b200.vector.make(env_id, N)
     monkeypatch.setenv("B200GYM_BOX2D_DEFER", "1")
+    monkeypatch.setenv("B200GYM_BOX2D_TOI_DEFER", "1")
     monkeypatch.setenv("B200GYM_HOST_CHUNKS", "3")
     deferred = gym_b200.vector.make(env_id, N)
     host = gym_b200.vector.make(env_id, N, backend="numpy")

@@ -626,6 +626,7 @@ __device__ __noinline__ void island_solve_toi(typename Scene::World &W, int body
     // the bit patterns); a single body against static geometry gets there within 10-20 iterations in ~90 % of the
     // TOI sub-steps (measured on the CPU checker), which matters because a warp waits for its slowest lane.
     uint32_t hist[2][3 + 4 * kMaxVC];   // state after the previous two iterations: slot (it & 1)
+    float raw[kMaxVC][2];               // the raw tangent increment of every point in the current iteration
 #pragma unroll 1
     for (int it = 0; it < 180; it++) {
         for (int k = 0; k < nic; k++) {
@@ -636,6 +637,7 @@ __device__ __noinline__ void island_solve_toi(typename Scene::World &W, int body
                 const v2 dv = add(vB, crs_sv(wB, cp.rB));
                 const float vt = dot(dv, tangent) - 0.0f;
                 float lambda = cp.tangentMass * (-vt);
+                raw[k][p] = lambda;                       // for the friction-drift exit below
                 const float maxF = q.friction * cp.nI;
                 const float newImp = clampf(cp.tI + lambda, -maxF, maxF);
                 lambda = newImp - cp.tI;
@@ -701,6 +703,45 @@ __device__ __noinline__ void island_solve_toi(typename Scene::World &W, int body
             if (same2) {
                 if ((179 - it) & 1) { vB.x = __uint_as_float(h1[0]); vB.y = __uint_as_float(h1[1]); wB = __uint_as_float(h1[2]); }
                 break;
+            }
+            // Third exit, "friction drift": v, w and every normal impulse are back where the iteration started, but a
+            // tangent impulse keeps creeping by a constant, tiny amount per iteration (its effect on v is undone by the
+            // normal step, or rounds away), so the state never repeats -- 16 % of LunarLander's TOI sub-steps, 24 % of
+            // BipedalWalker's.  Only (v, w) leave this loop (TOI impulses are discarded), so it may stop once the
+            // remaining iterations are KNOWN to reproduce this one.  The sub-steps of an iteration read tI only in
+            // the friction clamp, newImp = clamp(tI + r), and use d = newImp - tI; if every point's d is the same
+            // next time, every sub-step gets this iteration's inputs and returns its outputs, by induction over the
+            // sub-steps and then over the iterations.  Per point, with r its raw increment of THIS iteration:
+            //   (1) the next friction step applies the same increment: clamp(fl(tI + r)) - tI == d;
+            //   (2) so do the later ones: tI walks through multiples of its ulp and fl(tI + r) rounds r to the same
+            //       multiple as long as tI and tI + r stay inside one binade -- checked for 180 more steps, with
+            //       margin -- and r is not exactly half-way between two multiples (ties-to-even would alternate);
+            //   (3) tI stays strictly inside the friction cone mu * nI for those steps, so the clamp stays inactive.
+            if (it >= 1) {
+                bool fixed = cur[0] == h1[0] && cur[1] == h1[1] && cur[2] == h1[2];
+                for (int q = 3; q < nw && fixed; q += 2) fixed = cur[q] == h1[q];          // normal impulses
+                if (fixed) {
+                    bool repeats = true;
+                    int q = 3;
+                    for (int k = 0; k < nic && repeats; k++) {
+                        for (int p = 0; p < vc[k].pointCount && repeats; p++, q += 2) {
+                            const VCP &cp = vc[k].p[p];
+                            const float tI = cp.tI, d = tI - __uint_as_float(h1[q + 1]), r = raw[k][p];
+                            const float maxF = vc[k].friction * cp.nI;
+                            const float next = clampf(tI + r, -maxF, maxF);
+                            if (d == 0.0f) { repeats = (next - tI) == 0.0f; continue; }      // this point is at rest
+                            const uint32_t eb = __float_as_uint(tI) & 0x7f800000u;
+                            const float lo2 = __uint_as_float(eb);                           // 2^e <= |tI| < 2^(e+1)
+                            const float ulp = lo2 * 1.1920929e-07f;
+                            const float m = r / ulp, fr = m - floorf(m);
+                            const float end = fabsf(tI + 181.0f * d + r);
+                            repeats = eb != 0u && eb != 0x7f800000u && (next - tI) == d && fr != 0.5f &&
+                                      fabsf(tI) > 1.0001f * lo2 && end > 1.0001f * lo2 && end < 1.9999f * lo2 &&
+                                      end < 0.9999f * maxF && fabsf(tI) < 0.9999f * maxF;
+                        }
+                    }
+                    if (repeats) break;
+                }
             }
             for (int q = 0; q < nw; q++) hist[it & 1][q] = cur[q];
         }

@@ -421,7 +421,9 @@ def run_b200(args):
         sampler.start()
     barrier()
     gather_verified = None
-    launches_per_step = 1
+    # kernels of this repo launched per timed step: classic control 1; the Box2D tasks 3 (step kernel, TOI kernel over
+    # the parked envs, compacted reset kernel -- DESIGN.md 4.4)
+    launches_per_step = 3 if is_box2d(args.env) else 1
     if world == 1:
         per_step = time_steps_flushed(torch, env, pool, K, flush)
         ms_median, ms_mean = float(np.median(per_step)), float(per_step.mean())

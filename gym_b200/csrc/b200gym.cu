@@ -767,8 +767,6 @@ __global__ void __launch_bounds__(kLunarMaxThreads, 2) lunar_step_kernel(const S
             valid = !(act < 0 || act > 3);   // lunar_lander.py:482-484
         }
     }
-    // the lanes that step an env: they stay together through the solver's warp-synchronous TOI rounds
-    const unsigned live = __ballot_sync(0xffffffffu, valid);
     if (!in_range) return;
     if (!valid) {
         atomicAdd(a.invalid, 1ULL);
@@ -776,7 +774,6 @@ __global__ void __launch_bounds__(kLunarMaxThreads, 2) lunar_step_kernel(const S
         store_scalars_all(a, i, __longlong_as_double(0x7ff8000000000000LL), 0, 0);
         return;
     }
-    (void)live;
     const lunar::Opts &O = a.lunar_opts;
     lunar::World W;
     lunar::load_world(W, a.lunar_rec, a.n, i, O.wind != 0);

@@ -77,11 +77,17 @@ struct b200gym {
                                             // it takes reset() + its embedded world step off the critical path of the
                                             // envs that crash in a TOI sub-step (LunarLander 1.83 -> 1.74 ms, BipedalWalker
                                             // 7.9 -> 7.4 ms per 2^16-env step)
+    int box2d_split = 1;                    // Box2D tasks: 1 = the step kernel's resets overlap the TOI kernel on a side stream
+                                            // (B200GYM_BOX2D_SPLIT=0: one reset launch after the TOI kernel)
     int box2d_toi_defer = 1;                // Box2D tasks: 1 = envs with a possible TOI event finish in the compacted TOI kernel
                                             // (B200GYM_BOX2D_TOI_DEFER=0: SolveTOI inline in the step kernel)
     int32_t *toi_list = nullptr;            // [n] env offsets parked for the TOI kernel, per launch range
     int32_t *toi_count = nullptr;           // [kResetSlots]
     uint32_t *toi_mid = nullptr;            // [kToiMidWords][n] SoA side buffer of the parked envs
+    int32_t *reset_list2 = nullptr;         // [n] / [kResetSlots]: the resets of the TOI kernel (its own list, so that the
+    int32_t *reset_count2 = nullptr;        // step kernel's resets can run on the side stream while the TOI kernel runs)
+    cudaStream_t side = nullptr;            // Box2D tasks: side stream of the step-kernel resets (fork / join by events)
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     int32_t *reset_list = nullptr;          // [n] env offsets to reset, filled per launch range
     int32_t *reset_count = nullptr;         // [kResetSlots] one counter per concurrently running launch range
     // fused all-gather over peer memory (b200gym_p2p_*)
@@ -1399,6 +1405,18 @@ static int launch_step(b200gym *h, const StepArgs &a, int action_dtype, cudaStre
         int tg = 12;
         if (const char *tge = getenv("B200GYM_TOI_GRID")) { const int v = atoi(tge); if (v >= 1 && v <= 1024) tg = v; }
         const unsigned tgrid = (unsigned)std::min<int64_t>(b.count, (int64_t)tg * h->sm_count);
+        // With both on, the resets come from two kernels: those of the step kernel go onto list 1 and restart on the
+        // side stream WHILE the TOI kernel runs (a reset is a long serial chain -- terrain draw + an embedded world
+        // step, 1.1 ms for a batch of BipedalWalker resets -- but touches only its own env); those of the TOI kernel
+        // go onto list 2 and restart after it.  b2 = the arguments of the TOI kernel and of the second reset launch.
+        const bool split = defer && toi_defer && h->side && h->box2d_split;
+        StepArgs b2 = b;
+        if (split) {
+            const ptrdiff_t slot = b.reset_count - h->reset_count;   // the caller's counter slot
+            b2.reset_list = h->reset_list2;
+            b2.reset_count = h->reset_count2 + ((slot >= 0 && slot < kResetSlots) ? slot : 0);
+            CK(h, cudaMemsetAsync(b2.reset_count, 0, sizeof(int32_t), st));
+        }
         // at most this many CTAs of the compacted reset kernel (it strides over the list)
         const unsigned rgrid = (unsigned)std::min<int64_t>((b.count + kLunarThreads - 1) / kLunarThreads, 2 * h->sm_count);
         if (h->is_lunar) {
@@ -1417,11 +1435,18 @@ static int launch_step(b200gym *h, const StepArgs &a, int action_dtype, cudaStre
                 }
             }
             CK(h, cudaGetLastError());
+            if (split) {   // the step kernel's resets on the side stream, under the TOI kernel
+                CK(h, cudaEventRecord(h->ev_fork, st));
+                CK(h, cudaStreamWaitEvent(h->side, h->ev_fork, 0));
+                lunar_reset_list_kernel<<<rgrid, kLunarThreads, 0, h->side>>>(b);
+                CK(h, cudaEventRecord(h->ev_join, h->side));
+            }
             if (toi_defer) {
-                lunar_toi_kernel<<<tgrid, 32, 0, st>>>(b);
+                lunar_toi_kernel<<<tgrid, 32, 0, st>>>(b2);
                 CK(h, cudaGetLastError());
             }
-            if (defer) lunar_reset_list_kernel<<<rgrid, kLunarThreads, 0, st>>>(b);
+            if (defer) lunar_reset_list_kernel<<<rgrid, kLunarThreads, 0, st>>>(b2);
+            if (split) CK(h, cudaStreamWaitEvent(st, h->ev_join, 0));
         } else {
             if (action_dtype != B200GYM_ACT_F32) return fail(h, "Box env needs float32 actions (got dtype code %d)", action_dtype);
             if ((uintptr_t)b.actions % 16 != 0) return fail(h, "BipedalWalker actions must be 16-byte aligned");
@@ -1430,15 +1455,23 @@ static int launch_step(b200gym *h, const StepArgs &a, int action_dtype, cudaStre
             if (hc) walker_step_kernel<true><<<grid, kLunarThreads, 0, st>>>(b);
             else walker_step_kernel<false><<<grid, kLunarThreads, 0, st>>>(b);
             CK(h, cudaGetLastError());
+            if (split) {   // the step kernel's resets on the side stream, under the TOI kernel
+                CK(h, cudaEventRecord(h->ev_fork, st));
+                CK(h, cudaStreamWaitEvent(h->side, h->ev_fork, 0));
+                if (hc) walker_reset_list_kernel<true><<<rgrid, kLunarThreads, 0, h->side>>>(b);
+                else walker_reset_list_kernel<false><<<rgrid, kLunarThreads, 0, h->side>>>(b);
+                CK(h, cudaEventRecord(h->ev_join, h->side));
+            }
             if (toi_defer) {
-                if (hc) walker_toi_kernel<true><<<tgrid, 32, 0, st>>>(b);
-                else walker_toi_kernel<false><<<tgrid, 32, 0, st>>>(b);
+                if (hc) walker_toi_kernel<true><<<tgrid, 32, 0, st>>>(b2);
+                else walker_toi_kernel<false><<<tgrid, 32, 0, st>>>(b2);
                 CK(h, cudaGetLastError());
             }
             if (defer) {
-                if (hc) walker_reset_list_kernel<true><<<rgrid, kLunarThreads, 0, st>>>(b);
-                else walker_reset_list_kernel<false><<<rgrid, kLunarThreads, 0, st>>>(b);
+                if (hc) walker_reset_list_kernel<true><<<rgrid, kLunarThreads, 0, st>>>(b2);
+                else walker_reset_list_kernel<false><<<rgrid, kLunarThreads, 0, st>>>(b2);
             }
+            if (split) CK(h, cudaStreamWaitEvent(st, h->ev_join, 0));
         }
         CK(h, cudaGetLastError());
         return 0;
@@ -1549,6 +1582,8 @@ extern "C" int b200gym_create(const b200gym_config *cfg, int64_t num_envs, int d
         if (gb && (gb[0] == 'b' || gb[0] == 'd')) h->gather_bulk = gb[0] == 'b';
         const char *bb = getenv("B200GYM_BOX2D_BLOCK");
         if (bb && (atoi(bb) == 128 || atoi(bb) == 256)) h->box2d_block = atoi(bb);
+        const char *bsp = getenv("B200GYM_BOX2D_SPLIT");
+        if (bsp && (bsp[0] == '0' || bsp[0] == '1')) h->box2d_split = bsp[0] - '0';
         const char *btd = getenv("B200GYM_BOX2D_TOI_DEFER");
         if (btd && (btd[0] == '0' || btd[0] == '1')) h->box2d_toi_defer = btd[0] - '0';
         const char *bdf = getenv("B200GYM_BOX2D_DEFER");
@@ -1590,6 +1625,12 @@ extern "C" int b200gym_create(const b200gym_config *cfg, int64_t num_envs, int d
         if (cudaMalloc(&h->lunar_rec, sizeof(uint32_t) * words * n) != cudaSuccess ||
             cudaMemset(h->lunar_rec, 0, sizeof(uint32_t) * words * n) != cudaSuccess ||
             cudaMalloc((void **)&h->reset_list, sizeof(int32_t) * n) != cudaSuccess ||
+            cudaMalloc((void **)&h->reset_list2, sizeof(int32_t) * n) != cudaSuccess ||
+            cudaMalloc((void **)&h->reset_count2, sizeof(int32_t) * kResetSlots) != cudaSuccess ||
+            cudaMemset(h->reset_count2, 0, sizeof(int32_t) * kResetSlots) != cudaSuccess ||
+            cudaStreamCreateWithFlags(&h->side, cudaStreamNonBlocking) != cudaSuccess ||
+            cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming) != cudaSuccess ||
+            cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming) != cudaSuccess ||
             cudaMalloc((void **)&h->toi_list, sizeof(int32_t) * n) != cudaSuccess ||
             cudaMalloc((void **)&h->toi_count, sizeof(int32_t) * kResetSlots) != cudaSuccess ||
             cudaMemset(h->toi_count, 0, sizeof(int32_t) * kResetSlots) != cudaSuccess ||
@@ -1645,6 +1686,11 @@ extern "C" void b200gym_destroy(b200gym_t *h) {
     cudaFree(h->toi_list);
     cudaFree(h->toi_count);
     cudaFree(h->toi_mid);
+    cudaFree(h->reset_list2);
+    cudaFree(h->reset_count2);
+    if (h->side) cudaStreamDestroy(h->side);
+    if (h->ev_fork) cudaEventDestroy(h->ev_fork);
+    if (h->ev_join) cudaEventDestroy(h->ev_join);
     if (h->p2p.base) {
         for (int r = 0; r < h->p2p.world; r++)
             if (r != h->p2p.rank && h->p2p.peer[r]) cudaIpcCloseMemHandle(h->p2p.peer[r]);

@@ -77,8 +77,11 @@ struct b200gym {
                                             // it takes reset() + its embedded world step off the critical path of the
                                             // envs that crash in a TOI sub-step (LunarLander 1.83 -> 1.74 ms, BipedalWalker
                                             // 7.9 -> 7.4 ms per 2^16-env step)
-    int box2d_split = 1;                    // Box2D tasks: 1 = the step kernel's resets overlap the TOI kernel on a side stream
-                                            // (B200GYM_BOX2D_SPLIT=0: one reset launch after the TOI kernel)
+    int box2d_split = 0;                    // Box2D tasks: 1 = the step kernel's resets overlap the TOI kernel on a side stream
+                                            // (B200GYM_BOX2D_SPLIT=1).  Measured neutral (LunarLander 1.81 vs 1.82 ms,
+                                            // BipedalWalker 7.62 vs 7.67): the envs that end an episode are mostly the parked
+                                            // ones, whose resets can only follow the TOI kernel -- so the plain sequence is
+                                            // the default
     int box2d_toi_defer = 1;                // Box2D tasks: 1 = envs with a possible TOI event finish in the compacted TOI kernel
                                             // (B200GYM_BOX2D_TOI_DEFER=0: SolveTOI inline in the step kernel)
     int32_t *toi_list = nullptr;            // [n] env offsets parked for the TOI kernel, per launch range

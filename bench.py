@@ -57,10 +57,12 @@ BYTES_PER_ENV_STEP["BipedalWalkerHardcore-v3"] = BYTES_PER_ENV_STEP["BipedalWalk
 BOUND = {"CartPole-v1": "hbm", "CartPole-v0": "hbm", "Pendulum-v1": "hbm (latency: 1 wave at 2^18)",
          "MountainCar-v0": "hbm (latency: 1 wave at 2^18)", "MountainCarContinuous-v0": "hbm (latency: 1 wave at 2^18)",
          "Acrobot-v1": "fp64 pipe / issue slots (4 x RK4 stage, 21 glibc-exact sin/cos + 12 glibc-exact pow(x, 2) per env-step)",
-         "LunarLander-v2": "instruction issue under divergence (serial Gauss-Seidel solve per env)",
-         "LunarLanderContinuous-v2": "instruction issue under divergence (serial Gauss-Seidel solve per env)",
-         "BipedalWalker-v3": "instruction issue (serial Gauss-Seidel solve per env)",
-         "BipedalWalkerHardcore-v3": "instruction issue (serial Gauss-Seidel solve per env)"}
+         "LunarLander-v2": "dependent-instruction latency under divergence (serial Gauss-Seidel solve + TOI sub-steps per env); "
+                           "issue-slot utilisation 0.22 (step kernel) / 0.04 (TOI kernel), profiles/r2b_box2d_toi_kernel_sweep.txt",
+         "LunarLanderContinuous-v2": "dependent-instruction latency under divergence (serial Gauss-Seidel solve + TOI sub-steps per env)",
+         "BipedalWalker-v3": "dependent-instruction latency under divergence (serial Gauss-Seidel solve + TOI sub-steps per env); "
+                             "issue-slot utilisation 0.27 (step kernel) / 0.13 (TOI kernel), profiles/r2b_box2d_toi_kernel_sweep.txt",
+         "BipedalWalkerHardcore-v3": "dependent-instruction latency under divergence (serial Gauss-Seidel solve + TOI sub-steps per env)"}
 # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed ncu --set full capture (2^20 envs)
 NCU_DRAM = {"file": "profiles/r2b_cartpole_step_kernel_L_40reg_ncu_full.txt", "read": 52.76e6, "write": 22.86e6}
 FALLBACK_HBM_GBS = 6650.0  # /opt/skills/guides/B200_PROFILING.md fallback

@@ -354,6 +354,41 @@ def extra_config_line(torch, gym_b200, env_id, log2n, steps, dev, flush, peak):
             "hbm_gbs": gbs, "hbm_frac": gbs / peak}
 
 
+def uint8_actions_line(torch, gym_b200, log2n, steps, dev, flush, peak, e2e_steps):
+    """CartPole-v1 with uint8 actions, an ADDITIONAL line (the int64 line stays the headline: int64 is what
+    `Discrete.sample()` and the reference's batch_space produce): 7 bytes less per env-step for the kernel to read and
+    7/8 of the host->device traffic gone from the end-to-end path."""
+    n = 1 << log2n
+    env = gym_b200.vector.make(ENV_ID, n)
+    env.reset(seed=0)
+    gen = torch.Generator(device=dev).manual_seed(7)
+    pool = [torch.randint(0, 2, (n,), device=dev, dtype=torch.uint8, generator=gen) for _ in range(8)]
+    for w in range(20):
+        env.step(pool[w % 8])
+    ms = time_steps_flushed(torch, env, pool, steps, flush)
+    env.close()
+    med = float(np.median(ms))
+    bpe = BYTES_PER_ENV_STEP[ENV_ID] - 7
+    line = {"workload": f"{ENV_ID} num_envs=2^{log2n}, random uint8 actions resident in HBM, fused step+TimeLimit+autoreset",
+            "value": n / (med * 1e-3), "unit": "env-steps/s", "ms_per_step": med, "steps": steps, "bound": "hbm",
+            "bytes_per_env_step": bpe, "hbm_gbs": bpe * n / (med * 1e-3) / 1e9, "hbm_frac": bpe * n / (med * 1e-3) / 1e9 / peak}
+    host_env = gym_b200.vector.make(ENV_ID, n, backend="numpy", copy=False, dense_infos=True)
+    host_env.reset(seed=0)
+    hnp = [t.cpu().pin_memory().numpy() for t in pool[:4]]
+    for k in range(5):
+        host_env.step(hnp[k % 4])
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for k in range(e2e_steps):
+        host_env.step(hnp[k % 4])
+    torch.cuda.synchronize()
+    el = time.perf_counter() - t0
+    host_env.close()
+    line["e2e"] = {"value": n * e2e_steps / el, "unit": "env-steps/s", "ms_per_step": 1e3 * el / e2e_steps,
+                   "h2d_bytes_per_step": n, "steps": e2e_steps}
+    return line
+
+
 def run_b200(args):
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -586,6 +621,11 @@ def run_b200(args):
                 configs[env_id] = extra_config_line(torch, gym_b200, env_id, log2n, steps, dev, flush, peak)
             except Exception as exc:  # a failing side measurement must not lose the headline
                 configs[env_id] = {"error": repr(exc)[:200]}
+        try:
+            configs["CartPole-v1 (uint8 actions)"] = uint8_actions_line(torch, gym_b200, args.log2_envs, 200, dev, flush, peak,
+                                                                        max(10, min(args.e2e_steps, 100)))
+        except Exception as exc:
+            configs["CartPole-v1 (uint8 actions)"] = {"error": repr(exc)[:200]}
 
     # ---- cpu baseline (rank 0, N == 1 only)
     cpu = None

@@ -801,46 +801,63 @@ __device__ __noinline__ void solve_toi(typename Scene::World &W, float dt, bool 
         for (int oi = 0; oi < NB; oi++) toi_add_candidates<Scene>(W, cand, ncand, alphaS, statId, nstat, Scene::body_order(oi));
     }
     for (;;) {
-        int minIdx = -1;
-        float minAlpha = 1.0f;
+        // The search for the earliest event, in three passes so that the lanes of a warp run the expensive part
+        // together: (1) in contact-list order, the bookkeeping b2World::SolveTOI does before each b2TimeOfImpact (which
+        // sweep interval the pair is on, advancing a sweep to it) and the shortcut; pairs that need the real thing
+        // go onto a work list with a snapshot of their inputs -- b2TimeOfImpact reads state but changes none, so its
+        // evaluations can be taken out of the loop; (2) the w-th work item of every lane, all lanes at once;
+        // (3) the minimum, in contact-list order like the serial loop (the first of equal alphas wins).
+        int nwork = 0;
+        int work_ci[kMaxToiCand];
+        float work_alpha0[kMaxToiCand];
+        Sweep work_sB[kMaxToiCand];
         for (int ci = 0; ci < ncand; ci++) {
             ToiCand &c = cand[ci];
             if (!c.enabled) continue;
             if (c.toiCount > kMaxSubSteps) continue;
-            float alpha = 1.0f;
-            if (c.toiValid) alpha = c.toi;
-            else {
-                Body &B = W.b[c.body];
-                const ShapeConst &sh = Scene::shape(c.body);
-                float alpha0 = alphaS[c.sidx];
-                if (alphaS[c.sidx] < B.alpha0) { alpha0 = B.alpha0; alphaS[c.sidx] = alpha0; }
-                else if (B.alpha0 < alphaS[c.sidx]) {
-                    alpha0 = alphaS[c.sidx];
-                    Sweep s = body_sweep(B, sh);
-                    sweep_advance(s, alpha0);
-                    B.c0 = s.c0; B.a0 = s.a0; B.alpha0 = s.alpha0;
-                }
-                DProxy pA;
-                fixture_proxy<Scene>(W, c.f, pA);
-                const Sweep sB = body_sweep(B, sh);
-                B2L_STAT(0, 1);
-                const bool far_apart = toi_cannot_touch(sh, B.xf, sB, pA);
-                if (far_apart) alpha = 1.0f;
-                else {
-                    DProxy pB;
-                    pB.count = sh.count;
-                    for (int i = 0; i < sh.count; i++) pB.v[i] = sh.verts[i];
-                    Sweep sA;
-                    sA.localCenter = V(0.0f, 0.0f); sA.c0 = V(0.0f, 0.0f); sA.c = V(0.0f, 0.0f); sA.a0 = 0.0f; sA.a = 0.0f; sA.alpha0 = alpha0;
-                    float beta;
-                    B2L_STAT(3, 1);
-                    const int state = time_of_impact(beta, pA, sA, pB, sB, 1.0f);
-                    if (state == TOI_TOUCHING) alpha = fmin_(alpha0 + (1.0f - alpha0) * beta, 1.0f);
-                    else alpha = 1.0f;
-                }
-                c.toi = alpha; c.toiValid = true;
+            if (c.toiValid) continue;
+            Body &B = W.b[c.body];
+            const ShapeConst &sh = Scene::shape(c.body);
+            float alpha0 = alphaS[c.sidx];
+            if (alphaS[c.sidx] < B.alpha0) { alpha0 = B.alpha0; alphaS[c.sidx] = alpha0; }
+            else if (B.alpha0 < alphaS[c.sidx]) {
+                alpha0 = alphaS[c.sidx];
+                Sweep s = body_sweep(B, sh);
+                sweep_advance(s, alpha0);
+                B.c0 = s.c0; B.a0 = s.a0; B.alpha0 = s.alpha0;
             }
-            if (alpha < minAlpha) { minIdx = ci; minAlpha = alpha; }
+            DProxy pA;
+            fixture_proxy<Scene>(W, c.f, pA);
+            const Sweep sB = body_sweep(B, sh);
+            B2L_STAT(0, 1);
+            if (toi_cannot_touch(sh, B.xf, sB, pA)) { c.toi = 1.0f; c.toiValid = true; }
+            else { work_ci[nwork] = ci; work_alpha0[nwork] = alpha0; work_sB[nwork] = sB; nwork++; }
+        }
+        for (int w = 0; sync ? (__any_sync(live, w < nwork) != 0) : (w < nwork); w++) {
+            if (w < nwork) {
+                ToiCand &c = cand[work_ci[w]];
+                const ShapeConst &sh = Scene::shape(c.body);
+                const float alpha0 = work_alpha0[w];
+                DProxy pA, pB;
+                fixture_proxy<Scene>(W, c.f, pA);
+                pB.count = sh.count;
+                for (int i = 0; i < sh.count; i++) pB.v[i] = sh.verts[i];
+                Sweep sA;
+                sA.localCenter = V(0.0f, 0.0f); sA.c0 = V(0.0f, 0.0f); sA.c = V(0.0f, 0.0f); sA.a0 = 0.0f; sA.a = 0.0f; sA.alpha0 = alpha0;
+                float beta;
+                B2L_STAT(3, 1);
+                const int state = time_of_impact(beta, pA, sA, pB, work_sB[w], 1.0f);
+                c.toi = state == TOI_TOUCHING ? fmin_(alpha0 + (1.0f - alpha0) * beta, 1.0f) : 1.0f;
+                c.toiValid = true;
+            }
+        }
+        int minIdx = -1;
+        float minAlpha = 1.0f;
+        for (int ci = 0; ci < ncand; ci++) {
+            const ToiCand &c = cand[ci];
+            if (!c.enabled) continue;
+            if (c.toiCount > kMaxSubSteps) continue;
+            if (c.toi < minAlpha) { minIdx = ci; minAlpha = c.toi; }
         }
         const bool have = minIdx >= 0 && !(1.0f - 10.0f * kEpsilon < minAlpha);
         if (!(sync ? (__any_sync(live, have) != 0) : have)) break;

@@ -110,6 +110,9 @@ struct b200gym {
     unsigned long long *h_invalid = nullptr;   // page-locked landing word of the invalid-action counter
     cudaEvent_t hevent = nullptr;
     unsigned long long **d_peer_flags = nullptr;
+    unsigned int *p2p_done = nullptr;       // CTA counter of kernel G's fused step barrier
+    bool p2p_barrier_fused = false;         // set by the last launch_step: the barrier ran in kernel G's tail
+    int p2p_fuse = 1;                       // B200GYM_P2P_FUSE_BARRIER=0: always the separate p2p_sync_kernel
     cudaStream_t hstream[2] = {nullptr, nullptr};
     bool host_ready = false;
     mutable std::string err;
@@ -199,6 +202,15 @@ struct StepArgs {
     int32_t *ep_l;
     unsigned long long *ep_ring, *ep_counter;
     int32_t ep_ring_size;
+    // fused all-gather: the step barrier in kernel G's tail (null = the separate p2p_sync_kernel / no exchange).  The
+    // last CTA of the launch to finish its pushes publishes "my rows of step `p2p_step` are in your buffers" to every
+    // peer and waits for theirs, so the exchange costs no launch of its own
+    unsigned int *p2p_done;                       // device counter of finished CTAs (reset by the last one)
+    unsigned long long *const *p2p_peer_flags;    // [world] -> rank r's flag words (mapped)
+    const unsigned long long *p2p_my_flags;
+    int *p2p_timed_out;
+    unsigned long long p2p_step, p2p_timeout_ns;
+    int32_t p2p_world, p2p_rank;
     int32_t bulk_sink;   // 1: use kernel G's staged bulk stores even without peers (host path: the output arrays are
                          // mapped host memory, where many small stores are what hurts)
     int32_t npeer;
@@ -462,10 +474,18 @@ __device__ __forceinline__ void st_bulk(void *gmem_dst, const void *smem_src, ui
 }
 __device__ __forceinline__ void st_bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void st_bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+// ... until the bulk copies of this thread are COMPLETE (their writes performed), not just their source read
+__device__ __forceinline__ void st_bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 // generic-proxy writes to shared memory -> visible to the async proxy that executes the bulk copy
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
 }  // namespace acp
+
+__device__ __forceinline__ unsigned long long global_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
 
 // --- kernel P: persistent CTAs, per-thread asynchronous prefetch, CTA-deferred resets ---------------
 // Kernel A is latency-bound: every warp issues its six loads, waits a cold HBM round trip, runs a ~330
@@ -625,7 +645,36 @@ __global__ void __launch_bounds__(kThreads, Tuning<KIND>::kMinCtas) step_kernel_
         acp::st_bulk(term + i0, s_term, kThreads);
         acp::st_bulk(trunc + i0, s_trunc, kThreads);
         acp::st_bulk_commit();
-        acp::st_bulk_wait_read();    // the tile must stay in shared memory until the copy engine has read it
+        if (a.p2p_done) acp::st_bulk_wait_all();   // the step barrier below vouches for these writes
+        else acp::st_bulk_wait_read();             // the tile must stay in shared memory until the copy engine has read it
+    }
+    if (a.p2p_done) {
+        // the exchange's step barrier, fused: every CTA counts itself in once its pushes are complete; the last one
+        // of this rank tells every peer "my rows of this step are in your buffers" and waits for theirs
+        __syncthreads();
+        __shared__ int is_last;
+        if (threadIdx.x == 0) {
+            __threadfence_system();
+            const unsigned prev = atomicAdd(a.p2p_done, 1u);
+            is_last = prev == gridDim.x - 1;
+            if (is_last) *a.p2p_done = 0u;         // for the next launch (this one has no more increments coming)
+        }
+        __syncthreads();
+        if (is_last && (int)threadIdx.x < a.p2p_world && (int)threadIdx.x != a.p2p_rank) {
+            const int p = threadIdx.x;
+            __threadfence_system();
+            volatile unsigned long long *f = a.p2p_peer_flags[p] + a.p2p_rank;
+            *f = a.p2p_step;
+            const volatile unsigned long long *w = a.p2p_my_flags + p;
+            const unsigned long long t0 = global_ns();
+            while (*w < a.p2p_step) {
+                if (global_ns() - t0 > a.p2p_timeout_ns) {
+                    atomicExch(a.p2p_timed_out, p + 1);
+                    break;
+                }
+            }
+            __threadfence_system();
+        }
     }
 }
 
@@ -1219,12 +1268,6 @@ __global__ void rms_apply_kernel(const float *x, float *out, const double *rewar
 // bulk ones included; the system-scope fence orders them before the flag) and then waits for peer p's flag.
 // A peer that died does not hang the stream for ever: after `timeout_ns` the lane records the peer in
 // `*timed_out` (sticky, read by b200gym_p2p_status) and gives up.
-__device__ __forceinline__ unsigned long long global_ns() {
-    unsigned long long t;
-    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
-    return t;
-}
-
 __global__ void p2p_sync_kernel(unsigned long long *const *peer_flags, const unsigned long long *my_flags, int world,
                                 int rank, unsigned long long step, unsigned long long timeout_ns, int *timed_out) {
     const int p = threadIdx.x;
@@ -1296,9 +1339,15 @@ static int launch_step_typed(b200gym *h, const StepArgs &a, cudaStream_t st) {
         bool aligned = ok(a.obs, a.reward, a.terminated, a.truncated);
         for (int p = 0; p < a.npeer; p++) aligned = aligned && ok(a.peer_obs[p], a.peer_reward[p], a.peer_term[p], a.peer_trunc[p]);
         if (aligned) {
-            step_kernel_gather<KIND, ActT><<<(unsigned)tiles, kThreads, 0, st>>>(a);
+            StepArgs g = a;
+            // the fused step barrier needs the whole range in this one launch (a ragged tail goes through kernel A,
+            // whose stores the barrier would not cover): otherwise b200gym_step_p2p launches p2p_sync_kernel
+            const bool fused_barrier = a.p2p_done != nullptr && tiles * kThreads == a.count;
+            if (!fused_barrier) g.p2p_done = nullptr;
+            step_kernel_gather<KIND, ActT><<<(unsigned)tiles, kThreads, 0, st>>>(g);
             CK(h, cudaGetLastError());
             done = tiles * kThreads;
+            h->p2p_barrier_fused = fused_barrier;
         }
     }
     if (done == 0 && h->kernel_choice >= 1 && a.npeer == 0 && a.count >= (int64_t)h->sm_count * kThreads) {
@@ -1581,6 +1630,8 @@ extern "C" int b200gym_create(const b200gym_config *cfg, int64_t num_envs, int d
         const char *pc = getenv("B200GYM_P_CTAS");
         if (pc && atoi(pc) >= -1 && atoi(pc) <= 8) h->p_ctas = atoi(pc);
         if (fs && fs[0] == '1') h->kernel_choice = 0;
+        const char *pfb = getenv("B200GYM_P2P_FUSE_BARRIER");
+        if (pfb && (pfb[0] == '0' || pfb[0] == '1')) h->p2p_fuse = pfb[0] - '0';
         const char *gb = getenv("B200GYM_GATHER");
         if (gb && (gb[0] == 'b' || gb[0] == 'd')) h->gather_bulk = gb[0] == 'b';
         const char *bb = getenv("B200GYM_BOX2D_BLOCK");
@@ -1699,6 +1750,7 @@ extern "C" void b200gym_destroy(b200gym_t *h) {
             if (r != h->p2p.rank && h->p2p.peer[r]) cudaIpcCloseMemHandle(h->p2p.peer[r]);
         cudaFree(h->p2p.base);
         cudaFree(h->d_peer_flags);
+        cudaFree(h->p2p_done);
     }
     delete h;
 }
@@ -1762,6 +1814,8 @@ static StepArgs make_args(b200gym *h, const void *actions, float *obs, double *r
     a.lunar_opts = h->lunar_opts;
     a.reset_list = nullptr; a.reset_count = nullptr;
     a.toi_list = nullptr; a.toi_count = nullptr; a.toi_mid = nullptr;
+    a.p2p_done = nullptr; a.p2p_peer_flags = nullptr; a.p2p_my_flags = nullptr; a.p2p_timed_out = nullptr;
+    a.p2p_step = 0; a.p2p_timeout_ns = 0; a.p2p_world = 0; a.p2p_rank = 0;
     a.npeer = 0;
     a.bulk_sink = 0;
     a.ep_acc = h->ep.acc; a.ep_len = h->ep.len; a.ep_r = h->ep.r; a.ep_l = h->ep.l;
@@ -1934,15 +1988,25 @@ extern "C" int b200gym_step_p2p(b200gym_t *h, const void *actions_dev, int actio
         np++;
     }
     a.npeer = np;
-    if (launch_step(h, a, action_dtype, st)) return 1;
-    if (P.world > 1) {
-        // tell every peer that my rows of step `P.step` are in its buffers, then wait for theirs
+    if (P.world > 1 && !h->d_peer_flags) {
         unsigned long long *pf[B200GYM_MAX_PEERS + 1];
         for (int r = 0; r < P.world; r++) pf[r] = (unsigned long long *)(P.peer[r] + P.off_flags);
-        if (!h->d_peer_flags) {
-            CK(h, cudaMalloc((void **)&h->d_peer_flags, sizeof pf));
-            CK(h, cudaMemcpy(h->d_peer_flags, pf, sizeof pf, cudaMemcpyHostToDevice));
-        }
+        CK(h, cudaMalloc((void **)&h->d_peer_flags, sizeof pf));
+        CK(h, cudaMemcpy(h->d_peer_flags, pf, sizeof pf, cudaMemcpyHostToDevice));
+        CK(h, cudaMalloc((void **)&h->p2p_done, sizeof(unsigned int)));
+        CK(h, cudaMemset(h->p2p_done, 0, sizeof(unsigned int)));
+    }
+    if (P.world > 1 && h->p2p_fuse) {   // offer kernel G the step barrier (it takes it when it covers the whole range)
+        a.p2p_done = h->p2p_done;
+        a.p2p_peer_flags = h->d_peer_flags;
+        a.p2p_my_flags = (const unsigned long long *)(P.base + P.off_flags);
+        a.p2p_timed_out = (int *)(P.base + P.off_flags + 128);
+        a.p2p_step = P.step; a.p2p_timeout_ns = P.timeout_ns; a.p2p_world = P.world; a.p2p_rank = P.rank;
+    }
+    h->p2p_barrier_fused = false;
+    if (launch_step(h, a, action_dtype, st)) return 1;
+    if (P.world > 1 && !h->p2p_barrier_fused) {
+        // tell every peer that my rows of step `P.step` are in its buffers, then wait for theirs
         p2p_sync_kernel<<<1, 32, 0, st>>>(h->d_peer_flags, (const unsigned long long *)(P.base + P.off_flags), P.world,
                                           P.rank, P.step, P.timeout_ns, (int *)(P.base + P.off_flags + 128));
         CK(h, cudaGetLastError());

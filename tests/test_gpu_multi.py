@@ -154,7 +154,10 @@ def test_wrappers_across_gpus():
 
 
 @pytest.mark.skipif(_ngpus() < 2, reason="needs at least 2 GPUs")
-@pytest.mark.parametrize("env_id,n_local", [("CartPole-v1", 148 * 256 + 640), ("Pendulum-v1", 5000)])
+# 148*256+640: full tiles through kernel G + a ragged tail through kernel A, barrier by p2p_sync_kernel; 5000: ragged;
+# 300*256: whole tiles only -> the step barrier runs fused in kernel G's tail (no launch of its own)
+@pytest.mark.parametrize("env_id,n_local", [("CartPole-v1", 148 * 256 + 640), ("Pendulum-v1", 5000), ("CartPole-v1", 300 * 256),
+                                            ("Acrobot-v1", 64 * 256)])
 @pytest.mark.timeout(300)
 def test_sharded_step_matches_single_gpu(env_id, n_local):
     import torch.multiprocessing as mp

@@ -496,7 +496,7 @@ def run_b200(args):
         extra_timing = {"ms_per_step_median": max_over_ranks(float(np.median(gaps)))}
         # fused exchange: kernel G alone when the shard is whole 256-env tiles (the step barrier runs in its tail),
         # else kernel G + kernel A for the ragged tail + p2p_sync_kernel; NCCL: the step kernel + 4 all-gathers
-        fused_barrier = n % 256 == 0 and os.environ.get("B200GYM_P2P_FUSE_BARRIER", "1") != "0"
+        fused_barrier = n % 256 == 0 and os.environ.get("B200GYM_P2P_FUSE_BARRIER", "0") == "1"
         launches_per_step = (1 if fused_barrier else 2) if gather == "p2p" else 5
         # ---- verify the gather: per peer, checksum of ITS rows in MY copy == the checksum it computed itself
         acts = pool[3]
@@ -655,7 +655,7 @@ def run_b200(args):
                        "arm": f"{'int64' if inner.discrete else 'float32'} actions resident in HBM, fused "
                               "step+TimeLimit+autoreset kernel"
                               + ((", all-gather of (obs,reward,terminated,truncated) per step fused into the "
-                                  "step kernel (bulk pushes over NVLink peer memory, the flag exchange in the kernel's tail)"
+                                  "step kernel (bulk pushes over NVLink peer memory + one flag exchange)"
                                   if gather == "p2p" else
                                   ", NCCL all-gather of (obs,reward,terminated,truncated) per step")
                                  if world > 1 else ""),

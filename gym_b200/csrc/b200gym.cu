@@ -112,7 +112,13 @@ struct b200gym {
     unsigned long long **d_peer_flags = nullptr;
     unsigned int *p2p_done = nullptr;       // CTA counter of kernel G's fused step barrier
     bool p2p_barrier_fused = false;         // set by the last launch_step: the barrier ran in kernel G's tail
-    int p2p_fuse = 1;                       // B200GYM_P2P_FUSE_BARRIER=0: always the separate p2p_sync_kernel
+    int p2p_fuse = 0;                       // B200GYM_P2P_FUSE_BARRIER=1: the step barrier in kernel G's tail instead of the
+                                            // 32-thread p2p_sync_kernel.  Correct (tests/test_gpu_multi.py runs it) but
+                                            // measured SLOWER on 2 x B200, 82 vs 59 us per step: to vouch for its pushes a
+                                            // CTA must wait for their COMPLETION (cp.async.bulk.wait_group 0: an NVLink
+                                            // round trip per tile) instead of only for its tile to be read out of shared
+                                            // memory, and that costs more residency than the kernel boundary + one tiny
+                                            // launch save -- so the separate launch stays the default
     cudaStream_t hstream[2] = {nullptr, nullptr};
     bool host_ready = false;
     mutable std::string err;

@@ -82,63 +82,36 @@ __device__ __noinline__ void sincos_library(double x, double *sn, double *cs) {
 #endif
 }
 
-// the two fdlibm kernels themselves (valid for |x| < 0.7; straight-line)
-__device__ __forceinline__ void sincos_small_poly(double x, double &sn, double &cs) {
-    const double z = x * x;
-    double r = kSinCoef[5];
-    r = fma(r, z, kSinCoef[4]);
-    r = fma(r, z, kSinCoef[3]);
-    r = fma(r, z, kSinCoef[2]);
-    r = fma(r, z, kSinCoef[1]);
-    const double v = z * x;
-    sn = fma(v, fma(z, r, kSinCoef[0]), x);
-    double c = kCosCoef[5];
-    c = fma(c, z, kCosCoef[4]);
-    c = fma(c, z, kCosCoef[3]);
-    c = fma(c, z, kCosCoef[2]);
-    c = fma(c, z, kCosCoef[1]);
-    c = fma(c, z, kCosCoef[0]);
-    const double zr = z * c;
-    // 1 - (z/2 - z*r), with the fdlibm split that keeps the subtraction exact near |x| ~ 0.3 .. 0.7
-    const double qx = fabs(x) < 0.3 ? 0.0 : 0.25 * fabs(x);
-    const double hz = fma(0.5, z, -qx);
-    cs = (1.0 - qx) - (hz - z * zr);
-}
-
 __device__ __forceinline__ void sincos_small(double x, double &sn, double &cs) {
-    if (fabs(x) < 0.7) sincos_small_poly(x, sn, cs);
-    else sincos_library(x, &sn, &cs);
-}
-
-// div_by_const's fast sequence without its own branch: `ok` is cleared when x is outside the range in which the
-// sequence is proven exact (the caller then redoes the whole computation with `/`)
-__device__ __forceinline__ double div_by_const_unguarded(double x, double c, double rc, bool &ok) {
-    const double ax = fabs(x);
-    ok = ok && (ax < 1e290) && !(ax < 1e-290);
-    double q = x * rc;
-    double r = fma(-q, c, x);
-    q = fma(r, rc, q);
-    r = fma(-q, c, x);
-    return fma(r, rc, q);
+    if (fabs(x) < 0.7) {
+        const double z = x * x;
+        double r = kSinCoef[5];
+        r = fma(r, z, kSinCoef[4]);
+        r = fma(r, z, kSinCoef[3]);
+        r = fma(r, z, kSinCoef[2]);
+        r = fma(r, z, kSinCoef[1]);
+        const double v = z * x;
+        sn = fma(v, fma(z, r, kSinCoef[0]), x);
+        double c = kCosCoef[5];
+        c = fma(c, z, kCosCoef[4]);
+        c = fma(c, z, kCosCoef[3]);
+        c = fma(c, z, kCosCoef[2]);
+        c = fma(c, z, kCosCoef[1]);
+        c = fma(c, z, kCosCoef[0]);
+        const double zr = z * c;
+        // 1 - (z/2 - z*r), with the fdlibm split that keeps the subtraction exact near |x| ~ 0.3 .. 0.7
+        const double qx = fabs(x) < 0.3 ? 0.0 : 0.25 * fabs(x);
+        const double hz = fma(0.5, z, -qx);
+        cs = (1.0 - qx) - (hz - z * zr);
+    } else {
+        sincos_library(x, &sn, &cs);
+    }
 }
 
 __constant__ double kInvTotalMass = 1.0 / (0.1 + 1.0);
 
 // CartPole's physical constants, also kept in the constant bank (float64 immediates cost two UMOVs each)
 __constant__ double kCartPole[10] = {9.8, 0.1, 0.1 + 1.0, 0.5, 0.1 * 0.5, 10.0, 0.02, 12 * 2 * B200_PI / 360, 2.4, 4.0 / 3.0};
-
-// cartpole.py:136-147 with the library sin / cos and plain divisions: the path for pole angles beyond 0.7 rad
-// (plain-Env mode after termination) and for operands outside the exact-division range
-__device__ __noinline__ void cartpole_accel_general(double force, double theta, double theta_dot, double &thetaacc,
-                                                    double &xacc) {
-    const double gravity = kCartPole[0], masspole = kCartPole[1], total_mass = kCartPole[2], length = kCartPole[3];
-    const double polemass_length = kCartPole[4];
-    double sintheta, costheta;
-    sincos_small(theta, sintheta, costheta);
-    const double temp = (force + polemass_length * (theta_dot * theta_dot) * sintheta) / total_mass;
-    thetaacc = (gravity * sintheta - costheta * temp) / (length * (kCartPole[9] - masspole * (costheta * costheta) / total_mass));
-    xacc = temp - polemass_length * thetaacc * costheta / total_mass;
-}
 
 // ---------------------------------------------------------------------------
 // CartPole-v0/v1 -- gym/envs/classic_control/cartpole.py
@@ -179,23 +152,17 @@ struct Env<B200GYM_CARTPOLE> {
 
         double x = s[0], x_dot = s[1], theta = s[2], theta_dot = s[3];
         const double force = (action == 1) ? force_mag : -force_mag;         // :135
-        // Straight-line fast path: the small-angle sin / cos kernels and the exact constant divisions, with ONE
-        // validity flag instead of a branch (and a re-convergence point) at each of them; whenever any of their
-        // preconditions fails -- never for a state that is still stepped under autoreset -- the accelerations are
-        // recomputed by the general, out-of-line path.
-        bool ok = fabs(theta) < 0.7;
         double sintheta, costheta;
-        sincos_small_poly(theta, sintheta, costheta);                        // :136-137
+        sincos_small(theta, sintheta, costheta);                             // :136-137
         const double inv_total_mass = kInvTotalMass;     // RN(1 / total_mass), folded by the compiler
-        double temp = div_by_const_unguarded(
-            force + polemass_length * (theta_dot * theta_dot) * sintheta, total_mass, inv_total_mass, ok);  // :141-143
-        double thetaacc =
+        const double temp = div_by_const(
+            force + polemass_length * (theta_dot * theta_dot) * sintheta, total_mass, inv_total_mass);  // :141-143
+        const double thetaacc =
             (gravity * sintheta - costheta * temp) /
-            (length * (kCartPole[9] - div_by_const_unguarded(masspole * (costheta * costheta), total_mass,
-                                                             inv_total_mass, ok)));         // :144-146
-        double xacc = temp - div_by_const_unguarded(polemass_length * thetaacc * costheta, total_mass,
-                                                    inv_total_mass, ok);                   // :147
-        if (!ok) cartpole_accel_general(force, theta, theta_dot, thetaacc, xacc);
+            (length * (kCartPole[9] - div_by_const(masspole * (costheta * costheta), total_mass,
+                                                inv_total_mass)));                         // :144-146
+        const double xacc = temp - div_by_const(polemass_length * thetaacc * costheta, total_mass,
+                                                inv_total_mass);                           // :147
         x = x + tau * x_dot;                                                 // :150
         x_dot = x_dot + tau * xacc;                                          // :151
         theta = theta + tau * theta_dot;                                     // :152

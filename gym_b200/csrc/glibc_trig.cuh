@@ -34,7 +34,9 @@ namespace bgym {
 namespace gt {
 
 // {sin hi, sin lo, cos hi, cos lo} of k / 128, k = 0 .. 109
-__device__ const double kTab[440] = {
+// (32-byte aligned: one table entry {sin hi, sin lo, cos hi, cos lo} is fetched as two 16-byte loads)
+struct alignas(16) TabPair { double x, y; };
+alignas(32) __device__ const double kTab[440] = {
     0x0.0p+0, 0x0.0p+0, 0x1.0000000000000p+0, 0x0.0p+0,
     0x1.fffeaaaaeeeefp-8, -0x1.e45e2ec67b77cp-62, 0x1.fffc000155552p-1, 0x1.f4a01a0196daep-55,
     0x1.fffaaaaeeeed5p-7, -0x1.2ab639a9f0777p-63, 0x1.fff000155549fp-1, 0x1.28a28a03a5ef3p-55,
@@ -189,7 +191,8 @@ __device__ __forceinline__ double do_sin_tab(double a, double da) {
     pc = fma(xx, pc, kCs2);
     s = x + s;
     const double c = fma(da, x, xx * pc);
-    const double sn = kTab[k], ssn = kTab[k + 1], cs = kTab[k + 2], ccs = kTab[k + 3];
+    const TabPair ts = reinterpret_cast<const TabPair *>(kTab + k)[0], tc = reinterpret_cast<const TabPair *>(kTab + k)[1];
+    const double sn = ts.x, ssn = ts.y, cs = tc.x, ccs = tc.y;
     double cor = fma(s, ccs, ssn);
     cor = fma(-c, sn, cor);
     cor = fma(s, cs, cor);
@@ -215,7 +218,8 @@ __device__ __forceinline__ double do_cos(double a, double da) {
     double pc = fma(xx, kCs6, kCs4);
     pc = fma(xx, pc, kCs2);
     const double c = xx * pc;
-    const double sn = kTab[k], ssn = kTab[k + 1], cs = kTab[k + 2], ccs = kTab[k + 3];
+    const TabPair ts = reinterpret_cast<const TabPair *>(kTab + k)[0], tc = reinterpret_cast<const TabPair *>(kTab + k)[1];
+    const double sn = ts.x, ssn = ts.y, cs = tc.x, ccs = tc.y;
     double cor = fma(-s, ssn, ccs);
     cor = fma(-c, cs, cor);
     cor = fma(-s, sn, cor);

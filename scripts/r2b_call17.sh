@@ -1,7 +1,7 @@
 #!/bin/bash
 # round 2 (second session), call 17: per-kind register budgets at BASELINE's 2^18 envs (one round of tiles instead of two)
 mkdir -p gpurun_out
-for e in MountainCar-v0 MountainCarContinuous-v0 Pendulum-v1; do
+for e in Acrobot-v1 MountainCar-v0 MountainCarContinuous-v0 Pendulum-v1; do
   timeout 300 python bench.py --env $e --log2-envs 18 --steps 400 --warmup 50 --no-cpu-baseline --no-e2e --no-extra 2>/dev/null | grep '^{' | python -c "import json,sys; d=json.loads(sys.stdin.read()); print('default $e ms', d['ms_per_step'], 'value %.3g' % d['value'])"
 done
 for e in Pendulum-v1 CartPole-v1; do

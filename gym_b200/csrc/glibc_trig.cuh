@@ -34,20 +34,7 @@ namespace bgym {
 namespace gt {
 
 // {sin hi, sin lo, cos hi, cos lo} of k / 128, k = 0 .. 109
-// (32-byte aligned: one table entry {sin hi, sin lo, cos hi, cos lo} is fetched as two 16-byte read-only loads --
-// spelled in PTX so that the compiler neither splits them into four 8-byte loads nor fuses them into one 32-byte
-// load, which was measured slower for Acrobot: 65.5 vs 59.4 us per 2^18-env step)
-struct alignas(16) TabPair { double x, y; };
-__device__ __forceinline__ TabPair tab_pair(const double *p) {
-    TabPair t;
-#ifdef __CUDA_ARCH__
-    asm("ld.global.nc.v2.f64 {%0, %1}, [%2];" : "=d"(t.x), "=d"(t.y) : "l"(p));
-#else
-    t.x = p[0]; t.y = p[1];
-#endif
-    return t;
-}
-alignas(32) __device__ const double kTab[440] = {
+__device__ const double kTab[440] = {
     0x0.0p+0, 0x0.0p+0, 0x1.0000000000000p+0, 0x0.0p+0,
     0x1.fffeaaaaeeeefp-8, -0x1.e45e2ec67b77cp-62, 0x1.fffc000155552p-1, 0x1.f4a01a0196daep-55,
     0x1.fffaaaaeeeed5p-7, -0x1.2ab639a9f0777p-63, 0x1.fff000155549fp-1, 0x1.28a28a03a5ef3p-55,
@@ -202,8 +189,7 @@ __device__ __forceinline__ double do_sin_tab(double a, double da) {
     pc = fma(xx, pc, kCs2);
     s = x + s;
     const double c = fma(da, x, xx * pc);
-    const TabPair ts = tab_pair(kTab + k), tc = tab_pair(kTab + k + 2);
-    const double sn = ts.x, ssn = ts.y, cs = tc.x, ccs = tc.y;
+    const double sn = kTab[k], ssn = kTab[k + 1], cs = kTab[k + 2], ccs = kTab[k + 3];
     double cor = fma(s, ccs, ssn);
     cor = fma(-c, sn, cor);
     cor = fma(s, cs, cor);
@@ -229,8 +215,7 @@ __device__ __forceinline__ double do_cos(double a, double da) {
     double pc = fma(xx, kCs6, kCs4);
     pc = fma(xx, pc, kCs2);
     const double c = xx * pc;
-    const TabPair ts = tab_pair(kTab + k), tc = tab_pair(kTab + k + 2);
-    const double sn = ts.x, ssn = ts.y, cs = tc.x, ccs = tc.y;
+    const double sn = kTab[k], ssn = kTab[k + 1], cs = kTab[k + 2], ccs = kTab[k + 3];
     double cor = fma(-s, ssn, ccs);
     cor = fma(-c, cs, cor);
     cor = fma(-s, sn, cor);

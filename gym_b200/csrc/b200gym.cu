@@ -82,6 +82,7 @@ struct b200gym {
                                             // BipedalWalker 7.62 vs 7.67): the envs that end an episode are mostly the parked
                                             // ones, whose resets can only follow the TOI kernel -- so the plain sequence is
                                             // the default
+    int toi_grid = 12;                      // TOI kernel: one-warp CTAs per SM (B200GYM_TOI_GRID, tuning runs)
     int box2d_toi_defer = 1;                // Box2D tasks: 1 = envs with a possible TOI event finish in the compacted TOI kernel
                                             // (B200GYM_BOX2D_TOI_DEFER=0: SolveTOI inline in the step kernel)
     int32_t *toi_list = nullptr;            // [n] env offsets parked for the TOI kernel, per launch range
@@ -1462,9 +1463,7 @@ static int launch_step(b200gym *h, const StepArgs &a, int action_dtype, cudaStre
         // one warp per CTA, 12 CTAs per SM (what is resident with the 156-register kernel); the kernel strides over
         // the list.  Larger grids (fewer envs per warp) were measured: LunarLander 1.74 / 1.82 / 1.85 ms at 12 / 64 / 256
         // CTAs per SM, BipedalWalker (nearly every env parked) 7.4 / 12.2 / 17.1 ms
-        int tg = 12;
-        if (const char *tge = getenv("B200GYM_TOI_GRID")) { const int v = atoi(tge); if (v >= 1 && v <= 1024) tg = v; }
-        const unsigned tgrid = (unsigned)std::min<int64_t>(b.count, (int64_t)tg * h->sm_count);
+        const unsigned tgrid = (unsigned)std::min<int64_t>(b.count, (int64_t)h->toi_grid * h->sm_count);
         // With both on, the resets come from two kernels: those of the step kernel go onto list 1 and restart on the
         // side stream WHILE the TOI kernel runs (a reset is a long serial chain -- terrain draw + an embedded world
         // step, 1.1 ms for a batch of BipedalWalker resets -- but touches only its own env); those of the TOI kernel
@@ -1646,6 +1645,7 @@ extern "C" int b200gym_create(const b200gym_config *cfg, int64_t num_envs, int d
         if (bb && (atoi(bb) == 128 || atoi(bb) == 256)) h->box2d_block = atoi(bb);
         const char *bsp = getenv("B200GYM_BOX2D_SPLIT");
         if (bsp && (bsp[0] == '0' || bsp[0] == '1')) h->box2d_split = bsp[0] - '0';
+        if (const char *tge = getenv("B200GYM_TOI_GRID")) { const int v = atoi(tge); if (v >= 1 && v <= 1024) h->toi_grid = v; }
         const char *btd = getenv("B200GYM_BOX2D_TOI_DEFER");
         if (btd && (btd[0] == '0' || btd[0] == '1')) h->box2d_toi_defer = btd[0] - '0';
         const char *bdf = getenv("B200GYM_BOX2D_DEFER");

@@ -500,6 +500,25 @@ int orc_b2l_toi_probe(const float *poly_xy, int n, const float c0[2], float a0, 
     return time_of_impact(t_out, &pA, &sA, &pB, &sB, 1.0f);
 }
 
+/* test hook: b2Distance (GJK, b2lite_toi.h) between a convex polygon placed at (c, a) and the static edge v1-v2, core
+ * shapes without radii, from an empty simplex cache; also returns the GJK iteration count through *cache_count */
+float orc_b2l_distance_probe(const float *poly_xy, int n, const float c[2], float a, const float v1[2], const float v2_[2],
+                             int *cache_count)
+{
+    dproxy_t pA, pB;
+    pA.count = 2; pA.v[0] = V(v1[0], v1[1]); pA.v[1] = V(v2_[0], v2_[1]);
+    pB.count = n;
+    for (int i = 0; i < n && i < MAXV; i++) pB.v[i] = V(poly_xy[2 * i], poly_xy[2 * i + 1]);
+    xform xfA = XF_ID, xfB;
+    xfB.q = rot_of(a);
+    xfB.p = V(c[0], c[1]);
+    scache_t cache;
+    cache.count = 0;
+    float d = gjk_distance(&cache, &pA, xfA, &pB, xfB);
+    if (cache_count) *cache_count = cache.count;
+    return d;
+}
+
 /* test hook: overwrite the velocity of one body of env i (tunnelling tests) */
 void orc_lunar_set_body_velocity(orc_lunar *v, int64_t i, int body, float vx, float vy, float w)
 {

@@ -32,6 +32,8 @@ void orc_lunar_toi_stats(const orc_lunar *v, int64_t out[3]);
 void orc_lunar_set_toi(int on);
 int orc_b2l_toi_probe(const float *poly_xy, int n, const float c0[2], float a0, const float c1[2], float a1,
                       const float v1[2], const float v2_[2], float *t_out);
+float orc_b2l_distance_probe(const float *poly_xy, int n, const float c[2], float a, const float v1[2], const float v2_[2],
+                             int *cache_count);
 void orc_lunar_set_body_velocity(orc_lunar *v, int64_t i, int body, float vx, float vy, float w);
 #ifdef __cplusplus
 }

@@ -252,6 +252,21 @@ def toi_probe(poly, c0, a0, c1, a1, v1, v2):
     return int(st), float(t.value)
 
 
+def distance_probe(poly, c, a, v1, v2):
+    """b2Distance (GJK) between a convex polygon (local vertices) placed at (c, a) and the static edge v1-v2, without
+    radii -> (distance, number of simplex vertices at termination)."""
+    f = lib().orc_b2l_distance_probe
+    f.restype = ctypes.c_float
+    fp = ctypes.POINTER(ctypes.c_float)
+    f.argtypes = [fp, ctypes.c_int, fp, ctypes.c_float, fp, fp, ctypes.POINTER(ctypes.c_int)]
+    arr = lambda x: np.ascontiguousarray(x, dtype=np.float32).ravel()
+    P, C, V1, V2 = arr(poly), arr(c), arr(v1), arr(v2)
+    cnt = ctypes.c_int(0)
+    p_ = lambda z: z.ctypes.data_as(fp)
+    d = f(p_(P), len(P) // 2, p_(C), float(a), p_(V1), p_(V2), ctypes.byref(cnt))
+    return float(d), int(cnt.value)
+
+
 class OracleLunar:
     """SyncVectorEnv([make("LunarLander-v2")] * n) restated in C (oracle/lunar_oracle.c).
 

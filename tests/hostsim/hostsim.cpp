@@ -425,4 +425,14 @@ int hs_toi_probe(int shape, const float *c0, float a0, const float *c1, float a1
     return b2l::time_of_impact(*t_out, pA, sA, pB, sB, 1.0f);
 }
 
+// The task polygon `shape` as the device constants hold it: vertices (x, y pairs) into out, local centre into lc;
+// returns the vertex count.
+int hs_shape_verts(int shape, float *out, float *lc) {
+    ensure_consts();
+    const b2l::ShapeConst &sh = shape < 2 ? lunar::kC.shape[shape] : walker::kC.shape[shape - 2];
+    for (int i = 0; i < sh.count; i++) { out[2 * i] = sh.verts[i].x; out[2 * i + 1] = sh.verts[i].y; }
+    lc[0] = sh.localCenter.x; lc[1] = sh.localCenter.y;
+    return sh.count;
+}
+
 }  // extern "C"

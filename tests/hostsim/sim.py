@@ -221,6 +221,18 @@ def sincos_small(x):
     return sn, cs
 
 
+def shape_verts(shape):
+    """Vertices (n, 2) float32 and local centre (2,) of task polygon `shape` as the device constants hold them."""
+    fp = ctypes.POINTER(ctypes.c_float)
+    out = np.zeros(16, dtype=np.float32)
+    lc = np.zeros(2, dtype=np.float32)
+    f = lib().hs_shape_verts
+    f.restype = ctypes.c_int
+    f.argtypes = [ctypes.c_int, fp, fp]
+    n = f(int(shape), out.ctypes.data_as(fp), lc.ctypes.data_as(fp))
+    return out[:2 * n].reshape(n, 2).copy(), lc
+
+
 def toi_probe(shape, c0, a0, c1, a1, edge=None, box=None):
     """The device source's b2TimeOfImpact + its conservative shortcut for one sweep of a task polygon (0 lander, 1 its
     leg, 2 walker hull, 3 / 4 walker upper / lower leg) against a static edge ((x1, y1), (x2, y2)) or an axis-aligned

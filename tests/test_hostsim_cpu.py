@@ -304,3 +304,33 @@ def test_toi_shortcuts_never_dismiss_a_pair_that_touches():
     assert both == 0, f"{both} sweeps were dismissed although b2TimeOfImpact reports e_touching"
     assert fired > 5000 and touching > 5000, (fired, touching)
 
+
+
+def test_device_time_of_impact_equals_the_oracles_on_random_sweeps():
+    """`time_of_impact` / `gjk_distance` / the separation function of b2lite_toi.cuh (device source, compiled for the
+    host) against oracle/b2lite_toi.h on the same 20 000 sweeps of the three task boxes whose body origin is the
+    centre of mass (lander leg, walker upper / lower leg) against an edge: state and t bit for bit.  The roll-outs
+    above cover this through whole episodes; this pins the function itself, fast spins and tunnelling included."""
+    from oracle import oracle as orc
+    polys = {}
+    for shape in (1, 3, 4):
+        verts, lc = sim.shape_verts(shape)
+        assert len(verts) == 4 and not lc.any()
+        polys[shape] = verts
+    rng = np.random.default_rng(8)
+    states = {}
+    for k in range(20000):
+        shape = (1, 3, 4)[k % 3]
+        slope = rng.uniform(-0.6, 0.6)
+        edge = ((-2.0, -2.0 * slope), (2.0, 2.0 * slope))
+        x0 = rng.uniform(-1.0, 1.0)
+        c0 = (x0, slope * x0 + rng.uniform(0.0, 1.2))
+        a0 = rng.uniform(-3.2, 3.2)
+        scale = (0.01, 0.1, 1.0)[(k // 3) % 3]
+        c1 = (c0[0] + scale * rng.normal(0, 0.4), c0[1] - scale * abs(rng.normal(0, 1.0)))
+        a1 = a0 + scale * rng.normal(0, 1.0)
+        st, t, _ = sim.toi_probe(shape, c0, a0, c1, a1, edge=edge)
+        ost, ot = orc.toi_probe(polys[shape], c0, a0, c1, a1, edge[0], edge[1])
+        assert (st, np.float32(t).tobytes()) == (ost, np.float32(ot).tobytes()), (k, shape, st, t, ost, ot)
+        states[st] = states.get(st, 0) + 1
+    assert states.get(3, 0) > 3000 and states.get(4, 0) > 3000 and states.get(1, 0) == 0, states
